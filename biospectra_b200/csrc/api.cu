@@ -1,0 +1,878 @@
+// api.cu -- C ABI of libbiospectra_gpu.so (see include/biospectra_gpu.h).
+#include "../../include/biospectra_gpu.h"
+#include "gpu_index.cuh"
+
+#include <dirent.h>
+#include <errno.h>
+#include <mutex>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#define BSP_API extern "C" __attribute__((visibility("default")))
+
+static thread_local std::string g_last_error;
+
+static const char* IDX_FILE = "biospectra.idx";
+static const u64 IDX_MAGIC = 0x3130584449505342ull;   // "BSPIDX01"
+
+// ------------------------------------------------------------------ handles
+struct bsp_indexer {
+    std::mutex mu;
+    bsp_config conf;
+    std::string index_path;
+    RefStore* ref = nullptr;
+    cudaStream_t st = nullptr;
+    std::string last_error;
+    ~bsp_indexer() { delete ref; if (st) cudaStreamDestroy(st); }
+};
+
+struct Scratch {
+    DevBuf<u8> seq, scan_tmp; DevBuf<i64> seq_off, tok_off, tok_cap;
+    DevBuf<u64> tok_key; DevBuf<u32> tok_pos, tok_df, clause_row; DevBuf<float> clause_val;
+    DevBuf<i32> n_tok, n_clauses, msm, route, status_in, list_dense, list_pos, counts;
+    DevBuf<i32> part_n; DevBuf<u32> part_doc; DevBuf<float> part_score;
+    DevBuf<i32> o_status, o_label, o_nhits, o_ntop, o_doc; DevBuf<float> o_score;
+    u8* pin_in = nullptr; size_t pin_in_bytes = 0;
+    u8* pin_out = nullptr; size_t pin_out_bytes = 0;
+    ~Scratch() { if (pin_in) cudaFreeHost(pin_in); if (pin_out) cudaFreeHost(pin_out); }
+};
+
+struct bsp_classifier {
+    std::mutex mu;
+    bsp_config conf;
+    RefStore* ref = nullptr;
+    GpuIndex ix;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string last_error;
+    Scratch sc;
+    // scoring constants
+    DevBuf<float> idf_by_df, doc_w, pair_lut, tf_lut;
+    i64 global_docs = 0, global_sum_ttf = 0, doc_base_global = 0;
+    // last batch
+    std::vector<i32> last_routes;
+    i64 counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double score_ms = 0, pipe_ms = 0;
+    ~bsp_classifier() {
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (st) cudaStreamDestroy(st);
+        delete ref;
+    }
+};
+
+static int fail(std::string* slot, int code, const std::string& msg) {
+    g_last_error = msg;
+    if (slot) *slot = msg;
+    return code;
+}
+
+#define API_TRY(h) try {
+#define API_CATCH(h)                                                                           \
+    } catch (const BspError& e) { return fail((h) ? &(h)->last_error : nullptr, e.code, e.what()); } \
+    catch (const std::bad_alloc&) { return fail((h) ? &(h)->last_error : nullptr, BSP_ERR_NOMEM, "out of host memory"); } \
+    catch (const std::exception& e) { return fail((h) ? &(h)->last_error : nullptr, BSP_ERR_STATE, e.what()); }
+
+BSP_API const char* bsp_last_error(const void* handle) {
+    (void)handle;                       // messages are also kept per thread; handle-specific text mirrors it
+    return g_last_error.c_str();
+}
+BSP_API const char* bsp_version(void) { return "biospectra-b200 0.1 (sm_100a)"; }
+
+BSP_API void bsp_config_default(bsp_config* c) {         // Configuration.java:37-44
+    memset(c, 0, sizeof *c);
+    c->kmer_size = 10; c->kmer_skips = 5; c->min_strand_kmer = 0;
+    c->query_algorithm = BSP_PAIRED_PROXIMITY; c->scoring_algorithm = BSP_TFIDF;
+    c->worker_threads = 4; c->index_ram_buffer = 16; c->device = 0;
+    c->query_term_min_should_match = 0.5;
+    c->part_rank = 0; c->part_count = 1; c->dense_tables = 0; c->positional = 0;
+}
+
+static i64 env_i64(const char* name, i64 dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atoll(v);
+}
+
+// ------------------------------------------------------------------ filesystem
+static void wipe_directory(const std::string& path) {      // Indexer.java:253-264 cleanUpDirectory
+    DIR* d = opendir(path.c_str());
+    if (!d) return;
+    struct dirent* de;
+    while ((de = readdir(d)) != nullptr) {
+        if (!strcmp(de->d_name, ".") || !strcmp(de->d_name, "..")) continue;
+        std::string p = path + "/" + de->d_name;
+        struct stat sb;
+        if (lstat(p.c_str(), &sb) != 0) continue;
+        if (S_ISDIR(sb.st_mode)) { wipe_directory(p); rmdir(p.c_str()); }
+        else unlink(p.c_str());
+    }
+    closedir(d);
+}
+static void mkdirs(const std::string& path) {
+    std::string cur;
+    for (size_t i = 0; i <= path.size(); i++) {
+        if (i == path.size() || path[i] == '/') {
+            if (!cur.empty()) mkdir(cur.c_str(), 0777);
+        }
+        if (i < path.size()) cur.push_back(path[i]);
+    }
+}
+static bool is_dir(const std::string& p) {
+    struct stat sb;
+    return stat(p.c_str(), &sb) == 0 && S_ISDIR(sb.st_mode);
+}
+
+// ------------------------------------------------------------------ indexer
+BSP_API int bsp_index_create(const bsp_config* conf, const char* index_path, bsp_indexer** out) {
+    if (out) *out = nullptr;
+    bsp_indexer* h = nullptr;
+    API_TRY(h)
+    if (!conf) return fail(nullptr, BSP_ERR_ARG, "conf is null");                                   // Indexer.java:65-67
+    if (!index_path) return fail(nullptr, BSP_ERR_ARG, "indexPath is null");                        // :69-71
+    if (conf->kmer_size <= 0) return fail(nullptr, BSP_ERR_ARG, "kmerSize must be larger than 0");  // :73-75
+    if (conf->worker_threads <= 0) return fail(nullptr, BSP_ERR_ARG, "workerThreads must be larger than 0"); // :77-79
+    if (conf->kmer_size > 31) return fail(nullptr, BSP_ERR_UNSUPPORTED, "kmerSize > 31 is not supported");
+    if (!out) return fail(nullptr, BSP_ERR_ARG, "out is null");
+    CUDA_CHECK(cudaSetDevice(conf->device));
+    h = new bsp_indexer();
+    h->conf = *conf;
+    h->index_path = index_path;
+    if (*index_path) {
+        mkdirs(h->index_path);                                                                      // :85-87
+        if (is_dir(h->index_path)) wipe_directory(h->index_path);                                   // :89-91
+    }
+    CUDA_CHECK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    h->ref = new RefStore();
+    h->ref->k = conf->kmer_size;
+    h->ref->min_strand = conf->min_strand_kmer ? 1 : 0;
+    *out = h;
+    return BSP_OK;
+    } catch (const BspError& e) { delete h; return fail(nullptr, e.code, e.what()); }
+    catch (const std::exception& e) { delete h; return fail(nullptr, BSP_ERR_STATE, e.what()); }
+}
+
+static int index_add(bsp_indexer* h, const char* filename, const char* header, const char* taxonomy,
+                     const void* seq, i64 seq_len, bool on_device) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    std::lock_guard<std::mutex> lk(h->mu);
+    API_TRY(h)
+    if (!h->ref) return fail(&h->last_error, BSP_ERR_STATE, "indexer is closed");
+    if (seq_len < 0 || (!seq && seq_len > 0)) return fail(&h->last_error, BSP_ERR_ARG, "sequence is null");
+    CUDA_CHECK(cudaSetDevice(h->conf.device));
+    EntryMeta m;
+    m.filename = filename ? filename : "";
+    m.header = header ? header : "";
+    m.taxonomy = taxonomy ? taxonomy : "";
+    m.len = seq_len;
+    int rev_ok = on_device ? h->ref->append_device((const u8*)seq, seq_len, h->st)
+                           : h->ref->append_host((const char*)seq, seq_len, h->st);
+    h->ref->add(std::move(m), rev_ok);
+    return BSP_OK;
+    API_CATCH(h)
+}
+
+BSP_API int bsp_index_add_entry(bsp_indexer* h, const char* filename, const char* header, const char* taxonomy,
+                                const char* seq, int64_t seq_len) {
+    return index_add(h, filename, header, taxonomy, seq, seq_len, false);
+}
+BSP_API int bsp_index_add_entry_device(bsp_indexer* h, const char* filename, const char* header, const char* taxonomy,
+                                       const void* d_seq, int64_t seq_len) {
+    return index_add(h, filename, header, taxonomy, d_seq, seq_len, true);
+}
+
+// ---- index file: header, entry table, strings, packed words, mask words
+static void wr(FILE* f, const void* p, size_t n) {
+    if (n && fwrite(p, 1, n, f) != n) throw BspError(BSP_ERR_IO, std::string("write failed: ") + strerror(errno));
+}
+static void rd(FILE* f, void* p, size_t n) {
+    if (n && fread(p, 1, n, f) != n) throw BspError(BSP_ERR_IO, "index file truncated");
+}
+static void wr_str(FILE* f, const std::string& s) { u64 n = s.size(); wr(f, &n, 8); wr(f, s.data(), s.size()); }
+static std::string rd_str(FILE* f) {
+    u64 n; rd(f, &n, 8);
+    if (n > ((u64)1 << 32)) throw BspError(BSP_ERR_IO, "corrupt index file (string length)");
+    std::string s(n, '\0'); rd(f, &s[0], n); return s;
+}
+
+static void write_index_file(const std::string& dir, RefStore& ref, cudaStream_t st) {
+    std::string tmp = dir + "/" + IDX_FILE + ".tmp", fin = dir + "/" + IDX_FILE;
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) throw BspError(BSP_ERR_IO, "cannot create " + tmp + ": " + strerror(errno));
+    try {
+        u64 hdr[8] = {IDX_MAGIC, 1, (u64)ref.k, (u64)ref.min_strand, (u64)ref.entries.size(), (u64)ref.used_bases, 0, 0};
+        wr(f, hdr, sizeof hdr);
+        for (const EntryMeta& m : ref.entries) {
+            i64 v[3] = {m.len, m.base_off, (i64)m.rev_ok};
+            wr(f, v, sizeof v);
+            wr_str(f, m.filename); wr_str(f, m.header); wr_str(f, m.taxonomy);
+        }
+        const size_t CH = (size_t)16 << 20;     // words per copy
+        std::vector<u32> buf(CH);
+        for (int which = 0; which < 2; which++) {
+            const u32* src = which == 0 ? ref.packed.p : ref.mask.p;
+            size_t words = (size_t)(which == 0 ? ref.used_bases / 16 : ref.used_bases / 32);
+            for (size_t o = 0; o < words; o += CH) {
+                size_t n = std::min(CH, words - o);
+                CUDA_CHECK(cudaMemcpyAsync(buf.data(), src + o, n * 4, cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaStreamSynchronize(st));
+                wr(f, buf.data(), n * 4);
+            }
+        }
+        if (fflush(f) != 0) throw BspError(BSP_ERR_IO, "flush failed");
+        fsync(fileno(f));
+        fclose(f); f = nullptr;
+        if (rename(tmp.c_str(), fin.c_str()) != 0) throw BspError(BSP_ERR_IO, "rename failed: " + std::string(strerror(errno)));
+    } catch (...) {
+        if (f) fclose(f);
+        unlink(tmp.c_str());
+        throw;
+    }
+}
+
+static RefStore* read_index_file(const std::string& dir, int part_rank, int part_count, cudaStream_t st) {
+    std::string fin = dir + "/" + IDX_FILE;
+    FILE* f = fopen(fin.c_str(), "rb");
+    if (!f) throw BspError(BSP_ERR_IO, "cannot open " + fin + ": " + strerror(errno));
+    RefStore* ref = new RefStore();
+    try {
+        u64 hdr[8];
+        rd(f, hdr, sizeof hdr);
+        if (hdr[0] != IDX_MAGIC || hdr[1] != 1) throw BspError(BSP_ERR_IO, "not a biospectra-b200 index (bad magic/version)");
+        ref->k = (int)hdr[2]; ref->min_strand = (int)hdr[3];
+        u64 nE = hdr[4]; i64 used = (i64)hdr[5];
+        std::vector<EntryMeta> all(nE);
+        for (u64 e = 0; e < nE; e++) {
+            i64 v[3]; rd(f, v, sizeof v);
+            all[e].len = v[0]; all[e].base_off = v[1]; all[e].rev_ok = (int)v[2];
+            all[e].filename = rd_str(f); all[e].header = rd_str(f); all[e].taxonomy = rd_str(f);
+        }
+        long data_pos = ftell(f);
+        // partition: contiguous entry ranges balanced by bases
+        u64 e0 = 0, e1 = nE;
+        if (part_count > 1) {
+            i64 total = 0;
+            for (auto& m : all) total += m.len;
+            i64 lo = total * part_rank / part_count, hi = total * (part_rank + 1) / part_count;
+            i64 run = 0; e0 = nE; e1 = nE;
+            bool s0 = false;
+            for (u64 e = 0; e < nE; e++) {
+                i64 mid = run + all[e].len / 2;
+                if (!s0 && mid >= lo) { e0 = e; s0 = true; }
+                if (mid >= hi) { e1 = e; break; }
+                run += all[e].len;
+            }
+            if (!s0) e0 = nE;
+            if (part_rank == part_count - 1) e1 = nE;
+            if (e1 < e0) e1 = e0;
+        }
+        i64 b0 = e0 < nE ? all[e0].base_off : used;
+        i64 b1 = e1 < nE ? all[e1].base_off : used;
+        i64 span = b1 - b0;
+        ref->reserve_bases(span + 128, st);
+        const size_t CH = (size_t)16 << 20;
+        std::vector<u32> buf(CH);
+        for (int which = 0; which < 2; which++) {
+            u32* dst = which == 0 ? ref->packed.p : ref->mask.p;
+            i64 per = which == 0 ? 16 : 32;
+            i64 file_base = data_pos + (which == 0 ? 0 : (used / 16) * 4);
+            size_t words = (size_t)(span / per);
+            if (fseek(f, file_base + (b0 / per) * 4, SEEK_SET) != 0) throw BspError(BSP_ERR_IO, "seek failed");
+            for (size_t o = 0; o < words; o += CH) {
+                size_t n = std::min(CH, words - o);
+                rd(f, buf.data(), n * 4);
+                CUDA_CHECK(cudaMemcpyAsync(dst + o, buf.data(), n * 4, cudaMemcpyHostToDevice, st));
+                CUDA_CHECK(cudaStreamSynchronize(st));
+            }
+        }
+        for (u64 e = e0; e < e1; e++) {
+            EntryMeta m = std::move(all[e]);
+            m.base_off -= b0;
+            ref->entries.push_back(std::move(m));
+        }
+        ref->used_bases = span;
+        fclose(f);
+    } catch (...) {
+        fclose(f);
+        delete ref;
+        throw;
+    }
+    return ref;
+}
+
+// ------------------------------------------------------------------ classifier setup
+static void upload_scoring_constants(bsp_classifier* h) {
+    GpuIndex& ix = h->ix;
+    const i64 D = (i64)ix.docs.size();
+    const i64 maxdoc = h->global_docs;
+    // idf by df (host libm log: the same function the oracle uses)
+    std::vector<float> idf(maxdoc + 2);
+    for (i64 df = 0; df <= maxdoc + 1; df++) {
+        if (h->conf.scoring_algorithm == BSP_BM25)
+            idf[df] = (float)std::log(1.0 + ((double)(maxdoc - df) + 0.5) / ((double)df + 0.5));      // BM25Similarity#idf
+        else
+            idf[df] = (float)(std::log((double)maxdoc / (double)(df + 1)) + 1.0);                     // DefaultSimilarity#idf
+    }
+    h->idf_by_df.alloc(idf.size());
+    CUDA_CHECK(cudaMemcpyAsync(h->idf_by_df.p, idf.data(), idf.size() * 4, cudaMemcpyHostToDevice, h->st));
+    // per-doc weight
+    float cache[256];
+    if (h->conf.scoring_algorithm == BSP_BM25) {
+        volatile float avgdl = h->global_sum_ttf <= 0 ? 1.0f : (float)((double)h->global_sum_ttf / (double)maxdoc);
+        const float k1 = 1.2f, b = 0.75f;
+        for (int x = 0; x < 256; x++) {
+            volatile float f = h_byte315_to_float(x);
+            volatile float ff = f * f;
+            volatile float ln = 1.0f / ff;
+            volatile float t1 = b * ln;
+            volatile float t2 = t1 / avgdl;
+            volatile float t3 = (1.0f - b) + t2;
+            cache[x] = k1 * t3;
+        }
+    } else {
+        for (int x = 0; x < 256; x++) cache[x] = h_byte315_to_float(x);
+    }
+    std::vector<float> dw(round_up(std::max<i64>(D, 1), 16) + 16, 1.0f);
+    for (i64 d = 0; d < D; d++) dw[d] = cache[ix.doc_norm[d]];
+    h->doc_w.alloc(dw.size());
+    CUDA_CHECK(cudaMemcpyAsync(h->doc_w.p, dw.data(), dw.size() * 4, cudaMemcpyHostToDevice, h->st));
+    // LUTs for the dense path: tf-idf -> tf(freq) = (float)sqrt(freq); BM25 -> freq
+    std::vector<float> pl(256, 0.0f), tl(256, 0.0f);
+    for (int c = 1; c < 256; c++) {
+        float f = 0.0f;
+        if (ix.tables && c < 255 && ix.h_freq_vals.size() == 256 && ix.h_freq_vals[c] != 0xFFFFFFFFu)
+            memcpy(&f, &ix.h_freq_vals[c], 4);
+        pl[c] = h->conf.scoring_algorithm == BSP_BM25 ? f : (float)std::sqrt((double)f);
+        tl[c] = h->conf.scoring_algorithm == BSP_BM25 ? (float)c : (float)std::sqrt((double)c);
+    }
+    h->pair_lut.alloc(256); h->tf_lut.alloc(256);
+    CUDA_CHECK(cudaMemcpyAsync(h->pair_lut.p, pl.data(), 1024, cudaMemcpyHostToDevice, h->st));
+    CUDA_CHECK(cudaMemcpyAsync(h->tf_lut.p, tl.data(), 1024, cudaMemcpyHostToDevice, h->st));
+    CUDA_CHECK(cudaStreamSynchronize(h->st));
+}
+
+static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
+    bsp_classifier* h = new bsp_classifier();
+    try {
+        h->conf = *conf;
+        h->ref = ref;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+        for (auto& e : h->ev) CUDA_CHECK(cudaEventCreate(&e));
+        BuildOptions opt;
+        opt.want_tables = conf->dense_tables;
+        opt.want_positional = conf->positional;
+        opt.need_pair_table = conf->query_algorithm != BSP_NAIVE_KMER;
+        opt.seg_tokens = env_i64("BSP_SEG_TOKENS", (i64)1 << 28);
+        if (opt.seg_tokens < 1024) opt.seg_tokens = 1024;
+        build_gpu_index(h->ix, *ref, opt, h->st);
+        h->global_docs = (i64)h->ix.docs.size();
+        h->global_sum_ttf = h->ix.sum_ttf;
+        h->doc_base_global = 0;
+        upload_scoring_constants(h);
+    } catch (...) {
+        h->ref = nullptr;      // caller keeps ownership on failure
+        delete h;
+        throw;
+    }
+    return h;
+}
+
+static int check_query_conf(const bsp_config* conf) {
+    if (!conf) return fail(nullptr, BSP_ERR_ARG, "conf is null");                                          // Classifier.java:72-74
+    if (conf->kmer_size <= 0) return fail(nullptr, BSP_ERR_ARG, "kmerSize must be larger than 0");         // :80-82
+    if (conf->kmer_skips < 0) return fail(nullptr, BSP_ERR_ARG, "kmerSkips must be equal or larger than 0"); // :84-86
+    if (conf->kmer_size > 31) return fail(nullptr, BSP_ERR_UNSUPPORTED, "kmerSize > 31 is not supported");
+    if (conf->query_algorithm < 0 || conf->query_algorithm > 2) return fail(nullptr, BSP_ERR_ARG, "unknown query_algorithm");
+    return BSP_OK;
+}
+
+BSP_API int bsp_index_close(bsp_indexer* h) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    int rc = BSP_OK;
+    {
+        std::lock_guard<std::mutex> lk(h->mu);
+        try {
+            CUDA_CHECK(cudaSetDevice(h->conf.device));
+            if (h->ref && !h->index_path.empty()) write_index_file(h->index_path, *h->ref, h->st);
+        } catch (const BspError& e) { rc = fail(nullptr, e.code, e.what()); }
+        catch (const std::exception& e) { rc = fail(nullptr, BSP_ERR_STATE, e.what()); }
+    }
+    delete h;
+    return rc;
+}
+
+BSP_API int bsp_index_close_to_classifier(bsp_indexer* h, const bsp_config* query_conf, bsp_classifier** out) {
+    if (out) *out = nullptr;
+    if (!h || !out) return fail(nullptr, BSP_ERR_ARG, "handle/out is null");
+    int rc = check_query_conf(query_conf);
+    if (rc) return rc;
+    if (query_conf->kmer_size != h->conf.kmer_size || (query_conf->min_strand_kmer != 0) != (h->conf.min_strand_kmer != 0))
+        return fail(&h->last_error, BSP_ERR_ARG, "query configuration disagrees with the index (kmer_size / min_strand_kmer)");
+    try {
+        CUDA_CHECK(cudaSetDevice(h->conf.device));
+        bsp_config qc = *query_conf;
+        qc.device = h->conf.device;
+        RefStore* ref = h->ref;
+        bsp_classifier* c = make_classifier(&qc, ref);
+        h->ref = nullptr;
+        delete h;
+        *out = c;
+        return BSP_OK;
+    } catch (const BspError& e) { return fail(&h->last_error, e.code, e.what()); }
+    catch (const std::exception& e) { return fail(&h->last_error, BSP_ERR_STATE, e.what()); }
+}
+
+BSP_API int bsp_classifier_open(const bsp_config* conf, const char* index_path, bsp_classifier** out) {
+    if (out) *out = nullptr;
+    int rc = check_query_conf(conf);
+    if (rc) return rc;
+    if (!index_path) return fail(nullptr, BSP_ERR_ARG, "indexPath is null");                               // Classifier.java:76-78
+    if (!out) return fail(nullptr, BSP_ERR_ARG, "out is null");
+    if (!is_dir(index_path)) return fail(nullptr, BSP_ERR_ARG, "indexPath is not a directory or does not exist"); // :92-94
+    RefStore* ref = nullptr;
+    cudaStream_t st = nullptr;
+    try {
+        CUDA_CHECK(cudaSetDevice(conf->device));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        ref = read_index_file(index_path, conf->part_rank, conf->part_count > 0 ? conf->part_count : 1, st);
+        cudaStreamDestroy(st); st = nullptr;
+        if (ref->k != conf->kmer_size || ref->min_strand != (conf->min_strand_kmer ? 1 : 0)) {
+            delete ref;
+            return fail(nullptr, BSP_ERR_ARG, "configuration disagrees with the index (kmer_size / min_strand_kmer)");
+        }
+        *out = make_classifier(conf, ref);
+        return BSP_OK;
+    } catch (const BspError& e) { if (st) cudaStreamDestroy(st); delete ref; return fail(nullptr, e.code, e.what()); }
+    catch (const std::exception& e) { if (st) cudaStreamDestroy(st); delete ref; return fail(nullptr, BSP_ERR_STATE, e.what()); }
+}
+
+BSP_API int bsp_classifier_close(bsp_classifier* h) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    { std::lock_guard<std::mutex> lk(h->mu); cudaSetDevice(h->conf.device); cudaStreamSynchronize(h->st); }
+    delete h;
+    return BSP_OK;
+}
+
+// ------------------------------------------------------------------ classification
+__global__ void __launch_bounds__(256) route_compact_kernel(const i32* __restrict__ route, i32 n, i32* __restrict__ list_dense,
+                                                             i32* __restrict__ list_pos, i32* __restrict__ counts) {
+    i32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int rt = route[r];
+    if (rt == ROUTE_DENSE) list_dense[atomicAdd(&counts[0], 1)] = r;
+    else if (rt == ROUTE_POSITIONAL) list_pos[atomicAdd(&counts[1], 1)] = r;
+}
+
+__global__ void __launch_bounds__(256) tok_capacity_kernel(const i64* __restrict__ seq_off, i32 n, int k, i64* __restrict__ cap) {
+    i32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    i64 len = seq_off[r + 1] - seq_off[r];
+    i64 w = len - k + 1;
+    cap[r] = w > 0 ? w : 0;
+}
+
+struct BatchOut {     // device pointers (any may be null except status)
+    i32 *status, *label, *n_hits, *n_top, *top_doc; float* top_score;
+};
+
+// Runs the device pipeline on reads already resident in device memory.
+static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const i64* d_seq_off, i64 total_bytes,
+                               const BatchOut& out) {
+    GpuIndex& ix = h->ix;
+    Scratch& sc = h->sc;
+    cudaStream_t st = h->st;
+    const int k = ix.k;
+    i64 tok_cap_total = total_bytes;        // sum(max(len-k+1,0)) <= total bytes
+    sc.tok_off.ensure((size_t)n + 1);
+    sc.tok_key.ensure((size_t)tok_cap_total + 1); sc.tok_pos.ensure((size_t)tok_cap_total + 1);
+    sc.tok_df.ensure((size_t)tok_cap_total + 1); sc.clause_val.ensure((size_t)tok_cap_total + 1);
+    sc.clause_row.ensure((size_t)tok_cap_total + 1);
+    sc.n_tok.ensure(n); sc.n_clauses.ensure(n); sc.msm.ensure(n); sc.route.ensure(n); sc.status_in.ensure(n);
+    sc.list_dense.ensure(n); sc.list_pos.ensure(n); sc.counts.ensure(4);
+    CUDA_CHECK(cudaEventRecord(h->ev[0], st));
+    // token capacity offsets
+    sc.tok_cap.ensure((size_t)n + 1);
+    tok_capacity_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_seq_off, n, k, sc.tok_cap.p);
+    exclusive_scan<i64, i64>(sc.tok_cap.p, sc.tok_off.p, (u64)n, sc.tok_off.p + n, sc.scan_tmp, st);
+    tokenize_kernel<<<(unsigned)ceil_div((i64)n * 32, 256), 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, k, h->conf.kmer_skips,
+                                                                          ix.min_strand, sc.tok_key.p, sc.tok_pos.p, sc.n_tok.p);
+    token_df_kernel<<<(unsigned)ceil_div((i64)n * 32, 256), 256, 0, st>>>(sc.tok_key.p, sc.tok_off.p, sc.n_tok.p, n,
+                                                                          ix.direct ? ix.df_dense.p : nullptr, ix.d_segs.p,
+                                                                          ix.positional ? (int)ix.segs.size() : 0, sc.tok_df.p);
+    QueryParams qp;
+    qp.k = k; qp.skips = h->conf.kmer_skips; qp.min_strand = ix.min_strand; qp.alg = h->conf.query_algorithm;
+    qp.sim = h->conf.scoring_algorithm == BSP_BM25 ? SIM_BM25 : SIM_TFIDF;
+    qp.msm_ratio = h->conf.query_term_min_should_match;
+    qp.max_doc = h->global_docs;
+    qp.dense_ok = ix.tables && (qp.alg == ALG_NAIVE || ix.has_pair) && env_i64("BSP_DISABLE_DENSE", 0) == 0;
+    qp.positional_ok = ix.positional ? 1 : 0;
+    weights_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p,
+                                                               sc.tok_df.p, h->idf_by_df.p, qp, ix.tf_row_slow.p, ix.pair_row_slow.p,
+                                                               sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p,
+                                                               sc.route.p, sc.status_in.p);
+    CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 16, st));
+    route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, n, sc.list_dense.p, sc.list_pos.p, sc.counts.p);
+    KERNEL_CHECK();
+    i32 counts[2] = {0, 0};
+    CUDA_CHECK(cudaMemcpyAsync(counts, sc.counts.p, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    // partial top-10 buffers
+    const u32 D = (u32)ix.docs.size();
+    int dense_threads = (int)std::min<i64>(512, round_up(std::max<i64>(ceil_div(D, DENSE_DPT), 1), 32));
+    int n_tiles = (int)std::max<i64>(1, ceil_div(D, (i64)dense_threads * DENSE_DPT));
+    int parts_pos = ix.positional ? (int)ix.segs.size() : 0;
+    int parts_stride = std::max(std::max(n_tiles, parts_pos), 1);
+    i32* part_n; u32* part_doc; float* part_score;
+    sc.part_n.ensure((size_t)n * parts_stride);
+    sc.part_doc.ensure((size_t)n * parts_stride * TOPN);
+    sc.part_score.ensure((size_t)n * parts_stride * TOPN);
+    part_n = sc.part_n.p; part_doc = sc.part_doc.p; part_score = sc.part_score.p;
+    SimParams sp; sp.sim = qp.sim; sp.k1p1 = 1.2f + 1.0f;
+    const u32 gbase = (u32)h->doc_base_global;
+    CUDA_CHECK(cudaEventRecord(h->ev[1], st));
+    i64 launches = 6;
+    if (counts[0] > 0) {
+        unsigned grid = (unsigned)((i64)counts[0] * n_tiles);
+        if (qp.sim == SIM_TFIDF)
+            score_dense_kernel<SIM_TFIDF><<<grid, dense_threads, 0, st>>>(ix.tf_tab.p, ix.pair_tab.p, ix.d_pad, D, h->pair_lut.p, h->tf_lut.p,
+                sc.list_dense.p, counts[0], sc.tok_off.p, sc.n_tok.p, sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p,
+                h->doc_w.p, qp.alg, sp.k1p1, gbase, n_tiles, parts_stride, part_n, part_doc, part_score);
+        else
+            score_dense_kernel<SIM_BM25><<<grid, dense_threads, 0, st>>>(ix.tf_tab.p, ix.pair_tab.p, ix.d_pad, D, h->pair_lut.p, h->tf_lut.p,
+                sc.list_dense.p, counts[0], sc.tok_off.p, sc.n_tok.p, sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p,
+                h->doc_w.p, qp.alg, sp.k1p1, gbase, n_tiles, parts_stride, part_n, part_doc, part_score);
+        launches++;
+    }
+    if (counts[1] > 0) {
+        size_t smem = (size_t)ix.max_seg_docs * 10 + 16;
+        i64 blocks = (i64)counts[1] * parts_pos;
+        const i64 MAXG = 0x7FFFFFFF;
+        if (blocks > MAXG) throw BspError(BSP_ERR_UNSUPPORTED, "batch too large for the positional path");
+        score_positional_kernel<<<(unsigned)blocks, POS_THREADS, smem, st>>>(ix.d_segs.p, parts_pos, sc.list_pos.p, counts[1], sc.tok_off.p,
+            sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p, sc.clause_val.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, qp, sp, gbase,
+            parts_stride, part_n, part_doc, part_score);
+        launches++;
+    }
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaEventRecord(h->ev[2], st));
+    merge_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(n, sc.route.p, sc.status_in.p, n_tiles, parts_pos, parts_stride, part_n,
+                                                             part_doc, part_score, out.status, out.label, out.n_hits, out.n_top,
+                                                             out.top_doc, out.top_score);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaEventRecord(h->ev[3], st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    float ms_score = 0, ms_pipe = 0;
+    cudaEventElapsedTime(&ms_score, h->ev[1], h->ev[2]);
+    cudaEventElapsedTime(&ms_pipe, h->ev[0], h->ev[3]);
+    h->score_ms += ms_score; h->pipe_ms += ms_pipe;
+    h->counters[0] += n; h->counters[1] += counts[0]; h->counters[2] += counts[1]; h->counters[4] += launches + 1;
+}
+
+static int classify_packed_impl(bsp_classifier* h, i32 n, const char* seq_bytes, const i64* seq_offsets,
+                                i32* status, i32* label, i32* n_hits, i32* n_top, i32* top_doc, float* top_score) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    std::lock_guard<std::mutex> lk(h->mu);
+    API_TRY(h)
+    if (n < 0 || (n > 0 && (!seq_bytes || !seq_offsets || !status))) return fail(&h->last_error, BSP_ERR_ARG, "null argument");
+    CUDA_CHECK(cudaSetDevice(h->conf.device));
+    for (auto& c : h->counters) c = 0;
+    h->score_ms = 0; h->pipe_ms = 0;
+    h->last_routes.assign(n, 0);
+    const i32 SUB = (i32)env_i64("BSP_SUB_BATCH", 262144);
+    Scratch& sc = h->sc;
+    cudaStream_t st = h->st;
+    for (i32 r0 = 0; r0 < n; r0 += SUB) {
+        i32 m = std::min(SUB, n - r0);
+        i64 b0 = seq_offsets[r0], b1 = seq_offsets[r0 + m];
+        i64 bytes = b1 - b0;
+        sc.seq.ensure((size_t)bytes + 64);
+        sc.seq_off.ensure((size_t)m + 1);
+        // offsets rebased to the sub-batch
+        size_t in_need = (size_t)(m + 1) * 8;
+        if (in_need > sc.pin_in_bytes) {
+            if (sc.pin_in) cudaFreeHost(sc.pin_in);
+            sc.pin_in = nullptr; sc.pin_in_bytes = 0;
+            CUDA_CHECK(cudaMallocHost((void**)&sc.pin_in, in_need + in_need / 4));
+            sc.pin_in_bytes = in_need + in_need / 4;
+        }
+        i64* po = (i64*)sc.pin_in;
+        for (i32 i = 0; i <= m; i++) po[i] = seq_offsets[r0 + i] - b0;
+        CUDA_CHECK(cudaMemcpyAsync(sc.seq_off.p, po, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (bytes) CUDA_CHECK(cudaMemcpyAsync(sc.seq.p, seq_bytes + b0, (size_t)bytes, cudaMemcpyHostToDevice, st));
+        sc.o_status.ensure(m); sc.o_label.ensure(m); sc.o_nhits.ensure(m); sc.o_ntop.ensure(m);
+        sc.o_doc.ensure((size_t)m * TOPN); sc.o_score.ensure((size_t)m * TOPN);
+        BatchOut bo{sc.o_status.p, sc.o_label.p, sc.o_nhits.p, sc.o_ntop.p, sc.o_doc.p, sc.o_score.p};
+        classify_on_device(h, m, sc.seq.p, sc.seq_off.p, bytes, bo);
+        CUDA_CHECK(cudaMemcpyAsync(status + r0, sc.o_status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+        if (label) CUDA_CHECK(cudaMemcpyAsync(label + r0, sc.o_label.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+        if (n_hits) CUDA_CHECK(cudaMemcpyAsync(n_hits + r0, sc.o_nhits.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+        if (n_top) CUDA_CHECK(cudaMemcpyAsync(n_top + r0, sc.o_ntop.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+        if (top_doc) CUDA_CHECK(cudaMemcpyAsync(top_doc + (i64)r0 * TOPN, sc.o_doc.p, (size_t)m * TOPN * 4, cudaMemcpyDeviceToHost, st));
+        if (top_score) CUDA_CHECK(cudaMemcpyAsync(top_score + (i64)r0 * TOPN, sc.o_score.p, (size_t)m * TOPN * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(h->last_routes.data() + r0, sc.route.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    return BSP_OK;
+    API_CATCH(h)
+}
+
+BSP_API int bsp_classify_packed(bsp_classifier* h, int32_t n, const char* seq_bytes, const int64_t* seq_offsets,
+                                int32_t* status, int32_t* label, int32_t* n_hits, int32_t* n_top,
+                                int32_t* top_doc, float* top_score) {
+    return classify_packed_impl(h, n, seq_bytes, seq_offsets, status, label, n_hits, n_top, top_doc, top_score);
+}
+
+BSP_API int bsp_classify_batch(bsp_classifier* h, int32_t n, const char* const* seqs, const int32_t* seq_lens,
+                               int32_t* status, int32_t* label, int32_t* n_hits, int32_t* n_top,
+                               int32_t* top_doc, float* top_score) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    if (n < 0 || (n > 0 && (!seqs || !seq_lens))) return fail(&h->last_error, BSP_ERR_ARG, "null argument");
+    std::vector<i64> off((size_t)n + 1, 0);
+    for (i32 i = 0; i < n; i++) {
+        if (seq_lens[i] < 0 || (seq_lens[i] > 0 && !seqs[i])) return fail(&h->last_error, BSP_ERR_ARG, "sequence is null or empty");
+        off[i + 1] = off[i] + seq_lens[i];
+    }
+    std::string bytes((size_t)off[n], '\0');
+    for (i32 i = 0; i < n; i++) if (seq_lens[i]) memcpy(&bytes[off[i]], seqs[i], (size_t)seq_lens[i]);
+    return classify_packed_impl(h, n, bytes.data(), off.data(), status, label, n_hits, n_top, top_doc, top_score);
+}
+
+BSP_API int bsp_classify_device(bsp_classifier* h, int32_t n, const void* d_seq_bytes, const void* d_seq_offsets,
+                                int64_t total_bytes, int32_t max_len, void* d_status, void* d_label, void* d_n_hits,
+                                void* d_n_top, void* d_top_doc, void* d_top_score) {
+    (void)max_len;
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    std::lock_guard<std::mutex> lk(h->mu);
+    API_TRY(h)
+    if (n < 0 || (n > 0 && (!d_seq_bytes || !d_seq_offsets || !d_status))) return fail(&h->last_error, BSP_ERR_ARG, "null argument");
+    CUDA_CHECK(cudaSetDevice(h->conf.device));
+    for (auto& c : h->counters) c = 0;
+    h->score_ms = 0; h->pipe_ms = 0;
+    BatchOut bo{(i32*)d_status, (i32*)d_label, (i32*)d_n_hits, (i32*)d_n_top, (i32*)d_top_doc, (float*)d_top_score};
+    if (n) classify_on_device(h, n, (const u8*)d_seq_bytes, (const i64*)d_seq_offsets, total_bytes, bo);
+    return BSP_OK;
+    API_CATCH(h)
+}
+
+// ------------------------------------------------------------------ introspection
+BSP_API int bsp_doc_fields(bsp_classifier* h, int32_t doc, const char** filename, const char** header,
+                           const char** direction, const char** taxonomy) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    if (doc < 0 || doc >= (i32)h->ix.docs.size()) return fail(&h->last_error, BSP_ERR_ARG, "doc id out of range");
+    const DocMeta& d = h->ix.docs[doc];
+    const EntryMeta& m = h->ref->entries[d.entry];
+    static const char* DIR[3] = {"forward", "reverse", "min_strand"};       // Indexer.java:211,216,221
+    if (filename) *filename = m.filename.c_str();
+    if (header) *header = m.header.c_str();
+    if (direction) *direction = DIR[d.strand];
+    if (taxonomy) *taxonomy = m.taxonomy.c_str();
+    return BSP_OK;
+}
+
+BSP_API int bsp_index_stats(bsp_classifier* h, int64_t* n_docs, int64_t* n_terms, int64_t* n_postings, int64_t* n_positions) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    if (n_docs) *n_docs = (i64)h->ix.docs.size();
+    if (n_terms) *n_terms = h->ix.n_terms;
+    if (n_postings) *n_postings = h->ix.n_postings;
+    if (n_positions) *n_positions = h->ix.n_positions;
+    return BSP_OK;
+}
+
+BSP_API int bsp_doc_info(bsp_classifier* h, int32_t doc, int32_t* num_tokens, int32_t* norm_byte) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    if (doc < 0 || doc >= (i32)h->ix.docs.size()) return fail(&h->last_error, BSP_ERR_ARG, "doc id out of range");
+    if (num_tokens) *num_tokens = (i32)h->ix.doc_ntok[doc];
+    if (norm_byte) *norm_byte = h->ix.doc_norm[doc];
+    return BSP_OK;
+}
+
+__global__ void lookup_term_kernel(const SegDev* segs, int n_segs, u64 key, u32* out /* [n_segs*3]: t, a, b */) {
+    int s = threadIdx.x;
+    if (s >= n_segs) return;
+    u32 t = seg_find_term(segs[s], key);
+    out[3 * s] = t;
+    out[3 * s + 1] = t == NO_TERM ? 0 : segs[s].term_off[t];
+    out[3 * s + 2] = t == NO_TERM ? 0 : segs[s].term_off[t + 1];
+}
+
+BSP_API int bsp_term_postings(bsp_classifier* h, uint64_t packed_kmer, int64_t* df, int64_t* ttf,
+                              int32_t* docs, int32_t* tfs, int32_t* positions) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    std::lock_guard<std::mutex> lk(h->mu);
+    API_TRY(h)
+    GpuIndex& ix = h->ix;
+    if (!ix.positional) return fail(&h->last_error, BSP_ERR_STATE, "positional index is not resident");
+    CUDA_CHECK(cudaSetDevice(h->conf.device));
+    if (2 * ix.k < 64 && (packed_kmer >> (2 * ix.k))) { if (df) *df = 0; if (ttf) *ttf = 0; return BSP_OK; }
+    i64 ndf = 0, nttf = 0;
+    for (size_t si = 0; si < ix.segs.size(); si++) {
+        Segment& seg = ix.segs[si];
+        DevBuf<u32> d_out; d_out.alloc(3);
+        lookup_term_kernel<<<1, 32, 0, h->st>>>(ix.d_segs.p + si, 1, packed_kmer, d_out.p);
+        u32 o[3];
+        CUDA_CHECK(cudaMemcpyAsync(o, d_out.p, 12, cudaMemcpyDeviceToHost, h->st));
+        CUDA_CHECK(cudaStreamSynchronize(h->st));
+        if (o[0] == NO_TERM) continue;
+        u32 a = o[1], b = o[2], np = b - a;
+        std::vector<u32> pd(np), pp(np + 1);
+        CUDA_CHECK(cudaMemcpy(pd.data(), seg.post_doc.p + a, np * 4, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(pp.data(), seg.post_pos.p + a, (np + 1) * 4, cudaMemcpyDeviceToHost));
+        u32 npos = pp[np] - pp[0];
+        if (docs && tfs) for (u32 i = 0; i < np; i++) { docs[ndf + i] = (i32)(seg.doc_base + pd[i]); tfs[ndf + i] = (i32)(pp[i + 1] - pp[i]); }
+        if (positions) CUDA_CHECK(cudaMemcpy(positions + nttf, seg.positions.p + pp[0], (size_t)npos * 4, cudaMemcpyDeviceToHost));
+        ndf += np; nttf += npos;
+    }
+    if (df) *df = ndf;
+    if (ttf) *ttf = nttf;
+    return BSP_OK;
+    API_CATCH(h)
+}
+
+BSP_API int64_t bsp_tokenize(bsp_classifier* h, const char* seq, int32_t len, uint64_t* keys, int32_t* offsets, int64_t cap) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    std::lock_guard<std::mutex> lk(h->mu);
+    API_TRY(h)
+    if (len < 0 || (len > 0 && !seq)) return fail(&h->last_error, BSP_ERR_ARG, "sequence is null");
+    CUDA_CHECK(cudaSetDevice(h->conf.device));
+    cudaStream_t st = h->st;
+    DevBuf<u8> d_seq; d_seq.alloc((size_t)len + 64);
+    DevBuf<i64> d_off; d_off.alloc(2);
+    DevBuf<i64> d_tok_off; d_tok_off.alloc(2);
+    DevBuf<u64> d_keys; d_keys.alloc((size_t)len + 1);
+    DevBuf<u32> d_pos; d_pos.alloc((size_t)len + 1);
+    DevBuf<i32> d_n; d_n.alloc(1);
+    i64 off[2] = {0, len}, tz[2] = {0, 0};
+    CUDA_CHECK(cudaMemcpyAsync(d_seq.p, seq, (size_t)len, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(d_off.p, off, 16, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(d_tok_off.p, tz, 16, cudaMemcpyHostToDevice, st));
+    tokenize_kernel<<<1, 32, 0, st>>>(d_seq.p, d_off.p, 1, d_tok_off.p, h->ix.k, h->conf.kmer_skips, h->ix.min_strand, d_keys.p, d_pos.p, d_n.p);
+    KERNEL_CHECK();
+    i32 n = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n, d_n.p, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    i64 m = std::min<i64>(n, cap);
+    if (keys && m > 0) CUDA_CHECK(cudaMemcpy(keys, d_keys.p, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    if (offsets && m > 0) CUDA_CHECK(cudaMemcpy(offsets, d_pos.p, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    return n;
+    API_CATCH(h)
+}
+
+BSP_API int bsp_last_routes(bsp_classifier* h, int32_t n, int32_t* routes) {
+    if (!h || !routes) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    for (i32 i = 0; i < n; i++) routes[i] = i < (i32)h->last_routes.size() ? h->last_routes[i] : 0;
+    return BSP_OK;
+}
+
+BSP_API int bsp_last_counters(bsp_classifier* h, int64_t counters[8]) {
+    if (!h || !counters) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    for (int i = 0; i < 8; i++) counters[i] = h->counters[i];
+    return BSP_OK;
+}
+
+BSP_API int bsp_last_timings(bsp_classifier* h, double* score_kernel_ms, double* pipeline_ms) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (score_kernel_ms) *score_kernel_ms = h->score_ms;
+    if (pipeline_ms) *pipeline_ms = h->pipe_ms;
+    return BSP_OK;
+}
+
+BSP_API int bsp_memory_info(bsp_classifier* h, int64_t* positional_bytes, int64_t* table_bytes, int64_t* staged_bytes) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    if (positional_bytes) *positional_bytes = h->ix.positional ? (i64)h->ix.positional_bytes : 0;
+    if (table_bytes) *table_bytes = (i64)h->ix.table_bytes;
+    if (staged_bytes) *staged_bytes = (i64)(h->ref->packed.bytes() + h->ref->mask.bytes());
+    return BSP_OK;
+}
+
+// Cost model of SURVEY.md 8(d) on the actual index, for a read set (host buffers).
+BSP_API int bsp_read_cost(bsp_classifier* h, int32_t n, const char* seq_bytes, const int64_t* seq_offsets, int64_t out[8]) {
+    if (!h || !out) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    API_TRY(h)
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    if (n <= 0) return BSP_OK;
+    if (!seq_bytes || !seq_offsets) return fail(&h->last_error, BSP_ERR_ARG, "null argument");
+    CUDA_CHECK(cudaSetDevice(h->conf.device));
+    GpuIndex& ix = h->ix;
+    Scratch& sc = h->sc;
+    cudaStream_t st = h->st;
+    if (!ix.direct && !ix.positional) return fail(&h->last_error, BSP_ERR_STATE, "no term statistics resident");
+    DevBuf<unsigned long long> d_out; d_out.alloc(8);
+    CUDA_CHECK(cudaMemsetAsync(d_out.p, 0, 64, st));
+    const i32 SUB = 262144;
+    for (i32 r0 = 0; r0 < n; r0 += SUB) {
+        i32 m = std::min(SUB, n - r0);
+        i64 b0 = seq_offsets[r0], bytes = seq_offsets[r0 + m] - b0;
+        std::vector<i64> off((size_t)m + 1);
+        for (i32 i = 0; i <= m; i++) off[i] = seq_offsets[r0 + i] - b0;
+        sc.seq.ensure((size_t)bytes + 64); sc.seq_off.ensure((size_t)m + 1); sc.tok_off.ensure((size_t)m + 1);
+        sc.tok_cap.ensure((size_t)m + 1); sc.n_tok.ensure(m);
+        sc.tok_key.ensure((size_t)bytes + 1); sc.tok_pos.ensure((size_t)bytes + 1); sc.tok_df.ensure((size_t)bytes + 1);
+        CUDA_CHECK(cudaMemcpyAsync(sc.seq_off.p, off.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (bytes) CUDA_CHECK(cudaMemcpyAsync(sc.seq.p, seq_bytes + b0, (size_t)bytes, cudaMemcpyHostToDevice, st));
+        tok_capacity_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(sc.seq_off.p, m, ix.k, sc.tok_cap.p);
+        exclusive_scan<i64, i64>(sc.tok_cap.p, sc.tok_off.p, (u64)m, sc.tok_off.p + m, sc.scan_tmp, st);
+        tokenize_kernel<<<(unsigned)ceil_div((i64)m * 32, 256), 256, 0, st>>>(sc.seq.p, sc.seq_off.p, m, sc.tok_off.p, ix.k,
+            h->conf.kmer_skips, ix.min_strand, sc.tok_key.p, sc.tok_pos.p, sc.n_tok.p);
+        token_df_kernel<<<(unsigned)ceil_div((i64)m * 32, 256), 256, 0, st>>>(sc.tok_key.p, sc.tok_off.p, sc.n_tok.p, m,
+            ix.direct ? ix.df_dense.p : nullptr, ix.d_segs.p, ix.positional ? (int)ix.segs.size() : 0, sc.tok_df.p);
+        read_cost_kernel<<<(unsigned)ceil_div((i64)m * 32, 256), 256, 0, st>>>(sc.seq_off.p, m, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p,
+            sc.tok_df.p, ix.direct ? ix.ttf_dense.p : nullptr, ix.d_segs.p, ix.positional ? (int)ix.segs.size() : 0,
+            h->conf.query_algorithm, ix.d_pad, (u64)ix.docs.size(), d_out.p);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    unsigned long long ho[8];
+    CUDA_CHECK(cudaMemcpy(ho, d_out.p, 64, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; i++) out[i] = (i64)ho[i];
+    return BSP_OK;
+    API_CATCH(h)
+}
+
+// ------------------------------------------------------------------ doc-partitioned mode
+BSP_API int bsp_partition_df_buffer(bsp_classifier* h, void** d_df, int64_t* n_entries) {
+    if (!h || !d_df || !n_entries) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    if (!h->ix.direct) return fail(&h->last_error, BSP_ERR_UNSUPPORTED, "doc-partitioned mode needs the dense term space (k <= 12)");
+    *d_df = h->ix.df_dense.p;
+    *n_entries = (i64)1 << (2 * h->ix.k);
+    return BSP_OK;
+}
+
+BSP_API int bsp_partition_local_stats(bsp_classifier* h, int64_t* n_docs, int64_t* sum_total_term_freq) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    if (n_docs) *n_docs = (i64)h->ix.docs.size();
+    if (sum_total_term_freq) *sum_total_term_freq = h->ix.sum_ttf;
+    return BSP_OK;
+}
+
+BSP_API int bsp_partition_set_global(bsp_classifier* h, int64_t doc_base, int64_t global_docs, int64_t global_sum_total_term_freq) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    API_TRY(h)
+    CUDA_CHECK(cudaSetDevice(h->conf.device));
+    h->doc_base_global = doc_base;
+    h->global_docs = global_docs;
+    h->global_sum_ttf = global_sum_total_term_freq;
+    upload_scoring_constants(h);
+    return BSP_OK;
+    API_CATCH(h)
+}
+
+BSP_API int bsp_merge_topk_device(bsp_classifier* h, int32_t n, int32_t parts, const void* d_part_n_top, const void* d_part_doc,
+                                  const void* d_part_score, const void* d_part_status, void* d_status, void* d_label,
+                                  void* d_n_hits, void* d_n_top, void* d_top_doc, void* d_top_score) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    API_TRY(h)
+    CUDA_CHECK(cudaSetDevice(h->conf.device));
+    // layout: [n][parts] lists; status is taken from part 0 (identical on every rank: it depends on the read only)
+    merge_kernel<<<(unsigned)ceil_div(std::max(n, 1), 128), 128, 0, h->st>>>(n, nullptr, (const i32*)d_part_status, parts, parts, parts,
+        (const i32*)d_part_n_top, (const u32*)d_part_doc, (const float*)d_part_score, (i32*)d_status, (i32*)d_label, (i32*)d_n_hits,
+        (i32*)d_n_top, (i32*)d_top_doc, (float*)d_top_score);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaStreamSynchronize(h->st));
+    return BSP_OK;
+    API_CATCH(h)
+}

@@ -1,0 +1,737 @@
+// classify.cuh -- query-side kernels (K5-K8 of SURVEY.md 2.1).
+//
+//   K5 tokenize_kernel / weights_kernel   read -> tokens -> implicit clauses + Lucene weights
+//   K6/K7 score_positional_kernel         general path: term-major postings + positions,
+//                                         TermQuery and sloppy PhraseQuery scoring
+//   K6' score_dense_kernel                dense path (small k): u8 tf / pair-frequency rows,
+//                                         128-bit coalesced row reads, register accumulators
+//   K8 block top-10 (fused into both scorers) + merge_kernel (labels)
+//
+// Float semantics follow Lucene 5.3.1 operation by operation: explicit
+// __fmul_rn/__fadd_rn/__fdiv_rn (no FMA contraction), double accumulation of the per-clause
+// float scores, one (float) cast, then coord.
+#pragma once
+#include "common.cuh"
+#include "index_build.cuh"
+
+#define ALG_NAIVE 0
+#define ALG_CHAIN 1
+#define ALG_PAIRED 2
+#define SIM_TFIDF 0
+#define SIM_BM25 1
+#define TOPN 10
+#define MAX_CLAUSES 10000        // Classifier.java:110 BooleanQuery.setMaxClauseCount(10000)
+
+#define ROUTE_NONE 0             // dropped / error: no scoring
+#define ROUTE_DENSE 1
+#define ROUTE_POSITIONAL 2
+
+#define ST_OK 0
+#define ST_DROPPED 1
+#define ST_ERROR 2
+
+// ------------------------------------------------------- sloppy phrase (A.7)
+// lucene!search/SloppyPhraseScorer#phraseFreq for the phrase (t0@0, t1@1), t0 != t1.
+// A = positions of t0, B = positions of t1 (ascending, non-empty).  With two phrase
+// positions the priority queue degenerates to "the other one": after pp passes `next`
+// the other pp is strictly smaller, so pop() always returns it.
+__device__ __forceinline__ float sloppy_freq_distinct(const u32* __restrict__ A, int nA, const u32* __restrict__ B, int nB,
+                                                      int slop) {
+    int pa = (int)A[0], pb = (int)B[0] - 1;
+    int end = pa > pb ? pa : pb;
+    // PhraseQueue#lessThan: smaller position first, ties -> smaller offset (t0)
+    bool cur_is_a = pa <= pb;
+    const u32* cl = cur_is_a ? A : B; int cn = cur_is_a ? nA : nB; int co = cur_is_a ? 0 : 1; int cp = cur_is_a ? pa : pb;
+    const u32* ol = cur_is_a ? B : A; int on = cur_is_a ? nB : nA; int oo = cur_is_a ? 1 : 0; int op = cur_is_a ? pb : pa;
+    int ci = 1, oi = 1;
+    int ml = end - cp;
+    int next = op;
+    float freq = 0.0f;
+    while (ci < cn) {                                   // advancePP
+        cp = (int)cl[ci++] - co;
+        if (cp > end) end = cp;
+        if (cp > next) {
+            if (ml <= slop) freq = __fadd_rn(freq, __fdiv_rn(1.0f, (float)(ml + 1)));
+            // pq.add(pp); pp = pq.pop()  -> swap roles
+            const u32* tl = cl; cl = ol; ol = tl;
+            int t;
+            t = cn; cn = on; on = t;
+            t = co; co = oo; oo = t;
+            t = ci; ci = oi; oi = t;
+            t = cp; cp = op; op = t;
+            next = op;
+            ml = end - cp;
+        } else {
+            int ml2 = end - cp;
+            if (ml2 < ml) ml = ml2;
+        }
+    }
+    if (ml <= slop) freq = __fadd_rn(freq, __fdiv_rn(1.0f, (float)(ml + 1)));
+    return freq;
+}
+
+// Same-term phrase (t0 == t1): the repeat-group path, restated literally
+// (#initComplex/#advanceRepeatGroups/#advanceRpts/#collide/#lesser).
+struct PPd { const u32* pl; int n, idx, count, position, offset; };
+__device__ __forceinline__ bool ppd_next(PPd& p) {
+    if (p.count-- > 0) { p.position = (int)p.pl[p.idx++] - p.offset; return true; }
+    return false;
+}
+__device__ __forceinline__ bool ppd_less(const PPd& a, const PPd& b) {   // PhraseQueue#lessThan (ord == offset here)
+    if (a.position == b.position) return a.offset < b.offset;
+    return a.position < b.position;
+}
+__device__ __noinline__ float sloppy_freq_same(const u32* __restrict__ P, int n, int slop) {
+    PPd pp[2];
+    pp[0].pl = P; pp[0].n = n; pp[0].offset = 0;
+    pp[1].pl = P; pp[1].n = n; pp[1].offset = 1;
+    int end = INT_MIN;
+    for (int i = 0; i < 2; i++) { pp[i].count = n; pp[i].idx = 0; ppd_next(pp[i]); }   // placeFirstPositions
+    if (!ppd_next(pp[1])) return 0.0f;                                               // advanceRepeatGroups
+    for (int i = 0; i < 2; i++) if (pp[i].position > end) end = pp[i].position;       // fillQueue
+    int cur = ppd_less(pp[0], pp[1]) ? 0 : 1;                                         // pq.pop()
+    int ml = end - pp[cur].position;
+    int next = pp[1 - cur].position;                                                  // pq.top()
+    float freq = 0.0f;
+    while (true) {
+        // advancePP(pp)
+        if (!ppd_next(pp[cur])) break;
+        if (pp[cur].position > end) end = pp[cur].position;
+        // advanceRpts(pp): `p` is the local variable that #lesser rebinds
+        {
+            int p = cur;
+            bool exhausted = false;
+            while (true) {
+                int o = 1 - p;                                                        // #collide
+                if (pp[o].position + pp[o].offset != pp[p].position + pp[p].offset) break;
+                // #lesser(pp, rg[k])
+                int l = (pp[p].position < pp[o].position ||
+                         (pp[p].position == pp[o].position && pp[p].offset < pp[o].offset)) ? p : o;
+                p = l;
+                if (!ppd_next(pp[p])) { exhausted = true; break; }
+                if (pp[p].position > end) end = pp[p].position;
+            }
+            if (exhausted) break;
+        }
+        if (pp[cur].position > next) {
+            if (ml <= slop) freq = __fadd_rn(freq, __fdiv_rn(1.0f, (float)(ml + 1)));
+            // pq.add(pp); pp = pq.pop(): the queue holds both -> take the lesser
+            cur = ppd_less(pp[0], pp[1]) ? 0 : 1;
+            next = pp[1 - cur].position;
+            ml = end - pp[cur].position;
+        } else {
+            int ml2 = end - pp[cur].position;
+            if (ml2 < ml) ml = ml2;
+        }
+    }
+    if (ml <= slop) freq = __fadd_rn(freq, __fdiv_rn(1.0f, (float)(ml + 1)));
+    return freq;
+}
+
+// lower_bound of doc in post_doc[a,b); returns index or b
+__device__ __forceinline__ u32 find_posting(const u32* __restrict__ post_doc, u32 a, u32 b, u32 doc, u32 guess) {
+    if (guess >= a && guess < b && post_doc[guess] == doc) return guess;
+    u32 lo = a, hi = b;
+    while (lo < hi) {
+        u32 mid = (lo + hi) >> 1;
+        if (post_doc[mid] < doc) lo = mid + 1; else hi = mid;
+    }
+    return (lo < b && post_doc[lo] == doc) ? lo : b;
+}
+
+// phrase frequency of (t0, t1, slop) in the doc of posting i0 of t0; 0 if t1 is absent
+__device__ __forceinline__ float phrase_freq_at(const SegDev& s, u32 i0, u32 a1, u32 b1, u32 guess, int slop, bool same) {
+    const u32 p0 = s.post_pos[i0], n0 = s.post_pos[i0 + 1] - p0;
+    if (same) return sloppy_freq_same(s.positions + p0, (int)n0, slop);
+    u32 i1 = find_posting(s.post_doc, a1, b1, s.post_doc[i0], guess);
+    if (i1 == b1) return 0.0f;
+    const u32 p1 = s.post_pos[i1], n1 = s.post_pos[i1 + 1] - p1;
+    return sloppy_freq_distinct(s.positions + p0, (int)n0, s.positions + p1, (int)n1, slop);
+}
+
+// ------------------------------------------------- pair table build (dense path)
+// Warp per (k+1)-mer row u.  freq_vals[1..254]: dictionary of distinct float
+// frequencies (bit patterns), filled with atomicCAS in probe order; 0xFFFFFFFF = empty.
+__device__ __forceinline__ u32 freq_code(u32* __restrict__ freq_vals, float f) {
+    u32 bits = __float_as_uint(f);
+    for (int j = 1; j < 255; j++) {
+        u32 cur = ((volatile u32*)freq_vals)[j];
+        if (cur == bits) return (u32)j;
+        if (cur == 0xFFFFFFFFu) {
+            u32 old = atomicCAS(&freq_vals[j], 0xFFFFFFFFu, bits);
+            if (old == 0xFFFFFFFFu || old == bits) return (u32)j;
+        }
+    }
+    return 255u;
+}
+
+__global__ void __launch_bounds__(256) pair_table_kernel(SegDev s, int k, int min_strand, u8* __restrict__ pair_tab,
+                                                          u64 d_pad, u32* __restrict__ freq_vals,
+                                                          u32* __restrict__ pair_row_slow, u64 n_rows) {
+    const int lane = threadIdx.x & 31;
+    u64 u = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= n_rows) return;
+    const u64 kmask = (1ull << (2 * k)) - 1ull;
+    u64 t0 = canon_kmer(u >> 2, k, min_strand), t1 = canon_kmer(u & kmask, k, min_strand);
+    u32 lt0 = s.direct[t0];
+    if (lt0 == NO_TERM) return;
+    u32 lt1 = s.direct[t1];
+    if (lt1 == NO_TERM) return;
+    const bool same = t0 == t1;
+    const u32 a0 = s.term_off[lt0], b0 = s.term_off[lt0 + 1];
+    const u32 a1 = s.term_off[lt1], b1 = s.term_off[lt1 + 1];
+    u8* row = pair_tab + u * d_pad + s.doc_base;
+    bool slow = false;
+    for (u32 i = a0 + lane; i < b0; i += 32) {
+        float f = phrase_freq_at(s, i, a1, b1, a1 + (i - a0), 2, same);
+        if (f != 0.0f) {
+            u32 code = freq_code(freq_vals, f);
+            if (code == 255u) slow = true;
+            row[s.post_doc[i]] = (u8)code;
+        }
+    }
+    if (slow) atomicOr(&pair_row_slow[u >> 5], 1u << (u & 31));
+}
+
+// ------------------------------------------------------------------------ K5
+struct QueryParams {
+    int k, skips, min_strand, alg, sim;
+    double msm_ratio;
+    i64 max_doc;            // global maxDoc (all partitions)
+    int dense_ok;           // dense tables resident
+    int positional_ok;      // positional segments resident
+};
+
+__device__ __forceinline__ int base_code_dev(u8 c) {
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+}
+
+// Warp per read: lucene/KmerSequenceTokenizer.java:115-154 + SequenceCompressFilter.
+// tok_off[r] = capacity offset of read r's token slots (max(len-k+1,0) each).
+__global__ void __launch_bounds__(256) tokenize_kernel(const u8* __restrict__ seq, const i64* __restrict__ seq_off, i32 n_reads,
+                                                        const i64* __restrict__ tok_off, int k, int skips, int min_strand,
+                                                        u64* __restrict__ tok_key, u32* __restrict__ tok_pos,
+                                                        i32* __restrict__ n_tok) {
+    const int lane = threadIdx.x & 31;
+    const i32 r = (i32)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
+    if (r >= n_reads) return;
+    const u8* s = seq + seq_off[r];
+    const i64 len = seq_off[r + 1] - seq_off[r];
+    const i64 nwin = len - k + 1;
+    u64* keys = tok_key + tok_off[r];
+    u32* offs = tok_pos + tok_off[r];
+    i32 cnt = 0;
+    if (nwin > 0) {
+        if (skips == 0) {
+            // every valid window is a token: ordered compaction by ballot
+            for (i64 w0 = 0; w0 < nwin; w0 += 32) {
+                i64 w = w0 + lane;
+                bool ok = w < nwin;
+                u64 v = 0;
+                if (ok) {
+                    for (int i = 0; i < k; i++) {
+                        int b = base_code_dev(s[w + i]);
+                        if (b < 0) { ok = false; break; }
+                        v = (v << 2) | (u64)b;
+                    }
+                }
+                u32 bal = __ballot_sync(0xFFFFFFFFu, ok);
+                if (ok) {
+                    i32 o = cnt + __popc(bal & ((1u << lane) - 1u));
+                    keys[o] = canon_kmer(v, k, min_strand);
+                    offs[o] = (u32)w;
+                }
+                cnt += __popc(bal);
+            }
+        } else {
+            // stride rule: 1+skips after an emit, 1 while dropping and for the emit that ends a drop run
+            if (lane == 0) {
+                i64 pos = 0, scanned = 0, bad = -1;
+                while (true) {
+                    int cur_skip = skips;
+                    bool emitted = false;
+                    while (pos + k <= len) {
+                        while (scanned < pos + k) { if (base_code_dev(s[scanned]) < 0) bad = scanned; scanned++; }
+                        if (bad < pos) { offs[cnt++] = (u32)pos; pos += 1 + cur_skip; emitted = true; break; }
+                        cur_skip = 0;
+                        pos += 1;
+                    }
+                    if (!emitted) break;
+                }
+            }
+            cnt = __shfl_sync(0xFFFFFFFFu, cnt, 0);
+            __syncwarp();
+            for (i32 j = lane; j < cnt; j += 32) {
+                u32 w = offs[j];
+                u64 v = 0;
+                for (int i = 0; i < k; i++) v = (v << 2) | (u64)base_code_dev(s[w + i]);
+                keys[j] = canon_kmer(v, k, min_strand);
+            }
+        }
+    }
+    if (lane == 0) n_tok[r] = cnt;
+}
+
+// number of clauses for n tokens (Classifier.java:113-200; offsetDiff > 0 always holds)
+__host__ __device__ __forceinline__ i32 clause_count(int alg, i32 n) {
+    if (n <= 1) return 0;
+    if (alg == ALG_NAIVE) return n;
+    if (alg == ALG_CHAIN) return n - 1;
+    return (n + 1) / 2;
+}
+// clause c -> token indices (j0, j1); j1 < 0 for a Term clause
+__device__ __forceinline__ void clause_tokens(int alg, i32 n, i32 c, i32& j0, i32& j1) {
+    if (alg == ALG_NAIVE) { j0 = c; j1 = -1; }
+    else if (alg == ALG_CHAIN) { j0 = c; j1 = c + 1; }
+    else { j0 = 2 * c; j1 = (2 * c + 1 < n) ? 2 * c + 1 : -1; }
+}
+
+// local df of every token: sum over this handle's segments (or the dense df array)
+__global__ void __launch_bounds__(256) token_df_kernel(const u64* __restrict__ tok_key, const i64* __restrict__ tok_off,
+                                                        const i32* __restrict__ n_tok, i32 n_reads,
+                                                        const u32* __restrict__ df_dense, const SegDev* __restrict__ segs,
+                                                        int n_segs, u32* __restrict__ tok_df) {
+    const int lane = threadIdx.x & 31;
+    const i32 r = (i32)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
+    if (r >= n_reads) return;
+    const i64 base = tok_off[r];
+    const i32 n = n_tok[r];
+    for (i32 j = lane; j < n; j += 32) {
+        u64 key = tok_key[base + j];
+        u32 df = 0;
+        if (df_dense) df = df_dense[key];
+        else {
+            for (int sidx = 0; sidx < n_segs; sidx++) {
+                const SegDev& s = segs[sidx];
+                u32 t = seg_find_term(s, key);
+                if (t != NO_TERM) df += s.term_off[t + 1] - s.term_off[t];
+            }
+        }
+        tok_df[base + j] = df;
+    }
+}
+
+// Thread per read: msm, clause weights (A.5) and routing.
+//   clause_val[tok_off[r] + c] = value_c ; clause_row[...] = dense-table row (dense route)
+__global__ void __launch_bounds__(128) weights_kernel(const u8* __restrict__ seq, const i64* __restrict__ seq_off, i32 n_reads,
+                                                       const i64* __restrict__ tok_off, const i32* __restrict__ n_tok,
+                                                       const u64* __restrict__ tok_key, const u32* __restrict__ tok_pos,
+                                                       const u32* __restrict__ tok_df, const float* __restrict__ idf_by_df,
+                                                       QueryParams qp, const u32* __restrict__ tf_row_slow,
+                                                       const u32* __restrict__ pair_row_slow,
+                                                       float* __restrict__ clause_val, u32* __restrict__ clause_row,
+                                                       i32* __restrict__ n_clauses, i32* __restrict__ msm_out,
+                                                       i32* __restrict__ route, i32* __restrict__ status) {
+    const i32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const i64 base = tok_off[r];
+    const i32 n = n_tok[r];
+    const i32 nc = clause_count(qp.alg, n);
+    n_clauses[r] = nc;
+    if (n <= 1 || nc > MAX_CLAUSES) {               // Classifier.java:223-227 / TooManyClauses
+        msm_out[r] = 0; route[r] = ROUTE_NONE; status[r] = ST_DROPPED;
+        return;
+    }
+    msm_out[r] = (i32)(qp.msm_ratio * (double)nc);   // Classifier.java:257
+    bool dense = qp.dense_ok != 0;
+    float sum_sq = 0.0f;
+    for (i32 c = 0; c < nc; c++) {
+        i32 j0, j1;
+        clause_tokens(qp.alg, n, c, j0, j1);
+        float idf = idf_by_df[tok_df[base + j0]];
+        if (j1 >= 0) {
+            // TFIDFSimilarity#idfExplain(stats, TermStatistics[]): float sum, t0 first
+            idf = __fadd_rn(__fadd_rn(0.0f, idf), idf_by_df[tok_df[base + j1]]);
+            if (tok_pos[base + j1] - tok_pos[base + j0] != 1u) dense = false;      // slop != 2
+        }
+        clause_val[base + c] = idf;
+        float qw = __fmul_rn(idf, 1.0f);
+        sum_sq = __fadd_rn(sum_sq, __fmul_rn(qw, qw));
+    }
+    if (qp.sim == SIM_TFIDF) {
+        sum_sq = __fmul_rn(sum_sq, 1.0f);                                           // BooleanWeight#getValueForNormalization
+        float qn = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn((double)sum_sq)));   // DefaultSimilarity#queryNorm
+        if (isinf(qn) || isnan(qn)) qn = 1.0f;                                      // IndexSearcher#createNormalizedWeight
+        for (i32 c = 0; c < nc; c++) {
+            float idf = clause_val[base + c];
+            float qw = __fmul_rn(__fmul_rn(idf, 1.0f), __fmul_rn(qn, 1.0f));        // IDFStats#normalize
+            clause_val[base + c] = __fmul_rn(qw, idf);
+        }
+    }   // BM25Stats#normalize: weight = idf * 1 * 1
+    if (dense) {
+        const u8* s = seq + seq_off[r];
+        for (i32 c = 0; c < nc && dense; c++) {
+            i32 j0, j1;
+            clause_tokens(qp.alg, n, c, j0, j1);
+            if (j1 >= 0) {
+                u32 off = tok_pos[base + j0];
+                u64 u = 0;
+                for (int i = 0; i <= qp.k; i++) u = (u << 2) | (u64)base_code_dev(s[off + i]);
+                if (pair_row_slow[u >> 5] & (1u << (u & 31))) dense = false;
+                clause_row[base + c] = (u32)u;
+            } else {
+                u64 key = tok_key[base + j0];
+                if (tf_row_slow[key >> 5] & (1u << (key & 31))) dense = false;
+                clause_row[base + c] = (u32)key;
+            }
+        }
+    }
+    if (dense) { route[r] = ROUTE_DENSE; status[r] = ST_OK; }
+    else if (qp.positional_ok) { route[r] = ROUTE_POSITIONAL; status[r] = ST_OK; }
+    else { route[r] = ROUTE_NONE; status[r] = ST_ERROR; }
+}
+
+// ------------------------------------------------------------------ scoring math
+struct SimParams {
+    int sim;
+    float k1p1;              // BM25: k1 + 1f
+};
+// doc_w[d]: tf-idf -> decoded norm (DefaultSimilarity#decodeNormValue); BM25 -> cache[normByte]
+__device__ __forceinline__ float clause_doc_score(int sim, float freq_or_tf, float value, float doc_w, float k1p1) {
+    if (sim == SIM_TFIDF)      // TFIDFSimScorer#score: (tf(freq) * value) * norm ; freq_or_tf = tf(freq)
+        return __fmul_rn(__fmul_rn(freq_or_tf, value), doc_w);
+    // BM25DocScorer#score: weightValue * freq / (freq + norm), weightValue = weight * (k1 + 1)
+    return __fdiv_rn(__fmul_rn(__fmul_rn(value, k1p1), freq_or_tf), __fadd_rn(freq_or_tf, doc_w));
+}
+__device__ __forceinline__ float tf_of(float freq) {    // DefaultSimilarity#tf
+    return __double2float_rn(__dsqrt_rn((double)freq));
+}
+__device__ __forceinline__ float final_score(int sim, double sum, i32 m, i32 nc) {
+    float coord = 1.0f;      // BooleanWeight#coord / DefaultSimilarity#coord ; BM25: Similarity#coord = 1
+    if (sim == SIM_TFIDF && nc != 1) coord = __fdiv_rn((float)m, (float)nc);
+    return __fmul_rn(__double2float_rn(sum), coord);
+}
+
+// order key: larger = better (score desc, doc asc); scores are >= 0; 0 = no candidate
+__device__ __forceinline__ u64 cand_key(float score, u32 doc) {
+    return ((u64)__float_as_uint(score) << 32) | (u64)(0xFFFFFFFFu - doc);
+}
+
+__device__ __forceinline__ u64 block_max_u64(u64 v, u64* sm /* [33] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        u64 o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        if (o > v) v = o;
+    }
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        u64 w = lane < (int)((blockDim.x + 31) >> 5) ? sm[lane] : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            u64 o = __shfl_xor_sync(0xFFFFFFFFu, w, d);
+            if (o > w) w = o;
+        }
+        if (lane == 0) sm[32] = w;
+    }
+    __syncthreads();
+    return sm[32];
+}
+
+// ------------------------------------------------------------------- K6/K7
+// General path.  CTA per (segment, read): per-doc accumulators for the segment's docs
+// live in shared memory (double sum + u16 match count); clauses are walked one at a
+// time (each doc occurs at most once per clause -> no atomics), threads stride over
+// the postings of the clause's first term; then the fused block top-10.
+#define POS_THREADS 256
+#define POS_CHUNK 128            // clauses staged per round
+struct ClauseStage { u32 a0, b0, a1, b1; float val; int slop; };   // slop 0 = Term, <0 = same-term phrase (-slop)
+
+__global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
+        const SegDev* __restrict__ segs, int n_segs, const i32* __restrict__ read_list, i32 n_list,
+        const i64* __restrict__ tok_off, const i32* __restrict__ n_tok, const u64* __restrict__ tok_key,
+        const u32* __restrict__ tok_pos, const float* __restrict__ clause_val, const i32* __restrict__ n_clauses,
+        const i32* __restrict__ msm, const float* __restrict__ doc_w, QueryParams qp, SimParams sp, u32 global_doc_base,
+        int parts_stride, i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    __shared__ ClauseStage stage[POS_CHUNK];
+    __shared__ u64 red[33];
+    const int sidx = blockIdx.x % n_segs;
+    const i32 r = read_list[blockIdx.x / n_segs];
+    const SegDev s = segs[sidx];
+    double* acc = reinterpret_cast<double*>(smem_raw);
+    u16* cnt = reinterpret_cast<u16*>(smem_raw + (size_t)s.n_docs * 8);
+    for (u32 d = threadIdx.x; d < s.n_docs; d += blockDim.x) { acc[d] = 0.0; cnt[d] = 0; }
+    const i64 base = tok_off[r];
+    const i32 n = n_tok[r], nc = n_clauses[r];
+    const float* dw = doc_w + s.doc_base;
+    for (i32 c0 = 0; c0 < nc; c0 += POS_CHUNK) {
+        __syncthreads();
+        i32 c = c0 + threadIdx.x;
+        if (threadIdx.x < POS_CHUNK && c < nc) {
+            i32 j0, j1;
+            clause_tokens(qp.alg, n, c, j0, j1);
+            ClauseStage st;
+            st.val = clause_val[base + c];
+            u64 k0 = tok_key[base + j0];
+            u32 t0 = seg_find_term(s, k0);
+            st.a0 = st.b0 = st.a1 = st.b1 = 0; st.slop = 0;
+            if (t0 != NO_TERM) { st.a0 = s.term_off[t0]; st.b0 = s.term_off[t0 + 1]; }
+            if (j1 >= 0) {
+                u64 k1 = tok_key[base + j1];
+                int slop = (int)(tok_pos[base + j1] - tok_pos[base + j0]) + 1;       // Classifier.java:146,182
+                if (k1 == k0) { st.slop = -slop; st.a1 = st.a0; st.b1 = st.b0; }
+                else {
+                    st.slop = slop;
+                    u32 t1 = seg_find_term(s, k1);
+                    if (t1 != NO_TERM) { st.a1 = s.term_off[t1]; st.b1 = s.term_off[t1 + 1]; }
+                    else st.b0 = st.a0;                                              // conjunction is empty
+                }
+            }
+            stage[threadIdx.x] = st;
+        }
+        __syncthreads();
+        const i32 lim = min(POS_CHUNK, nc - c0);
+        for (i32 ci = 0; ci < lim; ci++) {
+            const ClauseStage st = stage[ci];
+            for (u32 i = st.a0 + threadIdx.x; i < st.b0; i += blockDim.x) {
+                const u32 d = s.post_doc[i];
+                float f;
+                if (st.slop == 0) {
+                    f = (float)(s.post_pos[i + 1] - s.post_pos[i]);                  // TermScorer: freq as float
+                } else {
+                    const bool same = st.slop < 0;
+                    f = phrase_freq_at(s, i, st.a1, st.b1, st.a1 + (i - st.a0), same ? -st.slop : st.slop, same);
+                }
+                if (f != 0.0f) {
+                    float sc = clause_doc_score(sp.sim, sp.sim == SIM_TFIDF ? tf_of(f) : f, st.val, dw[d], sp.k1p1);
+                    acc[d] += (double)sc;                                            // BooleanScorer: double sum
+                    cnt[d] += 1;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // final scores (in place: float in the low half of the double slot), msm filter
+    const i32 need = max(1, msm[r]);
+    for (u32 d = threadIdx.x; d < s.n_docs; d += blockDim.x) {
+        i32 m = cnt[d];
+        float sc = -1.0f;
+        if (m >= need) sc = final_score(sp.sim, acc[d], m, nc);
+        reinterpret_cast<float*>(&acc[d])[0] = sc;
+    }
+    __syncthreads();
+    // fused top-10: rounds of block arg-max
+    const i64 pbase = (i64)r * parts_stride + sidx;
+    i32 found = 0;
+    for (int round = 0; round < TOPN; round++) {
+        u64 best = 0;
+        for (u32 d = threadIdx.x; d < s.n_docs; d += blockDim.x) {
+            float sc = reinterpret_cast<float*>(&acc[d])[0];
+            if (sc >= 0.0f) { u64 kk = cand_key(sc, d); if (kk > best) best = kk; }
+        }
+        best = block_max_u64(best, red);
+        if (best == 0) break;
+        u32 d = 0xFFFFFFFFu - (u32)(best & 0xFFFFFFFFu);
+        if (threadIdx.x == 0) {
+            part_doc[pbase * TOPN + round] = global_doc_base + s.doc_base + d;
+            part_score[pbase * TOPN + round] = __uint_as_float((u32)(best >> 32));
+            reinterpret_cast<float*>(&acc[d])[0] = -1.0f;
+        }
+        found++;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part_n[pbase] = found;
+}
+
+// ------------------------------------------------------------------- K6'
+// Dense path.  CTA per (doc tile, read); each thread owns 16 consecutive docs: one
+// 128-bit load per table row, 16 double accumulators + match counts in registers.
+// Rows: clauses [0, n_pair) index pair_tab, the rest index tf_tab.
+#define DENSE_DPT 16
+#define DENSE_STAGE 256
+template <int SIM>
+__global__ void __launch_bounds__(512) score_dense_kernel(
+        const u8* __restrict__ tf_tab, const u8* __restrict__ pair_tab, u64 d_pad, u32 n_docs,
+        const float* __restrict__ pair_lut, const float* __restrict__ tf_lut,
+        const i32* __restrict__ read_list, i32 n_list, const i64* __restrict__ tok_off, const i32* __restrict__ n_tok,
+        const float* __restrict__ clause_val, const u32* __restrict__ clause_row, const i32* __restrict__ n_clauses,
+        const i32* __restrict__ msm, const float* __restrict__ doc_w, int alg, float k1p1, u32 global_doc_base,
+        int n_tiles, int parts_stride, i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score) {
+    __shared__ float s_pair[256], s_tf[256];
+    __shared__ float s_val[DENSE_STAGE];
+    __shared__ u32 s_row[DENSE_STAGE];
+    __shared__ u64 red[33];
+    const int tile = blockIdx.x % n_tiles;
+    const i32 r = read_list[blockIdx.x / n_tiles];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_pair[i] = pair_lut[i]; s_tf[i] = tf_lut[i]; }
+    const i64 base = tok_off[r];
+    const i32 n = n_tok[r], nc = n_clauses[r];
+    const i32 n_pair = alg == ALG_NAIVE ? 0 : (alg == ALG_CHAIN ? nc : n / 2);
+    const u32 d0 = ((u32)tile * blockDim.x + threadIdx.x) * DENSE_DPT;
+    const bool active = d0 < n_docs;                    // d_pad is a multiple of 16: the 16-doc group is in-row
+    double acc[DENSE_DPT];
+    u32 cnt[DENSE_DPT / 2];                              // two u16 counters per register
+    float w[DENSE_DPT];
+#pragma unroll
+    for (int i = 0; i < DENSE_DPT; i++) acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < DENSE_DPT / 2; i++) cnt[i] = 0;
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < DENSE_DPT; i += 4) {
+            float4 v = *reinterpret_cast<const float4*>(doc_w + d0 + i);
+            w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
+        }
+    }
+    for (i32 c0 = 0; c0 < nc; c0 += DENSE_STAGE) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < DENSE_STAGE && c0 + i < nc; i += blockDim.x) {
+            s_val[i] = clause_val[base + c0 + i];
+            s_row[i] = clause_row[base + c0 + i];
+        }
+        __syncthreads();
+        if (!active) continue;
+        const i32 lim = min(DENSE_STAGE, nc - c0);
+#pragma unroll 2
+        for (i32 ci = 0; ci < lim; ci++) {
+            const bool is_pair = (c0 + ci) < n_pair;
+            const u8* rowp = (is_pair ? pair_tab : tf_tab) + (u64)s_row[ci] * d_pad + d0;
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(rowp));
+            const float* lut = is_pair ? s_pair : s_tf;
+            const float val = SIM == SIM_TFIDF ? s_val[ci] : __fmul_rn(s_val[ci], k1p1);
+            const u32 qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < DENSE_DPT; i++) {
+                const u32 code = (qq[i >> 2] >> (8 * (i & 3))) & 255u;
+                const float f = lut[code];               // tf-idf: tf(freq) ; BM25: freq ; lut[0] = 0
+                float sc;
+                if (SIM == SIM_TFIDF) sc = __fmul_rn(__fmul_rn(f, val), w[i]);
+                else sc = code ? __fdiv_rn(__fmul_rn(val, f), __fadd_rn(f, w[i])) : 0.0f;
+                acc[i] += (double)sc;
+                cnt[i >> 1] += (code ? 1u : 0u) << (16 * (i & 1));
+            }
+        }
+    }
+    // final scores + fused top-10
+    const i32 need = max(1, msm[r]);
+    float sc[DENSE_DPT];
+#pragma unroll
+    for (int i = 0; i < DENSE_DPT; i++) {
+        i32 m = (i32)((cnt[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+        sc[i] = (active && d0 + i < n_docs && m >= need) ? final_score(SIM, acc[i], m, nc) : -1.0f;
+    }
+    const i64 pbase = (i64)r * parts_stride + tile;
+    i32 found = 0;
+    u64 mine = 0;
+    bool dirty = true;
+    for (int round = 0; round < TOPN; round++) {
+        if (dirty) {
+            mine = 0;
+#pragma unroll
+            for (int i = 0; i < DENSE_DPT; i++)
+                if (sc[i] >= 0.0f) { u64 kk = cand_key(sc[i], d0 + i); if (kk > mine) mine = kk; }
+            dirty = false;
+        }
+        u64 best = block_max_u64(mine, red);
+        if (best == 0) break;
+        if (best == mine) {                               // unique: keys embed the doc id
+            u32 d = 0xFFFFFFFFu - (u32)(best & 0xFFFFFFFFu);
+            part_doc[pbase * TOPN + round] = global_doc_base + d;
+            part_score[pbase * TOPN + round] = __uint_as_float((u32)(best >> 32));
+#pragma unroll
+            for (int i = 0; i < DENSE_DPT; i++) if (d0 + i == d) sc[i] = -1.0f;
+            dirty = true;
+        }
+        found++;
+    }
+    if (threadIdx.x == 0) part_n[pbase] = found;
+}
+
+// ------------------------------------------------------------------------ K8
+// Thread per read: merge the per-part top-10 lists (each sorted score desc, doc asc)
+// into the final list; n_hits = entries equal to the max (Classifier.java:358-366);
+// label by score tier (Classifier.java:263-339 without taxonomy).
+__global__ void __launch_bounds__(128) merge_kernel(i32 n_reads, const i32* __restrict__ route, const i32* __restrict__ status_in,
+                                                     int parts_dense, int parts_pos, int parts_stride,
+                                                     const i32* __restrict__ part_n, const u32* __restrict__ part_doc,
+                                                     const float* __restrict__ part_score,
+                                                     i32* __restrict__ status, i32* __restrict__ label, i32* __restrict__ n_hits,
+                                                     i32* __restrict__ n_top, i32* __restrict__ top_doc,
+                                                     float* __restrict__ top_score) {
+    const i32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    float bs[TOPN];
+    u32 bd[TOPN];
+    int nt = 0;
+    const int rt = route ? route[r] : ROUTE_POSITIONAL;
+    const int parts = rt == ROUTE_DENSE ? parts_dense : (rt == ROUTE_POSITIONAL ? parts_pos : 0);
+    for (int p = 0; p < parts; p++) {
+        const i64 pb = (i64)r * parts_stride + p;
+        const int np = part_n[pb];
+        for (int j = 0; j < np; j++) {
+            const float s = part_score[pb * TOPN + j];
+            const u32 d = part_doc[pb * TOPN + j];
+            int pos = nt;
+            while (pos > 0 && (bs[pos - 1] < s || (bs[pos - 1] == s && bd[pos - 1] > d))) pos--;
+            if (pos >= TOPN) break;                       // the rest of this part is not better
+            const int last = nt < TOPN ? nt : TOPN - 1;
+            for (int q = last; q > pos; q--) { bs[q] = bs[q - 1]; bd[q] = bd[q - 1]; }
+            bs[pos] = s; bd[pos] = d;
+            if (nt < TOPN) nt++;
+        }
+    }
+    int nh = 0;
+    for (int j = 0; j < nt; j++) if ((double)bs[0] - (double)bs[j] == 0.0) nh++;
+    if (status) status[r] = status_in[r];
+    if (label) label[r] = nh == 0 ? 0 : (nh == 1 ? 2 : 1);
+    if (n_hits) n_hits[r] = nh;
+    if (n_top) n_top[r] = nt;
+    for (int j = 0; j < TOPN; j++) {
+        if (top_doc) top_doc[(i64)r * TOPN + j] = j < nt ? (i32)bd[j] : -1;
+        if (top_score) top_score[(i64)r * TOPN + j] = j < nt ? bs[j] : 0.0f;
+    }
+}
+
+// ------------------------------------------------------------- cost model (8d)
+// Warp per read.  out[0] reads, [1] tokens, [2] unique terms (= probes), [3] sum df,
+// [4] sum ttf, [5] A_read (CSR formula of SURVEY.md 8d), [6] dense-layout bytes, [7] clauses.
+__global__ void __launch_bounds__(256) read_cost_kernel(const i64* __restrict__ seq_off, i32 n_reads, const i64* __restrict__ tok_off,
+                                                         const i32* __restrict__ n_tok, const u64* __restrict__ tok_key,
+                                                         const u32* __restrict__ tok_df, const u32* __restrict__ ttf_dense,
+                                                         const SegDev* __restrict__ segs, int n_segs, int alg, u64 d_pad,
+                                                         u64 n_docs, unsigned long long* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const i32 r = (i32)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
+    if (r >= n_reads) return;
+    const i64 base = tok_off[r];
+    const i32 n = n_tok[r];
+    const i32 nc = clause_count(alg, n);
+    unsigned long long uniq = 0, sdf = 0, sttf = 0;
+    if (nc > 0 && nc <= MAX_CLAUSES) {
+        for (i32 j = lane; j < n; j += 32) {
+            u64 key = tok_key[base + j];
+            bool first = true;
+            for (i32 q = 0; q < j; q++) if (tok_key[base + q] == key) { first = false; break; }
+            if (!first) continue;
+            uniq++;
+            sdf += tok_df[base + j];
+            if (ttf_dense) sttf += ttf_dense[key];
+            else for (int s = 0; s < n_segs; s++) {
+                u32 t = seg_find_term(segs[s], key);
+                if (t != NO_TERM) sttf += segs[s].post_pos[segs[s].term_off[t + 1]] - segs[s].post_pos[segs[s].term_off[t]];
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        uniq += __shfl_xor_sync(0xFFFFFFFFu, uniq, d);
+        sdf += __shfl_xor_sync(0xFFFFFFFFu, sdf, d);
+        sttf += __shfl_xor_sync(0xFFFFFFFFu, sttf, d);
+    }
+    if (lane == 0 && nc > 0 && nc <= MAX_CLAUSES) {
+        unsigned long long len = (unsigned long long)(seq_off[r + 1] - seq_off[r]);
+        unsigned long long P = alg == ALG_NAIVE ? 0ull : 1ull;
+        atomicAdd(&out[0], 1ull);
+        atomicAdd(&out[1], (unsigned long long)n);
+        atomicAdd(&out[2], uniq);
+        atomicAdd(&out[3], sdf);
+        atomicAdd(&out[4], sttf);
+        atomicAdd(&out[5], len + 16ull * uniq + 8ull * sdf + P * 4ull * sttf + 80ull);
+        atomicAdd(&out[6], len + (unsigned long long)nc * (unsigned long long)d_pad + 4ull * n_docs + 80ull);
+        atomicAdd(&out[7], (unsigned long long)nc);
+    }
+}

@@ -1,0 +1,204 @@
+// json_mini.hpp -- minimal JSON value/parser/writer for the host-side mirror
+// (configuration.json, .taxd lineages, .result / .result.sum output).
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace jsonm {
+
+struct Value;
+typedef std::shared_ptr<Value> ValuePtr;
+
+struct Value {
+    enum Type { Null, Bool, Number, String, Array, Object } type = Null;
+    bool b = false;
+    double num = 0;
+    bool is_int = false;
+    long long inum = 0;
+    std::string str;
+    std::vector<ValuePtr> arr;
+    std::vector<std::pair<std::string, ValuePtr>> obj;   // insertion order kept
+
+    const Value* get(const std::string& key) const {
+        for (auto& kv : obj) if (kv.first == key) return kv.second.get();
+        return nullptr;
+    }
+};
+
+class Parser {
+public:
+    explicit Parser(const std::string& s) : s_(s), p_(0) {}
+    ValuePtr parse() {
+        ValuePtr v = value();
+        ws();
+        if (p_ != s_.size()) fail("trailing characters");
+        return v;
+    }
+
+private:
+    const std::string& s_;
+    size_t p_;
+    [[noreturn]] void fail(const char* m) { throw std::runtime_error(std::string("JSON parse error: ") + m + " at " + std::to_string(p_)); }
+    void ws() { while (p_ < s_.size() && (s_[p_] == ' ' || s_[p_] == '\t' || s_[p_] == '\n' || s_[p_] == '\r')) p_++; }
+    ValuePtr value() {
+        ws();
+        if (p_ >= s_.size()) fail("unexpected end");
+        char c = s_[p_];
+        auto v = std::make_shared<Value>();
+        if (c == '{') {
+            v->type = Value::Object; p_++; ws();
+            if (p_ < s_.size() && s_[p_] == '}') { p_++; return v; }
+            while (true) {
+                ws();
+                if (p_ >= s_.size() || s_[p_] != '"') fail("expected key");
+                std::string k = string();
+                ws();
+                if (p_ >= s_.size() || s_[p_] != ':') fail("expected ':'");
+                p_++;
+                v->obj.emplace_back(k, value());
+                ws();
+                if (p_ < s_.size() && s_[p_] == ',') { p_++; continue; }
+                if (p_ < s_.size() && s_[p_] == '}') { p_++; break; }
+                fail("expected ',' or '}'");
+            }
+        } else if (c == '[') {
+            v->type = Value::Array; p_++; ws();
+            if (p_ < s_.size() && s_[p_] == ']') { p_++; return v; }
+            while (true) {
+                v->arr.push_back(value());
+                ws();
+                if (p_ < s_.size() && s_[p_] == ',') { p_++; continue; }
+                if (p_ < s_.size() && s_[p_] == ']') { p_++; break; }
+                fail("expected ',' or ']'");
+            }
+        } else if (c == '"') {
+            v->type = Value::String; v->str = string();
+        } else if (!s_.compare(p_, 4, "true")) { v->type = Value::Bool; v->b = true; p_ += 4; }
+        else if (!s_.compare(p_, 5, "false")) { v->type = Value::Bool; v->b = false; p_ += 5; }
+        else if (!s_.compare(p_, 4, "null")) { v->type = Value::Null; p_ += 4; }
+        else {
+            size_t st = p_;
+            bool isint = true;
+            if (p_ < s_.size() && (s_[p_] == '-' || s_[p_] == '+')) p_++;
+            while (p_ < s_.size() && (isdigit((unsigned char)s_[p_]) || s_[p_] == '.' || s_[p_] == 'e' || s_[p_] == 'E' || s_[p_] == '-' || s_[p_] == '+')) {
+                if (s_[p_] == '.' || s_[p_] == 'e' || s_[p_] == 'E') isint = false;
+                p_++;
+            }
+            if (p_ == st) fail("unexpected character");
+            std::string t = s_.substr(st, p_ - st);
+            v->type = Value::Number; v->num = strtod(t.c_str(), nullptr); v->is_int = isint;
+            v->inum = isint ? strtoll(t.c_str(), nullptr, 10) : (long long)v->num;
+        }
+        return v;
+    }
+    static void put_utf8(std::string& o, unsigned cp) {
+        if (cp < 0x80) o.push_back((char)cp);
+        else if (cp < 0x800) { o.push_back((char)(0xC0 | (cp >> 6))); o.push_back((char)(0x80 | (cp & 0x3F))); }
+        else if (cp < 0x10000) { o.push_back((char)(0xE0 | (cp >> 12))); o.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); o.push_back((char)(0x80 | (cp & 0x3F))); }
+        else { o.push_back((char)(0xF0 | (cp >> 18))); o.push_back((char)(0x80 | ((cp >> 12) & 0x3F))); o.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); o.push_back((char)(0x80 | (cp & 0x3F))); }
+    }
+    std::string string() {
+        std::string o;
+        p_++;   // opening quote
+        while (true) {
+            if (p_ >= s_.size()) fail("unterminated string");
+            char c = s_[p_++];
+            if (c == '"') break;
+            if (c != '\\') { o.push_back(c); continue; }
+            if (p_ >= s_.size()) fail("bad escape");
+            char e = s_[p_++];
+            switch (e) {
+                case '"': o.push_back('"'); break;
+                case '\\': o.push_back('\\'); break;
+                case '/': o.push_back('/'); break;
+                case 'b': o.push_back('\b'); break;
+                case 'f': o.push_back('\f'); break;
+                case 'n': o.push_back('\n'); break;
+                case 'r': o.push_back('\r'); break;
+                case 't': o.push_back('\t'); break;
+                case 'u': {
+                    if (p_ + 4 > s_.size()) fail("bad \\u escape");
+                    unsigned cp = (unsigned)strtoul(s_.substr(p_, 4).c_str(), nullptr, 16);
+                    p_ += 4;
+                    if (cp >= 0xD800 && cp < 0xDC00 && p_ + 6 <= s_.size() && s_[p_] == '\\' && s_[p_ + 1] == 'u') {
+                        unsigned lo = (unsigned)strtoul(s_.substr(p_ + 2, 4).c_str(), nullptr, 16);
+                        if (lo >= 0xDC00 && lo < 0xE000) { cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00); p_ += 6; }
+                    }
+                    put_utf8(o, cp);
+                    break;
+                }
+                default: fail("bad escape");
+            }
+        }
+        return o;
+    }
+};
+
+inline ValuePtr parse(const std::string& s) { return Parser(s).parse(); }
+
+// Jackson-style string escaping (JsonStringEncoder): ", \ and control chars
+inline void write_string(std::string& o, const std::string& s) {
+    o.push_back('"');
+    for (unsigned char c : s) {
+        switch (c) {
+            case '"': o += "\\\""; break;
+            case '\\': o += "\\\\"; break;
+            case '\b': o += "\\b"; break;
+            case '\f': o += "\\f"; break;
+            case '\n': o += "\\n"; break;
+            case '\r': o += "\\r"; break;
+            case '\t': o += "\\t"; break;
+            default:
+                if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04X", c); o += b; }
+                else o.push_back((char)c);
+        }
+    }
+    o.push_back('"');
+}
+
+// java.lang.Double#toString layout: shortest digits that round-trip; plain decimal for
+// 1e-3 <= |d| < 1e7, otherwise d.dddE[-]n
+inline std::string java_double(double d) {
+    if (std::isnan(d)) return "NaN";
+    if (std::isinf(d)) return d > 0 ? "Infinity" : "-Infinity";
+    if (d == 0) return std::signbit(d) ? "-0.0" : "0.0";
+    char buf[64];
+    int prec = 1;
+    for (; prec <= 17; prec++) {
+        snprintf(buf, sizeof buf, "%.*e", prec - 1, d);
+        if (strtod(buf, nullptr) == d) break;
+    }
+    // buf = [-]d.ddddde[+-]xx
+    std::string s(buf);
+    bool neg = s[0] == '-';
+    if (neg) s = s.substr(1);
+    size_t epos = s.find('e');
+    int exp10 = atoi(s.c_str() + epos + 1);
+    std::string digits;
+    for (size_t i = 0; i < epos; i++) if (s[i] != '.') digits.push_back(s[i]);
+    std::string out;
+    double ad = std::fabs(d);
+    if (ad >= 1e-3 && ad < 1e7) {
+        if (exp10 >= 0) {
+            std::string ip = digits.substr(0, std::min<size_t>(digits.size(), (size_t)exp10 + 1));
+            while ((int)ip.size() < exp10 + 1) ip.push_back('0');
+            std::string fp = digits.size() > (size_t)exp10 + 1 ? digits.substr(exp10 + 1) : "0";
+            out = ip + "." + fp;
+        } else {
+            out = "0." + std::string((size_t)(-exp10 - 1), '0') + digits;
+        }
+    } else {
+        std::string fp = digits.size() > 1 ? digits.substr(1) : "0";
+        out = digits.substr(0, 1) + "." + fp + "E" + std::to_string(exp10);
+    }
+    return neg ? "-" + out : out;
+}
+
+}  // namespace jsonm
