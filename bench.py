@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s classified on the BASELINE.json workload.
+
+Default (N=1): config C2 of BASELINE.json -- ~3,000 synthetic genomes / ~10 Gbp indexed on one B200,
+1 M reads of ~100 bp at 4 % error, configuration.json as shipped by the reference
+(k=10, skips=0, msm=0.5, PAIRED_PROXIMITY, tfidf).  One "step" = one pass of the classify hot path over
+the whole read batch.  N>1 (torchrun): read-sharded replicas, weak scaling, no collective on the data path.
+
+  value : reads/s with reads already resident in HBM (bsp_classify_device)
+  e2e   : reads/s through the reference-facing call with HOST buffers (bsp_classify_packed: H2D of the
+          reads + D2H of labels/top-10 inside the timed region)
+  --impl reference : the reference's CPU implementation of the path.  No JVM exists in this image, so
+          this is the C/OpenMP oracle restatement (oracle/bsp_oracle.c) on all host cores, on a bounded
+          sample (see cpu_baseline.sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: genomes, total bp, reads per GPU, read length, error
+    "C2": dict(genomes=3000, total_bp=10_000_000_000, reads=1_000_000, R=100, err=0.04, seed=2, read_seed=12),
+    "C1": dict(genomes=10, total_bp=20_000_000, reads=10_000, R=100, err=0.04, seed=1, read_seed=11, equal=True),
+    "mid": dict(genomes=300, total_bp=1_000_000_000, reads=200_000, R=100, err=0.04, seed=4, read_seed=14),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def shipped_config(**kw):
+    from biospectra_b200 import Configuration
+    # /root/reference/configuration.json as shipped
+    c = Configuration(index_path="", kmer_size=10, kmer_skips=0, min_strand_kmer=False, query_term_min_should_match=0.5,
+                      worker_threads=4, index_ram_buffer=16, query_algorithm="PAIRED_PROXIMITY", scoring_algorithm="tfidf")
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def sample_plan(wl, lengths):
+    """CPU baseline sample: the first S genomes (<= ~120 Mbp) of the same reference, reads drawn from them."""
+    budget_bp = int(os.environ.get("BSP_CPU_SAMPLE_BP", 120_000_000))
+    S = 1
+    while S < len(lengths) and lengths[:S + 1].sum() <= budget_bp:
+        S += 1
+    return S
+
+
+def cpu_baseline(wl, lengths, kept, n_reads, threads=None, algorithm=2):
+    """Times the oracle restatement on the host cores.  Index = kept sample genomes; reads sampled from them
+    with the same simulator.  Per-read cost is linear in the number of documents (at k=10 every term occurs
+    in ~all documents), so the full-index estimate is measured reads/s * S/G."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_lib as ol
+    from biospectra_b200 import synth
+    if threads is None:
+        threads = os.cpu_count() or 1
+    S = len(kept)
+    t0 = time.time()
+    ox = ol.OracleIndex(10, False)
+    gl = []
+    for g in sorted(kept):
+        ox.add_entry(kept[g])
+        gl.append(np.frombuffer(kept[g], np.uint8))
+    ox.finish()
+    t_index = time.time() - t0
+    rng = np.random.Generator(np.random.PCG64(wl["read_seed"] + 1000))
+    reads = []
+    for i in range(n_reads):
+        reads.append(synth.reads_from_genome_numpy(rng, gl[int(rng.integers(0, S))], 1, wl["R"], wl["err"])[0].tobytes())
+    ox.classify(reads[:64], skips=0, algorithm=algorithm, scoring=0, msm=0.5, threads=threads)   # warm
+    t0 = time.time()
+    res = ox.classify(reads, skips=0, algorithm=algorithm, scoring=0, msm=0.5, threads=threads)
+    dt = time.time() - t0
+    sample_bp = int(sum(len(x) for x in gl))
+    rps_sample = n_reads / dt
+    scale = S / float(len(lengths))
+    return {"value": rps_sample * scale, "unit": "reads/s", "cores": threads, "kind": "port",
+            "sample": "oracle restatement (no JVM in this image): index of the first %d of %d genomes (%.0f Mbp, %d docs), "
+                      "%d reads drawn from them; measured %.1f reads/s on the sample index, scaled by %d/%d because per-read "
+                      "cost is linear in the document count" % (S, len(lengths), sample_bp / 1e6, 2 * S, n_reads, rps_sample, S, len(lengths)),
+            "measured_reads_per_s_on_sample": rps_sample, "index_seconds": t_index, "classify_seconds": dt,
+            "classified_fraction": float((res["label"] == 2).mean())}
+
+
+def gen_sample_genomes(wl, lengths, S):
+    """the first S genomes of the workload, byte-identical to what the GPU arm indexes (same CUDA Philox streams)"""
+    import torch
+    from biospectra_b200 import synth
+    if torch.cuda.is_available():
+        r = synth.build_reference_and_reads_cuda(None, lengths[:S], 0, wl["R"], wl["err"], wl["seed"], wl["read_seed"],
+                                                 torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))), keep_genomes=set(range(S)))
+        return r["kept"]
+    return {g: synth.genome_numpy(wl["seed"], g, int(lengths[g])).tobytes() for g in range(S)}
+
+
+def run_reference(args, wl, lengths):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    S = sample_plan(wl, lengths)
+    kept = gen_sample_genomes(wl, lengths, S)
+    n_reads = int(os.environ.get("BSP_CPU_SAMPLE_READS", 300))
+    vals = []
+    last = None
+    for it in range(args.warmup + args.steps):
+        last = cpu_baseline(wl, lengths, kept, n_reads)
+        if it >= args.warmup:
+            vals.append(last)
+    v = float(np.mean([x["value"] for x in vals]))
+    ms = float(np.mean([x["classify_seconds"] for x in vals])) * 1e3
+    line = {"impl": "reference", "metric": "reads/sec classified", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 scores, f64 accumulate", "data": "synthetic",
+            "config": workload_config(args, wl), "cpu_baseline": dict(last, value=v),
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, wl):
+    return {"workload": "%s: %d synthetic genomes / %.2f Gbp indexed per GPU (k=10, both strands), %d reads of ~%d bp at %.0f%% "
+                        "error per GPU; configuration.json as shipped (skips=0, msm=0.5, PAIRED_PROXIMITY, tfidf)"
+                        % (args.workload, wl["genomes"], wl["total_bp"] / 1e9, wl["reads"], wl["R"], wl["err"] * 100),
+            "parallelism": "read-sharded replicas x%d (no collective)" % args.gpus,
+            "l2": "inputs larger than L2: the dense index rows read per step span the whole table (>> 126 MB)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default=os.environ.get("BSP_WORKLOAD", "C2"))
+    ap.add_argument("--algorithm", default="PAIRED_PROXIMITY")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    from biospectra_b200 import synth
+    lengths = synth.genome_lengths(wl["genomes"], wl["total_bp"], wl["seed"], *((1, 1) if wl.get("equal") else (1.5e6, 6.5e6)))
+    if args.impl == "reference":
+        return run_reference(args, wl, lengths)
+
+    import torch
+    import torch.distributed as dist
+    from biospectra_b200 import Indexer
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- build: synthetic reference generated in HBM, indexed on the GPU (not timed as part of the metric)
+    iconf = shipped_config(device=local)
+    qconf = shipped_config(device=local, query_algorithm=args.algorithm)
+    S = sample_plan(wl, lengths)
+    t0 = time.time()
+    ix = Indexer(iconf)
+    # every rank indexes the same reference (replica) but classifies its own reads (read_seed + rank)
+    data = synth.build_reference_and_reads_cuda(ix, lengths, wl["reads"], wl["R"], wl["err"], wl["seed"], wl["read_seed"] + rank,
+                                                dev, keep_genomes=set(range(S)) if rank == 0 else ())
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    t0 = time.time()
+    clf = ix.close_to_classifier(qconf)
+    t_build = time.time() - t0
+    stats = clf.stats()
+    mem = clf.memory_info()
+    n = len(data["offsets"]) - 1
+    total_bytes = int(data["offsets"][-1])
+    d_seq, d_off = data["d_seq"], data["d_off"]
+    o = {k: torch.empty(n, dtype=torch.int32, device=dev) for k in ("status", "label", "n_hits", "n_top")}
+    o["top_doc"] = torch.empty(n, 10, dtype=torch.int32, device=dev)
+    o["top_score"] = torch.empty(n, 10, dtype=torch.float32, device=dev)
+
+    def step_device():
+        clf.classify_device(n, d_seq.data_ptr(), d_off.data_ptr(), total_bytes, o["status"].data_ptr(), o["label"].data_ptr(),
+                            o["n_hits"].data_ptr(), o["n_top"].data_ptr(), o["top_doc"].data_ptr(), o["top_score"].data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        t = time.perf_counter()
+        kernel_ms = 0.0
+        pipe_ms = 0.0
+        launches = 0
+        for _ in range(steps):
+            fn()
+            tm = clf.last_timings()
+            kernel_ms += tm["score_kernel_ms"]
+            pipe_ms += tm["pipeline_ms"]
+            launches += clf.last_counters()["launches"]
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t
+        if world > 1:
+            tt = torch.tensor([el, pipe_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            el, pipe_ms = float(tt[0]), float(tt[1])
+        return el, kernel_ms, pipe_ms, launches
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    # device-resident metric: device time (CUDA events on the library's stream, whole pipeline), max over ranks
+    el_dev, kernel_ms, pipe_ms, launches = timed(step_device, args.steps)
+    # end to end through the host-buffer call
+    host_out = {}
+
+    def step_host():
+        host_out["r"] = clf.classify_packed(data["seq_bytes"], data["offsets"])
+
+    step_host()
+    el_e2e, _, _, _ = timed(step_host, args.steps)
+    sampler.stop_flag.set()
+    sampler.join()
+    res = host_out["r"]
+    dres = {k: v.cpu().numpy() for k, v in o.items()}
+    assert np.array_equal(dres["label"], res["label"]) and np.array_equal(dres["top_doc"], res["top_doc"]), "device/host paths disagree"
+    cnt = clf.last_counters()
+    # correctness properties at full size: the source genome's forward doc must be the (tied) top hit
+    ok = res["status"] == 0
+    top = res["top_doc"][:, 0]
+    src_doc = 2 * data["src"].astype(np.int64)
+    recovered = float(((top == src_doc) & ok).sum() / max(ok.sum(), 1))
+    labels = {nm: int((res["label"][ok] == i).sum()) for i, nm in enumerate(("unknown", "vague", "classified"))}
+
+    total_reads = n * world
+    steps = args.steps
+    value = total_reads * steps / el_dev
+    e2e = total_reads * steps / el_e2e
+    line = None
+    if rank == 0:
+        cost = clf.read_cost(data["seq_bytes"], data["offsets"])
+        peak, peak_src = peaks()
+        per_launch_s = (kernel_ms / 1e3) / steps
+        alg_bytes_dense = cost["bytes_dense"]
+        alg_bytes_csr = cost["bytes_csr"]
+        achieved = alg_bytes_dense / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": "score_dense_kernel" if cnt["dense_reads"] >= cnt["positional_reads"] else "score_positional_kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes_dense,
+                "csr_formula_bytes_per_launch": alg_bytes_csr, "csr_formula_gbs": alg_bytes_csr / per_launch_s / 1e9 if per_launch_s > 0 else 0.0,
+                "kernel_ms_per_launch": per_launch_s * 1e3,
+                "note": "achieved = bytes the dense u8-row layout must read (clauses x padded docs + per-doc weights + I/O) / score-kernel "
+                        "time from CUDA events; csr_formula_* is SURVEY.md 8(d)'s A_read for a posting-list layout (the dense rows move fewer bytes)"}
+        line = {"metric": "reads/sec classified", "value": value, "unit": "reads/s", "n_gpus": world, "steps": steps,
+                "warmup": args.warmup, "ms_per_step": el_dev / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 scores, f64 accumulate", "data": "synthetic", "config": workload_config(args, wl),
+                "clocks": sampler.summary(),
+                "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(total_bytes + 8 * (n + 1)),
+                        "d2h_bytes_per_step": int(n * (4 * 4 + 80) + 4 * n)},
+                "gpu_launches": int(launches), "roofline": roof,
+                "probes_per_s": cost["unique_terms"] * world * steps / el_dev,
+                "device_event_ms_per_step": pipe_ms / steps,
+                "timing": "value/e2e: wall clock of exactly K steps between barrier+synchronize, max over ranks; "
+                          "device_event_ms_per_step and roofline: CUDA events on the library's stream",
+                "index": dict(stats, gen_seconds=t_gen, build_seconds=t_build, build_gbp_per_s=wl["total_bp"] / 1e9 / t_build, **mem),
+                "routes": {"dense": cnt["dense_reads"], "positional": cnt["positional_reads"], "reads": cnt["reads"]},
+                "parity_properties": {"source_doc_is_top_hit": recovered, "labels": labels, "dropped": int((res["status"] == 1).sum()),
+                                      "errors": int((res["status"] == 2).sum())}}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl, lengths, data["kept"], int(os.environ.get("BSP_CPU_SAMPLE_READS", 300)),
+                                                algorithm={"NAIVE_KMER": 0, "CHAIN_PROXIMITY": 1, "PAIRED_PROXIMITY": 2}[args.algorithm])
+        print(json.dumps(line))
+    clf.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -45,7 +45,8 @@ EXPORTS = [
     "bsp_index_stats", "bsp_doc_info", "bsp_term_postings", "bsp_tokenize", "bsp_last_routes", "bsp_last_counters",
     "bsp_last_timings", "bsp_memory_info", "bsp_partition_df_buffer", "bsp_partition_local_stats",
     "bsp_partition_set_global", "bsp_merge_topk_device", "bsp_read_cost",
-    "bsp_host_index", "bsp_host_classify_local",
+    "bsp_host_index", "bsp_host_classify_local", "bsp_host_last_error", "bsp_host_label_json", "bsp_host_read_fasta",
+    "bsp_host_double_to_string", "bsp_host_parse_config",
 ]
 
 _lib = None
@@ -91,9 +92,13 @@ def lib():
     L.bsp_partition_set_global.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
     L.bsp_merge_topk_device.argtypes = [vp, C.c_int32, C.c_int32] + [vp] * 10
     L.bsp_read_cost.argtypes = [vp, C.c_int32, vp, vp, vp]
-    if hasattr(L, "bsp_host_index"):
-        L.bsp_host_index.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32]
-        L.bsp_host_classify_local.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32]
+    L.bsp_host_index.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32]
+    L.bsp_host_classify_local.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32]
+    L.bsp_host_last_error.restype = C.c_char_p
+    L.bsp_host_label_json.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.c_char_p, C.c_int32]
+    L.bsp_host_read_fasta.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, i64p]
+    L.bsp_host_double_to_string.argtypes = [C.c_double, C.c_char_p, C.c_int32]
+    L.bsp_host_parse_config.argtypes = [C.c_char_p, cfgp, C.c_char_p, C.c_int32]
     _lib = L
     return L
 

@@ -1,0 +1,130 @@
+// bsp_host.hpp -- C++ mirror of the reference's host-side interface for the hot path
+// (see bsp_host.cpp for the file:line map onto the reference).
+#pragma once
+#include "../../../include/biospectra_gpu.h"
+#include "json_mini.hpp"
+
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace bsp {
+
+struct IllegalArgument : public std::invalid_argument { using std::invalid_argument::invalid_argument; };
+struct IOError : public std::runtime_error { using std::runtime_error::runtime_error; };
+struct FASTADataError : public IOError { using IOError::IOError; };
+
+// src/biospectra/Configuration.java: same keys, same defaults
+struct Configuration {
+    std::string indexPath; bool hasIndexPath = false;
+    int kmerSize = 10;                        // DEFAULT_KMERSIZE
+    int kmerSkips = 5;                        // DEFAULT_KMERSKIPS
+    bool minStrandKmer = false;
+    double queryMinShouldMatch = 0.5;
+    int workerThreads = 4;
+    std::string scoringAlgorithm = "default";
+    int queryAlgorithm = BSP_PAIRED_PROXIMITY;
+    int ramBufferSizeForIndex = 16;
+    // GPU placement: not part of configuration.json (the reference's Jackson mapper rejects unknown keys)
+    int device = 0, denseTables = 0, positional = 0;
+
+    static Configuration createInstance(const std::string& json);
+    static Configuration createInstanceFromFile(const std::string& path);
+    int scoringId() const;
+    bsp_config toStruct() const;
+};
+
+struct FastaFileFilter { static bool accept(const std::string& name); };
+struct CompressedFileFilter { static bool accept(const std::string& name); };
+struct FastaFileHelper {
+    static std::vector<std::string> findFastaDocs(const std::string& path);
+    static std::string findTaxonHierarchyDoc(const std::string& fastaPath);
+};
+
+struct FASTAEntry { std::string headerLine, sequence; };
+class FASTAReader {
+public:
+    explicit FASTAReader(const std::string& path);
+    bool readNext(FASTAEntry& e);      // false at EOF; throws FASTADataError
+private:
+    bool readLine(std::string& line);
+    std::string data_;
+    size_t pos_ = 0;
+    std::string pending_;
+    bool have_pending_ = false;
+};
+
+class Indexer {
+public:
+    explicit Indexer(const Configuration* conf);
+    ~Indexer();
+    void index(const std::vector<std::string>& fastaDocs);
+    void index(const std::string& fastaDoc);
+    void index(const std::string& fastaDoc, const std::string& taxonDoc);
+    void close();
+private:
+    std::mutex mu_;
+    bsp_indexer* h_ = nullptr;
+};
+
+struct Taxonomy { int taxid = 0; std::string name; bool hasName = false; int parent = 0; std::string rank; bool hasRank = false; };
+struct TaxonTreeDescription {
+    static std::vector<Taxonomy> parse(const std::string& json);
+    static std::vector<Taxonomy> classifiable(const std::vector<Taxonomy>& tree);
+};
+
+struct SearchResultEntry {
+    int docId = 0, rank = 0;
+    std::string filename, header, sequenceDirection, taxonHierarchy;
+    double score = 0;
+};
+struct ClassificationResult {
+    std::string queryHeader, query;
+    std::vector<SearchResultEntry> result;
+    std::string type = "UNKNOWN", taxonRank = "unknown", taxonName;
+    bool nameIsNull = false;
+    std::string toJson() const;
+};
+void makeClassificationResult(ClassificationResult& r);
+
+struct ClassificationResultSummary {
+    std::string queryFilename;
+    long long total = 0, unknown = 0, vague = 0, classified = 0, startTime = 0, endTime = 0;
+    void report(const ClassificationResult& r);
+    std::string toJson() const;
+};
+
+class Classifier {
+public:
+    explicit Classifier(const Configuration* conf);
+    ~Classifier();
+    // false when the reference would have thrown inside classify (read dropped by its callers)
+    bool classify(const std::string& header, const std::string& sequence, ClassificationResult& out);
+    void classifyBatch(const std::vector<std::string>& headers, const std::vector<std::string>& sequences,
+                       std::vector<ClassificationResult>& out, std::vector<int>& status);
+    void close();
+    bsp_classifier* handle() { return h_; }
+private:
+    bsp_classifier* h_ = nullptr;
+};
+
+class LocalClassifier {
+public:
+    explicit LocalClassifier(const Configuration* conf);
+    bool classify(const std::string& header, const std::string& sequence, ClassificationResult& out) {
+        return classifier_.classify(header, sequence, out);
+    }
+    void classify(const std::string& inputFasta, const std::string& classifyOutput, const std::string& summaryOutput);
+    void close() { classifier_.close(); }
+    const ClassificationResultSummary& lastSummary() const { return lastSummary_; }
+private:
+    Classifier classifier_;
+    ClassificationResultSummary lastSummary_;
+};
+
+void runIndex(const std::string& jsonConfiguration, const std::string& indexDir, const std::string& referenceDir, int device);
+void runClassifyLocal(const std::string& jsonConfiguration, const std::string& indexDir, const std::string& inputDir,
+                      const std::string& outputDir, int device);
+
+}  // namespace bsp

@@ -180,6 +180,24 @@ int bsp_merge_topk_device(bsp_classifier* h, int32_t n, int32_t parts,
                           void* d_status, void* d_label, void* d_n_hits, void* d_n_top,
                           void* d_top_doc, void* d_top_score);
 
+/* ------------------------------------------------ host-side entry points
+ * The reference's drivers above the two classes, restated in C++ (no JVM here):
+ *   BioSpectra.index         (src/biospectra/BioSpectra.java:110-134)  -> bsp_host_index
+ *   BioSpectra.classifyLocal (src/biospectra/BioSpectra.java:136-161)  -> bsp_host_classify_local
+ * json_conf: path of a configuration.json, or NULL to use defaults + index_dir.  They find
+ * FASTA files like FastaFileHelper.findFastaDocs (sorted by path), read them with
+ * FASTAReader semantics, pick up "<fasta>.taxd" sidecars, and write "<name>.result" /
+ * "<name>.result.sum" in the reference's JSON formats. */
+int bsp_host_index(const char* json_conf, const char* index_dir, const char* reference_dir, int32_t device);
+int bsp_host_classify_local(const char* json_conf, const char* index_dir, const char* input_dir,
+                            const char* output_dir, int32_t device);
+const char* bsp_host_last_error(void);
+/* pure host helpers (no GPU): used by the CPU-side tests */
+int bsp_host_label_json(const char* const* taxon_hierarchies, int32_t n, char* out, int32_t cap);
+int bsp_host_read_fasta(const char* path, char* out, int64_t cap, int64_t* needed);
+int bsp_host_double_to_string(double d, char* out, int32_t cap);
+int bsp_host_parse_config(const char* json, bsp_config* out, char* index_path, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif
