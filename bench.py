@@ -292,13 +292,16 @@ def main():
         alg_bytes_dense = cost["bytes_dense"]
         alg_bytes_csr = cost["bytes_csr"]
         achieved = alg_bytes_dense / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
-        roof = {"bound": "hbm", "kernel": "score_dense_kernel" if cnt["dense_reads"] >= cnt["positional_reads"] else "score_positional_kernel",
+        top = max((("filter_score_kernel", cnt["filter_reads"]), ("exact_score_kernel", cnt["dense_reads"]),
+                   ("score_positional_kernel", cnt["positional_reads"])), key=lambda x: x[1])[0]
+        roof = {"bound": "hbm", "kernel": top,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_dense,
                 "csr_formula_bytes_per_launch": alg_bytes_csr, "csr_formula_gbs": alg_bytes_csr / per_launch_s / 1e9 if per_launch_s > 0 else 0.0,
                 "kernel_ms_per_launch": per_launch_s * 1e3,
-                "note": "achieved = bytes the dense u8-row layout must read (clauses x padded docs + per-doc weights + I/O) / score-kernel "
-                        "time from CUDA events; csr_formula_* is SURVEY.md 8(d)'s A_read for a posting-list layout (the dense rows move fewer bytes)"}
+                "note": "achieved = bytes the dense 4-bit row layout must read (clauses x row bytes + per-doc weights + I/O) / scoring-kernel "
+                        "time from CUDA events on the library's stream; csr_formula_* is SURVEY.md 8(d)'s A_read for a posting-list layout "
+                        "(the dense rows move fewer bytes)"}
         line = {"metric": "reads/sec classified", "value": value, "unit": "reads/s", "n_gpus": world, "steps": steps,
                 "warmup": args.warmup, "ms_per_step": el_dev / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 scores, f64 accumulate", "data": "synthetic", "config": workload_config(args, wl),
@@ -311,7 +314,9 @@ def main():
                 "timing": "value/e2e: wall clock of exactly K steps between barrier+synchronize, max over ranks; "
                           "device_event_ms_per_step and roofline: CUDA events on the library's stream",
                 "index": dict(stats, gen_seconds=t_gen, build_seconds=t_build, build_gbp_per_s=wl["total_bp"] / 1e9 / t_build, **mem),
-                "routes": {"dense": cnt["dense_reads"], "positional": cnt["positional_reads"], "reads": cnt["reads"]},
+                "routes": {"filter": cnt["filter_reads"], "exact_dense": cnt["dense_reads"], "positional": cnt["positional_reads"],
+                           "reads": cnt["reads"], "filter_rescored_docs_per_read": cnt["filter_candidates"] / max(cnt["filter_reads"], 1),
+                           "filter_exception_cells": cnt["filter_exception_cells"], "filter_overflow_reads": cnt["filter_overflow_reads"]},
                 "parity_properties": {"source_doc_is_top_hit": recovered, "labels": labels, "dropped": int((res["status"] == 1).sum()),
                                       "errors": int((res["status"] == 2).sum())}}
         if not args.no_cpu_baseline:

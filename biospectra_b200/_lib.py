@@ -18,7 +18,7 @@ TFIDF, BM25 = 0, 1
 READ_OK, READ_DROPPED, READ_ERROR = 0, 1, 2
 UNKNOWN, VAGUE, CLASSIFIED = 0, 1, 2
 LABEL_NAMES = ("UNKNOWN", "VAGUE", "CLASSIFIED")
-ROUTE_DENSE, ROUTE_POSITIONAL = 1, 2
+ROUTE_DENSE, ROUTE_POSITIONAL, ROUTE_FILTER = 1, 2, 3
 
 
 class BspConfig(C.Structure):

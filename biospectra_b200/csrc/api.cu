@@ -29,7 +29,8 @@ struct bsp_indexer {
 struct Scratch {
     DevBuf<u8> seq, scan_tmp; DevBuf<i64> seq_off, tok_off, tok_cap;
     DevBuf<u64> tok_key; DevBuf<u32> tok_pos, tok_df, clause_row; DevBuf<float> clause_val;
-    DevBuf<i32> n_tok, n_clauses, msm, route, status_in, list_dense, list_pos, counts;
+    DevBuf<i32> n_tok, n_clauses, msm, route, status_in, list_dense, list_pos, list_filter, counts;
+    DevBuf<FilterStats> fstats;
     DevBuf<i32> part_n; DevBuf<u32> part_doc; DevBuf<float> part_score;
     DevBuf<i32> o_status, o_label, o_nhits, o_ntop, o_doc; DevBuf<float> o_score;
     u8* pin_in = nullptr; size_t pin_in_bytes = 0;
@@ -47,7 +48,7 @@ struct bsp_classifier {
     std::string last_error;
     Scratch sc;
     // scoring constants
-    DevBuf<float> idf_by_df, doc_w, pair_lut, tf_lut;
+    DevBuf<float> idf_by_df, doc_w, tf16;
     i64 global_docs = 0, global_sum_ttf = 0, doc_base_global = 0;
     // last batch
     std::vector<i32> last_routes;
@@ -331,22 +332,15 @@ static void upload_scoring_constants(bsp_classifier* h) {
     } else {
         for (int x = 0; x < 256; x++) cache[x] = h_byte315_to_float(x);
     }
-    std::vector<float> dw(round_up(std::max<i64>(D, 1), 16) + 16, 1.0f);
+    std::vector<float> dw(round_up(std::max<i64>(D, 1), 32 * 32) + 32, 1.0f);
     for (i64 d = 0; d < D; d++) dw[d] = cache[ix.doc_norm[d]];
     h->doc_w.alloc(dw.size());
     CUDA_CHECK(cudaMemcpyAsync(h->doc_w.p, dw.data(), dw.size() * 4, cudaMemcpyHostToDevice, h->st));
-    // LUTs for the dense path: tf-idf -> tf(freq) = (float)sqrt(freq); BM25 -> freq
-    std::vector<float> pl(256, 0.0f), tl(256, 0.0f);
-    for (int c = 1; c < 256; c++) {
-        float f = 0.0f;
-        if (ix.tables && c < 255 && ix.h_freq_vals.size() == 256 && ix.h_freq_vals[c] != 0xFFFFFFFFu)
-            memcpy(&f, &ix.h_freq_vals[c], 4);
-        pl[c] = h->conf.scoring_algorithm == BSP_BM25 ? f : (float)std::sqrt((double)f);
-        tl[c] = h->conf.scoring_algorithm == BSP_BM25 ? (float)c : (float)std::sqrt((double)c);
-    }
-    h->pair_lut.alloc(256); h->tf_lut.alloc(256);
-    CUDA_CHECK(cudaMemcpyAsync(h->pair_lut.p, pl.data(), 1024, cudaMemcpyHostToDevice, h->st));
-    CUDA_CHECK(cudaMemcpyAsync(h->tf_lut.p, tl.data(), 1024, cudaMemcpyHostToDevice, h->st));
+    // nibble -> per-clause frequency factor: tf-idf tf(freq) = (float)sqrt(freq) (DefaultSimilarity#tf); BM25: freq
+    float tl[16];
+    for (int c = 0; c < 16; c++) tl[c] = h->conf.scoring_algorithm == BSP_BM25 ? (float)c : (float)std::sqrt((double)c);
+    h->tf16.alloc(16);
+    CUDA_CHECK(cudaMemcpyAsync(h->tf16.p, tl, sizeof tl, cudaMemcpyHostToDevice, h->st));
     CUDA_CHECK(cudaStreamSynchronize(h->st));
 }
 
@@ -362,6 +356,7 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
         opt.want_positional = conf->positional;
         opt.need_pair_table = conf->query_algorithm != BSP_NAIVE_KMER;
         opt.seg_tokens = env_i64("BSP_SEG_TOKENS", (i64)1 << 28);
+        opt.exc_cap = std::max<i64>(env_i64("BSP_EXC_CAP", (i64)1 << 26), 1024);
         if (opt.seg_tokens < 1024) opt.seg_tokens = 1024;
         build_gpu_index(h->ix, *ref, opt, h->st);
         h->global_docs = (i64)h->ix.docs.size();
@@ -453,13 +448,16 @@ BSP_API int bsp_classifier_close(bsp_classifier* h) {
 }
 
 // ------------------------------------------------------------------ classification
+// counts: [0] exact-dense reads, [1] positional reads, [2] filter reads, [3] filter overflow (appended to list_dense)
 __global__ void __launch_bounds__(256) route_compact_kernel(const i32* __restrict__ route, i32 n, i32* __restrict__ list_dense,
-                                                             i32* __restrict__ list_pos, i32* __restrict__ counts) {
+                                                             i32* __restrict__ list_pos, i32* __restrict__ list_filter,
+                                                             i32* __restrict__ counts) {
     i32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     int rt = route[r];
     if (rt == ROUTE_DENSE) list_dense[atomicAdd(&counts[0], 1)] = r;
     else if (rt == ROUTE_POSITIONAL) list_pos[atomicAdd(&counts[1], 1)] = r;
+    else if (rt == ROUTE_FILTER) list_filter[atomicAdd(&counts[2], 1)] = r;
 }
 
 __global__ void __launch_bounds__(256) tok_capacity_kernel(const i64* __restrict__ seq_off, i32 n, int k, i64* __restrict__ cap) {
@@ -505,20 +503,27 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
     qp.max_doc = h->global_docs;
     qp.dense_ok = ix.tables && (qp.alg == ALG_NAIVE || ix.has_pair) && env_i64("BSP_DISABLE_DENSE", 0) == 0;
     qp.positional_ok = ix.positional ? 1 : 0;
+    qp.pair_row0 = ix.pair_row0;
+    // fast filter path: tf-idf, every doc of the handle inside one CTA (32 docs per thread, <= 512 threads).
+    // BSP_FILTER: 0 off, 1 whenever usable, unset = only where it pays (enough docs to fill a CTA)
+    const u32 D = (u32)ix.docs.size();
+    const i64 filter_mode = env_i64("BSP_FILTER", -1);
+    qp.filter_ok = qp.dense_ok && qp.sim == SIM_TFIDF && ix.d_pad <= 512 * FK_DOCS && filter_mode != 0 &&
+                   (filter_mode == 1 || D >= 1024);
     weights_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p,
-                                                               sc.tok_df.p, h->idf_by_df.p, qp, ix.tf_row_slow.p, ix.pair_row_slow.p,
-                                                               sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p,
-                                                               sc.route.p, sc.status_in.p);
+                                                               sc.tok_df.p, h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p,
+                                                               sc.n_clauses.p, sc.msm.p, sc.route.p, sc.status_in.p);
+    sc.list_filter.ensure(n);
     CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 16, st));
-    route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, n, sc.list_dense.p, sc.list_pos.p, sc.counts.p);
+    route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, n, sc.list_dense.p, sc.list_pos.p, sc.list_filter.p,
+                                                                     sc.counts.p);
     KERNEL_CHECK();
-    i32 counts[2] = {0, 0};
-    CUDA_CHECK(cudaMemcpyAsync(counts, sc.counts.p, 8, cudaMemcpyDeviceToHost, st));
+    i32 counts[4] = {0, 0, 0, 0};
+    CUDA_CHECK(cudaMemcpyAsync(counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     // partial top-10 buffers
-    const u32 D = (u32)ix.docs.size();
-    int dense_threads = (int)std::min<i64>(512, round_up(std::max<i64>(ceil_div(D, DENSE_DPT), 1), 32));
-    int n_tiles = (int)std::max<i64>(1, ceil_div(D, (i64)dense_threads * DENSE_DPT));
+    int dense_threads = (int)std::min<i64>(512, round_up(std::max<i64>(ceil_div(ix.d_pad, EX_DPT), 1), 32));
+    int n_tiles = (int)std::max<i64>(1, ceil_div(ix.d_pad, (i64)dense_threads * EX_DPT));
     int parts_pos = ix.positional ? (int)ix.segs.size() : 0;
     int parts_stride = std::max(std::max(n_tiles, parts_pos), 1);
     i32* part_n; u32* part_doc; float* part_score;
@@ -528,18 +533,35 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
     part_n = sc.part_n.p; part_doc = sc.part_doc.p; part_score = sc.part_score.p;
     SimParams sp; sp.sim = qp.sim; sp.k1p1 = 1.2f + 1.0f;
     const u32 gbase = (u32)h->doc_base_global;
+    const Tab4Dev T = ix.tab4_view();
     CUDA_CHECK(cudaEventRecord(h->ev[1], st));
     i64 launches = 6;
-    if (counts[0] > 0) {
-        unsigned grid = (unsigned)((i64)counts[0] * n_tiles);
+    FilterStats fs = {0, 0, 0};
+    if (counts[2] > 0) {
+        if (!sc.fstats.p) sc.fstats.alloc(1);
+        CUDA_CHECK(cudaMemsetAsync(sc.fstats.p, 0, sizeof(FilterStats), st));
+        int threads = (int)round_up(std::max<i64>(ceil_div(ix.d_pad, FK_DOCS), 1), 32);
+        filter_score_kernel<<<(unsigned)counts[2], threads, 0, st>>>(T, D, h->tf16.p, sc.list_filter.p, sc.tok_off.p, sc.n_tok.p,
+            sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n, part_doc,
+            part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p);
+        KERNEL_CHECK();
+        launches++;
+        // reads the filter could not bound (exception or candidate overflow) were appended to the exact list
+        CUDA_CHECK(cudaMemcpyAsync(&counts[3], sc.counts.p + 3, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(&fs, sc.fstats.p, sizeof fs, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    const i32 n_exact = counts[0] + counts[3];
+    if (n_exact > 0) {
+        unsigned grid = (unsigned)((i64)n_exact * n_tiles);
         if (qp.sim == SIM_TFIDF)
-            score_dense_kernel<SIM_TFIDF><<<grid, dense_threads, 0, st>>>(ix.tf_tab.p, ix.pair_tab.p, ix.d_pad, D, h->pair_lut.p, h->tf_lut.p,
-                sc.list_dense.p, counts[0], sc.tok_off.p, sc.n_tok.p, sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p,
-                h->doc_w.p, qp.alg, sp.k1p1, gbase, n_tiles, parts_stride, part_n, part_doc, part_score);
+            exact_score_kernel<SIM_TFIDF><<<grid, dense_threads, 0, st>>>(T, D, h->tf16.p, sc.list_dense.p, sc.tok_off.p, sc.n_tok.p,
+                sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, sp.k1p1, gbase, n_tiles, parts_stride,
+                part_n, part_doc, part_score);
         else
-            score_dense_kernel<SIM_BM25><<<grid, dense_threads, 0, st>>>(ix.tf_tab.p, ix.pair_tab.p, ix.d_pad, D, h->pair_lut.p, h->tf_lut.p,
-                sc.list_dense.p, counts[0], sc.tok_off.p, sc.n_tok.p, sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p,
-                h->doc_w.p, qp.alg, sp.k1p1, gbase, n_tiles, parts_stride, part_n, part_doc, part_score);
+            exact_score_kernel<SIM_BM25><<<grid, dense_threads, 0, st>>>(T, D, h->tf16.p, sc.list_dense.p, sc.tok_off.p, sc.n_tok.p,
+                sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, sp.k1p1, gbase, n_tiles, parts_stride,
+                part_n, part_doc, part_score);
         launches++;
     }
     if (counts[1] > 0) {
@@ -564,7 +586,9 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
     cudaEventElapsedTime(&ms_score, h->ev[1], h->ev[2]);
     cudaEventElapsedTime(&ms_pipe, h->ev[0], h->ev[3]);
     h->score_ms += ms_score; h->pipe_ms += ms_pipe;
-    h->counters[0] += n; h->counters[1] += counts[0]; h->counters[2] += counts[1]; h->counters[4] += launches + 1;
+    h->counters[0] += n; h->counters[1] += n_exact; h->counters[2] += counts[1]; h->counters[3] += counts[2] - counts[3];
+    h->counters[4] += launches + 1; h->counters[5] += (i64)fs.candidates; h->counters[6] += (i64)fs.forced;
+    h->counters[7] += counts[3];
 }
 
 static int classify_packed_impl(bsp_classifier* h, i32 n, const char* seq_bytes, const i64* seq_offsets,
@@ -820,7 +844,7 @@ BSP_API int bsp_read_cost(bsp_classifier* h, int32_t n, const char* seq_bytes, c
             ix.direct ? ix.df_dense.p : nullptr, ix.d_segs.p, ix.positional ? (int)ix.segs.size() : 0, sc.tok_df.p);
         read_cost_kernel<<<(unsigned)ceil_div((i64)m * 32, 256), 256, 0, st>>>(sc.seq_off.p, m, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p,
             sc.tok_df.p, ix.direct ? ix.ttf_dense.p : nullptr, ix.d_segs.p, ix.positional ? (int)ix.segs.size() : 0,
-            h->conf.query_algorithm, ix.d_pad, (u64)ix.docs.size(), d_out.p);
+            h->conf.query_algorithm, ix.row_bytes, (u64)ix.docs.size(), d_out.p);
         KERNEL_CHECK();
         CUDA_CHECK(cudaStreamSynchronize(st));
     }

@@ -3,8 +3,8 @@
 //   K5 tokenize_kernel / weights_kernel   read -> tokens -> implicit clauses + Lucene weights
 //   K6/K7 score_positional_kernel         general path: term-major postings + positions,
 //                                         TermQuery and sloppy PhraseQuery scoring
-//   K6' score_dense_kernel                dense path (small k): u8 tf / pair-frequency rows,
-//                                         128-bit coalesced row reads, register accumulators
+//   K6' dense4.cuh                        dense path (small k): 4-bit frequency tables, packed-SIMD
+//                                         filter + exact rescoring, and the all-exact scorer
 //   K8 block top-10 (fused into both scorers) + merge_kernel (labels)
 //
 // Float semantics follow Lucene 5.3.1 operation by operation: explicit
@@ -23,8 +23,9 @@
 #define MAX_CLAUSES 10000        // Classifier.java:110 BooleanQuery.setMaxClauseCount(10000)
 
 #define ROUTE_NONE 0             // dropped / error: no scoring
-#define ROUTE_DENSE 1
+#define ROUTE_DENSE 1            // exact_score_kernel over the 4-bit tables
 #define ROUTE_POSITIONAL 2
+#define ROUTE_FILTER 3           // filter_score_kernel (tf-idf, <= 255 clauses)
 
 #define ST_OK 0
 #define ST_DROPPED 1
@@ -149,50 +150,6 @@ __device__ __forceinline__ float phrase_freq_at(const SegDev& s, u32 i0, u32 a1,
     return sloppy_freq_distinct(s.positions + p0, (int)n0, s.positions + p1, (int)n1, slop);
 }
 
-// ------------------------------------------------- pair table build (dense path)
-// Warp per (k+1)-mer row u.  freq_vals[1..254]: dictionary of distinct float
-// frequencies (bit patterns), filled with atomicCAS in probe order; 0xFFFFFFFF = empty.
-__device__ __forceinline__ u32 freq_code(u32* __restrict__ freq_vals, float f) {
-    u32 bits = __float_as_uint(f);
-    for (int j = 1; j < 255; j++) {
-        u32 cur = ((volatile u32*)freq_vals)[j];
-        if (cur == bits) return (u32)j;
-        if (cur == 0xFFFFFFFFu) {
-            u32 old = atomicCAS(&freq_vals[j], 0xFFFFFFFFu, bits);
-            if (old == 0xFFFFFFFFu || old == bits) return (u32)j;
-        }
-    }
-    return 255u;
-}
-
-__global__ void __launch_bounds__(256) pair_table_kernel(SegDev s, int k, int min_strand, u8* __restrict__ pair_tab,
-                                                          u64 d_pad, u32* __restrict__ freq_vals,
-                                                          u32* __restrict__ pair_row_slow, u64 n_rows) {
-    const int lane = threadIdx.x & 31;
-    u64 u = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (u >= n_rows) return;
-    const u64 kmask = (1ull << (2 * k)) - 1ull;
-    u64 t0 = canon_kmer(u >> 2, k, min_strand), t1 = canon_kmer(u & kmask, k, min_strand);
-    u32 lt0 = s.direct[t0];
-    if (lt0 == NO_TERM) return;
-    u32 lt1 = s.direct[t1];
-    if (lt1 == NO_TERM) return;
-    const bool same = t0 == t1;
-    const u32 a0 = s.term_off[lt0], b0 = s.term_off[lt0 + 1];
-    const u32 a1 = s.term_off[lt1], b1 = s.term_off[lt1 + 1];
-    u8* row = pair_tab + u * d_pad + s.doc_base;
-    bool slow = false;
-    for (u32 i = a0 + lane; i < b0; i += 32) {
-        float f = phrase_freq_at(s, i, a1, b1, a1 + (i - a0), 2, same);
-        if (f != 0.0f) {
-            u32 code = freq_code(freq_vals, f);
-            if (code == 255u) slow = true;
-            row[s.post_doc[i]] = (u8)code;
-        }
-    }
-    if (slow) atomicOr(&pair_row_slow[u >> 5], 1u << (u & 31));
-}
-
 // ------------------------------------------------------------------------ K5
 struct QueryParams {
     int k, skips, min_strand, alg, sim;
@@ -200,6 +157,8 @@ struct QueryParams {
     i64 max_doc;            // global maxDoc (all partitions)
     int dense_ok;           // dense tables resident
     int positional_ok;      // positional segments resident
+    int filter_ok;          // fast filter path usable (tf-idf, doc count within one CTA)
+    u64 pair_row0;          // first pair row of the dense table (= 4^k)
 };
 
 __device__ __forceinline__ int base_code_dev(u8 c) {
@@ -317,8 +276,7 @@ __global__ void __launch_bounds__(128) weights_kernel(const u8* __restrict__ seq
                                                        const i64* __restrict__ tok_off, const i32* __restrict__ n_tok,
                                                        const u64* __restrict__ tok_key, const u32* __restrict__ tok_pos,
                                                        const u32* __restrict__ tok_df, const float* __restrict__ idf_by_df,
-                                                       QueryParams qp, const u32* __restrict__ tf_row_slow,
-                                                       const u32* __restrict__ pair_row_slow,
+                                                       QueryParams qp,
                                                        float* __restrict__ clause_val, u32* __restrict__ clause_row,
                                                        i32* __restrict__ n_clauses, i32* __restrict__ msm_out,
                                                        i32* __restrict__ route, i32* __restrict__ status) {
@@ -360,23 +318,23 @@ __global__ void __launch_bounds__(128) weights_kernel(const u8* __restrict__ seq
     }   // BM25Stats#normalize: weight = idf * 1 * 1
     if (dense) {
         const u8* s = seq + seq_off[r];
-        for (i32 c = 0; c < nc && dense; c++) {
+        for (i32 c = 0; c < nc; c++) {
             i32 j0, j1;
             clause_tokens(qp.alg, n, c, j0, j1);
-            if (j1 >= 0) {
+            if (j1 >= 0) {      // pair row: the raw (k+1)-mer at the first token's offset
                 u32 off = tok_pos[base + j0];
                 u64 u = 0;
                 for (int i = 0; i <= qp.k; i++) u = (u << 2) | (u64)base_code_dev(s[off + i]);
-                if (pair_row_slow[u >> 5] & (1u << (u & 31))) dense = false;
-                clause_row[base + c] = (u32)u;
+                clause_row[base + c] = (u32)(qp.pair_row0 + u);
             } else {
-                u64 key = tok_key[base + j0];
-                if (tf_row_slow[key >> 5] & (1u << (key & 31))) dense = false;
-                clause_row[base + c] = (u32)key;
+                clause_row[base + c] = (u32)tok_key[base + j0];
             }
         }
     }
-    if (dense) { route[r] = ROUTE_DENSE; status[r] = ST_OK; }
+    // u16 weight lanes / u8 count lanes of the filter kernel: <= 255 pair clauses, <= 181 term clauses
+    const bool fast = dense && qp.filter_ok && nc <= (qp.alg == ALG_NAIVE ? 181 : 255);
+    if (fast) { route[r] = ROUTE_FILTER; status[r] = ST_OK; }
+    else if (dense) { route[r] = ROUTE_DENSE; status[r] = ST_OK; }
     else if (qp.positional_ok) { route[r] = ROUTE_POSITIONAL; status[r] = ST_OK; }
     else { route[r] = ROUTE_NONE; status[r] = ST_ERROR; }
 }
@@ -537,110 +495,6 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
     if (threadIdx.x == 0) part_n[pbase] = found;
 }
 
-// ------------------------------------------------------------------- K6'
-// Dense path.  CTA per (doc tile, read); each thread owns 16 consecutive docs: one
-// 128-bit load per table row, 16 double accumulators + match counts in registers.
-// Rows: clauses [0, n_pair) index pair_tab, the rest index tf_tab.
-#define DENSE_DPT 16
-#define DENSE_STAGE 256
-template <int SIM>
-__global__ void __launch_bounds__(512) score_dense_kernel(
-        const u8* __restrict__ tf_tab, const u8* __restrict__ pair_tab, u64 d_pad, u32 n_docs,
-        const float* __restrict__ pair_lut, const float* __restrict__ tf_lut,
-        const i32* __restrict__ read_list, i32 n_list, const i64* __restrict__ tok_off, const i32* __restrict__ n_tok,
-        const float* __restrict__ clause_val, const u32* __restrict__ clause_row, const i32* __restrict__ n_clauses,
-        const i32* __restrict__ msm, const float* __restrict__ doc_w, int alg, float k1p1, u32 global_doc_base,
-        int n_tiles, int parts_stride, i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score) {
-    __shared__ float s_pair[256], s_tf[256];
-    __shared__ float s_val[DENSE_STAGE];
-    __shared__ u32 s_row[DENSE_STAGE];
-    __shared__ u64 red[33];
-    const int tile = blockIdx.x % n_tiles;
-    const i32 r = read_list[blockIdx.x / n_tiles];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_pair[i] = pair_lut[i]; s_tf[i] = tf_lut[i]; }
-    const i64 base = tok_off[r];
-    const i32 n = n_tok[r], nc = n_clauses[r];
-    const i32 n_pair = alg == ALG_NAIVE ? 0 : (alg == ALG_CHAIN ? nc : n / 2);
-    const u32 d0 = ((u32)tile * blockDim.x + threadIdx.x) * DENSE_DPT;
-    const bool active = d0 < n_docs;                    // d_pad is a multiple of 16: the 16-doc group is in-row
-    double acc[DENSE_DPT];
-    u32 cnt[DENSE_DPT / 2];                              // two u16 counters per register
-    float w[DENSE_DPT];
-#pragma unroll
-    for (int i = 0; i < DENSE_DPT; i++) acc[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < DENSE_DPT / 2; i++) cnt[i] = 0;
-    if (active) {
-#pragma unroll
-        for (int i = 0; i < DENSE_DPT; i += 4) {
-            float4 v = *reinterpret_cast<const float4*>(doc_w + d0 + i);
-            w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
-        }
-    }
-    for (i32 c0 = 0; c0 < nc; c0 += DENSE_STAGE) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < DENSE_STAGE && c0 + i < nc; i += blockDim.x) {
-            s_val[i] = clause_val[base + c0 + i];
-            s_row[i] = clause_row[base + c0 + i];
-        }
-        __syncthreads();
-        if (!active) continue;
-        const i32 lim = min(DENSE_STAGE, nc - c0);
-#pragma unroll 2
-        for (i32 ci = 0; ci < lim; ci++) {
-            const bool is_pair = (c0 + ci) < n_pair;
-            const u8* rowp = (is_pair ? pair_tab : tf_tab) + (u64)s_row[ci] * d_pad + d0;
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(rowp));
-            const float* lut = is_pair ? s_pair : s_tf;
-            const float val = SIM == SIM_TFIDF ? s_val[ci] : __fmul_rn(s_val[ci], k1p1);
-            const u32 qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int i = 0; i < DENSE_DPT; i++) {
-                const u32 code = (qq[i >> 2] >> (8 * (i & 3))) & 255u;
-                const float f = lut[code];               // tf-idf: tf(freq) ; BM25: freq ; lut[0] = 0
-                float sc;
-                if (SIM == SIM_TFIDF) sc = __fmul_rn(__fmul_rn(f, val), w[i]);
-                else sc = code ? __fdiv_rn(__fmul_rn(val, f), __fadd_rn(f, w[i])) : 0.0f;
-                acc[i] += (double)sc;
-                cnt[i >> 1] += (code ? 1u : 0u) << (16 * (i & 1));
-            }
-        }
-    }
-    // final scores + fused top-10
-    const i32 need = max(1, msm[r]);
-    float sc[DENSE_DPT];
-#pragma unroll
-    for (int i = 0; i < DENSE_DPT; i++) {
-        i32 m = (i32)((cnt[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
-        sc[i] = (active && d0 + i < n_docs && m >= need) ? final_score(SIM, acc[i], m, nc) : -1.0f;
-    }
-    const i64 pbase = (i64)r * parts_stride + tile;
-    i32 found = 0;
-    u64 mine = 0;
-    bool dirty = true;
-    for (int round = 0; round < TOPN; round++) {
-        if (dirty) {
-            mine = 0;
-#pragma unroll
-            for (int i = 0; i < DENSE_DPT; i++)
-                if (sc[i] >= 0.0f) { u64 kk = cand_key(sc[i], d0 + i); if (kk > mine) mine = kk; }
-            dirty = false;
-        }
-        u64 best = block_max_u64(mine, red);
-        if (best == 0) break;
-        if (best == mine) {                               // unique: keys embed the doc id
-            u32 d = 0xFFFFFFFFu - (u32)(best & 0xFFFFFFFFu);
-            part_doc[pbase * TOPN + round] = global_doc_base + d;
-            part_score[pbase * TOPN + round] = __uint_as_float((u32)(best >> 32));
-#pragma unroll
-            for (int i = 0; i < DENSE_DPT; i++) if (d0 + i == d) sc[i] = -1.0f;
-            dirty = true;
-        }
-        found++;
-    }
-    if (threadIdx.x == 0) part_n[pbase] = found;
-}
-
 // ------------------------------------------------------------------------ K8
 // Thread per read: merge the per-part top-10 lists (each sorted score desc, doc asc)
 // into the final list; n_hits = entries equal to the max (Classifier.java:358-366);
@@ -658,7 +512,7 @@ __global__ void __launch_bounds__(128) merge_kernel(i32 n_reads, const i32* __re
     u32 bd[TOPN];
     int nt = 0;
     const int rt = route ? route[r] : ROUTE_POSITIONAL;
-    const int parts = rt == ROUTE_DENSE ? parts_dense : (rt == ROUTE_POSITIONAL ? parts_pos : 0);
+    const int parts = rt == ROUTE_DENSE ? parts_dense : (rt == ROUTE_POSITIONAL ? parts_pos : (rt == ROUTE_FILTER ? 1 : 0));
     for (int p = 0; p < parts; p++) {
         const i64 pb = (i64)r * parts_stride + p;
         const int np = part_n[pb];
@@ -692,7 +546,7 @@ __global__ void __launch_bounds__(128) merge_kernel(i32 n_reads, const i32* __re
 __global__ void __launch_bounds__(256) read_cost_kernel(const i64* __restrict__ seq_off, i32 n_reads, const i64* __restrict__ tok_off,
                                                          const i32* __restrict__ n_tok, const u64* __restrict__ tok_key,
                                                          const u32* __restrict__ tok_df, const u32* __restrict__ ttf_dense,
-                                                         const SegDev* __restrict__ segs, int n_segs, int alg, u64 d_pad,
+                                                         const SegDev* __restrict__ segs, int n_segs, int alg, u64 row_bytes,
                                                          u64 n_docs, unsigned long long* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const i32 r = (i32)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
@@ -731,7 +585,7 @@ __global__ void __launch_bounds__(256) read_cost_kernel(const i64* __restrict__ 
         atomicAdd(&out[3], sdf);
         atomicAdd(&out[4], sttf);
         atomicAdd(&out[5], len + 16ull * uniq + 8ull * sdf + P * 4ull * sttf + 80ull);
-        atomicAdd(&out[6], len + (unsigned long long)nc * (unsigned long long)d_pad + 4ull * n_docs + 80ull);
+        atomicAdd(&out[6], len + (unsigned long long)nc * (unsigned long long)row_bytes + 4ull * n_docs + 80ull);
         atomicAdd(&out[7], (unsigned long long)nc);
     }
 }

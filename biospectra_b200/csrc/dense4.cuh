@@ -1,0 +1,601 @@
+// dense4.cuh -- 4-bit dense frequency tables and the two scorers that stream them.
+//
+// Layout in HBM (per handle): one table of rows x row_bytes, row_bytes = d_pad/2 (d_pad =
+// docs rounded up to 32, so a row is a whole number of 16-byte vectors).  Cell (row, doc) is
+// the nibble at byte doc/2, bits 4*(doc&1): 8 consecutive docs per little-endian u32.
+//   term rows   [0, 4^k)            cell = tf(term, doc)                       if 1 <= tf <= 14
+//   pair rows   [4^k, 4^k+4^(k+1))  cell = sloppyFreq(t0,t1,slop 2) in the doc  if it is an integer 1..7
+//                                   (row u = the raw (k+1)-mer; t0 = canon(u[0:k]), t1 = canon(u[1:k+1]))
+//   everything else (no match, or a frequency the nibble cannot hold) is 0; the latter are
+//   kept exactly in the exception list: per row, sorted (doc, float freq) pairs.
+//
+// Scorers (CTA per read):
+//   filter_score_kernel   tf-idf fast path.  Pass 1 streams the read's rows once with packed
+//                         integer SIMD: a per-clause 8-entry byte LUT applied with PRMT turns 8
+//                         nibbles into quantised weights (q = round(S*tf(f)*value_c)), summed in
+//                         u16 lanes, match counts in u8 lanes: ~2 issue slots per (clause, doc) cell,
+//                         so the kernel is bound by the HBM stream, not by fp64.  The sums give
+//                         rigorous lower/upper bounds of Lucene's score; docs whose upper bound
+//                         reaches the 10th best lower bound (plus docs with exception cells) are
+//                         rescored exactly (float ops in Lucene's order, double accumulation) and the
+//                         top-10 is taken among them -- identical to scoring every doc exactly.
+//   exact_score_kernel    every doc exact (tf-idf or BM25, any clause count, doc tiles): BM25, reads
+//                         with > 255 clauses, candidate overflow, and the reference path for tests.
+#pragma once
+#include "classify.cuh"
+
+#define T4_TF_MAX 14u
+#define T4_PAIR_MAX 7u
+
+struct Tab4Dev {
+    const u8* tab;
+    u64 row_bytes;
+    u64 pair_row0;          // 4^k
+    const u32* exc_off;     // [n_rows + 1]
+    const u32* exc_doc;     // handle-global doc ids, ascending within a row
+    const float* exc_freq;
+};
+
+struct ExcBuild {           // append buffer used while the tables are built
+    u32* row; u32* doc; float* freq;
+    unsigned long long* count;
+    u64 cap;
+};
+
+__device__ __forceinline__ void exc_append(const ExcBuild& ex, u32 row, u32 doc, float f) {
+    unsigned long long i = atomicAdd(ex.count, 1ull);
+    if (i < ex.cap) { ex.row[i] = row; ex.doc[i] = doc; ex.freq[i] = f; }
+}
+
+// All 32 lanes call this.  Lanes whose docs share a u32 (8 docs) combine their nibbles and
+// the first of them issues one atomicOr (rows are zero-initialised; a row is written by one
+// warp per segment, segments run one after another on one stream).
+__device__ __forceinline__ void nibble_or(u32* __restrict__ row32, u32 doc, u32 code, bool has, int lane) {
+    u32 wi = has ? (doc >> 3) : (0x80000000u | (u32)lane);
+    u32 grp = __match_any_sync(0xFFFFFFFFu, wi);
+    u32 v = has ? (code << (4 * (doc & 7u))) : 0u;
+    u32 orv = __reduce_or_sync(grp, v);
+    if (has && lane == __ffs(grp) - 1) atomicOr(&row32[wi], orv);
+}
+
+// warp per term of the segment
+__global__ void __launch_bounds__(256) tf_table4_kernel(SegDev s, u32* __restrict__ tab32, u64 row_words, ExcBuild ex) {
+    const int lane = threadIdx.x & 31;
+    const u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= s.n_terms) return;
+    const u64 key = s.term_key[t];
+    const u32 a = s.term_off[t], b = s.term_off[t + 1];
+    u32* row = tab32 + key * row_words;
+    for (u32 i0 = a; i0 < b; i0 += 32) {
+        const u32 i = i0 + lane;
+        bool has = i < b;
+        u32 doc = 0, code = 0;
+        if (has) {
+            doc = s.doc_base + s.post_doc[i];
+            u32 tf = s.post_pos[i + 1] - s.post_pos[i];
+            if (tf <= T4_TF_MAX) code = tf;
+            else { exc_append(ex, (u32)key, doc, (float)tf); has = false; }
+        }
+        nibble_or(row, doc, code, has, lane);
+    }
+}
+
+// warp per (k+1)-mer row u
+__global__ void __launch_bounds__(256) pair_table4_kernel(SegDev s, int k, int min_strand, u32* __restrict__ tab32, u64 row_words,
+                                                           u64 pair_row0, ExcBuild ex, u64 n_rows) {
+    const int lane = threadIdx.x & 31;
+    const u64 u = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= n_rows) return;
+    const u64 kmask = (1ull << (2 * k)) - 1ull;
+    const u64 t0 = canon_kmer(u >> 2, k, min_strand), t1 = canon_kmer(u & kmask, k, min_strand);
+    const u32 lt0 = s.direct[t0];
+    if (lt0 == NO_TERM) return;
+    const u32 lt1 = s.direct[t1];
+    if (lt1 == NO_TERM) return;
+    const bool same = t0 == t1;
+    const u32 a0 = s.term_off[lt0], b0 = s.term_off[lt0 + 1];
+    const u32 a1 = s.term_off[lt1], b1 = s.term_off[lt1 + 1];
+    u32* row = tab32 + (pair_row0 + u) * row_words;
+    for (u32 i0 = a0; i0 < b0; i0 += 32) {
+        const u32 i = i0 + lane;
+        bool has = false;
+        u32 doc = 0, code = 0;
+        if (i < b0) {
+            const float f = phrase_freq_at(s, i, a1, b1, a1 + (i - a0), 2, same);
+            if (f != 0.0f) {
+                doc = s.doc_base + s.post_doc[i];
+                const u32 c = (u32)f;
+                if ((float)c == f && c >= 1u && c <= T4_PAIR_MAX) { code = c; has = true; }
+                else exc_append(ex, (u32)(pair_row0 + u), doc, f);
+            }
+        }
+        nibble_or(row, doc, code, has, lane);
+    }
+}
+
+// ---- exception list finalisation: sort by (row, doc), then per-row offsets
+__global__ void __launch_bounds__(256) exc_keys_kernel(const u32* __restrict__ row, const u32* __restrict__ doc, u32 n,
+                                                        u64* __restrict__ keys, u32* __restrict__ vals) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = ((u64)row[i] << 32) | (u64)doc[i];
+    vals[i] = i;
+}
+__global__ void __launch_bounds__(256) exc_gather_kernel(const u64* __restrict__ keys, const u32* __restrict__ vals,
+                                                          const float* __restrict__ freq_in, u32 n, u32* __restrict__ doc_out,
+                                                          float* __restrict__ freq_out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    doc_out[i] = (u32)(keys[i] & 0xFFFFFFFFull);
+    freq_out[i] = freq_in[vals[i]];
+}
+// exc_off[r] = first sorted entry whose row >= r, for r in [0, n_rows]
+__global__ void __launch_bounds__(256) exc_offsets_kernel(const u64* __restrict__ keys, u32 n, u64 n_rows, u32* __restrict__ exc_off) {
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rows) return;
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+        u32 mid = (lo + hi) >> 1;
+        if ((keys[mid] >> 32) < r) lo = mid + 1; else hi = mid;
+    }
+    exc_off[r] = lo;
+}
+
+// ------------------------------------------------------------------ shared helpers
+__device__ __forceinline__ u64 warp_max_u64(u64 v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        u64 o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        if (o > v) v = o;
+    }
+    return v;
+}
+
+// 10th largest of the per-thread keys (0 when fewer than 10 are non-zero).  Non-zero keys are unique.
+__device__ __forceinline__ u64 block_tenth_largest(u64 v, u64* sm /* [32*TOPN + 1] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
+    u64 mine = v;
+#pragma unroll
+    for (int r = 0; r < TOPN; r++) {
+        u64 mx = warp_max_u64(mine);
+        if (lane == 0) sm[warp * TOPN + r] = mx;
+        if (mine == mx) mine = 0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        u64 loc[TOPN];
+#pragma unroll
+        for (int j = 0; j < TOPN; j++) { int idx = lane + 32 * j; loc[j] = idx < nw * TOPN ? sm[idx] : 0ull; }
+        u64 res = 0;
+#pragma unroll
+        for (int r = 0; r < TOPN; r++) {
+            u64 lm = 0;
+#pragma unroll
+            for (int j = 0; j < TOPN; j++) if (loc[j] > lm) lm = loc[j];
+            u64 mx = warp_max_u64(lm);
+            res = mx;
+#pragma unroll
+            for (int j = 0; j < TOPN; j++) if (loc[j] == mx) loc[j] = 0;
+        }
+        if (lane == 0) sm[32 * TOPN] = res;
+    }
+    __syncthreads();
+    return sm[32 * TOPN];
+}
+
+// PRMT with a register selector: byte i of the result = byte (c >> 4i) & 7 of {a, b}.  Bit 3 of a selector
+// nibble would switch to sign replication; pair rows only hold codes 0..7 (the __byte_perm intrinsic masks the
+// selector with an extra LOP, which this avoids).
+__device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 c) {
+    u32 d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// one u32 of a pair row (8 docs) through the clause's 8-entry LUT into the u16 weight lanes and u8 count lanes
+__device__ __forceinline__ void pair_word(u32 word, const uint2 lut, u32& w0, u32& w1, u32& w2, u32& w3, u32& c0, u32& c1) {
+    const u32 hi = word >> 16;
+    const u32 m0 = prmt(lut.x, lut.y, word);
+    const u32 m1 = prmt(lut.x, lut.y, hi);
+    w0 += prmt(m0, 0u, 0x4140u);
+    w1 += prmt(m0, 0u, 0x4342u);
+    w2 += prmt(m1, 0u, 0x4140u);
+    w3 += prmt(m1, 0u, 0x4342u);
+    c0 += prmt(0x01010100u, 0x01010101u, word);
+    c1 += prmt(0x01010100u, 0x01010101u, hi);
+}
+
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {     // read-only path, do not keep in L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_stream8(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ u32 cell_code(const Tab4Dev& T, u32 row, u32 doc) {
+    const u32 byte = __ldg(T.tab + (u64)row * T.row_bytes + (doc >> 1));
+    return (byte >> (4u * (doc & 1u))) & 15u;
+}
+
+// ------------------------------------------------------------------ fast path
+#define FK_DOCS 32                 // docs per thread: one 16-byte vector per row
+#define FK_MAX_CLAUSES 255         // u8 match counters
+#define FK_CAND_CAP 128
+#define FK_EXC_CAP 64
+#define FK_QMAX 255.0f
+#define FK_ROUND_SLACK 0.51f       // |q - S*tf*value| <= 0.5 (+ float rounding of the product)
+#define FK_REL_SLACK 4e-6f         // float roundings of Lucene's score and of the bound arithmetic
+
+struct FilterStats { unsigned long long candidates, forced, overflow_reads; };
+
+__global__ void __launch_bounds__(512) filter_score_kernel(
+        Tab4Dev T, u32 n_docs, const float* __restrict__ tf16, const i32* __restrict__ read_list,
+        const i64* __restrict__ tok_off, const i32* __restrict__ n_tok, const float* __restrict__ clause_val,
+        const u32* __restrict__ clause_row, const i32* __restrict__ n_clauses, const i32* __restrict__ msm,
+        const float* __restrict__ doc_w, int alg, u32 global_doc_base, int parts_stride, i32* __restrict__ part_n,
+        u32* __restrict__ part_doc, float* __restrict__ part_score, i32* __restrict__ route,
+        i32* __restrict__ overflow_list, i32* __restrict__ overflow_count, FilterStats* __restrict__ stats) {
+    __shared__ uint2 s_lut[FK_MAX_CLAUSES + 1];          // pair clauses: q for codes 0..3 | 4..7
+    __shared__ u32 s_row[FK_MAX_CLAUSES + 1];
+    __shared__ float s_val[FK_MAX_CLAUSES + 1];
+    __shared__ float s_tf[16];
+    __shared__ u64 s_red[32 * TOPN + 1];
+    __shared__ u32 s_cand[FK_CAND_CAP];
+    __shared__ u64 s_ckey[FK_CAND_CAP];
+    __shared__ u32 s_exc_c[FK_EXC_CAP], s_exc_d[FK_EXC_CAP];
+    __shared__ float s_exc_f[FK_EXC_CAP];
+    __shared__ int s_ncand, s_nexc;
+    __shared__ float s_scale;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
+    const i32 r = read_list[blockIdx.x];
+    const i64 base = tok_off[r];
+    const i32 n = n_tok[r], nc = n_clauses[r];
+    const i32 n_pair = alg == ALG_NAIVE ? 0 : (alg == ALG_CHAIN ? nc : n / 2);
+    const i32 need = max(1, msm[r]);
+    if (threadIdx.x < 16) s_tf[threadIdx.x] = tf16[threadIdx.x];
+    if (threadIdx.x == 0) { s_ncand = 0; s_nexc = 0; }
+    // ---- stage clauses, find the scale: S * value_c * tf(7) <= 255 for every clause
+    float vmax = 0.0f;
+    for (i32 c = threadIdx.x; c < nc; c += blockDim.x) {
+        const float v = clause_val[base + c];
+        s_val[c] = v;
+        s_row[c] = clause_row[base + c];
+        vmax = fmaxf(vmax, v);
+    }
+    {
+        u64 m = block_max_u64((u64)__float_as_uint(vmax), s_red);      // values are > 0: bit order = float order
+        if (threadIdx.x == 0) s_scale = FK_QMAX / (__uint_as_float((u32)m) * tf16[T4_PAIR_MAX]);
+    }
+    __syncthreads();
+    const float S = s_scale;
+    for (i32 c = threadIdx.x; c < nc; c += blockDim.x) {
+        const float sv = S * s_val[c];
+        if (c < n_pair) {
+            u32 q[8];
+            q[0] = 0;
+#pragma unroll
+            for (int j = 1; j < 8; j++) q[j] = min((u32)__float2int_rn(sv * s_tf[j]), 255u);
+            s_lut[c] = make_uint2(q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24), q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24));
+        }
+        // exceptions of this clause's row
+        const u32 row = s_row[c];
+        const u32 a = T.exc_off[row], b = T.exc_off[row + 1];
+        for (u32 j = a; j < b; j++) {
+            int idx = atomicAdd(&s_nexc, 1);
+            if (idx < FK_EXC_CAP) { s_exc_c[idx] = (u32)c; s_exc_d[idx] = T.exc_doc[j]; s_exc_f[idx] = T.exc_freq[j]; }
+        }
+    }
+    __syncthreads();
+    const int n_exc = s_nexc;
+    bool overflow = n_exc > FK_EXC_CAP;
+
+    // ---- pass 1: stream the rows.  Thread owns docs [32t, 32t+32): wacc[i] = u16 lanes (doc 2i, 2i+1),
+    //      cacc[j] = u8 lanes (docs 4j..4j+3)
+    const u32 d0 = threadIdx.x * FK_DOCS;
+    const bool active = (u64)d0 < T.row_bytes * 2;
+    u32 wacc[16], cacc[8];
+#pragma unroll
+    for (int i = 0; i < 16; i++) wacc[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) cacc[i] = 0;
+    const u8* tbase = T.tab + (u64)threadIdx.x * 16;
+    if (active && !overflow) {
+        i32 c = 0;
+        for (; c + 4 <= n_pair; c += 4) {
+            uint4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) q[u] = ldg_stream16(tbase + (u64)s_row[c + u] * T.row_bytes);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint2 lut = s_lut[c + u];
+                pair_word(q[u].x, lut, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1]);
+                pair_word(q[u].y, lut, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3]);
+                pair_word(q[u].z, lut, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5]);
+                pair_word(q[u].w, lut, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7]);
+            }
+        }
+        for (; c < n_pair; c++) {
+            const uint4 q = ldg_stream16(tbase + (u64)s_row[c] * T.row_bytes);
+            const uint2 lut = s_lut[c];
+            pair_word(q.x, lut, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1]);
+            pair_word(q.y, lut, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3]);
+            pair_word(q.z, lut, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5]);
+            pair_word(q.w, lut, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7]);
+        }
+        // Term clauses (tf 1..14): nibble at a time
+        for (; c < nc; c++) {
+            const uint4 q = ldg_stream16(tbase + (u64)s_row[c] * T.row_bytes);
+            const float sv = S * s_val[c];
+            const u32 w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const u32 code = (w[x] >> (4 * j)) & 15u;
+                    const u32 qv = (u32)__float2int_rn(sv * s_tf[code]);
+                    wacc[4 * x + (j >> 1)] += qv << (16 * (j & 1));
+                    cacc[2 * x + (j >> 2)] += (code ? 1u : 0u) << (8 * (j & 3));
+                }
+            }
+        }
+    }
+    // ---- bounds.  exact = fl(fl(sum_c t_c) * coord), t_c = fl(fl(tf*value_c)*norm_d) = tf*value_c*norm_d*(1+-2^-23)
+    const float invS = 1.0f / S;
+    const float fnc = (float)nc;
+    u64 my_best = 0;
+    if (active && !overflow) {
+#pragma unroll
+        for (int i = 0; i < FK_DOCS; i++) {
+            const u32 Q = (wacc[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+            const u32 m = (cacc[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            const u32 d = d0 + i;
+            if (d < n_docs && (i32)m >= need) {
+                const float fm = (float)m;
+                const float coord = nc == 1 ? 1.0f : fm / fnc;
+                const float lo = fmaxf((float)Q - FK_ROUND_SLACK * fm, 0.0f) * invS * doc_w[d] * coord * (1.0f - FK_REL_SLACK);
+                const u64 key = cand_key(lo, d);
+                if (key > my_best) my_best = key;
+            }
+        }
+    }
+    const u64 tenth = block_tenth_largest(my_best, s_red);
+    const float tau = __uint_as_float((u32)(tenth >> 32));         // 0 when fewer than 10 threads hold a valid doc
+    // ---- candidates: forced (exception cells) + upper bound >= tau
+    if (!overflow) {
+        for (int e = threadIdx.x; e < n_exc; e += blockDim.x) {
+            int idx = atomicAdd(&s_ncand, 1);
+            if (idx < FK_CAND_CAP) s_cand[idx] = s_exc_d[e];
+        }
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < FK_DOCS; i++) {
+                const u32 Q = (wacc[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+                const u32 m = (cacc[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                const u32 d = d0 + i;
+                if (d < n_docs && (i32)m >= need) {
+                    const float fm = (float)m;
+                    const float coord = nc == 1 ? 1.0f : fm / fnc;
+                    const float hi = ((float)Q + FK_ROUND_SLACK * fm) * invS * doc_w[d] * coord * (1.0f + FK_REL_SLACK);
+                    if (hi >= tau) {
+                        int idx = atomicAdd(&s_ncand, 1);
+                        if (idx < FK_CAND_CAP) s_cand[idx] = d;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int n_cand = s_ncand;
+    if (n_cand > FK_CAND_CAP) overflow = true;
+    const i64 pbase = (i64)r * parts_stride;
+    if (overflow) {                                       // hand the read to exact_score_kernel
+        if (threadIdx.x == 0) {
+            overflow_list[atomicAdd(overflow_count, 1)] = r;
+            route[r] = ROUTE_DENSE;
+            part_n[pbase] = 0;
+            if (stats) atomicAdd(&stats->overflow_reads, 1ull);
+        }
+        return;
+    }
+    // ---- exact rescoring: warp per candidate, lanes over clauses
+    for (int j = warp; j < n_cand; j += nw) {
+        const u32 d = s_cand[j];
+        const float nrm = doc_w[d];
+        bool forced = false;
+        for (int e = 0; e < n_exc; e++) forced |= s_exc_d[e] == d;
+        double sum = 0.0;
+        i32 m = 0;
+        for (i32 c = lane; c < nc; c += 32) {
+            const u32 code = cell_code(T, s_row[c], d);
+            float tf = s_tf[code];
+            if (code == 0u && forced) {
+                for (int e = 0; e < n_exc; e++)
+                    if (s_exc_c[e] == (u32)c && s_exc_d[e] == d) tf = tf_of(s_exc_f[e]);
+            }
+            if (tf != 0.0f) {
+                sum += (double)__fmul_rn(__fmul_rn(tf, s_val[c]), nrm);          // TFIDFSimScorer#score
+                m++;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+            m += __shfl_xor_sync(0xFFFFFFFFu, m, o);
+        }
+        if (lane == 0) s_ckey[j] = m >= need ? cand_key(final_score(SIM_TFIDF, sum, m, nc), d) : 0ull;
+    }
+    __syncthreads();
+    // ---- top-10 among the candidates (duplicates carry equal keys and are removed together)
+    if (warp == 0) {
+        u64 loc[FK_CAND_CAP / 32];
+#pragma unroll
+        for (int j = 0; j < FK_CAND_CAP / 32; j++) { int idx = lane + 32 * j; loc[j] = idx < n_cand ? s_ckey[idx] : 0ull; }
+        i32 found = 0;
+        for (int round = 0; round < TOPN; round++) {
+            u64 lm = 0;
+#pragma unroll
+            for (int j = 0; j < FK_CAND_CAP / 32; j++) if (loc[j] > lm) lm = loc[j];
+            const u64 best = warp_max_u64(lm);
+            if (best == 0) break;
+#pragma unroll
+            for (int j = 0; j < FK_CAND_CAP / 32; j++) if (loc[j] == best) loc[j] = 0;
+            if (lane == 0) {
+                part_doc[pbase * TOPN + round] = global_doc_base + (0xFFFFFFFFu - (u32)(best & 0xFFFFFFFFu));
+                part_score[pbase * TOPN + round] = __uint_as_float((u32)(best >> 32));
+            }
+            found++;
+        }
+        if (lane == 0) {
+            part_n[pbase] = found;
+            if (stats) { atomicAdd(&stats->candidates, (unsigned long long)n_cand); atomicAdd(&stats->forced, (unsigned long long)n_exc); }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ exact path
+// CTA per (doc tile, read); thread owns 16 consecutive docs (one 8-byte vector per row), 16 double
+// accumulators + packed u16 match counts in registers.  Exception cells are applied per clause stage.
+#define EX_DPT 16
+#define EX_STAGE 256
+#define EX_EXC_CAP 256
+template <int SIM>
+__global__ void __launch_bounds__(512) exact_score_kernel(
+        Tab4Dev T, u32 n_docs, const float* __restrict__ tf16, const i32* __restrict__ read_list,
+        const i64* __restrict__ tok_off, const i32* __restrict__ n_tok, const float* __restrict__ clause_val,
+        const u32* __restrict__ clause_row, const i32* __restrict__ n_clauses, const i32* __restrict__ msm,
+        const float* __restrict__ doc_w, float k1p1, u32 global_doc_base, int n_tiles, int parts_stride,
+        i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score) {
+    __shared__ float s_tf[16];
+    __shared__ float s_val[EX_STAGE];
+    __shared__ u32 s_row[EX_STAGE];
+    __shared__ u64 red[33];
+    __shared__ u32 s_scan[33];
+    __shared__ u32 s_exc_c[EX_EXC_CAP], s_exc_d[EX_EXC_CAP];
+    __shared__ float s_exc_f[EX_EXC_CAP];
+    const int tile = blockIdx.x % n_tiles;
+    const i32 r = read_list[blockIdx.x / n_tiles];
+    if (threadIdx.x < 16) s_tf[threadIdx.x] = tf16[threadIdx.x];
+    const i64 base = tok_off[r];
+    const i32 nc = n_clauses[r];
+    const u32 d0 = ((u32)tile * blockDim.x + threadIdx.x) * EX_DPT;
+    const bool active = (u64)d0 < T.row_bytes * 2;
+    double acc[EX_DPT];
+    u32 cnt[EX_DPT / 2];
+    float w[EX_DPT];
+#pragma unroll
+    for (int i = 0; i < EX_DPT; i++) { acc[i] = 0.0; w[i] = 1.0f; }
+#pragma unroll
+    for (int i = 0; i < EX_DPT / 2; i++) cnt[i] = 0;
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < EX_DPT; i += 4) {
+            float4 v = *reinterpret_cast<const float4*>(doc_w + d0 + i);
+            w[i] = v.x; w[i + 1] = v.y; w[i + 2] = v.z; w[i + 3] = v.w;
+        }
+    }
+    const u8* tbase = T.tab + (u64)d0 / 2;
+    const i32 stage = min(EX_STAGE, (i32)blockDim.x);     // thread i owns the exception list of staged clause i
+    for (i32 c0 = 0; c0 < nc; c0 += stage) {
+        __syncthreads();
+        const i32 lim = min(stage, nc - c0);
+        for (int i = threadIdx.x; i < lim; i += blockDim.x) {
+            s_val[i] = clause_val[base + c0 + i];
+            s_row[i] = clause_row[base + c0 + i];
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 2
+            for (i32 ci = 0; ci < lim; ci++) {
+                const uint2 q = ldg_stream8(tbase + (u64)s_row[ci] * T.row_bytes);
+                const float val = SIM == SIM_TFIDF ? s_val[ci] : __fmul_rn(s_val[ci], k1p1);
+#pragma unroll
+                for (int i = 0; i < EX_DPT; i++) {
+                    const u32 code = ((i < 8 ? q.x : q.y) >> (4 * (i & 7))) & 15u;
+                    const float f = s_tf[code];                 // tf-idf: tf(freq); BM25: freq; [0] = 0
+                    float sc;
+                    if (SIM == SIM_TFIDF) sc = __fmul_rn(__fmul_rn(f, val), w[i]);
+                    else sc = code ? __fdiv_rn(__fmul_rn(val, f), __fadd_rn(f, w[i])) : 0.0f;
+                    acc[i] += (double)sc;
+                    cnt[i >> 1] += (code ? 1u : 0u) << (16 * (i & 1));
+                }
+            }
+        }
+        // exception cells of this stage, in windows of EX_EXC_CAP
+        u32 my_a = 0, my_n = 0;
+        if ((int)threadIdx.x < lim) {
+            const u32 row = s_row[threadIdx.x];
+            my_a = T.exc_off[row];
+            my_n = T.exc_off[row + 1] - my_a;
+        }
+        u32 total;
+        const u32 my_base = block_exclusive_scan<u32>(my_n, &total, s_scan);
+        for (u32 w0 = 0; w0 < total; w0 += EX_EXC_CAP) {
+            __syncthreads();
+            for (u32 j = 0; j < my_n; j++) {
+                const u32 g = my_base + j;
+                if (g >= w0 && g < w0 + EX_EXC_CAP) {
+                    s_exc_c[g - w0] = threadIdx.x;
+                    s_exc_d[g - w0] = T.exc_doc[my_a + j];
+                    s_exc_f[g - w0] = T.exc_freq[my_a + j];
+                }
+            }
+            __syncthreads();
+            const u32 ne = min((u32)EX_EXC_CAP, total - w0);
+            for (u32 e = 0; e < ne; e++) {
+                const u32 d = s_exc_d[e];
+                if (active && d >= d0 && d < d0 + EX_DPT) {
+                    const float fr = s_exc_f[e];
+                    const float val = SIM == SIM_TFIDF ? s_val[s_exc_c[e]] : __fmul_rn(s_val[s_exc_c[e]], k1p1);
+                    const float f = SIM == SIM_TFIDF ? tf_of(fr) : fr;
+#pragma unroll
+                    for (int i = 0; i < EX_DPT; i++) {      // predicated, statically indexed: accumulators stay in registers
+                        const bool hit = d - d0 == (u32)i;
+                        float sc;
+                        if (SIM == SIM_TFIDF) sc = __fmul_rn(__fmul_rn(f, val), w[i]);
+                        else sc = __fdiv_rn(__fmul_rn(val, f), __fadd_rn(f, w[i]));
+                        acc[i] += hit ? (double)sc : 0.0;
+                        cnt[i >> 1] += hit ? (1u << (16 * (i & 1))) : 0u;
+                    }
+                }
+            }
+        }
+    }
+    // final scores + fused top-10
+    const i32 need = max(1, msm[r]);
+    float sc[EX_DPT];
+#pragma unroll
+    for (int i = 0; i < EX_DPT; i++) {
+        i32 m = (i32)((cnt[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+        sc[i] = (active && d0 + i < n_docs && m >= need) ? final_score(SIM, acc[i], m, nc) : -1.0f;
+    }
+    const i64 pbase = (i64)r * parts_stride + tile;
+    i32 found = 0;
+    u64 mine = 0;
+    bool dirty = true;
+    for (int round = 0; round < TOPN; round++) {
+        if (dirty) {
+            mine = 0;
+#pragma unroll
+            for (int i = 0; i < EX_DPT; i++)
+                if (sc[i] >= 0.0f) { u64 kk = cand_key(sc[i], d0 + i); if (kk > mine) mine = kk; }
+            dirty = false;
+        }
+        u64 best = block_max_u64(mine, red);
+        if (best == 0) break;
+        if (best == mine) {
+            u32 d = 0xFFFFFFFFu - (u32)(best & 0xFFFFFFFFu);
+            part_doc[pbase * TOPN + round] = global_doc_base + d;
+            part_score[pbase * TOPN + round] = __uint_as_float((u32)(best >> 32));
+#pragma unroll
+            for (int i = 0; i < EX_DPT; i++) if (d0 + i == d) sc[i] = -1.0f;
+            dirty = true;
+        }
+        found++;
+    }
+    if (threadIdx.x == 0) part_n[pbase] = found;
+}

@@ -7,9 +7,10 @@
 //   Segment    (optional, "positional") term-major postings of a contiguous doc range
 //              (<= 4096 docs, <= seg_tokens tokens): term dictionary (direct table or
 //              open-addressing hash), post_doc[], post_pos[], positions[].
-//   DenseTabs  (optional, small k) tf_tab[4^k][D] and pair_tab[4^(k+1)][D] u8 rows.
+//   Tab4       (optional, small k) 4-bit frequency table: 4^k term rows + 4^(k+1) pair rows of
+//              d_pad/2 bytes, plus the sorted exception list (see dense4.cuh).
 #pragma once
-#include "classify.cuh"
+#include "dense4.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -140,6 +141,7 @@ struct BuildOptions {
     int want_positional = 0;      // 0 auto 1 on 2 off
     int need_pair_table = 1;      // query algorithm uses phrases
     i64 seg_tokens = (i64)1 << 28;
+    i64 exc_cap = (i64)1 << 26;   // capacity of the exception append buffer (entries)
 };
 
 struct GpuIndex {
@@ -154,10 +156,15 @@ struct GpuIndex {
     i64 n_terms = 0, n_postings = 0, n_positions = 0, sum_ttf = 0;
     // direct mode term statistics (this handle's docs)
     DevBuf<u32> df_dense; DevBuf<u32> ttf_dense;
-    // dense tables
-    DevBuf<u8> tf_tab, pair_tab; u64 d_pad = 0;
-    DevBuf<u32> tf_row_slow, pair_row_slow, freq_vals;
-    std::vector<u32> h_freq_vals;
+    // dense 4-bit table
+    DevBuf<u8> tab4; u64 d_pad = 0, row_bytes = 0, n_rows = 0, pair_row0 = 0;
+    DevBuf<u32> exc_off, exc_doc; DevBuf<float> exc_freq; i64 n_exc = 0;
+    Tab4Dev tab4_view() const {
+        Tab4Dev t;
+        t.tab = tab4.p; t.row_bytes = row_bytes; t.pair_row0 = pair_row0;
+        t.exc_off = exc_off.p; t.exc_doc = exc_doc.p; t.exc_freq = exc_freq.p;
+        return t;
+    }
     u32 max_seg_docs = 0;
     size_t positional_bytes = 0, table_bytes = 0;
     std::string notes;
@@ -327,10 +334,14 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
     // ---- residency decisions
     size_t free_b = 0, total_b = 0;
     CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-    ix.d_pad = (u64)round_up(std::max<i64>(D, 1), 16);
-    const bool can_tables = ix.direct && k <= 15;
-    u64 tf_bytes = can_tables ? ((1ull << (2 * k)) * ix.d_pad) : 0;
-    u64 pair_bytes = (can_tables && opt.need_pair_table) ? ((1ull << (2 * (k + 1))) * ix.d_pad) : 0;
+    ix.d_pad = (u64)round_up(std::max<i64>(D, 1), 32);
+    ix.row_bytes = ix.d_pad / 2;
+    const bool can_tables = ix.direct;          // 2k <= 24: at most 5 * 4^12 rows
+    ix.pair_row0 = 1ull << (2 * k);
+    ix.n_rows = can_tables ? (ix.pair_row0 + (opt.need_pair_table ? (1ull << (2 * (k + 1))) : 0ull)) : 0ull;
+    u64 tf_bytes = can_tables ? ix.pair_row0 * ix.row_bytes : 0;
+    u64 pair_bytes = (can_tables && opt.need_pair_table) ? ((1ull << (2 * (k + 1))) * ix.row_bytes) : 0;
+    if (ix.n_rows >= ((u64)1 << 32) - 1) throw BspError(-5, "dense table row count exceeds 2^32");
     bool tables = false;
     if (can_tables && opt.want_tables != 2) {
         if (opt.want_tables == 1) tables = true;
@@ -351,20 +362,18 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
         positional = true;    // something must be resident; let allocation fail loudly if it cannot fit
     }
     ix.tables = tables; ix.positional = positional; ix.has_pair = tables && opt.need_pair_table;
+    DevBuf<u32> ex_row, ex_doc; DevBuf<float> ex_freq; DevBuf<unsigned long long> ex_count;
+    ExcBuild exb{nullptr, nullptr, nullptr, nullptr, 0};
     if (tables) {
-        ix.tf_tab.alloc(tf_bytes);
-        CUDA_CHECK(cudaMemsetAsync(ix.tf_tab.p, 0, tf_bytes, st));
-        ix.tf_row_slow.alloc(((1ull << (2 * k)) + 31) / 32);
-        CUDA_CHECK(cudaMemsetAsync(ix.tf_row_slow.p, 0, ix.tf_row_slow.bytes(), st));
-        ix.freq_vals.alloc(256);
-        CUDA_CHECK(cudaMemsetAsync(ix.freq_vals.p, 0xFF, 256 * 4, st));
-        ix.pair_row_slow.alloc(((1ull << (2 * (k + 1))) + 31) / 32);
-        CUDA_CHECK(cudaMemsetAsync(ix.pair_row_slow.p, 0, ix.pair_row_slow.bytes(), st));
-        if (ix.has_pair) {
-            ix.pair_tab.alloc(pair_bytes);
-            CUDA_CHECK(cudaMemsetAsync(ix.pair_tab.p, 0, pair_bytes, st));
-        }
-        ix.table_bytes = tf_bytes + (ix.has_pair ? pair_bytes : 0);
+        ix.tab4.alloc(tf_bytes + pair_bytes);
+        CUDA_CHECK(cudaMemsetAsync(ix.tab4.p, 0, tf_bytes + pair_bytes, st));
+        ix.table_bytes = tf_bytes + pair_bytes;
+        // a cell can only be an exception where a term posting exists: <= tokens (term rows) + 4 * tokens (pair rows)
+        exb.cap = (u64)std::min<i64>(opt.exc_cap, 5 * total_tok + 1024);
+        ex_row.alloc((size_t)exb.cap); ex_doc.alloc((size_t)exb.cap); ex_freq.alloc((size_t)exb.cap);
+        ex_count.alloc(1);
+        CUDA_CHECK(cudaMemsetAsync(ex_count.p, 0, 8, st));
+        exb.row = ex_row.p; exb.doc = ex_doc.p; exb.freq = ex_freq.p; exb.count = ex_count.p;
     }
     if (ix.direct) {
         u64 sz = 1ull << (2 * k);
@@ -439,11 +448,11 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
                 count_new_terms_kernel<<<(unsigned)ceil_div(seg.n_terms, 256), 256, 0, st>>>(v, d_prev.p, (int)views.size(), d_counter.p);
         }
         if (tables && seg.n_terms) {
-            tf_table_kernel<<<(unsigned)ceil_div((u64)seg.n_terms * 32, 256), 256, 0, st>>>(v, ix.tf_tab.p, ix.d_pad, ix.tf_row_slow.p);
+            tf_table4_kernel<<<(unsigned)ceil_div((u64)seg.n_terms * 32, 256), 256, 0, st>>>(v, (u32*)ix.tab4.p, ix.row_bytes / 4, exb);
             if (ix.has_pair) {
                 u64 rows = 1ull << (2 * (k + 1));
-                pair_table_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(v, k, ix.min_strand, ix.pair_tab.p, ix.d_pad,
-                                                                                     ix.freq_vals.p, ix.pair_row_slow.p, rows);
+                pair_table4_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(v, k, ix.min_strand, (u32*)ix.tab4.p,
+                                                                                      ix.row_bytes / 4, ix.pair_row0, exb, rows);
             }
         }
         KERNEL_CHECK();
@@ -470,8 +479,30 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
             CUDA_CHECK(cudaMemcpyAsync(ix.d_segs.p, views.data(), views.size() * sizeof(SegDev), cudaMemcpyHostToDevice, st));
     }
     if (tables) {
-        ix.h_freq_vals.resize(256);
-        CUDA_CHECK(cudaMemcpyAsync(ix.h_freq_vals.data(), ix.freq_vals.p, 256 * 4, cudaMemcpyDeviceToHost, st));
+        // exception list: sort by (row, doc), gather, per-row offsets
+        unsigned long long ne = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&ne, ex_count.p, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (ne > (unsigned long long)exb.cap)
+            throw BspError(-6, "dense table exception list overflow (" + std::to_string(ne) + " entries); raise BSP_EXC_CAP");
+        ix.n_exc = (i64)ne;
+        const u32 n = (u32)ne;
+        ix.exc_off.alloc(ix.n_rows + 2);
+        ix.exc_doc.alloc(std::max<size_t>(n, 1)); ix.exc_freq.alloc(std::max<size_t>(n, 1));
+        DevBuf<u64> ka, kb; DevBuf<u32> va, vb;
+        ka.alloc(std::max<size_t>(n, 1)); kb.alloc(std::max<size_t>(n, 1)); va.alloc(std::max<size_t>(n, 1)); vb.alloc(std::max<size_t>(n, 1));
+        u64* keys = ka.p; u64* keys_alt = kb.p; u32* vals = va.p; u32* vals_alt = vb.p;
+        if (n) {
+            exc_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ex_row.p, ex_doc.p, n, keys, vals);
+            int row_bits = 1;
+            while ((1ull << row_bits) < ix.n_rows) row_bits++;
+            radix_sort_pairs<u64>(&keys, &vals, &keys_alt, &vals_alt, n, 32 + row_bits, rst, st);
+            exc_gather_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(keys, vals, ex_freq.p, n, ix.exc_doc.p, ix.exc_freq.p);
+        }
+        exc_offsets_kernel<<<(unsigned)ceil_div(ix.n_rows + 1, 256), 256, 0, st>>>(keys, n, ix.n_rows, ix.exc_off.p);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        ix.table_bytes += ix.exc_off.bytes() + ix.exc_doc.bytes() + ix.exc_freq.bytes();
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
 }

@@ -257,25 +257,3 @@ __device__ __forceinline__ u32 seg_find_term(const SegDev& s, u64 key) {
     }
 }
 
-// ------------------------------------------------------- dense tables (small k)
-// tf_tab[key][doc]  = min(tf, 255)                        (row stride = d_pad bytes)
-// pair_tab[u][doc]  = code of sloppyFreq(t0(u), t1(u), slop 2) where u is a (k+1)-mer,
-//                     t0 = canon(u[0:k]), t1 = canon(u[1:k+1]); 0 = no match,
-//                     1..254 index freq_vals[], 255 = escape (row flagged slow).
-// See classify.cuh for the sloppy-phrase state machine.
-__global__ void __launch_bounds__(256) tf_table_kernel(SegDev s, u8* __restrict__ tf_tab, u64 d_pad,
-                                                        u32* __restrict__ tf_row_slow) {
-    const int lane = threadIdx.x & 31;
-    u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;        // warp per term
-    if (t >= s.n_terms) return;
-    u64 key = s.term_key[t];
-    u32 a = s.term_off[t], b = s.term_off[t + 1];
-    u8* row = tf_tab + key * d_pad + s.doc_base;
-    bool slow = false;
-    for (u32 i = a + lane; i < b; i += 32) {
-        u32 tf = s.post_pos[i + 1] - s.post_pos[i];
-        if (tf >= 255) { tf = 255; slow = true; }
-        row[s.post_doc[i]] = (u8)tf;
-    }
-    if (slow) atomicOr(&tf_row_slow[key >> 5], 1u << (key & 31));
-}

@@ -153,8 +153,8 @@ class Classifier:
     def last_counters(self):
         c = np.zeros(8, np.int64)
         _lib.check(self.L.bsp_last_counters(self.h, c.ctypes.data), self.h)
-        return dict(zip(("reads", "dense_reads", "positional_reads", "probes", "launches", "bytes_dense", "bytes_csr",
-                         "tokens"), [int(x) for x in c]))
+        return dict(zip(("reads", "dense_reads", "positional_reads", "filter_reads", "launches", "filter_candidates",
+                         "filter_exception_cells", "filter_overflow_reads"), [int(x) for x in c]))
 
     def last_timings(self):
         a, b = C.c_double(), C.c_double()

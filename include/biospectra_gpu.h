@@ -147,11 +147,12 @@ int bsp_term_postings(bsp_classifier* h, uint64_t packed_kmer, int64_t* df, int6
  * returns the count; keys/offsets may be NULL */
 int64_t bsp_tokenize(bsp_classifier* h, const char* seq, int32_t len, uint64_t* keys, int32_t* offsets,
                      int64_t cap);
-/* which scoring path handled read i of the last batch: 1 dense tables, 2 positional */
+/* which scoring path handled read i of the last batch: 1 dense tables scored exactly for every doc,
+ * 2 positional postings, 3 dense tables through the bound-and-rescore filter */
 int bsp_last_routes(bsp_classifier* h, int32_t n, int32_t* routes);
-/* counters of the last batch: [0] reads, [1] dense-path reads, [2] positional-path reads,
- * [3] unique-term probes, [4] kernels launched, [5] algorithmic bytes (dense layout),
- * [6] algorithmic bytes (CSR formula of SURVEY.md 8d), [7] tokens */
+/* counters of the last batch: [0] reads, [1] reads scored by the exact dense kernel, [2] positional-path reads,
+ * [3] reads finished by the filter kernel, [4] kernels launched, [5] docs the filter rescored exactly,
+ * [6] exception cells met by the filter, [7] reads the filter handed to the exact kernel */
 int bsp_last_counters(bsp_classifier* h, int64_t counters[8]);
 /* kernel time (ms, CUDA events on the handle's stream) of the dominant scoring kernel
  * and of the whole device pipeline in the last batch */

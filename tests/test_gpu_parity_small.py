@@ -19,7 +19,7 @@ for _i in range(36):
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "s%d-k%d" % (c["seed"], c["k"]))
-def test_index_and_classify_bit_exact(case, oracle_lib):
+def test_index_and_classify_bit_exact(case, oracle_lib, monkeypatch):
     ents = common.make_corpus(case["seed"], junk=case["junk"])
     reads = common.make_reads(1000 + case["seed"], ents, n=24)
     k, ms = case["k"], case["min_strand"]
@@ -38,14 +38,19 @@ def test_index_and_classify_bit_exact(case, oracle_lib):
         assert set(g.last_routes(len(reads))[res_o["status"] == 0]) <= {2}
     finally:
         g.close()
-    # dense tables on (small k): reads whose clauses all have slop 2 take the dense route
+    # dense 4-bit tables on (small k): reads whose clauses all have slop 2 take a dense route --
+    # every doc scored exactly (BSP_FILTER=0), or bound-and-rescore (BSP_FILTER=1, tf-idf only)
     if k <= 8:
-        g = common.build_gpu(ents, k, ms, dict(qkw, dense_tables=1, positional=1))
-        try:
-            res_g = g.classify_batch(reads)
-            common.assert_classify_equal(res_g, res_o, reads, "dense+positional")
-        finally:
-            g.close()
+        for filt in ("0", "1"):
+            monkeypatch.setenv("BSP_FILTER", filt)
+            g = common.build_gpu(ents, k, ms, dict(qkw, dense_tables=1, positional=1))
+            try:
+                res_g = g.classify_batch(reads)
+                common.assert_classify_equal(res_g, res_o, reads, "dense+positional filter=" + filt)
+                routes = set(g.last_routes(len(reads))[res_o["status"] == 0])
+                assert routes <= ({1, 2} if (filt == "0" or case["sim"]) else {1, 2, 3}), routes
+            finally:
+                g.close()
 
 
 def test_multi_segment_matches_single(oracle_lib, monkeypatch):
@@ -59,9 +64,10 @@ def test_multi_segment_matches_single(oracle_lib, monkeypatch):
         ox = common.build_oracle(oracle_lib, ents, k, False)
         res_o = ox.classify([r.encode() for r in reads], skips=0, algorithm=alg, scoring=sim, msm=0.5, threads=4)
         alg_name = ["NAIVE_KMER", "CHAIN_PROXIMITY", "PAIRED_PROXIMITY"][alg]
-        for dense in (2, 1):
+        for dense, filt in ((2, "0"), (1, "0"), (1, "1")):
             if dense == 1 and k > 8:
                 continue
+            monkeypatch.setenv("BSP_FILTER", filt)
             g = common.build_gpu(ents, k, False, dict(kmer_skips=0, query_algorithm=alg_name,
                                                       scoring_algorithm="bm25" if sim else "tfidf", dense_tables=dense,
                                                       positional=1))
@@ -69,9 +75,77 @@ def test_multi_segment_matches_single(oracle_lib, monkeypatch):
                 if dense == 2:
                     common.assert_index_equal(g, ox, sample_terms=[ox.term_at(i) for i in range(0, ox.stats()["n_terms"], 37)])
                 res_g = g.classify_batch(reads)
-                common.assert_classify_equal(res_g, res_o, reads, "k%d dense%d" % (k, dense))
+                common.assert_classify_equal(res_g, res_o, reads, "k%d dense%d filter%s" % (k, dense, filt))
                 if dense == 1:
                     routes = g.last_routes(len(reads))
-                    assert (routes == 1).sum() > 0
+                    assert ((routes == 1) | (routes == 3)).sum() > 0
+                    if filt == "1" and not sim:
+                        assert (routes == 3).sum() > 0
             finally:
                 g.close()
+
+
+def _many_docs_corpus(seed, n_docs, length, k):
+    """many short related docs: a few ancestor sequences, each doc a mutated copy (so scores are close and ties,
+    repeats and exception cells occur), plus homopolymer / periodic docs"""
+    rng = random.Random(seed)
+    anc = [common.rand_seq(rng, length) for _ in range(6)]
+    ents = []
+    for i in range(n_docs):
+        mode = rng.random()
+        if mode < 0.04:
+            ents.append(rng.choice("ACGT") * rng.randint(k + 2, length))
+        elif mode < 0.08:
+            ents.append((common.rand_seq(rng, rng.randint(2, 5)) * length)[:length])
+        else:
+            a = list(rng.choice(anc))
+            for j in range(len(a)):
+                if rng.random() < 0.03:
+                    a[j] = rng.choice("ACGT")
+            lo = rng.randint(0, length // 3)
+            ents.append("".join(a[lo:lo + rng.randint(length // 2, length)]))
+    return ents
+
+
+@pytest.mark.parametrize("k,alg,n_docs", [(5, 2, 700), (4, 1, 1300), (6, 0, 500), (5, 2, 90)])
+def test_filter_path_many_docs(oracle_lib, monkeypatch, k, alg, n_docs):
+    """The bound-and-rescore kernel with CTAs of several warps (>= 10 threads hold valid docs, so the 10th-best
+    lower bound really prunes), forced candidates from exception cells, and candidate overflow (many exact ties)
+    falling back to the exact kernel."""
+    ents = _many_docs_corpus(40 + k, n_docs // 2, 260, k)          # 2 docs per entry
+    reads = common.make_reads(900 + k, ents, n=160, max_len=140, n_frac=0.0)
+    ox = common.build_oracle(oracle_lib, ents, k, False)
+    res_o = ox.classify([r.encode() for r in reads], skips=0, algorithm=alg, scoring=0, msm=0.5, threads=4)
+    alg_name = ["NAIVE_KMER", "CHAIN_PROXIMITY", "PAIRED_PROXIMITY"][alg]
+    monkeypatch.setenv("BSP_FILTER", "1")
+    g = common.build_gpu(ents, k, False, dict(kmer_skips=0, query_algorithm=alg_name, scoring_algorithm="tfidf",
+                                              dense_tables=1, positional=2))
+    try:
+        res_g = g.classify_batch(reads)
+        common.assert_classify_equal(res_g, res_o, reads, "filter k%d alg%d" % (k, alg))
+        cnt = g.last_counters()
+        assert cnt["filter_reads"] > 0, cnt
+        assert cnt["filter_candidates"] > 0
+    finally:
+        g.close()
+
+
+def test_filter_overflow_falls_back(oracle_lib, monkeypatch):
+    """> 128 docs tie exactly at the top: the filter cannot keep the candidate list and hands the read to the
+    exact kernel; results stay identical."""
+    rng = random.Random(9)
+    core = common.rand_seq(rng, 120)
+    ents = [core for _ in range(150)] + [common.rand_seq(rng, 120) for _ in range(40)]
+    reads = [core[5:95], core[20:80], common.rand_seq(rng, 80)] + [e[3:90] for e in ents[150:160]]
+    ox = common.build_oracle(oracle_lib, ents, 5, False)
+    res_o = ox.classify([r.encode() for r in reads], skips=0, algorithm=2, scoring=0, msm=0.5, threads=2)
+    monkeypatch.setenv("BSP_FILTER", "1")
+    g = common.build_gpu(ents, 5, False, dict(kmer_skips=0, query_algorithm="PAIRED_PROXIMITY", scoring_algorithm="tfidf",
+                                              dense_tables=1, positional=2))
+    try:
+        res_g = g.classify_batch(reads)
+        common.assert_classify_equal(res_g, res_o, reads, "overflow")
+        cnt = g.last_counters()
+        assert cnt["filter_overflow_reads"] >= 2, cnt
+    finally:
+        g.close()
