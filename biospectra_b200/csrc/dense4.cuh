@@ -151,38 +151,6 @@ __device__ __forceinline__ u64 warp_max_u64(u64 v) {
     return v;
 }
 
-// 10th largest of the per-thread keys (0 when fewer than 10 are non-zero).  Non-zero keys are unique.
-__device__ __forceinline__ u64 block_tenth_largest(u64 v, u64* sm /* [32*TOPN + 1] */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
-    u64 mine = v;
-#pragma unroll
-    for (int r = 0; r < TOPN; r++) {
-        u64 mx = warp_max_u64(mine);
-        if (lane == 0) sm[warp * TOPN + r] = mx;
-        if (mine == mx) mine = 0;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        u64 loc[TOPN];
-#pragma unroll
-        for (int j = 0; j < TOPN; j++) { int idx = lane + 32 * j; loc[j] = idx < nw * TOPN ? sm[idx] : 0ull; }
-        u64 res = 0;
-#pragma unroll
-        for (int r = 0; r < TOPN; r++) {
-            u64 lm = 0;
-#pragma unroll
-            for (int j = 0; j < TOPN; j++) if (loc[j] > lm) lm = loc[j];
-            u64 mx = warp_max_u64(lm);
-            res = mx;
-#pragma unroll
-            for (int j = 0; j < TOPN; j++) if (loc[j] == mx) loc[j] = 0;
-        }
-        if (lane == 0) sm[32 * TOPN] = res;
-    }
-    __syncthreads();
-    return sm[32 * TOPN];
-}
-
 // PRMT with a register selector: byte i of the result = byte (c >> 4i) & 7 of {a, b}.  Bit 3 of a selector
 // nibble would switch to sign replication; pair rows only hold codes 0..7 (the __byte_perm intrinsic masks the
 // selector with an extra LOP, which this avoids).
@@ -226,11 +194,53 @@ __device__ __forceinline__ u32 cell_code(const Tab4Dev& T, u32 row, u32 doc) {
 #define FK_MAX_CLAUSES 255         // u8 match counters
 #define FK_CAND_CAP 128
 #define FK_EXC_CAP 64
+#define FK_CODE_CAP 6144           // candidate x clause cells staged in shared memory for the exact pass
 #define FK_QMAX 255.0f
 #define FK_ROUND_SLACK 0.51f       // |q - S*tf*value| <= 0.5 (+ float rounding of the product)
 #define FK_REL_SLACK 4e-6f         // float roundings of Lucene's score and of the bound arithmetic
 
 struct FilterStats { unsigned long long candidates, forced, overflow_reads; };
+
+// 10th largest of the per-thread values (bit patterns of non-negative floats; 0 when fewer than 10 are
+// non-zero).  Equal values may be removed together, which can only lower the result (a valid, weaker bound).
+__device__ __forceinline__ u32 warp_max_u32(u32 v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
+    return v;
+}
+__device__ __forceinline__ u32 block_tenth_largest_u32(u32 v, u32* sm /* [16*TOPN + 1] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
+    u32 mine = v;
+#pragma unroll 1
+    for (int r = 0; r < TOPN; r++) {
+        const u32 mx = warp_max_u32(mine);
+        if (lane == 0) sm[warp * TOPN + r] = mx;
+        if (mine == mx) mine = 0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        u32 loc[5];                                   // nw <= 16 warps -> <= 160 values
+#pragma unroll
+        for (int j = 0; j < 5; j++) { int idx = lane + 32 * j; loc[j] = idx < nw * TOPN ? sm[idx] : 0u; }
+        u32 res = 0;
+#pragma unroll 1
+        for (int r = 0; r < TOPN; r++) {
+            u32 lm = max(max(max(loc[0], loc[1]), max(loc[2], loc[3])), loc[4]);
+            res = warp_max_u32(lm);
+#pragma unroll
+            for (int j = 0; j < 5; j++) if (loc[j] == res) loc[j] = 0;
+        }
+        if (lane == 0) sm[16 * TOPN] = res;
+    }
+    __syncthreads();
+    return sm[16 * TOPN];
+}
+
+// E(d) = Q*m*norm_d for docs with m >= need (else 0): the score estimate both bounds derive from
+__device__ __forceinline__ float estimate(u32 Q, u32 m, i32 need, float nrm) {
+    const u32 t = (i32)m >= need ? Q * m : 0u;        // <= 65535 * 255 < 2^24: exact in float
+    return (float)t * nrm;
+}
 
 __global__ void __launch_bounds__(512) filter_score_kernel(
         Tab4Dev T, u32 n_docs, const float* __restrict__ tf16, const i32* __restrict__ read_list,
@@ -243,13 +253,15 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     __shared__ u32 s_row[FK_MAX_CLAUSES + 1];
     __shared__ float s_val[FK_MAX_CLAUSES + 1];
     __shared__ float s_tf[16];
-    __shared__ u64 s_red[32 * TOPN + 1];
+    __shared__ u64 s_red[33];
+    __shared__ u32 s_sel[16 * TOPN + 1];
     __shared__ u32 s_cand[FK_CAND_CAP];
     __shared__ u64 s_ckey[FK_CAND_CAP];
     __shared__ u32 s_exc_c[FK_EXC_CAP], s_exc_d[FK_EXC_CAP];
     __shared__ float s_exc_f[FK_EXC_CAP];
+    __shared__ u8 s_code[FK_CODE_CAP];
     __shared__ int s_ncand, s_nexc;
-    __shared__ float s_scale;
+    __shared__ float s_scale, s_delta;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
     const i32 r = read_list[blockIdx.x];
@@ -259,17 +271,27 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     const i32 need = max(1, msm[r]);
     if (threadIdx.x < 16) s_tf[threadIdx.x] = tf16[threadIdx.x];
     if (threadIdx.x == 0) { s_ncand = 0; s_nexc = 0; }
-    // ---- stage clauses, find the scale: S * value_c * tf(7) <= 255 for every clause
-    float vmax = 0.0f;
+    // ---- stage clauses; scale S: S * value_c * tf(7) <= 255 for every clause; q_min = smallest non-zero weight
+    float vmax = 0.0f, vmin = 3.0e38f;
     for (i32 c = threadIdx.x; c < nc; c += blockDim.x) {
         const float v = clause_val[base + c];
         s_val[c] = v;
         s_row[c] = clause_row[base + c];
         vmax = fmaxf(vmax, v);
+        vmin = fminf(vmin, v);
     }
     {
-        u64 m = block_max_u64((u64)__float_as_uint(vmax), s_red);      // values are > 0: bit order = float order
-        if (threadIdx.x == 0) s_scale = FK_QMAX / (__uint_as_float((u32)m) * tf16[T4_PAIR_MAX]);
+        // values are > 0: bit order = float order; the minimum rides along complemented
+        const u64 packed = ((u64)__float_as_uint(vmax) << 32) | (u64)(0xFFFFFFFFu - __float_as_uint(vmin));
+        const u64 m = block_max_u64(packed, s_red);
+        if (threadIdx.x == 0) {
+            const float S = FK_QMAX / (__uint_as_float((u32)(m >> 32)) * tf16[T4_PAIR_MAX]);
+            const float qmin = rintf(S * __uint_as_float(0xFFFFFFFFu - (u32)(m & 0xFFFFFFFFull)));
+            s_scale = S;
+            // exact score of doc d = E(d)/(S*nc) * (1 +- delta): the cell weights err by <= 0.51 each and the cell
+            // sum is >= q_min per matching clause; FK_REL_SLACK covers the float roundings
+            s_delta = qmin >= 2.0f ? FK_ROUND_SLACK / qmin + FK_REL_SLACK : 1.0f;
+        }
     }
     __syncthreads();
     const float S = s_scale;
@@ -306,6 +328,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     const u8* tbase = T.tab + (u64)threadIdx.x * 16;
     if (active && !overflow) {
         i32 c = 0;
+#pragma unroll 1
         for (; c + 4 <= n_pair; c += 4) {
             uint4 q[4];
 #pragma unroll
@@ -319,6 +342,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
                 pair_word(q[u].w, lut, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7]);
             }
         }
+#pragma unroll 1
         for (; c < n_pair; c++) {
             const uint4 q = ldg_stream16(tbase + (u64)s_row[c] * T.row_bytes);
             const uint2 lut = s_lut[c];
@@ -328,6 +352,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
             pair_word(q.w, lut, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7]);
         }
         // Term clauses (tf 1..14): nibble at a time
+#pragma unroll 1
         for (; c < nc; c++) {
             const uint4 q = ldg_stream16(tbase + (u64)s_row[c] * T.row_bytes);
             const float sv = S * s_val[c];
@@ -344,46 +369,46 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
             }
         }
     }
-    // ---- bounds.  exact = fl(fl(sum_c t_c) * coord), t_c = fl(fl(tf*value_c)*norm_d) = tf*value_c*norm_d*(1+-2^-23)
-    const float invS = 1.0f / S;
-    const float fnc = (float)nc;
-    u64 my_best = 0;
+    // ---- pass 2: per-thread best estimate, then the block's 10th best.  Padded docs have no cells (m = 0).
+    float e_best = 0.0f;
     if (active && !overflow) {
 #pragma unroll
-        for (int i = 0; i < FK_DOCS; i++) {
-            const u32 Q = (wacc[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-            const u32 m = (cacc[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-            const u32 d = d0 + i;
-            if (d < n_docs && (i32)m >= need) {
-                const float fm = (float)m;
-                const float coord = nc == 1 ? 1.0f : fm / fnc;
-                const float lo = fmaxf((float)Q - FK_ROUND_SLACK * fm, 0.0f) * invS * doc_w[d] * coord * (1.0f - FK_REL_SLACK);
-                const u64 key = cand_key(lo, d);
-                if (key > my_best) my_best = key;
+        for (int i4 = 0; i4 < FK_DOCS; i4 += 4) {
+            const float4 nv = *reinterpret_cast<const float4*>(doc_w + d0 + i4);
+            const float nr[4] = {nv.x, nv.y, nv.z, nv.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = i4 + k;
+                const u32 Q = prmt(wacc[i >> 1], 0u, (i & 1) ? 0x4432u : 0x4410u);
+                const u32 m = prmt(cacc[i >> 2], 0u, 0x4440u | (u32)(i & 3));
+                e_best = fmaxf(e_best, estimate(Q, m, need, nr[k]));
             }
         }
     }
-    const u64 tenth = block_tenth_largest(my_best, s_red);
-    const float tau = __uint_as_float((u32)(tenth >> 32));         // 0 when fewer than 10 threads hold a valid doc
-    // ---- candidates: forced (exception cells) + upper bound >= tau
+    const float tau_e = __uint_as_float(block_tenth_largest_u32(__float_as_uint(e_best), s_sel));
+    // a doc can reach the top 10 only if E(d)*(1+delta) >= tau_e*(1-delta)
+    const float delta = s_delta;
+    const float theta = delta < 1.0f ? tau_e * ((1.0f - delta) / (1.0f + delta)) * (1.0f - FK_REL_SLACK) : 0.0f;
+    // ---- candidates: forced (exception cells) + estimate >= theta
     if (!overflow) {
         for (int e = threadIdx.x; e < n_exc; e += blockDim.x) {
             int idx = atomicAdd(&s_ncand, 1);
             if (idx < FK_CAND_CAP) s_cand[idx] = s_exc_d[e];
         }
-        if (active) {
+        if (active && e_best >= theta && e_best > 0.0f) {
 #pragma unroll
-            for (int i = 0; i < FK_DOCS; i++) {
-                const u32 Q = (wacc[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
-                const u32 m = (cacc[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-                const u32 d = d0 + i;
-                if (d < n_docs && (i32)m >= need) {
-                    const float fm = (float)m;
-                    const float coord = nc == 1 ? 1.0f : fm / fnc;
-                    const float hi = ((float)Q + FK_ROUND_SLACK * fm) * invS * doc_w[d] * coord * (1.0f + FK_REL_SLACK);
-                    if (hi >= tau) {
+            for (int i4 = 0; i4 < FK_DOCS; i4 += 4) {
+                const float4 nv = *reinterpret_cast<const float4*>(doc_w + d0 + i4);
+                const float nr[4] = {nv.x, nv.y, nv.z, nv.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int i = i4 + k;
+                    const u32 Q = prmt(wacc[i >> 1], 0u, (i & 1) ? 0x4432u : 0x4410u);
+                    const u32 m = prmt(cacc[i >> 2], 0u, 0x4440u | (u32)(i & 3));
+                    const float e = estimate(Q, m, need, nr[k]);
+                    if (e >= theta && e > 0.0f) {
                         int idx = atomicAdd(&s_ncand, 1);
-                        if (idx < FK_CAND_CAP) s_cand[idx] = d;
+                        if (idx < FK_CAND_CAP) s_cand[idx] = d0 + i;
                     }
                 }
             }
@@ -402,7 +427,29 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         }
         return;
     }
-    // ---- exact rescoring: warp per candidate, lanes over clauses
+    // ---- exact rescoring.  The candidates' cells are fetched in one batch of independent loads
+    //      (item = candidate j, clause c), then each warp sums one candidate from shared memory.
+    const int n_items = n_cand * nc;
+    const bool staged = n_items <= FK_CODE_CAP;
+    if (staged) {
+#pragma unroll 1
+        for (int it0 = threadIdx.x; it0 < n_items; it0 += 4 * blockDim.x) {
+            u32 code[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int it = it0 + u * blockDim.x;
+                code[u] = 0;
+                if (it < n_items) { const int j = it / nc, c = it - j * nc; code[u] = cell_code(T, s_row[c], s_cand[j]); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int it = it0 + u * blockDim.x;
+                if (it < n_items) s_code[it] = (u8)code[u];
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll 1
     for (int j = warp; j < n_cand; j += nw) {
         const u32 d = s_cand[j];
         const float nrm = doc_w[d];
@@ -410,8 +457,9 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         for (int e = 0; e < n_exc; e++) forced |= s_exc_d[e] == d;
         double sum = 0.0;
         i32 m = 0;
+#pragma unroll 1
         for (i32 c = lane; c < nc; c += 32) {
-            const u32 code = cell_code(T, s_row[c], d);
+            const u32 code = staged ? (u32)s_code[j * nc + c] : cell_code(T, s_row[c], d);
             float tf = s_tf[code];
             if (code == 0u && forced) {
                 for (int e = 0; e < n_exc; e++)
@@ -436,6 +484,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
 #pragma unroll
         for (int j = 0; j < FK_CAND_CAP / 32; j++) { int idx = lane + 32 * j; loc[j] = idx < n_cand ? s_ckey[idx] : 0ull; }
         i32 found = 0;
+#pragma unroll 1
         for (int round = 0; round < TOPN; round++) {
             u64 lm = 0;
 #pragma unroll
