@@ -27,6 +27,7 @@ class BspConfig(C.Structure):
         ("query_algorithm", C.c_int32), ("scoring_algorithm", C.c_int32), ("worker_threads", C.c_int32),
         ("index_ram_buffer", C.c_int32), ("device", C.c_int32), ("query_term_min_should_match", C.c_double),
         ("part_rank", C.c_int32), ("part_count", C.c_int32), ("dense_tables", C.c_int32), ("positional", C.c_int32),
+        ("full_topn", C.c_int32),
     ]
 
 

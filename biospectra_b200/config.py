@@ -32,6 +32,7 @@ class Configuration:
         self.part_count = 1
         self.dense_tables = 0                       # 0 auto, 1 on, 2 off
         self.positional = 0
+        self.full_topn = 0                          # 1: report the whole top-10 list, not only the hits equal to the max
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise TypeError("unknown configuration key %r" % k)
@@ -90,4 +91,5 @@ class Configuration:
         c.part_count = int(self.part_count)
         c.dense_tables = int(self.dense_tables)
         c.positional = int(self.positional)
+        c.full_topn = int(self.full_topn)
         return c

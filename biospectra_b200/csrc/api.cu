@@ -85,7 +85,7 @@ BSP_API void bsp_config_default(bsp_config* c) {         // Configuration.java:3
     c->query_algorithm = BSP_PAIRED_PROXIMITY; c->scoring_algorithm = BSP_TFIDF;
     c->worker_threads = 4; c->index_ram_buffer = 16; c->device = 0;
     c->query_term_min_should_match = 0.5;
-    c->part_rank = 0; c->part_count = 1; c->dense_tables = 0; c->positional = 0;
+    c->part_rank = 0; c->part_count = 1; c->dense_tables = 0; c->positional = 0; c->full_topn = 0;
 }
 
 static i64 env_i64(const char* name, i64 dflt) {
@@ -534,6 +534,7 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
     SimParams sp; sp.sim = qp.sim; sp.k1p1 = 1.2f + 1.0f;
     const u32 gbase = (u32)h->doc_base_global;
     const Tab4Dev T = ix.tab4_view();
+    const int full_topn = (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0;
     CUDA_CHECK(cudaEventRecord(h->ev[1], st));
     i64 launches = 6;
     FilterStats fs = {0, 0, 0};
@@ -541,9 +542,15 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
         if (!sc.fstats.p) sc.fstats.alloc(1);
         CUDA_CHECK(cudaMemsetAsync(sc.fstats.p, 0, sizeof(FilterStats), st));
         int threads = (int)round_up(std::max<i64>(ceil_div(ix.d_pad, FK_DOCS), 1), 32);
-        filter_score_kernel<<<(unsigned)counts[2], threads, 0, st>>>(T, D, h->tf16.p, sc.list_filter.p, sc.tok_off.p, sc.n_tok.p,
+        const size_t ring_bytes = (size_t)FK_STAGES * threads * 16;
+        static bool attr_set[64] = {false};      // per device: allow the 512-thread ring (64 KB dynamic shared memory)
+        if (!attr_set[h->conf.device & 63]) {
+            CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
+            attr_set[h->conf.device & 63] = true;
+        }
+        filter_score_kernel<<<(unsigned)counts[2], threads, ring_bytes, st>>>(T, D, h->tf16.p, sc.list_filter.p, sc.tok_off.p, sc.n_tok.p,
             sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n, part_doc,
-            part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p);
+            part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p, full_topn);
         KERNEL_CHECK();
         launches++;
         // reads the filter could not bound (exception or candidate overflow) were appended to the exact list
@@ -578,7 +585,7 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
     CUDA_CHECK(cudaEventRecord(h->ev[2], st));
     merge_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(n, sc.route.p, sc.status_in.p, n_tiles, parts_pos, parts_stride, part_n,
                                                              part_doc, part_score, out.status, out.label, out.n_hits, out.n_top,
-                                                             out.top_doc, out.top_score);
+                                                             out.top_doc, out.top_score, full_topn);
     KERNEL_CHECK();
     CUDA_CHECK(cudaEventRecord(h->ev[3], st));
     CUDA_CHECK(cudaStreamSynchronize(st));
@@ -894,7 +901,7 @@ BSP_API int bsp_merge_topk_device(bsp_classifier* h, int32_t n, int32_t parts, c
     // layout: [n][parts] lists; status is taken from part 0 (identical on every rank: it depends on the read only)
     merge_kernel<<<(unsigned)ceil_div(std::max(n, 1), 128), 128, 0, h->st>>>(n, nullptr, (const i32*)d_part_status, parts, parts, parts,
         (const i32*)d_part_n_top, (const u32*)d_part_doc, (const float*)d_part_score, (i32*)d_status, (i32*)d_label, (i32*)d_n_hits,
-        (i32*)d_n_top, (i32*)d_top_doc, (float*)d_top_score);
+        (i32*)d_n_top, (i32*)d_top_doc, (float*)d_top_score, (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0);
     KERNEL_CHECK();
     CUDA_CHECK(cudaStreamSynchronize(h->st));
     return BSP_OK;

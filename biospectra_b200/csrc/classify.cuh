@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(128) merge_kernel(i32 n_reads, const i32* __re
                                                      const float* __restrict__ part_score,
                                                      i32* __restrict__ status, i32* __restrict__ label, i32* __restrict__ n_hits,
                                                      i32* __restrict__ n_top, i32* __restrict__ top_doc,
-                                                     float* __restrict__ top_score) {
+                                                     float* __restrict__ top_score, int full_topn) {
     const i32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     float bs[TOPN];
@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(128) merge_kernel(i32 n_reads, const i32* __re
     }
     int nh = 0;
     for (int j = 0; j < nt; j++) if ((double)bs[0] - (double)bs[j] == 0.0) nh++;
+    if (!full_topn) nt = nh;        // result-set mode: only the hits equal to the maximum are reported
     if (status) status[r] = status_in[r];
     if (label) label[r] = nh == 0 ? 0 : (nh == 1 ? 2 : 1);
     if (n_hits) n_hits[r] = nh;

@@ -173,6 +173,29 @@ __device__ __forceinline__ void pair_word(u32 word, const uint2 lut, u32& w0, u3
     c1 += prmt(0x01010100u, 0x01010101u, hi);
 }
 
+// cp.async (LDGSTS) 16-byte copy global -> shared, bypassing L1; one commit group per table row
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const u32 sa = (u32)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// two rows at once: written as a + b + acc so that the compiler emits one IADD3 per lane register
+__device__ __forceinline__ void pair_word2(u32 wa, u32 wb, const uint2 la, const uint2 lb, u32& w0, u32& w1, u32& w2, u32& w3,
+                                           u32& c0, u32& c1) {
+    const u32 ha = wa >> 16, hb = wb >> 16;
+    const u32 a0 = prmt(la.x, la.y, wa), a1 = prmt(la.x, la.y, ha);
+    const u32 b0 = prmt(lb.x, lb.y, wb), b1 = prmt(lb.x, lb.y, hb);
+    w0 += prmt(a0, 0u, 0x4140u) + prmt(b0, 0u, 0x4140u);
+    w1 += prmt(a0, 0u, 0x4342u) + prmt(b0, 0u, 0x4342u);
+    w2 += prmt(a1, 0u, 0x4140u) + prmt(b1, 0u, 0x4140u);
+    w3 += prmt(a1, 0u, 0x4342u) + prmt(b1, 0u, 0x4342u);
+    c0 += prmt(0x01010100u, 0x01010101u, wa) + prmt(0x01010100u, 0x01010101u, wb);
+    c1 += prmt(0x01010100u, 0x01010101u, ha) + prmt(0x01010100u, 0x01010101u, hb);
+}
+
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {     // read-only path, do not keep in L1
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -195,6 +218,7 @@ __device__ __forceinline__ u32 cell_code(const Tab4Dev& T, u32 row, u32 doc) {
 #define FK_CAND_CAP 128
 #define FK_EXC_CAP 64
 #define FK_CODE_CAP 6144           // candidate x clause cells staged in shared memory for the exact pass
+#define FK_STAGES 8                // rows in flight per thread (cp.async ring in shared memory)
 #define FK_QMAX 255.0f
 #define FK_ROUND_SLACK 0.51f       // |q - S*tf*value| <= 0.5 (+ float rounding of the product)
 #define FK_REL_SLACK 4e-6f         // float roundings of Lucene's score and of the bound arithmetic
@@ -248,7 +272,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         const u32* __restrict__ clause_row, const i32* __restrict__ n_clauses, const i32* __restrict__ msm,
         const float* __restrict__ doc_w, int alg, u32 global_doc_base, int parts_stride, i32* __restrict__ part_n,
         u32* __restrict__ part_doc, float* __restrict__ part_score, i32* __restrict__ route,
-        i32* __restrict__ overflow_list, i32* __restrict__ overflow_count, FilterStats* __restrict__ stats) {
+        i32* __restrict__ overflow_list, i32* __restrict__ overflow_count, FilterStats* __restrict__ stats, int full_topn) {
     __shared__ uint2 s_lut[FK_MAX_CLAUSES + 1];          // pair clauses: q for codes 0..3 | 4..7
     __shared__ u32 s_row[FK_MAX_CLAUSES + 1];
     __shared__ float s_val[FK_MAX_CLAUSES + 1];
@@ -259,9 +283,11 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     __shared__ u64 s_ckey[FK_CAND_CAP];
     __shared__ u32 s_exc_c[FK_EXC_CAP], s_exc_d[FK_EXC_CAP];
     __shared__ float s_exc_f[FK_EXC_CAP];
+    __shared__ u32 s_exc_q[FK_EXC_CAP];
     __shared__ u8 s_code[FK_CODE_CAP];
     __shared__ int s_ncand, s_nexc;
-    __shared__ float s_scale, s_delta;
+    __shared__ u32 s_excsum, s_qmin;
+    __shared__ float s_scale;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
     const i32 r = read_list[blockIdx.x];
@@ -270,7 +296,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     const i32 n_pair = alg == ALG_NAIVE ? 0 : (alg == ALG_CHAIN ? nc : n / 2);
     const i32 need = max(1, msm[r]);
     if (threadIdx.x < 16) s_tf[threadIdx.x] = tf16[threadIdx.x];
-    if (threadIdx.x == 0) { s_ncand = 0; s_nexc = 0; }
+    if (threadIdx.x == 0) { s_ncand = 0; s_nexc = 0; s_excsum = 0; }
     // ---- stage clauses; scale S: S * value_c * tf(7) <= 255 for every clause; q_min = smallest non-zero weight
     float vmax = 0.0f, vmin = 3.0e38f;
     for (i32 c = threadIdx.x; c < nc; c += blockDim.x) {
@@ -286,11 +312,8 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         const u64 m = block_max_u64(packed, s_red);
         if (threadIdx.x == 0) {
             const float S = FK_QMAX / (__uint_as_float((u32)(m >> 32)) * tf16[T4_PAIR_MAX]);
-            const float qmin = rintf(S * __uint_as_float(0xFFFFFFFFu - (u32)(m & 0xFFFFFFFFull)));
             s_scale = S;
-            // exact score of doc d = E(d)/(S*nc) * (1 +- delta): the cell weights err by <= 0.51 each and the cell
-            // sum is >= q_min per matching clause; FK_REL_SLACK covers the float roundings
-            s_delta = qmin >= 2.0f ? FK_ROUND_SLACK / qmin + FK_REL_SLACK : 1.0f;
+            s_qmin = (u32)__float2int_rn(S * __uint_as_float(0xFFFFFFFFu - (u32)(m & 0xFFFFFFFFull)));   // smallest table weight
         }
     }
     __syncthreads();
@@ -309,12 +332,23 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         const u32 a = T.exc_off[row], b = T.exc_off[row + 1];
         for (u32 j = a; j < b; j++) {
             int idx = atomicAdd(&s_nexc, 1);
-            if (idx < FK_EXC_CAP) { s_exc_c[idx] = (u32)c; s_exc_d[idx] = T.exc_doc[j]; s_exc_f[idx] = T.exc_freq[j]; }
+            if (idx < FK_EXC_CAP) {
+                const float f = T.exc_freq[j];
+                const u32 qe = (u32)min(__float2int_rn(sv * tf_of(f)), 1 << 20);      // same quantisation as the table cells
+                s_exc_c[idx] = (u32)c; s_exc_d[idx] = T.exc_doc[j]; s_exc_f[idx] = f; s_exc_q[idx] = qe;
+                atomicAdd(&s_excsum, qe);
+                atomicMin(&s_qmin, qe);
+            }
         }
     }
     __syncthreads();
     const int n_exc = s_nexc;
-    bool overflow = n_exc > FK_EXC_CAP;
+    // u16 lanes: pair-row weights <= 255, term-row weights <= 255*tf(14)/tf(7) < 362, plus whatever the exception cells add
+    bool overflow = n_exc > FK_EXC_CAP || 255u * (u32)n_pair + 362u * (u32)(nc - n_pair) + s_excsum > 65535u;
+    // exact score of doc d = E(d)/(S*nc) * (1 +- delta): each weight errs by <= 0.51 and is >= q_min;
+    // FK_REL_SLACK covers the float roundings of Lucene's score and of the estimate
+    const float qmin = (float)s_qmin;
+    const float delta = qmin >= 2.0f ? FK_ROUND_SLACK / qmin + FK_REL_SLACK : 1.0f;
 
     // ---- pass 1: stream the rows.  Thread owns docs [32t, 32t+32): wacc[i] = u16 lanes (doc 2i, 2i+1),
     //      cacc[j] = u8 lanes (docs 4j..4j+3)
@@ -327,49 +361,78 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     for (int i = 0; i < 8; i++) cacc[i] = 0;
     const u8* tbase = T.tab + (u64)threadIdx.x * 16;
     if (active && !overflow) {
+        // Each thread prefetches its own 16-byte slice of the next FK_STAGES rows into its private slots of the
+        // ring (no cross-thread hand-off, so no barriers): FK_STAGES x 16 B in flight per thread.
+        extern __shared__ __align__(16) uint4 ring[];
+        uint4* slot = ring + threadIdx.x;
+        const u32 stride = blockDim.x;
+#pragma unroll
+        for (int st = 0; st < FK_STAGES; st++) {
+            if (st < nc) cp_async16(slot + st * stride, tbase + (u64)s_row[st] * T.row_bytes);
+            cp_async_commit();
+        }
         i32 c = 0;
 #pragma unroll 1
-        for (; c + 4 <= n_pair; c += 4) {
-            uint4 q[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) q[u] = ldg_stream16(tbase + (u64)s_row[c + u] * T.row_bytes);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint2 lut = s_lut[c + u];
-                pair_word(q[u].x, lut, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1]);
-                pair_word(q[u].y, lut, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3]);
-                pair_word(q[u].z, lut, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5]);
-                pair_word(q[u].w, lut, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7]);
-            }
+        for (; c + 2 <= n_pair; c += 2) {             // two pair rows per iteration: the lane adds pair up (IADD3)
+            cp_async_wait<FK_STAGES - 2>();
+            uint4* my0 = slot + (c % FK_STAGES) * stride;
+            uint4* my1 = slot + ((c + 1) % FK_STAGES) * stride;
+            const uint4 q0 = *my0, q1 = *my1;
+            const uint2 l0 = s_lut[c], l1 = s_lut[c + 1];
+            pair_word2(q0.x, q1.x, l0, l1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1]);
+            pair_word2(q0.y, q1.y, l0, l1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3]);
+            pair_word2(q0.z, q1.z, l0, l1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5]);
+            pair_word2(q0.w, q1.w, l0, l1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7]);
+            if (c + FK_STAGES < nc) cp_async16(my0, tbase + (u64)s_row[c + FK_STAGES] * T.row_bytes);
+            cp_async_commit();
+            if (c + 1 + FK_STAGES < nc) cp_async16(my1, tbase + (u64)s_row[c + 1 + FK_STAGES] * T.row_bytes);
+            cp_async_commit();
         }
-#pragma unroll 1
-        for (; c < n_pair; c++) {
-            const uint4 q = ldg_stream16(tbase + (u64)s_row[c] * T.row_bytes);
-            const uint2 lut = s_lut[c];
-            pair_word(q.x, lut, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1]);
-            pair_word(q.y, lut, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3]);
-            pair_word(q.z, lut, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5]);
-            pair_word(q.w, lut, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7]);
-        }
-        // Term clauses (tf 1..14): nibble at a time
 #pragma unroll 1
         for (; c < nc; c++) {
-            const uint4 q = ldg_stream16(tbase + (u64)s_row[c] * T.row_bytes);
-            const float sv = S * s_val[c];
-            const u32 w[4] = {q.x, q.y, q.z, q.w};
+            cp_async_wait<FK_STAGES - 1>();
+            uint4* my = slot + (c % FK_STAGES) * stride;
+            const uint4 q = *my;
+            if (c < n_pair) {
+                const uint2 lut = s_lut[c];
+                pair_word(q.x, lut, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1]);
+                pair_word(q.y, lut, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3]);
+                pair_word(q.z, lut, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5]);
+                pair_word(q.w, lut, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7]);
+            } else {                                  // Term clause (tf 1..14): nibble at a time
+                const float sv = S * s_val[c];
+                const u32 w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int x = 0; x < 4; x++) {
+                for (int x = 0; x < 4; x++) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const u32 code = (w[x] >> (4 * j)) & 15u;
-                    const u32 qv = (u32)__float2int_rn(sv * s_tf[code]);
-                    wacc[4 * x + (j >> 1)] += qv << (16 * (j & 1));
-                    cacc[2 * x + (j >> 2)] += (code ? 1u : 0u) << (8 * (j & 3));
+                    for (int j = 0; j < 8; j++) {
+                        const u32 code = (w[x] >> (4 * j)) & 15u;
+                        const u32 qv = (u32)__float2int_rn(sv * s_tf[code]);
+                        wacc[4 * x + (j >> 1)] += qv << (16 * (j & 1));
+                        cacc[2 * x + (j >> 2)] += (code ? 1u : 0u) << (8 * (j & 3));
+                    }
                 }
+            }
+            // the slot's data now lives in registers: refill it with the row FK_STAGES ahead
+            if (c + FK_STAGES < nc) cp_async16(my, tbase + (u64)s_row[c + FK_STAGES] * T.row_bytes);
+            cp_async_commit();
+        }
+    }
+    // ---- exception cells (stored as 0 in the table) join their doc's lanes: predicated, statically indexed adds
+    if (active && !overflow) {
+        for (int e = 0; e < n_exc; e++) {
+            const u32 d = s_exc_d[e];
+            if ((d >> 5) == threadIdx.x) {
+                const u32 li = d & 31u, qv = s_exc_q[e] << (16 * (li & 1u)), one = 1u << (8 * (li & 3u));
+#pragma unroll
+                for (int i = 0; i < 16; i++) wacc[i] += (u32)i == (li >> 1) ? qv : 0u;
+#pragma unroll
+                for (int i = 0; i < 8; i++) cacc[i] += (u32)i == (li >> 2) ? one : 0u;
             }
         }
     }
-    // ---- pass 2: per-thread best estimate, then the block's 10th best.  Padded docs have no cells (m = 0).
+    // ---- pass 2: per-thread best estimate, then the block's 10th best (full list) or best (result set only).
+    //      Padded docs have no cells (m = 0).
     float e_best = 0.0f;
     if (active && !overflow) {
 #pragma unroll
@@ -385,16 +448,15 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
             }
         }
     }
-    const float tau_e = __uint_as_float(block_tenth_largest_u32(__float_as_uint(e_best), s_sel));
-    // a doc can reach the top 10 only if E(d)*(1+delta) >= tau_e*(1-delta)
-    const float delta = s_delta;
+    // full_topn: 10 docs are known to score >= tau_e*(1-delta); otherwise only the docs that can tie at the maximum
+    // matter (Classifier.java:358-366 keeps the hits equal to the top score), so tau_e is the best estimate
+    const u32 sel = full_topn ? block_tenth_largest_u32(__float_as_uint(e_best), s_sel)
+                              : (u32)block_max_u64((u64)__float_as_uint(e_best), s_red);
+    const float tau_e = __uint_as_float(sel);
+    // a doc can reach the list only if E(d)*(1+delta) >= tau_e*(1-delta)
     const float theta = delta < 1.0f ? tau_e * ((1.0f - delta) / (1.0f + delta)) * (1.0f - FK_REL_SLACK) : 0.0f;
-    // ---- candidates: forced (exception cells) + estimate >= theta
+    // ---- candidates: estimate >= theta
     if (!overflow) {
-        for (int e = threadIdx.x; e < n_exc; e += blockDim.x) {
-            int idx = atomicAdd(&s_ncand, 1);
-            if (idx < FK_CAND_CAP) s_cand[idx] = s_exc_d[e];
-        }
         if (active && e_best >= theta && e_best > 0.0f) {
 #pragma unroll
             for (int i4 = 0; i4 < FK_DOCS; i4 += 4) {
@@ -429,7 +491,9 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     }
     // ---- exact rescoring.  The candidates' cells are fetched in one batch of independent loads
     //      (item = candidate j, clause c), then each warp sums one candidate from shared memory.
-    const int n_items = n_cand * nc;
+    int pitch_log = 5;                                    // clause pitch of the staging buffer: power of two >= nc
+    while ((1 << pitch_log) < nc) pitch_log++;
+    const int n_items = n_cand << pitch_log;
     const bool staged = n_items <= FK_CODE_CAP;
     if (staged) {
 #pragma unroll 1
@@ -439,7 +503,8 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
             for (int u = 0; u < 4; u++) {
                 const int it = it0 + u * blockDim.x;
                 code[u] = 0;
-                if (it < n_items) { const int j = it / nc, c = it - j * nc; code[u] = cell_code(T, s_row[c], s_cand[j]); }
+                const int j = it >> pitch_log, c = it & ((1 << pitch_log) - 1);
+                if (it < n_items && c < nc) code[u] = cell_code(T, s_row[c], s_cand[j]);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -459,7 +524,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         i32 m = 0;
 #pragma unroll 1
         for (i32 c = lane; c < nc; c += 32) {
-            const u32 code = staged ? (u32)s_code[j * nc + c] : cell_code(T, s_row[c], d);
+            const u32 code = staged ? (u32)s_code[(j << pitch_log) + c] : cell_code(T, s_row[c], d);
             float tf = s_tf[code];
             if (code == 0u && forced) {
                 for (int e = 0; e < n_exc; e++)

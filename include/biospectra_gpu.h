@@ -72,6 +72,10 @@ typedef struct bsp_config {
     /* index residency: 0 auto, 1 force on, 2 force off */
     int32_t dense_tables;               /* dense tf / pair-frequency tables (small k) */
     int32_t positional;                 /* term-major positional postings (general path) */
+    /* 0: report the reference's result set only -- the hits whose score equals the maximum (what
+     *    Classifier.classify returns, Classifier.java:358-366); n_top == n_hits.
+     * 1: also report the rest of the top-10 list Lucene's collector held (verification, diagnostics). */
+    int32_t full_topn;
 } bsp_config;
 
 typedef struct bsp_indexer bsp_indexer;
@@ -110,7 +114,8 @@ int bsp_index_close_to_classifier(bsp_indexer* h, const bsp_config* query_conf, 
  *   bsp_classify_batch.  Per read i:
  *     status[i]  BSP_READ_*; label[i] BSP_UNKNOWN/VAGUE/CLASSIFIED;
  *     n_hits[i]  #hits whose score equals the max (the reference's result list, <= 10);
- *     n_top[i]   #entries of the top-10 list (score desc, doc asc);
+ *     n_top[i]   #entries reported in the list below: n_hits[i], or with conf.full_topn the whole top-10 list
+ *                (score desc, doc asc);
  *     top_doc[i*10+j], top_score[i*10+j]  the list; rank of entry j is j.
  *   Any of the output pointers except status may be NULL. */
 int bsp_classifier_open(const bsp_config* conf, const char* index_path, bsp_classifier** out);

@@ -70,6 +70,8 @@ def build_gpu(ents, k, min_strand, qconf_kw, index_path=""):
     ix = Indexer(iconf)
     for i, s in enumerate(ents):
         ix.add_entry("f%d.fa" % i, "h%d" % i, "", s)
+    qconf_kw = dict(qconf_kw)
+    qconf_kw.setdefault("full_topn", 1)        # compare the whole top-10 list unless a test asks for the result set only
     q = Configuration(index_path=index_path, kmer_size=k, min_strand_kmer=min_strand, **qconf_kw)
     return ix.close_to_classifier(q)
 
@@ -88,9 +90,14 @@ def assert_index_equal(gpu, ox, all_terms=True, sample_terms=None):
         assert np.array_equal(np.concatenate(opos) if opos else np.zeros(0, np.int32), gpos), t
 
 
-def assert_classify_equal(res_g, res_o, reads=None, what=""):
+def assert_classify_equal(res_g, res_o, reads=None, what="", hits_only=False):
+    """hits_only: the GPU ran in result-set mode (conf.full_topn = 0): it reports exactly the hits equal to the maximum
+    (n_top == n_hits), which must equal the head of the oracle's top-10 list."""
     n = len(res_o["status"])
     assert np.array_equal(res_g["status"], res_o["status"]), (what, np.nonzero(res_g["status"] != res_o["status"]))
+    if hits_only:
+        assert np.array_equal(res_g["n_top"], res_g["n_hits"]), what
+        res_o = dict(res_o, n_top=res_o["n_hits"])
     for key in ("n_top", "n_hits", "label"):
         bad = np.nonzero(res_g[key] != res_o[key])[0]
         assert bad.size == 0, (what, key, bad[:5], reads[bad[0]] if reads is not None else None,

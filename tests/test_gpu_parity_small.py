@@ -128,6 +128,16 @@ def test_filter_path_many_docs(oracle_lib, monkeypatch, k, alg, n_docs):
         assert cnt["filter_candidates"] > 0
     finally:
         g.close()
+    # result-set mode (the default): only the hits equal to the maximum are reported, from fewer rescored docs
+    g = common.build_gpu(ents, k, False, dict(kmer_skips=0, query_algorithm=alg_name, scoring_algorithm="tfidf",
+                                              dense_tables=1, positional=2, full_topn=0))
+    try:
+        res_h = g.classify_batch(reads)
+        common.assert_classify_equal(res_h, res_o, reads, "filter hits-only k%d alg%d" % (k, alg), hits_only=True)
+        cnt_h = g.last_counters()
+        assert cnt_h["filter_reads"] > 0 and cnt_h["filter_candidates"] <= cnt["filter_candidates"]
+    finally:
+        g.close()
 
 
 def test_filter_overflow_falls_back(oracle_lib, monkeypatch):
