@@ -258,7 +258,10 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     # device-resident metric: device time (CUDA events on the library's stream, whole pipeline), max over ranks
+    # `ncu --profile-from-start off` captures exactly the timed device-resident steps
+    torch.cuda.cudart().cudaProfilerStart()
     el_dev, kernel_ms, pipe_ms, launches = timed(step_device, args.steps)
+    torch.cuda.cudart().cudaProfilerStop()
     # end to end through the host-buffer call
     host_out = {}
 

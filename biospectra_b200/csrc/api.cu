@@ -550,7 +550,7 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
         }
         filter_score_kernel<<<(unsigned)counts[2], threads, ring_bytes, st>>>(T, D, h->tf16.p, sc.list_filter.p, sc.tok_off.p, sc.n_tok.p,
             sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n, part_doc,
-            part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p, full_topn);
+            part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p, full_topn, 1u);
         KERNEL_CHECK();
         launches++;
         // reads the filter could not bound (exception or candidate overflow) were appended to the exact list

@@ -182,18 +182,24 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// two rows at once: written as a + b + acc so that the compiler emits one IADD3 per lane register
+// acc += x on the FMA pipe (IMAD x*1+acc): PRMT/SHF/IADD3 all issue on the ALU pipe, which runs at half the
+// warp-issue rate, so the lane adds are moved to the otherwise idle pipe
+// (`one` is a kernel argument equal to 1: with a literal 1 ptxas folds the multiply back into IADD3)
+__device__ __forceinline__ void add_fma_pipe(u32& acc, u32 x, u32 one) {
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(x), "r"(one));
+}
+// two rows at once
 __device__ __forceinline__ void pair_word2(u32 wa, u32 wb, const uint2 la, const uint2 lb, u32& w0, u32& w1, u32& w2, u32& w3,
-                                           u32& c0, u32& c1) {
+                                           u32& c0, u32& c1, u32 one) {
     const u32 ha = wa >> 16, hb = wb >> 16;
     const u32 a0 = prmt(la.x, la.y, wa), a1 = prmt(la.x, la.y, ha);
     const u32 b0 = prmt(lb.x, lb.y, wb), b1 = prmt(lb.x, lb.y, hb);
-    w0 += prmt(a0, 0u, 0x4140u) + prmt(b0, 0u, 0x4140u);
-    w1 += prmt(a0, 0u, 0x4342u) + prmt(b0, 0u, 0x4342u);
-    w2 += prmt(a1, 0u, 0x4140u) + prmt(b1, 0u, 0x4140u);
-    w3 += prmt(a1, 0u, 0x4342u) + prmt(b1, 0u, 0x4342u);
-    c0 += prmt(0x01010100u, 0x01010101u, wa) + prmt(0x01010100u, 0x01010101u, wb);
-    c1 += prmt(0x01010100u, 0x01010101u, ha) + prmt(0x01010100u, 0x01010101u, hb);
+    add_fma_pipe(w0, prmt(a0, 0u, 0x4140u), one); add_fma_pipe(w0, prmt(b0, 0u, 0x4140u), one);
+    add_fma_pipe(w1, prmt(a0, 0u, 0x4342u), one); add_fma_pipe(w1, prmt(b0, 0u, 0x4342u), one);
+    add_fma_pipe(w2, prmt(a1, 0u, 0x4140u), one); add_fma_pipe(w2, prmt(b1, 0u, 0x4140u), one);
+    add_fma_pipe(w3, prmt(a1, 0u, 0x4342u), one); add_fma_pipe(w3, prmt(b1, 0u, 0x4342u), one);
+    add_fma_pipe(c0, prmt(0x01010100u, 0x01010101u, wa), one); add_fma_pipe(c0, prmt(0x01010100u, 0x01010101u, wb), one);
+    add_fma_pipe(c1, prmt(0x01010100u, 0x01010101u, ha), one); add_fma_pipe(c1, prmt(0x01010100u, 0x01010101u, hb), one);
 }
 
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {     // read-only path, do not keep in L1
@@ -272,7 +278,8 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         const u32* __restrict__ clause_row, const i32* __restrict__ n_clauses, const i32* __restrict__ msm,
         const float* __restrict__ doc_w, int alg, u32 global_doc_base, int parts_stride, i32* __restrict__ part_n,
         u32* __restrict__ part_doc, float* __restrict__ part_score, i32* __restrict__ route,
-        i32* __restrict__ overflow_list, i32* __restrict__ overflow_count, FilterStats* __restrict__ stats, int full_topn) {
+        i32* __restrict__ overflow_list, i32* __restrict__ overflow_count, FilterStats* __restrict__ stats, int full_topn,
+        u32 one /* = 1, see add_fma_pipe */) {
     __shared__ uint2 s_lut[FK_MAX_CLAUSES + 1];          // pair clauses: q for codes 0..3 | 4..7
     __shared__ u32 s_row[FK_MAX_CLAUSES + 1];
     __shared__ float s_val[FK_MAX_CLAUSES + 1];
@@ -379,10 +386,10 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
             uint4* my1 = slot + ((c + 1) % FK_STAGES) * stride;
             const uint4 q0 = *my0, q1 = *my1;
             const uint2 l0 = s_lut[c], l1 = s_lut[c + 1];
-            pair_word2(q0.x, q1.x, l0, l1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1]);
-            pair_word2(q0.y, q1.y, l0, l1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3]);
-            pair_word2(q0.z, q1.z, l0, l1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5]);
-            pair_word2(q0.w, q1.w, l0, l1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7]);
+            pair_word2(q0.x, q1.x, l0, l1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1], one);
+            pair_word2(q0.y, q1.y, l0, l1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3], one);
+            pair_word2(q0.z, q1.z, l0, l1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5], one);
+            pair_word2(q0.w, q1.w, l0, l1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7], one);
             if (c + FK_STAGES < nc) cp_async16(my0, tbase + (u64)s_row[c + FK_STAGES] * T.row_bytes);
             cp_async_commit();
             if (c + 1 + FK_STAGES < nc) cp_async16(my1, tbase + (u64)s_row[c + 1 + FK_STAGES] * T.row_bytes);
