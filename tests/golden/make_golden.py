@@ -51,6 +51,9 @@ def main():
     for case in CASES:
         rng = random.Random(case["seed"])
         seqs = common.make_corpus(500 + case["seed"], n_entries=(4, 7), length=(20, 260), junk=case["junk"])
+        # what FASTAReader#readNext would hand over (upper-cased, trimmed), so that a FASTA round trip is the identity
+        seqs = [so.java_trim(x.upper()) for x in seqs]
+        seqs = [x if x else "ACGT" for x in seqs]
         entries = []
         for i, s in enumerate(seqs):
             tax = "" if i % 4 == 3 else lineage(rng, i // 4, i // 2, i)
