@@ -241,6 +241,9 @@ typedef struct {
     int32_t* positions;                          /* [nt] */
     int32_t* direct;                             /* key -> term idx (or -1) when 4^k <= 2^24 */
     int finished;
+    /* doc-partitioned checks: statistics of the WHOLE collection (lucene!search/IndexSearcher#termStatistics,
+     * #collectionStatistics are global); unset (g_max_doc == 0) = this index is the whole collection */
+    int64_t g_max_doc, g_sum_ttf; uint32_t* g_df;   /* g_df: dense [4^k] */
 } ora_index;
 
 ORA_API ora_index* ora_index_new(int k, int min_strand) {
@@ -373,7 +376,7 @@ ORA_API void ora_index_free(ora_index* ix) {
     if (!ix) return;
     free(ix->t_key); free(ix->t_doc); free(ix->t_pos); free(ix->doc_ntok); free(ix->doc_norm);
     free(ix->term_key); free(ix->term_off); free(ix->post_doc); free(ix->post_pos);
-    free(ix->positions); free(ix->direct); free(ix);
+    free(ix->positions); free(ix->direct); free(ix->g_df); free(ix);
 }
 
 ORA_API int ora_index_stats(const ora_index* ix, int64_t* n_docs, int64_t* n_terms, int64_t* n_postings, int64_t* n_positions) {
@@ -470,6 +473,7 @@ static inline float doc_score(const SimCtx* c, float freq, float value, int norm
 }
 
 static int64_t df_of(const ora_index* ix, uint64_t key) {
+    if (ix->g_df) return (int64_t)ix->g_df[key];
     int64_t t = find_term(ix, key);
     return t < 0 ? 0 : ix->term_off[t + 1] - ix->term_off[t];
 }
@@ -509,7 +513,7 @@ static int classify_one(const ora_index* ix, const ora_query_conf* qc, const Sim
     }
     int32_t msm = (int32_t)(qc->query_term_min_should_match * (double)nc); /* Classifier.java:257 */
     *n_clauses_out = (int32_t)nc; *msm_out = msm;
-    int64_t max_doc = ix->n_docs;
+    int64_t max_doc = ix->g_max_doc ? ix->g_max_doc : ix->n_docs;
     /* weights (A.5) */
     for (int64_t c = 0; c < nc; c++) {
         float a = sc->sim == SIM_TFIDF ? ora_idf_tfidf(df_of(ix, s->cl[c].t0), max_doc)
@@ -602,9 +606,10 @@ static void sim_init(SimCtx* c, const ora_index* ix, int sim) {
     c->sim = sim;
     for (int b = 0; b < 256; b++) c->norm_table[b] = ora_byte315_to_float(b);
     if (sim == SIM_BM25) {
-        int64_t stt = 0;
+        int64_t stt = 0, nd = ix->n_docs;
         for (int32_t d = 0; d < ix->n_docs; d++) stt += ix->doc_ntok[d];
-        float avgdl = stt <= 0 ? 1.0f : (float)((double)stt / (double)ix->n_docs);   /* BM25Similarity#avgFieldLength */
+        if (ix->g_max_doc) { stt = ix->g_sum_ttf; nd = ix->g_max_doc; }
+        float avgdl = stt <= 0 ? 1.0f : (float)((double)stt / (double)nd);           /* BM25Similarity#avgFieldLength */
         const float k1 = 1.2f, b = 0.75f;
         for (int x = 0; x < 256; x++) {
             float f = c->norm_table[x];
@@ -643,6 +648,31 @@ ORA_API int ora_classify_batch(const ora_index* ix, const ora_query_conf* qc, in
     }
     (void)threads;
     return 0;
+}
+
+/* dense per-term document frequencies of this index (k <= 12): out[4^k] */
+ORA_API int ora_index_dense_df(const ora_index* ix, uint32_t* out) {
+    if (!ix->finished || ix->k > 12) return -1;
+    memset(out, 0, ((size_t)1 << (2 * ix->k)) * sizeof(uint32_t));
+    for (int64_t t = 0; t < ix->n_terms; t++) out[ix->term_key[t]] = (uint32_t)(ix->term_off[t + 1] - ix->term_off[t]);
+    return 0;
+}
+
+/* score against collection-wide statistics (doc-partitioned mode): max_doc, sum of doc lengths, dense df[4^k] (copied) */
+ORA_API int ora_index_set_global(ora_index* ix, int64_t max_doc, int64_t sum_ttf, const uint32_t* dense_df) {
+    if (!ix->finished || ix->k > 12) return -1;
+    size_t n = (size_t)1 << (2 * ix->k);
+    free(ix->g_df);
+    ix->g_df = (uint32_t*)malloc(n * sizeof(uint32_t));
+    memcpy(ix->g_df, dense_df, n * sizeof(uint32_t));
+    ix->g_max_doc = max_doc; ix->g_sum_ttf = sum_ttf;
+    return 0;
+}
+
+ORA_API int64_t ora_index_sum_ttf(const ora_index* ix) {
+    int64_t s = 0;
+    for (int32_t d = 0; d < ix->n_docs; d++) s += ix->doc_ntok[d];
+    return s;
 }
 
 ORA_API int ora_max_threads(void) {

@@ -59,6 +59,10 @@ def lib():
     L.ora_classify_batch.argtypes = [C.c_void_p, C.POINTER(QueryConf), C.c_int32, C.POINTER(C.c_char_p),
                                      C.c_void_p] + [C.c_void_p] * 8
     L.ora_max_threads.restype = C.c_int
+    L.ora_index_dense_df.argtypes = [C.c_void_p, C.c_void_p]
+    L.ora_index_set_global.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    L.ora_index_sum_ttf.restype = C.c_int64
+    L.ora_index_sum_ttf.argtypes = [C.c_void_p]
     _LIB = L
     return L
 
@@ -147,6 +151,21 @@ class OracleIndex:
         if rc:
             raise RuntimeError("ora_classify_batch rc=%d" % rc)
         return out
+
+    # ---- doc-partitioned checks: collection-wide statistics
+    def dense_df(self):
+        out = np.zeros(1 << (2 * self.k), np.uint32)
+        if self.L.ora_index_dense_df(self.h, out.ctypes.data):
+            raise ValueError("dense df needs k <= 12")
+        return out
+
+    def sum_ttf(self):
+        return int(self.L.ora_index_sum_ttf(self.h))
+
+    def set_global(self, max_doc, sum_ttf, dense_df):
+        d = np.ascontiguousarray(dense_df, np.uint32)
+        if self.L.ora_index_set_global(self.h, int(max_doc), int(sum_ttf), d.ctypes.data):
+            raise ValueError("set_global failed")
 
     def close(self):
         if self.h:

@@ -1,0 +1,62 @@
+"""Doc-partitioned mode on one GPU: two handles hold the two halves of the reference (what two ranks would hold);
+the df all-reduce is done by hand on the exposed device buffers, the hit lists are stacked like the all_gather does,
+and bsp_merge_topk_device must reproduce the single-index oracle (which is also what Lucene would return: idf, maxDoc
+and avgdl are collection-wide)."""
+import random
+
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("k,alg,sim,full", [(5, 2, 0, 1), (6, 0, 1, 1), (4, 1, 0, 0), (10, 2, 0, 0)])
+def test_two_partitions_merge_to_single_index(oracle_lib, k, alg, sim, full):
+    import torch
+    from biospectra_b200 import Configuration, Indexer, partition
+    rng = random.Random(50 + k)
+    ents = [common.rand_seq(rng, rng.randint(80, 500)) for _ in range(13)]
+    ents[5] = ents[2][:300] + common.rand_seq(rng, 40)
+    ents[11] = ents[2][20:280]
+    ents[7] = ents[7][:50] + "*" + ents[7][50:]                      # no reverse doc
+    reads = common.make_reads(600 + k, ents, n=64, max_len=130)
+    ox = common.build_oracle(oracle_lib, ents, k, False)
+    res_o = ox.classify([r.encode() for r in reads], skips=0, algorithm=alg, scoring=sim, msm=0.5, threads=2)
+    alg_name = ["NAIVE_KMER", "CHAIN_PROXIMITY", "PAIRED_PROXIMITY"][alg]
+    dev = torch.device("cuda", 0)
+    plan = partition.plan_entries([len(s) for s in ents], 2)
+    engines = []
+    for r, (e0, e1) in enumerate(plan):
+        ix = Indexer(Configuration(index_path="", kmer_size=k))
+        for i in range(e0, e1):
+            ix.add_entry("f%d.fa" % i, "h%d" % i, "", ents[i])
+        clf = ix.close_to_classifier(Configuration(index_path="", kmer_size=k, kmer_skips=0, query_algorithm=alg_name,
+                                                   scoring_algorithm="bm25" if sim else "tfidf", full_topn=full))
+        engines.append(partition.GpuPartitionEngine(clf, dev))
+    try:
+        # what DocPartitionedClassifier.sync_statistics does with all_gather / all_reduce
+        stats = [e.local_stats() for e in engines]
+        dfs = [e.df_tensor() for e in engines]
+        total = dfs[0] + dfs[1]
+        for d in dfs:
+            d.copy_(total)
+        torch.cuda.synchronize()
+        base = 0
+        for e, (nd, _) in zip(engines, stats):
+            e.set_global(base, sum(s[0] for s in stats), sum(s[1] for s in stats))
+            base += nd
+        data = np.frombuffer(b"".join(r.encode() for r in reads), np.uint8)
+        off = np.zeros(len(reads) + 1, np.int64)
+        np.cumsum([len(r) for r in reads], out=off[1:])
+        lists = [e.classify_lists(data, off) for e in engines]
+        torch.cuda.synchronize()
+        g = {key: torch.stack([l[key] for l in lists], dim=1).contiguous() for key in ("n_top", "top_doc", "top_score")}
+        out = engines[0].merge(len(reads), 2, lists[0]["status"], g["n_top"], g["top_doc"], g["top_score"])
+        torch.cuda.synchronize()
+        res_g = {key: v.cpu().numpy() for key, v in out.items()}
+        common.assert_classify_equal(res_g, res_o, reads, "two partitions k%d" % k, hits_only=not full)
+    finally:
+        for e in engines:
+            e.clf.close()
