@@ -75,6 +75,22 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def measured_traffic(args, kernel):
+    """dram__bytes_read+write per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r1_ncu_kernel_metrics.json); only valid for the workload the capture was taken on"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_kernel_metrics.json")) as f:
+            m = json.load(f)["r1_filter_cpasync_resultset_C2"]
+        if args.workload != "C2" or kernel != "filter_score_kernel" or args.algorithm != "PAIRED_PROXIMITY":
+            return None
+        def gb(k):
+            v, u = float(m[k]["value"]), m[k]["unit"]
+            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+        return gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
+    except Exception:
+        return None
+
+
 def shipped_config(**kw):
     from biospectra_b200 import Configuration
     # /root/reference/configuration.json as shipped
@@ -94,41 +110,54 @@ def sample_plan(wl, lengths):
     return S
 
 
+class CpuArm:
+    """The reference's CPU implementation of the path, as far as it can exist here: the Java/Lucene reference cannot
+    run (no JVM in the image), so this is the C/OpenMP oracle restatement (oracle/bsp_oracle.c) on all host cores.
+    Bounded sample: index = the first S genomes of the same reference (<= ~120 Mbp: the oracle's index build is
+    sort-based and slow), reads drawn from them with the same simulator.  At k=10 every term occurs in ~all documents,
+    so per-read cost is linear in the document count: the full-workload estimate is measured reads/s * S/G."""
+
+    def __init__(self, wl, lengths, kept, n_reads, threads=None, algorithm=2):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_lib as ol
+        from biospectra_b200 import synth
+        self.threads = threads or (os.cpu_count() or 1)
+        self.algorithm = algorithm
+        self.S, self.G = len(kept), len(lengths)
+        t0 = time.time()
+        self.ox = ol.OracleIndex(10, False)
+        gl = []
+        for g in sorted(kept):
+            self.ox.add_entry(kept[g])
+            gl.append(np.frombuffer(kept[g], np.uint8))
+        self.ox.finish()
+        self.index_seconds = time.time() - t0
+        self.sample_bp = int(sum(len(x) for x in gl))
+        self.reads, _ = synth.sample_reads_numpy(gl, n_reads, wl["R"], wl["err"], wl["read_seed"] + 1000)
+        self.ox.classify(self.reads[:256], skips=0, algorithm=algorithm, scoring=0, msm=0.5, threads=self.threads)   # warm
+
+    def step(self):
+        t0 = time.time()
+        res = self.ox.classify(self.reads, skips=0, algorithm=self.algorithm, scoring=0, msm=0.5, threads=self.threads)
+        dt = time.time() - t0
+        return dt, res
+
+    def report(self, dt, res):
+        n = len(self.reads)
+        rps_sample = n / dt
+        return {"value": rps_sample * self.S / float(self.G), "unit": "reads/s", "cores": self.threads, "kind": "port",
+                "sample": "oracle restatement of the reference's Lucene path (no JVM in this image): index of the first %d of %d "
+                          "genomes (%.0f Mbp, %d docs), %d reads drawn from them; measured %.1f reads/s on the sample index, "
+                          "scaled by %d/%d because per-read cost is linear in the document count"
+                          % (self.S, self.G, self.sample_bp / 1e6, 2 * self.S, n, rps_sample, self.S, self.G),
+                "measured_reads_per_s_on_sample": rps_sample, "index_seconds": self.index_seconds, "classify_seconds": dt,
+                "classified_fraction": float((res["label"] == 2).mean())}
+
+
 def cpu_baseline(wl, lengths, kept, n_reads, threads=None, algorithm=2):
-    """Times the oracle restatement on the host cores.  Index = kept sample genomes; reads sampled from them
-    with the same simulator.  Per-read cost is linear in the number of documents (at k=10 every term occurs
-    in ~all documents), so the full-index estimate is measured reads/s * S/G."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_lib as ol
-    from biospectra_b200 import synth
-    if threads is None:
-        threads = os.cpu_count() or 1
-    S = len(kept)
-    t0 = time.time()
-    ox = ol.OracleIndex(10, False)
-    gl = []
-    for g in sorted(kept):
-        ox.add_entry(kept[g])
-        gl.append(np.frombuffer(kept[g], np.uint8))
-    ox.finish()
-    t_index = time.time() - t0
-    rng = np.random.Generator(np.random.PCG64(wl["read_seed"] + 1000))
-    reads = []
-    for i in range(n_reads):
-        reads.append(synth.reads_from_genome_numpy(rng, gl[int(rng.integers(0, S))], 1, wl["R"], wl["err"])[0].tobytes())
-    ox.classify(reads[:64], skips=0, algorithm=algorithm, scoring=0, msm=0.5, threads=threads)   # warm
-    t0 = time.time()
-    res = ox.classify(reads, skips=0, algorithm=algorithm, scoring=0, msm=0.5, threads=threads)
-    dt = time.time() - t0
-    sample_bp = int(sum(len(x) for x in gl))
-    rps_sample = n_reads / dt
-    scale = S / float(len(lengths))
-    return {"value": rps_sample * scale, "unit": "reads/s", "cores": threads, "kind": "port",
-            "sample": "oracle restatement (no JVM in this image): index of the first %d of %d genomes (%.0f Mbp, %d docs), "
-                      "%d reads drawn from them; measured %.1f reads/s on the sample index, scaled by %d/%d because per-read "
-                      "cost is linear in the document count" % (S, len(lengths), sample_bp / 1e6, 2 * S, n_reads, rps_sample, S, len(lengths)),
-            "measured_reads_per_s_on_sample": rps_sample, "index_seconds": t_index, "classify_seconds": dt,
-            "classified_fraction": float((res["label"] == 2).mean())}
+    arm = CpuArm(wl, lengths, kept, n_reads, threads, algorithm)
+    dt, res = arm.step()
+    return arm.report(dt, res)
 
 
 def gen_sample_genomes(wl, lengths, S):
@@ -148,19 +177,17 @@ def run_reference(args, wl, lengths):
         return
     S = sample_plan(wl, lengths)
     kept = gen_sample_genomes(wl, lengths, S)
-    n_reads = int(os.environ.get("BSP_CPU_SAMPLE_READS", 300))
-    vals = []
-    last = None
-    for it in range(args.warmup + args.steps):
-        last = cpu_baseline(wl, lengths, kept, n_reads)
-        if it >= args.warmup:
-            vals.append(last)
-    v = float(np.mean([x["value"] for x in vals]))
-    ms = float(np.mean([x["classify_seconds"] for x in vals])) * 1e3
+    n_reads = int(os.environ.get("BSP_CPU_SAMPLE_READS", 200000))
+    arm = CpuArm(wl, lengths, kept, n_reads)
+    for _ in range(args.warmup):
+        arm.step()
+    reps = [arm.report(*arm.step()) for _ in range(args.steps)]
+    v = float(np.mean([x["value"] for x in reps]))
+    ms = float(np.mean([x["classify_seconds"] for x in reps])) * 1e3
     line = {"impl": "reference", "metric": "reads/sec classified", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 scores, f64 accumulate", "data": "synthetic",
-            "config": workload_config(args, wl), "cpu_baseline": dict(last, value=v),
+            "config": workload_config(args, wl), "cpu_baseline": dict(reps[-1], value=v),
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -263,10 +290,10 @@ def main():
     el_dev, kernel_ms, pipe_ms, launches = timed(step_device, args.steps)
     torch.cuda.cudart().cudaProfilerStop()
     # end to end through the host-buffer call
-    host_out = {}
+    host_out = {"r": clf.alloc_outputs(n, pinned=True)}     # caller-provided result arrays, page-locked like the reads
 
     def step_host():
-        host_out["r"] = clf.classify_packed(data["seq_bytes"], data["offsets"])
+        clf.classify_packed(data["seq_bytes"], data["offsets"], out=host_out["r"])
 
     step_host()
     el_e2e, _, _, _ = timed(step_host, args.steps)
@@ -298,7 +325,7 @@ def main():
         top = max((("filter_score_kernel", cnt["filter_reads"]), ("exact_score_kernel", cnt["dense_reads"]),
                    ("score_positional_kernel", cnt["positional_reads"])), key=lambda x: x[1])[0]
         roof = {"bound": "hbm", "kernel": top,
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args, top), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_dense,
                 "csr_formula_bytes_per_launch": alg_bytes_csr, "csr_formula_gbs": alg_bytes_csr / per_launch_s / 1e9 if per_launch_s > 0 else 0.0,
                 "kernel_ms_per_launch": per_launch_s * 1e3,
@@ -323,7 +350,7 @@ def main():
                 "parity_properties": {"source_doc_is_top_hit": recovered, "labels": labels, "dropped": int((res["status"] == 1).sum()),
                                       "errors": int((res["status"] == 2).sum())}}
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl, lengths, data["kept"], int(os.environ.get("BSP_CPU_SAMPLE_READS", 300)),
+            line["cpu_baseline"] = cpu_baseline(wl, lengths, data["kept"], int(os.environ.get("BSP_CPU_SAMPLE_READS", 200000)),
                                                 algorithm={"NAIVE_KMER": 0, "CHAIN_PROXIMITY": 1, "PAIRED_PROXIMITY": 2}[args.algorithm])
         print(json.dumps(line))
     clf.close()

@@ -26,6 +26,7 @@ struct bsp_indexer {
     ~bsp_indexer() { delete ref; if (st) cudaStreamDestroy(st); }
 };
 
+// Per pipeline slot: device scratch of one sub-batch, its stream, events and pinned host mailboxes.
 struct Scratch {
     DevBuf<u8> seq, scan_tmp; DevBuf<i64> seq_off, tok_off, tok_cap;
     DevBuf<u64> tok_key; DevBuf<u32> tok_pos, tok_df, clause_row; DevBuf<float> clause_val;
@@ -33,9 +34,27 @@ struct Scratch {
     DevBuf<FilterStats> fstats;
     DevBuf<i32> part_n; DevBuf<u32> part_doc; DevBuf<float> part_score;
     DevBuf<i32> o_status, o_label, o_nhits, o_ntop, o_doc; DevBuf<float> o_score;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     u8* pin_in = nullptr; size_t pin_in_bytes = 0;
-    u8* pin_out = nullptr; size_t pin_out_bytes = 0;
-    ~Scratch() { if (pin_in) cudaFreeHost(pin_in); if (pin_out) cudaFreeHost(pin_out); }
+    i32* h_counts = nullptr;            // pinned: [0..3] route counts, [4] filter overflow
+    FilterStats* h_fstats = nullptr;    // pinned
+    // state between the two phases of a sub-batch
+    i32 n = 0; int n_tiles = 1, parts_pos = 0, parts_stride = 1, dense_threads = 32; QueryParams qp; bool busy = false;
+    i32 r0 = 0;                         // first read of the sub-batch in the caller's arrays
+    void init() {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+        CUDA_CHECK(cudaMallocHost((void**)&h_counts, 8 * sizeof(i32)));
+        CUDA_CHECK(cudaMallocHost((void**)&h_fstats, sizeof(FilterStats)));
+    }
+    ~Scratch() {
+        if (pin_in) cudaFreeHost(pin_in);
+        if (h_counts) cudaFreeHost(h_counts);
+        if (h_fstats) cudaFreeHost(h_fstats);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (st) cudaStreamDestroy(st);
+    }
 };
 
 struct bsp_classifier {
@@ -43,10 +62,9 @@ struct bsp_classifier {
     bsp_config conf;
     RefStore* ref = nullptr;
     GpuIndex ix;
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t st = nullptr;          // build / introspection stream (= slot 0's stream)
     std::string last_error;
-    Scratch sc;
+    Scratch sc[2];                      // two sub-batches in flight: copies of one overlap the kernels of the other
     // scoring constants
     DevBuf<float> idf_by_df, doc_w, tf16;
     i64 global_docs = 0, global_sum_ttf = 0, doc_base_global = 0;
@@ -54,11 +72,7 @@ struct bsp_classifier {
     std::vector<i32> last_routes;
     i64 counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double score_ms = 0, pipe_ms = 0;
-    ~bsp_classifier() {
-        for (auto& e : ev) if (e) cudaEventDestroy(e);
-        if (st) cudaStreamDestroy(st);
-        delete ref;
-    }
+    ~bsp_classifier() { delete ref; }
 };
 
 static int fail(std::string* slot, int code, const std::string& msg) {
@@ -349,8 +363,8 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
     try {
         h->conf = *conf;
         h->ref = ref;
-        CUDA_CHECK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-        for (auto& e : h->ev) CUDA_CHECK(cudaEventCreate(&e));
+        for (auto& sc : h->sc) sc.init();
+        h->st = h->sc[0].st;
         BuildOptions opt;
         opt.want_tables = conf->dense_tables;
         opt.want_positional = conf->positional;
@@ -472,12 +486,12 @@ struct BatchOut {     // device pointers (any may be null except status)
     i32 *status, *label, *n_hits, *n_top, *top_doc; float* top_score;
 };
 
-// Runs the device pipeline on reads already resident in device memory.
-static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const i64* d_seq_off, i64 total_bytes,
-                               const BatchOut& out) {
+// ---- the device pipeline of one sub-batch, in two phases so that two sub-batches can be in flight:
+//   phase 1 (enqueue only): tokenize -> df -> weights/routing -> route lists; the route counts travel to a pinned mailbox
+//   phase 2: wait for the counts, launch the scorers (grid sizes depend on the counts), merge; everything on sc.st
+static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_seq, const i64* d_seq_off, i64 total_bytes) {
     GpuIndex& ix = h->ix;
-    Scratch& sc = h->sc;
-    cudaStream_t st = h->st;
+    cudaStream_t st = sc.st;
     const int k = ix.k;
     i64 tok_cap_total = total_bytes;        // sum(max(len-k+1,0)) <= total bytes
     sc.tok_off.ensure((size_t)n + 1);
@@ -485,8 +499,10 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
     sc.tok_df.ensure((size_t)tok_cap_total + 1); sc.clause_val.ensure((size_t)tok_cap_total + 1);
     sc.clause_row.ensure((size_t)tok_cap_total + 1);
     sc.n_tok.ensure(n); sc.n_clauses.ensure(n); sc.msm.ensure(n); sc.route.ensure(n); sc.status_in.ensure(n);
-    sc.list_dense.ensure(n); sc.list_pos.ensure(n); sc.counts.ensure(4);
-    CUDA_CHECK(cudaEventRecord(h->ev[0], st));
+    sc.list_dense.ensure(n); sc.list_pos.ensure(n); sc.list_filter.ensure(n); sc.counts.ensure(8);
+    if (!sc.fstats.p) sc.fstats.alloc(1);
+    sc.n = n; sc.busy = true;
+    CUDA_CHECK(cudaEventRecord(sc.ev[0], st));
     // token capacity offsets
     sc.tok_cap.ensure((size_t)n + 1);
     tok_capacity_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_seq_off, n, k, sc.tok_cap.p);
@@ -496,7 +512,7 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
     token_df_kernel<<<(unsigned)ceil_div((i64)n * 32, 256), 256, 0, st>>>(sc.tok_key.p, sc.tok_off.p, sc.n_tok.p, n,
                                                                           ix.direct ? ix.df_dense.p : nullptr, ix.d_segs.p,
                                                                           ix.positional ? (int)ix.segs.size() : 0, sc.tok_df.p);
-    QueryParams qp;
+    QueryParams& qp = sc.qp;
     qp.k = k; qp.skips = h->conf.kmer_skips; qp.min_strand = ix.min_strand; qp.alg = h->conf.query_algorithm;
     qp.sim = h->conf.scoring_algorithm == BSP_BM25 ? SIM_BM25 : SIM_TFIDF;
     qp.msm_ratio = h->conf.query_term_min_should_match;
@@ -513,33 +529,39 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
     weights_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p,
                                                                sc.tok_df.p, h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p,
                                                                sc.n_clauses.p, sc.msm.p, sc.route.p, sc.status_in.p);
-    sc.list_filter.ensure(n);
-    CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 16, st));
+    CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));
     route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, n, sc.list_dense.p, sc.list_pos.p, sc.list_filter.p,
                                                                      sc.counts.p);
     KERNEL_CHECK();
-    i32 counts[4] = {0, 0, 0, 0};
-    CUDA_CHECK(cudaMemcpyAsync(counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(cudaMemcpyAsync(sc.h_counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
     // partial top-10 buffers
-    int dense_threads = (int)std::min<i64>(512, round_up(std::max<i64>(ceil_div(ix.d_pad, EX_DPT), 1), 32));
-    int n_tiles = (int)std::max<i64>(1, ceil_div(ix.d_pad, (i64)dense_threads * EX_DPT));
-    int parts_pos = ix.positional ? (int)ix.segs.size() : 0;
-    int parts_stride = std::max(std::max(n_tiles, parts_pos), 1);
-    i32* part_n; u32* part_doc; float* part_score;
-    sc.part_n.ensure((size_t)n * parts_stride);
-    sc.part_doc.ensure((size_t)n * parts_stride * TOPN);
-    sc.part_score.ensure((size_t)n * parts_stride * TOPN);
-    part_n = sc.part_n.p; part_doc = sc.part_doc.p; part_score = sc.part_score.p;
+    sc.dense_threads = (int)std::min<i64>(512, round_up(std::max<i64>(ceil_div(ix.d_pad, EX_DPT), 1), 32));
+    sc.n_tiles = (int)std::max<i64>(1, ceil_div(ix.d_pad, (i64)sc.dense_threads * EX_DPT));
+    sc.parts_pos = ix.positional ? (int)ix.segs.size() : 0;
+    sc.parts_stride = std::max(std::max(sc.n_tiles, sc.parts_pos), 1);
+    sc.part_n.ensure((size_t)n * sc.parts_stride);
+    sc.part_doc.ensure((size_t)n * sc.parts_stride * TOPN);
+    sc.part_score.ensure((size_t)n * sc.parts_stride * TOPN);
+}
+
+static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out) {
+    GpuIndex& ix = h->ix;
+    cudaStream_t st = sc.st;
+    const i32 n = sc.n;
+    const QueryParams& qp = sc.qp;
+    CUDA_CHECK(cudaStreamSynchronize(st));                  // route counts have arrived
+    i32 counts[4] = {sc.h_counts[0], sc.h_counts[1], sc.h_counts[2], 0};
+    const u32 D = (u32)ix.docs.size();
+    const int n_tiles = sc.n_tiles, parts_pos = sc.parts_pos, parts_stride = sc.parts_stride;
+    i32* part_n = sc.part_n.p; u32* part_doc = sc.part_doc.p; float* part_score = sc.part_score.p;
     SimParams sp; sp.sim = qp.sim; sp.k1p1 = 1.2f + 1.0f;
     const u32 gbase = (u32)h->doc_base_global;
     const Tab4Dev T = ix.tab4_view();
     const int full_topn = (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0;
-    CUDA_CHECK(cudaEventRecord(h->ev[1], st));
+    CUDA_CHECK(cudaEventRecord(sc.ev[1], st));
     i64 launches = 6;
     FilterStats fs = {0, 0, 0};
     if (counts[2] > 0) {
-        if (!sc.fstats.p) sc.fstats.alloc(1);
         CUDA_CHECK(cudaMemsetAsync(sc.fstats.p, 0, sizeof(FilterStats), st));
         int threads = (int)round_up(std::max<i64>(ceil_div(ix.d_pad, FK_DOCS), 1), 32);
         const size_t ring_bytes = (size_t)FK_STAGES * threads * 16;
@@ -554,19 +576,21 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
         KERNEL_CHECK();
         launches++;
         // reads the filter could not bound (exception or candidate overflow) were appended to the exact list
-        CUDA_CHECK(cudaMemcpyAsync(&counts[3], sc.counts.p + 3, 4, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaMemcpyAsync(&fs, sc.fstats.p, sizeof fs, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 4, sc.counts.p + 3, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(sc.h_fstats, sc.fstats.p, sizeof(FilterStats), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
+        counts[3] = sc.h_counts[4];
+        fs = *sc.h_fstats;
     }
     const i32 n_exact = counts[0] + counts[3];
     if (n_exact > 0) {
         unsigned grid = (unsigned)((i64)n_exact * n_tiles);
         if (qp.sim == SIM_TFIDF)
-            exact_score_kernel<SIM_TFIDF><<<grid, dense_threads, 0, st>>>(T, D, h->tf16.p, sc.list_dense.p, sc.tok_off.p, sc.n_tok.p,
+            exact_score_kernel<SIM_TFIDF><<<grid, sc.dense_threads, 0, st>>>(T, D, h->tf16.p, sc.list_dense.p, sc.tok_off.p, sc.n_tok.p,
                 sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, sp.k1p1, gbase, n_tiles, parts_stride,
                 part_n, part_doc, part_score);
         else
-            exact_score_kernel<SIM_BM25><<<grid, dense_threads, 0, st>>>(T, D, h->tf16.p, sc.list_dense.p, sc.tok_off.p, sc.n_tok.p,
+            exact_score_kernel<SIM_BM25><<<grid, sc.dense_threads, 0, st>>>(T, D, h->tf16.p, sc.list_dense.p, sc.tok_off.p, sc.n_tok.p,
                 sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, sp.k1p1, gbase, n_tiles, parts_stride,
                 part_n, part_doc, part_score);
         launches++;
@@ -582,20 +606,50 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
         launches++;
     }
     KERNEL_CHECK();
-    CUDA_CHECK(cudaEventRecord(h->ev[2], st));
+    CUDA_CHECK(cudaEventRecord(sc.ev[2], st));
     merge_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(n, sc.route.p, sc.status_in.p, n_tiles, parts_pos, parts_stride, part_n,
                                                              part_doc, part_score, out.status, out.label, out.n_hits, out.n_top,
                                                              out.top_doc, out.top_score, full_topn);
     KERNEL_CHECK();
-    CUDA_CHECK(cudaEventRecord(h->ev[3], st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    float ms_score = 0, ms_pipe = 0;
-    cudaEventElapsedTime(&ms_score, h->ev[1], h->ev[2]);
-    cudaEventElapsedTime(&ms_pipe, h->ev[0], h->ev[3]);
-    h->score_ms += ms_score; h->pipe_ms += ms_pipe;
+    CUDA_CHECK(cudaEventRecord(sc.ev[3], st));
     h->counters[0] += n; h->counters[1] += n_exact; h->counters[2] += counts[1]; h->counters[3] += counts[2] - counts[3];
     h->counters[4] += launches + 1; h->counters[5] += (i64)fs.candidates; h->counters[6] += (i64)fs.forced;
     h->counters[7] += counts[3];
+}
+
+// after the slot's stream has been synchronised: add its CUDA-event timings to the handle
+static void pipeline_collect(bsp_classifier* h, Scratch& sc) {
+    if (!sc.busy) return;
+    float ms_score = 0, ms_pipe = 0;
+    cudaEventElapsedTime(&ms_score, sc.ev[1], sc.ev[2]);
+    cudaEventElapsedTime(&ms_pipe, sc.ev[0], sc.ev[3]);
+    h->score_ms += ms_score; h->pipe_ms += ms_pipe;
+    sc.busy = false;
+}
+
+// Runs the device pipeline on reads already resident in device memory (one sub-batch, slot 0).
+static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const i64* d_seq_off, i64 total_bytes,
+                               const BatchOut& out) {
+    Scratch& sc = h->sc[0];
+    pipeline_phase1(h, sc, n, d_seq, d_seq_off, total_bytes);
+    pipeline_phase2(h, sc, out);
+    CUDA_CHECK(cudaStreamSynchronize(sc.st));
+    pipeline_collect(h, sc);
+}
+
+// D2H of a finished sub-batch into the caller's arrays (async on the slot's stream; pinned destinations overlap
+// with the other slot's kernels, pageable ones are staged by the driver)
+static void enqueue_outputs(bsp_classifier* h, Scratch& sc, i32* status, i32* label, i32* n_hits, i32* n_top, i32* top_doc,
+                            float* top_score) {
+    const i32 r0 = sc.r0, m = sc.n;
+    cudaStream_t st = sc.st;
+    CUDA_CHECK(cudaMemcpyAsync(status + r0, sc.o_status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    if (label) CUDA_CHECK(cudaMemcpyAsync(label + r0, sc.o_label.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    if (n_hits) CUDA_CHECK(cudaMemcpyAsync(n_hits + r0, sc.o_nhits.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    if (n_top) CUDA_CHECK(cudaMemcpyAsync(n_top + r0, sc.o_ntop.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    if (top_doc) CUDA_CHECK(cudaMemcpyAsync(top_doc + (i64)r0 * TOPN, sc.o_doc.p, (size_t)m * TOPN * 4, cudaMemcpyDeviceToHost, st));
+    if (top_score) CUDA_CHECK(cudaMemcpyAsync(top_score + (i64)r0 * TOPN, sc.o_score.p, (size_t)m * TOPN * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h->last_routes.data() + r0, sc.route.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
 }
 
 static int classify_packed_impl(bsp_classifier* h, i32 n, const char* seq_bytes, const i64* seq_offsets,
@@ -608,39 +662,57 @@ static int classify_packed_impl(bsp_classifier* h, i32 n, const char* seq_bytes,
     for (auto& c : h->counters) c = 0;
     h->score_ms = 0; h->pipe_ms = 0;
     h->last_routes.assign(n, 0);
-    const i32 SUB = (i32)env_i64("BSP_SUB_BATCH", 262144);
-    Scratch& sc = h->sc;
-    cudaStream_t st = h->st;
-    for (i32 r0 = 0; r0 < n; r0 += SUB) {
-        i32 m = std::min(SUB, n - r0);
-        i64 b0 = seq_offsets[r0], b1 = seq_offsets[r0 + m];
-        i64 bytes = b1 - b0;
-        sc.seq.ensure((size_t)bytes + 64);
-        sc.seq_off.ensure((size_t)m + 1);
-        // offsets rebased to the sub-batch
-        size_t in_need = (size_t)(m + 1) * 8;
-        if (in_need > sc.pin_in_bytes) {
-            if (sc.pin_in) cudaFreeHost(sc.pin_in);
-            sc.pin_in = nullptr; sc.pin_in_bytes = 0;
-            CUDA_CHECK(cudaMallocHost((void**)&sc.pin_in, in_need + in_need / 4));
-            sc.pin_in_bytes = in_need + in_need / 4;
+    const i32 SUB = (i32)std::max<i64>(1, env_i64("BSP_SUB_BATCH", 131072));
+    // Software pipeline over sub-batches, two slots: while slot A's scorers run, slot B's reads are copied in and
+    // tokenised and slot A's previous results are copied out.
+    int slot = 0;
+    Scratch* prev = nullptr;
+    try {
+        for (i32 r0 = 0; r0 < n; r0 += SUB) {
+            Scratch& sc = h->sc[slot];
+            if (sc.busy) {          // the slot's previous sub-batch (two iterations ago) must be completely done
+                CUDA_CHECK(cudaStreamSynchronize(sc.st));
+                pipeline_collect(h, sc);
+            }
+            const i32 m = std::min(SUB, n - r0);
+            const i64 b0 = seq_offsets[r0], bytes = seq_offsets[r0 + m] - b0;
+            sc.seq.ensure((size_t)bytes + 64);
+            sc.seq_off.ensure((size_t)m + 1);
+            const size_t in_need = (size_t)(m + 1) * 8;           // offsets rebased to the sub-batch, staged in pinned memory
+            if (in_need > sc.pin_in_bytes) {
+                if (sc.pin_in) cudaFreeHost(sc.pin_in);
+                sc.pin_in = nullptr; sc.pin_in_bytes = 0;
+                CUDA_CHECK(cudaMallocHost((void**)&sc.pin_in, in_need + in_need / 4));
+                sc.pin_in_bytes = in_need + in_need / 4;
+            }
+            i64* po = (i64*)sc.pin_in;
+            for (i32 i = 0; i <= m; i++) po[i] = seq_offsets[r0 + i] - b0;
+            CUDA_CHECK(cudaMemcpyAsync(sc.seq_off.p, po, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, sc.st));
+            if (bytes) CUDA_CHECK(cudaMemcpyAsync(sc.seq.p, seq_bytes + b0, (size_t)bytes, cudaMemcpyHostToDevice, sc.st));
+            sc.o_status.ensure(m); sc.o_label.ensure(m); sc.o_nhits.ensure(m); sc.o_ntop.ensure(m);
+            sc.o_doc.ensure((size_t)m * TOPN); sc.o_score.ensure((size_t)m * TOPN);
+            sc.r0 = r0;
+            pipeline_phase1(h, sc, m, sc.seq.p, sc.seq_off.p, bytes);
+            if (prev) {             // the other slot: scorers + merge + copy-out, queued behind this slot's phase 1
+                BatchOut bo{prev->o_status.p, prev->o_label.p, prev->o_nhits.p, prev->o_ntop.p, prev->o_doc.p, prev->o_score.p};
+                pipeline_phase2(h, *prev, bo);
+                enqueue_outputs(h, *prev, status, label, n_hits, n_top, top_doc, top_score);
+            }
+            prev = &sc;
+            slot ^= 1;
         }
-        i64* po = (i64*)sc.pin_in;
-        for (i32 i = 0; i <= m; i++) po[i] = seq_offsets[r0 + i] - b0;
-        CUDA_CHECK(cudaMemcpyAsync(sc.seq_off.p, po, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, st));
-        if (bytes) CUDA_CHECK(cudaMemcpyAsync(sc.seq.p, seq_bytes + b0, (size_t)bytes, cudaMemcpyHostToDevice, st));
-        sc.o_status.ensure(m); sc.o_label.ensure(m); sc.o_nhits.ensure(m); sc.o_ntop.ensure(m);
-        sc.o_doc.ensure((size_t)m * TOPN); sc.o_score.ensure((size_t)m * TOPN);
-        BatchOut bo{sc.o_status.p, sc.o_label.p, sc.o_nhits.p, sc.o_ntop.p, sc.o_doc.p, sc.o_score.p};
-        classify_on_device(h, m, sc.seq.p, sc.seq_off.p, bytes, bo);
-        CUDA_CHECK(cudaMemcpyAsync(status + r0, sc.o_status.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-        if (label) CUDA_CHECK(cudaMemcpyAsync(label + r0, sc.o_label.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-        if (n_hits) CUDA_CHECK(cudaMemcpyAsync(n_hits + r0, sc.o_nhits.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-        if (n_top) CUDA_CHECK(cudaMemcpyAsync(n_top + r0, sc.o_ntop.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-        if (top_doc) CUDA_CHECK(cudaMemcpyAsync(top_doc + (i64)r0 * TOPN, sc.o_doc.p, (size_t)m * TOPN * 4, cudaMemcpyDeviceToHost, st));
-        if (top_score) CUDA_CHECK(cudaMemcpyAsync(top_score + (i64)r0 * TOPN, sc.o_score.p, (size_t)m * TOPN * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaMemcpyAsync(h->last_routes.data() + r0, sc.route.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (prev) {
+            BatchOut bo{prev->o_status.p, prev->o_label.p, prev->o_nhits.p, prev->o_ntop.p, prev->o_doc.p, prev->o_score.p};
+            pipeline_phase2(h, *prev, bo);
+            enqueue_outputs(h, *prev, status, label, n_hits, n_top, top_doc, top_score);
+        }
+        for (auto& sc : h->sc) {
+            CUDA_CHECK(cudaStreamSynchronize(sc.st));
+            pipeline_collect(h, sc);
+        }
+    } catch (...) {
+        for (auto& sc : h->sc) { cudaStreamSynchronize(sc.st); sc.busy = false; }
+        throw;
     }
     return BSP_OK;
     API_CATCH(h)
@@ -827,7 +899,7 @@ BSP_API int bsp_read_cost(bsp_classifier* h, int32_t n, const char* seq_bytes, c
     if (!seq_bytes || !seq_offsets) return fail(&h->last_error, BSP_ERR_ARG, "null argument");
     CUDA_CHECK(cudaSetDevice(h->conf.device));
     GpuIndex& ix = h->ix;
-    Scratch& sc = h->sc;
+    Scratch& sc = h->sc[0];
     cudaStream_t st = h->st;
     if (!ix.direct && !ix.positional) return fail(&h->last_error, BSP_ERR_STATE, "no term statistics resident");
     DevBuf<unsigned long long> d_out; d_out.alloc(8);

@@ -84,13 +84,25 @@ class Classifier:
         data = b"".join(_b(s) for s in seqs)
         return np.frombuffer(data, np.uint8), off
 
-    def classify_packed(self, seq_bytes: np.ndarray, offsets: np.ndarray):
+    @staticmethod
+    def alloc_outputs(n: int, pinned: bool = False):
+        """result arrays of bsp_classify_packed; pinned=True page-locks them (torch) so that the copy-out of one
+        sub-batch overlaps the kernels of the next"""
+        shapes = {"status": ((n,), np.int32), "label": ((n,), np.int32), "n_hits": ((n,), np.int32), "n_top": ((n,), np.int32),
+                  "top_doc": ((n, 10), np.int32), "top_score": ((n, 10), np.float32)}
+        if not pinned:
+            return {k: np.zeros(sh, dt) for k, (sh, dt) in shapes.items()}
+        import torch
+        keep = {k: torch.zeros(sh, dtype=torch.int32 if dt == np.int32 else torch.float32, pin_memory=True)
+                for k, (sh, dt) in shapes.items()}
+        out = {k: v.numpy() for k, v in keep.items()}
+        out["_pinned"] = keep
+        return out
+
+    def classify_packed(self, seq_bytes: np.ndarray, offsets: np.ndarray, out=None):
         n = len(offsets) - 1
-        out = {
-            "status": np.zeros(n, np.int32), "label": np.zeros(n, np.int32), "n_hits": np.zeros(n, np.int32),
-            "n_top": np.zeros(n, np.int32), "top_doc": np.full((n, 10), -1, np.int32),
-            "top_score": np.zeros((n, 10), np.float32),
-        }
+        if out is None:
+            out = self.alloc_outputs(n)
         seq_bytes = np.ascontiguousarray(seq_bytes, np.uint8)
         offsets = np.ascontiguousarray(offsets, np.int64)
         _lib.check(self.L.bsp_classify_packed(self.h, n, seq_bytes.ctypes.data if seq_bytes.size else None, offsets.ctypes.data,

@@ -57,6 +57,40 @@ def reads_from_genome_numpy(rng, genome: np.ndarray, n: int, R: int, err: float)
     return out
 
 
+def sample_reads_numpy(genomes, n_reads: int, R: int, err: float, seed: int):
+    """Vectorised version of reads_from_genome_numpy over several genomes (uint8 arrays): same distribution
+    (uniform genome by length, uniform start, length R + U{-R/10..R/10-1}, exactly floor(len*err) substitutions at
+    distinct positions).  -> (list of bytes, source genome index array)"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lens_g = np.array([len(g) for g in genomes], np.int64)
+    per = rng.multinomial(n_reads, lens_g / lens_g.sum())
+    maxlen = R + max(R // 5, 1)
+    out, src = [], []
+    for gi, g in enumerate(genomes):
+        n = int(per[gi])
+        if not n:
+            continue
+        L = len(g)
+        ln = R + rng.integers(0, max(R // 5, 1), n) - R // 10
+        ln = np.minimum(np.where(ln <= 0, R, ln), L)
+        st = (rng.random(n) * (L - ln + 1)).astype(np.int64)
+        st = np.minimum(st, L - ln)
+        cols = np.arange(maxlen)[None, :]
+        valid = cols < ln[:, None]
+        win = g[np.minimum(st[:, None] + cols, L - 1)]
+        ne = np.floor(ln * err).astype(np.int64)
+        key = np.where(valid, rng.random((n, maxlen)), 2.0)
+        rank = key.argsort(axis=1).argsort(axis=1)
+        sub = (rank < ne[:, None]) & valid
+        code = np.searchsorted(ASCII, win)
+        win = np.where(sub, ASCII[(code + rng.integers(1, 4, (n, maxlen))) % 4], win)
+        for i in range(n):
+            out.append(win[i, :ln[i]].tobytes())
+        src.extend([gi] * n)
+    order = rng.permutation(len(out))
+    return [out[i] for i in order], np.asarray(src, np.int64)[order]
+
+
 def make_small_workload(n_genomes=10, genome_len=2_000_000, n_reads=10_000, R=100, err=0.04, seed=1, read_seed=11):
     """C1-style workload entirely on the CPU.  Returns (genomes[list of bytes], reads[list of bytes], src[list])."""
     genomes = [genome_numpy(seed, g, genome_len) for g in range(n_genomes)]
