@@ -154,10 +154,38 @@ class CpuArm:
                 "classified_fraction": float((res["label"] == 2).mean())}
 
 
-def cpu_baseline(wl, lengths, kept, n_reads, threads=None, algorithm=2):
+def cpu_baseline(wl, lengths, kept, n_reads, threads=None, algorithm=2, gpu_check=None):
     arm = CpuArm(wl, lengths, kept, n_reads, threads, algorithm)
     dt, res = arm.step()
-    return arm.report(dt, res)
+    rep = arm.report(dt, res)
+    if gpu_check is not None:
+        rep["gpu_parity_on_sample"] = gpu_check(arm, res)
+    return rep
+
+
+def gpu_parity_on_sample(kept, qconf_kw, device):
+    """The oracle is the checker here, never the thing measured: index the CPU arm's sample genomes with the CUDA library
+    and require bit-identical results (status, label, hit count, hit doc ids and score bit patterns) on the arm's reads."""
+    def check(arm, res_o):
+        from biospectra_b200 import Indexer
+        ix = Indexer(shipped_config(device=device))
+        for g in sorted(kept):
+            ix.add_entry("%d.fna" % g, "syn|%d|" % g, "", kept[g])
+        clf = ix.close_to_classifier(shipped_config(device=device, **qconf_kw))
+        try:
+            os.environ["BSP_FILTER"] = "1"
+            res_g = clf.classify_batch(arm.reads)
+        finally:
+            os.environ.pop("BSP_FILTER", None)
+            clf.close()
+        n = len(arm.reads)
+        same = (res_g["status"] == res_o["status"]) & (res_g["label"] == res_o["label"]) & (res_g["n_hits"] == res_o["n_hits"])
+        for j in range(10):
+            live = res_o["n_hits"] > j
+            same &= ~live | ((res_g["top_doc"][:, j] == res_o["top_doc"][:, j]) &
+                             (res_g["top_score"][:, j].view(np.uint32) == res_o["top_score"][:, j].view(np.uint32)))
+        return {"reads": n, "identical": int(same.sum()), "mismatching_reads": np.nonzero(~same)[0][:10].tolist()}
+    return check
 
 
 def gen_sample_genomes(wl, lengths, S):
@@ -351,7 +379,8 @@ def main():
                                       "errors": int((res["status"] == 2).sum())}}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl, lengths, data["kept"], int(os.environ.get("BSP_CPU_SAMPLE_READS", 200000)),
-                                                algorithm={"NAIVE_KMER": 0, "CHAIN_PROXIMITY": 1, "PAIRED_PROXIMITY": 2}[args.algorithm])
+                                                algorithm={"NAIVE_KMER": 0, "CHAIN_PROXIMITY": 1, "PAIRED_PROXIMITY": 2}[args.algorithm],
+                                                gpu_check=gpu_parity_on_sample(data["kept"], dict(query_algorithm=args.algorithm), local))
         print(json.dumps(line))
     clf.close()
     if world > 1:
