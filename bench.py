@@ -364,8 +364,10 @@ def main():
                 "warmup": args.warmup, "ms_per_step": el_dev / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 scores, f64 accumulate", "data": "synthetic", "config": workload_config(args, wl),
                 "clocks": sampler.summary(),
-                "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(total_bytes + 8 * (n + 1)),
-                        "d2h_bytes_per_step": int(n * (4 * 4 + 80) + 4 * n)},
+                "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(total_bytes + 8 * (n + 1)) * world,
+                        "d2h_bytes_per_step": int(n * (4 * 4 + 80) + 4 * n) * world,
+                        "note": "bsp_classify_packed with page-locked host buffers: reads + offsets in, status/label/n_hits/n_top/"
+                                "top_doc/top_score/routes out, all inside the timed region; bytes are summed over ranks"},
                 "gpu_launches": int(launches), "roofline": roof,
                 "probes_per_s": cost["unique_terms"] * world * steps / el_dev,
                 "device_event_ms_per_step": pipe_ms / steps,
