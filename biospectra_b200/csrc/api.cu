@@ -31,7 +31,7 @@ struct Scratch {
     DevBuf<u8> seq, scan_tmp; DevBuf<i64> seq_off, tok_off, tok_cap;
     DevBuf<u64> tok_key; DevBuf<u32> tok_pos, tok_df, clause_row; DevBuf<float> clause_val;
     DevBuf<i32> n_tok, n_clauses, msm, route, status_in, list_dense, list_pos, list_filter, counts;
-    DevBuf<FilterStats> fstats;
+    DevBuf<FilterStats> fstats; DevBuf<float2> vrange;
     DevBuf<i32> part_n; DevBuf<u32> part_doc; DevBuf<float> part_score;
     DevBuf<i32> o_status, o_label, o_nhits, o_ntop, o_doc; DevBuf<float> o_score;
     cudaStream_t st = nullptr;
@@ -499,7 +499,7 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     sc.tok_df.ensure((size_t)tok_cap_total + 1); sc.clause_val.ensure((size_t)tok_cap_total + 1);
     sc.clause_row.ensure((size_t)tok_cap_total + 1);
     sc.n_tok.ensure(n); sc.n_clauses.ensure(n); sc.msm.ensure(n); sc.route.ensure(n); sc.status_in.ensure(n);
-    sc.list_dense.ensure(n); sc.list_pos.ensure(n); sc.list_filter.ensure(n); sc.counts.ensure(8);
+    sc.list_dense.ensure(n); sc.list_pos.ensure(n); sc.list_filter.ensure(n); sc.counts.ensure(8); sc.vrange.ensure(n);
     if (!sc.fstats.p) sc.fstats.alloc(1);
     sc.n = n; sc.busy = true;
     CUDA_CHECK(cudaEventRecord(sc.ev[0], st));
@@ -528,7 +528,7 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
                    (filter_mode == 1 || D >= 1024);
     weights_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p,
                                                                sc.tok_df.p, h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p,
-                                                               sc.n_clauses.p, sc.msm.p, sc.route.p, sc.status_in.p);
+                                                               sc.n_clauses.p, sc.msm.p, sc.route.p, sc.status_in.p, sc.vrange.p);
     CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));
     route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, n, sc.list_dense.p, sc.list_pos.p, sc.list_filter.p,
                                                                      sc.counts.p);
@@ -571,8 +571,8 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
             attr_set[h->conf.device & 63] = true;
         }
         filter_score_kernel<<<(unsigned)counts[2], threads, ring_bytes, st>>>(T, D, h->tf16.p, sc.list_filter.p, sc.tok_off.p, sc.n_tok.p,
-            sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n, part_doc,
-            part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p, full_topn, 1u);
+            sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.vrange.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n,
+            part_doc, part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p, full_topn, 1u);
         KERNEL_CHECK();
         launches++;
         // reads the filter could not bound (exception or candidate overflow) were appended to the exact list

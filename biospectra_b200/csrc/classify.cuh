@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(128) weights_kernel(const u8* __restrict__ seq
                                                        QueryParams qp,
                                                        float* __restrict__ clause_val, u32* __restrict__ clause_row,
                                                        i32* __restrict__ n_clauses, i32* __restrict__ msm_out,
-                                                       i32* __restrict__ route, i32* __restrict__ status) {
+                                                       i32* __restrict__ route, i32* __restrict__ status,
+                                                       float2* __restrict__ vrange /* per read: (max, min) clause value */) {
     const i32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_reads) return;
     const i64 base = tok_off[r];
@@ -310,11 +311,15 @@ __global__ void __launch_bounds__(128) weights_kernel(const u8* __restrict__ seq
         sum_sq = __fmul_rn(sum_sq, 1.0f);                                           // BooleanWeight#getValueForNormalization
         float qn = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn((double)sum_sq)));   // DefaultSimilarity#queryNorm
         if (isinf(qn) || isnan(qn)) qn = 1.0f;                                      // IndexSearcher#createNormalizedWeight
+        float vmax = 0.0f, vmin = 3.0e38f;
         for (i32 c = 0; c < nc; c++) {
             float idf = clause_val[base + c];
             float qw = __fmul_rn(__fmul_rn(idf, 1.0f), __fmul_rn(qn, 1.0f));        // IDFStats#normalize
-            clause_val[base + c] = __fmul_rn(qw, idf);
+            const float v = __fmul_rn(qw, idf);
+            clause_val[base + c] = v;
+            vmax = fmaxf(vmax, v); vmin = fminf(vmin, v);
         }
+        vrange[r] = make_float2(vmax, vmin);
     }   // BM25Stats#normalize: weight = idf * 1 * 1
     if (dense) {
         const u8* s = seq + seq_off[r];

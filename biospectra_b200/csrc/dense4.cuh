@@ -222,7 +222,6 @@ __device__ __forceinline__ u32 cell_code(const Tab4Dev& T, u32 row, u32 doc) {
 #define FK_DOCS 32                 // docs per thread: one 16-byte vector per row
 #define FK_MAX_CLAUSES 255         // u8 match counters
 #define FK_CAND_CAP 128
-#define FK_EXC_CAP 64
 #define FK_CODE_CAP 6144           // candidate x clause cells staged in shared memory for the exact pass
 #define FK_STAGES 8                // rows in flight per thread (cp.async ring in shared memory)
 #define FK_QMAX 255.0f
@@ -272,29 +271,37 @@ __device__ __forceinline__ float estimate(u32 Q, u32 m, i32 need, float nrm) {
     return (float)t * nrm;
 }
 
+// exception entry of (row c, doc d): binary search in the row's sorted doc list; 0 if the cell is a true zero
+__device__ __forceinline__ float exc_lookup(const Tab4Dev& T, u32 a, u32 n, u32 d) {
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (__ldg(T.exc_doc + a + mid) < d) lo = mid + 1; else hi = mid;
+    }
+    return (lo < n && __ldg(T.exc_doc + a + lo) == d) ? __ldg(T.exc_freq + a + lo) : 0.0f;
+}
+
 __global__ void __launch_bounds__(512) filter_score_kernel(
         Tab4Dev T, u32 n_docs, const float* __restrict__ tf16, const i32* __restrict__ read_list,
         const i64* __restrict__ tok_off, const i32* __restrict__ n_tok, const float* __restrict__ clause_val,
         const u32* __restrict__ clause_row, const i32* __restrict__ n_clauses, const i32* __restrict__ msm,
-        const float* __restrict__ doc_w, int alg, u32 global_doc_base, int parts_stride, i32* __restrict__ part_n,
-        u32* __restrict__ part_doc, float* __restrict__ part_score, i32* __restrict__ route,
+        const float2* __restrict__ read_vrange, const float* __restrict__ doc_w, int alg, u32 global_doc_base, int parts_stride,
+        i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score, i32* __restrict__ route,
         i32* __restrict__ overflow_list, i32* __restrict__ overflow_count, FilterStats* __restrict__ stats, int full_topn,
         u32 one /* = 1, see add_fma_pipe */) {
     __shared__ uint2 s_lut[FK_MAX_CLAUSES + 1];          // pair clauses: q for codes 0..3 | 4..7
     __shared__ u32 s_row[FK_MAX_CLAUSES + 1];
     __shared__ float s_val[FK_MAX_CLAUSES + 1];
+    __shared__ u32 s_exa[FK_MAX_CLAUSES + 1], s_exn[FK_MAX_CLAUSES + 1];     // exception list of each clause's row
+    __shared__ u8 s_exrows[FK_MAX_CLAUSES + 1];          // the clauses whose row has exceptions
     __shared__ float s_tf[16];
-    __shared__ u64 s_red[33];
     __shared__ u32 s_sel[16 * TOPN + 1];
+    __shared__ u32 s_wmax[16];
     __shared__ u32 s_cand[FK_CAND_CAP];
     __shared__ u64 s_ckey[FK_CAND_CAP];
-    __shared__ u32 s_exc_c[FK_EXC_CAP], s_exc_d[FK_EXC_CAP];
-    __shared__ float s_exc_f[FK_EXC_CAP];
-    __shared__ u32 s_exc_q[FK_EXC_CAP];
     __shared__ u8 s_code[FK_CODE_CAP];
-    __shared__ int s_ncand, s_nexc;
-    __shared__ u32 s_excsum, s_qmin;
-    __shared__ float s_scale;
+    __shared__ int s_ncand, s_nexrows, s_over;
+    __shared__ u32 s_qmin, s_nexc;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
     const i32 r = read_list[blockIdx.x];
@@ -302,60 +309,32 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     const i32 n = n_tok[r], nc = n_clauses[r];
     const i32 n_pair = alg == ALG_NAIVE ? 0 : (alg == ALG_CHAIN ? nc : n / 2);
     const i32 need = max(1, msm[r]);
+    // scale S: S * value_c * tf(7) <= 255 for every clause; q_min = smallest non-zero cell weight (weights_kernel
+    // recorded the largest and smallest clause value of the read)
+    const float2 vr = read_vrange[r];
+    const float S = FK_QMAX / (vr.x * tf16[T4_PAIR_MAX]);
     if (threadIdx.x < 16) s_tf[threadIdx.x] = tf16[threadIdx.x];
-    if (threadIdx.x == 0) { s_ncand = 0; s_nexc = 0; s_excsum = 0; }
-    // ---- stage clauses; scale S: S * value_c * tf(7) <= 255 for every clause; q_min = smallest non-zero weight
-    float vmax = 0.0f, vmin = 3.0e38f;
+    if (threadIdx.x == 0) { s_ncand = 0; s_nexrows = 0; s_over = 0; s_nexc = 0; s_qmin = (u32)__float2int_rn(S * vr.y); }
+    __syncthreads();
     for (i32 c = threadIdx.x; c < nc; c += blockDim.x) {
         const float v = clause_val[base + c];
+        const u32 row = clause_row[base + c];
         s_val[c] = v;
-        s_row[c] = clause_row[base + c];
-        vmax = fmaxf(vmax, v);
-        vmin = fminf(vmin, v);
-    }
-    {
-        // values are > 0: bit order = float order; the minimum rides along complemented
-        const u64 packed = ((u64)__float_as_uint(vmax) << 32) | (u64)(0xFFFFFFFFu - __float_as_uint(vmin));
-        const u64 m = block_max_u64(packed, s_red);
-        if (threadIdx.x == 0) {
-            const float S = FK_QMAX / (__uint_as_float((u32)(m >> 32)) * tf16[T4_PAIR_MAX]);
-            s_scale = S;
-            s_qmin = (u32)__float2int_rn(S * __uint_as_float(0xFFFFFFFFu - (u32)(m & 0xFFFFFFFFull)));   // smallest table weight
-        }
-    }
-    __syncthreads();
-    const float S = s_scale;
-    for (i32 c = threadIdx.x; c < nc; c += blockDim.x) {
-        const float sv = S * s_val[c];
+        s_row[c] = row;
+        const float sv = S * v;
         if (c < n_pair) {
             u32 q[8];
             q[0] = 0;
 #pragma unroll
-            for (int j = 1; j < 8; j++) q[j] = min((u32)__float2int_rn(sv * s_tf[j]), 255u);
+            for (int j = 1; j < 8; j++) q[j] = min((u32)__float2int_rn(sv * tf16[j]), 255u);
             s_lut[c] = make_uint2(q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24), q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24));
         }
-        // exceptions of this clause's row
-        const u32 row = s_row[c];
         const u32 a = T.exc_off[row], b = T.exc_off[row + 1];
-        for (u32 j = a; j < b; j++) {
-            int idx = atomicAdd(&s_nexc, 1);
-            if (idx < FK_EXC_CAP) {
-                const float f = T.exc_freq[j];
-                const u32 qe = (u32)min(__float2int_rn(sv * tf_of(f)), 1 << 20);      // same quantisation as the table cells
-                s_exc_c[idx] = (u32)c; s_exc_d[idx] = T.exc_doc[j]; s_exc_f[idx] = f; s_exc_q[idx] = qe;
-                atomicAdd(&s_excsum, qe);
-                atomicMin(&s_qmin, qe);
-            }
-        }
+        s_exa[c] = a;
+        s_exn[c] = b - a;
+        if (b > a) s_exrows[atomicAdd(&s_nexrows, 1)] = (u8)c;
     }
     __syncthreads();
-    const int n_exc = s_nexc;
-    // u16 lanes: pair-row weights <= 255, term-row weights <= 255*tf(14)/tf(7) < 362, plus whatever the exception cells add
-    bool overflow = n_exc > FK_EXC_CAP || 255u * (u32)n_pair + 362u * (u32)(nc - n_pair) + s_excsum > 65535u;
-    // exact score of doc d = E(d)/(S*nc) * (1 +- delta): each weight errs by <= 0.51 and is >= q_min;
-    // FK_REL_SLACK covers the float roundings of Lucene's score and of the estimate
-    const float qmin = (float)s_qmin;
-    const float delta = qmin >= 2.0f ? FK_ROUND_SLACK / qmin + FK_REL_SLACK : 1.0f;
 
     // ---- pass 1: stream the rows.  Thread owns docs [32t, 32t+32): wacc[i] = u16 lanes (doc 2i, 2i+1),
     //      cacc[j] = u8 lanes (docs 4j..4j+3)
@@ -367,7 +346,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
 #pragma unroll
     for (int i = 0; i < 8; i++) cacc[i] = 0;
     const u8* tbase = T.tab + (u64)threadIdx.x * 16;
-    if (active && !overflow) {
+    if (active) {
         // Each thread prefetches its own 16-byte slice of the next FK_STAGES rows into its private slots of the
         // ring (no cross-thread hand-off, so no barriers): FK_STAGES x 16 B in flight per thread.
         extern __shared__ __align__(16) uint4 ring[];
@@ -380,7 +359,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         }
         i32 c = 0;
 #pragma unroll 1
-        for (; c + 2 <= n_pair; c += 2) {             // two pair rows per iteration: the lane adds pair up (IADD3)
+        for (; c + 2 <= n_pair; c += 2) {             // two pair rows per iteration
             cp_async_wait<FK_STAGES - 2>();
             uint4* my0 = slot + (c % FK_STAGES) * stride;
             uint4* my1 = slot + ((c + 1) % FK_STAGES) * stride;
@@ -424,24 +403,41 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
             if (c + FK_STAGES < nc) cp_async16(my, tbase + (u64)s_row[c + FK_STAGES] * T.row_bytes);
             cp_async_commit();
         }
-    }
-    // ---- exception cells (stored as 0 in the table) join their doc's lanes: predicated, statically indexed adds
-    if (active && !overflow) {
-        for (int e = 0; e < n_exc; e++) {
-            const u32 d = s_exc_d[e];
-            if ((d >> 5) == threadIdx.x) {
-                const u32 li = d & 31u, qv = s_exc_q[e] << (16 * (li & 1u)), one = 1u << (8 * (li & 3u));
+        // ---- exception cells (stored as 0 in the table) of this thread's docs join their lanes with the same
+        //      quantisation: per listed row, binary search to the thread's doc range
+        const int n_exrows = s_nexrows;
+        u32 exc_sum = 0, exc_cnt = 0;
+#pragma unroll 1
+        for (int i = 0; i < n_exrows; i++) {
+            const u32 c = s_exrows[i], a = s_exa[c], ne = s_exn[c];
+            u32 lo = 0, hi = ne;
+            while (lo < hi) {
+                const u32 mid = (lo + hi) >> 1;
+                if (__ldg(T.exc_doc + a + mid) < d0) lo = mid + 1; else hi = mid;
+            }
+#pragma unroll 1
+            for (; lo < ne; lo++) {
+                const u32 d = __ldg(T.exc_doc + a + lo);
+                if (d >= d0 + FK_DOCS) break;
+                const u32 qe = (u32)min(__float2int_rn(S * s_val[c] * tf_of(__ldg(T.exc_freq + a + lo))), 1 << 20);
+                const u32 li = d - d0, qv = qe << (16 * (li & 1u)), cnt1 = 1u << (8 * (li & 3u));
 #pragma unroll
-                for (int i = 0; i < 16; i++) wacc[i] += (u32)i == (li >> 1) ? qv : 0u;
+                for (int k = 0; k < 16; k++) wacc[k] += (u32)k == (li >> 1) ? qv : 0u;     // predicated, statically indexed
 #pragma unroll
-                for (int i = 0; i < 8; i++) cacc[i] += (u32)i == (li >> 2) ? one : 0u;
+                for (int k = 0; k < 8; k++) cacc[k] += (u32)k == (li >> 2) ? cnt1 : 0u;
+                exc_sum += qe;
+                exc_cnt++;
+                atomicMin(&s_qmin, qe);
             }
         }
+        // u16 lanes: pair-row weights <= 255, term-row weights <= 255*tf(14)/tf(7) < 362, plus this thread's exception cells
+        if (255u * (u32)n_pair + 362u * (u32)(nc - n_pair) + exc_sum > 65535u) s_over = 1;
+        if (exc_cnt) atomicAdd(&s_nexc, exc_cnt);
     }
     // ---- pass 2: per-thread best estimate, then the block's 10th best (full list) or best (result set only).
     //      Padded docs have no cells (m = 0).
     float e_best = 0.0f;
-    if (active && !overflow) {
+    if (active) {
 #pragma unroll
         for (int i4 = 0; i4 < FK_DOCS; i4 += 4) {
             const float4 nv = *reinterpret_cast<const float4*>(doc_w + d0 + i4);
@@ -457,37 +453,46 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     }
     // full_topn: 10 docs are known to score >= tau_e*(1-delta); otherwise only the docs that can tie at the maximum
     // matter (Classifier.java:358-366 keeps the hits equal to the top score), so tau_e is the best estimate
-    const u32 sel = full_topn ? block_tenth_largest_u32(__float_as_uint(e_best), s_sel)
-                              : (u32)block_max_u64((u64)__float_as_uint(e_best), s_red);
+    u32 sel;
+    if (full_topn) sel = block_tenth_largest_u32(__float_as_uint(e_best), s_sel);
+    else {
+        const u32 wm = warp_max_u32(__float_as_uint(e_best));
+        if (lane == 0) s_wmax[warp] = wm;
+        __syncthreads();
+        sel = 0;
+        for (int w = 0; w < nw; w++) sel = max(sel, s_wmax[w]);
+    }
     const float tau_e = __uint_as_float(sel);
+    const bool lane_overflow = s_over != 0;              // published by the barrier inside the selection
+    // exact score of doc d = E(d)/(S*nc) * (1 +- delta): each weight errs by <= 0.51 and is >= q_min;
+    // FK_REL_SLACK covers the float roundings of Lucene's score and of the estimate
+    const float qmin = (float)s_qmin;
+    const float delta = qmin >= 2.0f ? FK_ROUND_SLACK / qmin + FK_REL_SLACK : 1.0f;
     // a doc can reach the list only if E(d)*(1+delta) >= tau_e*(1-delta)
     const float theta = delta < 1.0f ? tau_e * ((1.0f - delta) / (1.0f + delta)) * (1.0f - FK_REL_SLACK) : 0.0f;
     // ---- candidates: estimate >= theta
-    if (!overflow) {
-        if (active && e_best >= theta && e_best > 0.0f) {
+    if (active && !lane_overflow && e_best >= theta && e_best > 0.0f) {
 #pragma unroll
-            for (int i4 = 0; i4 < FK_DOCS; i4 += 4) {
-                const float4 nv = *reinterpret_cast<const float4*>(doc_w + d0 + i4);
-                const float nr[4] = {nv.x, nv.y, nv.z, nv.w};
+        for (int i4 = 0; i4 < FK_DOCS; i4 += 4) {
+            const float4 nv = *reinterpret_cast<const float4*>(doc_w + d0 + i4);
+            const float nr[4] = {nv.x, nv.y, nv.z, nv.w};
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int i = i4 + k;
-                    const u32 Q = prmt(wacc[i >> 1], 0u, (i & 1) ? 0x4432u : 0x4410u);
-                    const u32 m = prmt(cacc[i >> 2], 0u, 0x4440u | (u32)(i & 3));
-                    const float e = estimate(Q, m, need, nr[k]);
-                    if (e >= theta && e > 0.0f) {
-                        int idx = atomicAdd(&s_ncand, 1);
-                        if (idx < FK_CAND_CAP) s_cand[idx] = d0 + i;
-                    }
+            for (int k = 0; k < 4; k++) {
+                const int i = i4 + k;
+                const u32 Q = prmt(wacc[i >> 1], 0u, (i & 1) ? 0x4432u : 0x4410u);
+                const u32 m = prmt(cacc[i >> 2], 0u, 0x4440u | (u32)(i & 3));
+                const float e = estimate(Q, m, need, nr[k]);
+                if (e >= theta && e > 0.0f) {
+                    int idx = atomicAdd(&s_ncand, 1);
+                    if (idx < FK_CAND_CAP) s_cand[idx] = d0 + i;
                 }
             }
         }
     }
     __syncthreads();
     const int n_cand = s_ncand;
-    if (n_cand > FK_CAND_CAP) overflow = true;
     const i64 pbase = (i64)r * parts_stride;
-    if (overflow) {                                       // hand the read to exact_score_kernel
+    if (lane_overflow || n_cand > FK_CAND_CAP) {          // hand the read to exact_score_kernel
         if (threadIdx.x == 0) {
             overflow_list[atomicAdd(overflow_count, 1)] = r;
             route[r] = ROUTE_DENSE;
@@ -496,12 +501,12 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         }
         return;
     }
-    // ---- exact rescoring.  The candidates' cells are fetched in one batch of independent loads
-    //      (item = candidate j, clause c), then each warp sums one candidate from shared memory.
+    // ---- exact rescoring.  Few candidates: one warp each, lanes over clauses.  Many (full list): the cells are first
+    //      fetched in one batch of independent loads (item = candidate j, clause c) into shared memory.
     int pitch_log = 5;                                    // clause pitch of the staging buffer: power of two >= nc
     while ((1 << pitch_log) < nc) pitch_log++;
     const int n_items = n_cand << pitch_log;
-    const bool staged = n_items <= FK_CODE_CAP;
+    const bool staged = n_cand > nw && n_items <= FK_CODE_CAP;
     if (staged) {
 #pragma unroll 1
         for (int it0 = threadIdx.x; it0 < n_items; it0 += 4 * blockDim.x) {
@@ -525,17 +530,15 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     for (int j = warp; j < n_cand; j += nw) {
         const u32 d = s_cand[j];
         const float nrm = doc_w[d];
-        bool forced = false;
-        for (int e = 0; e < n_exc; e++) forced |= s_exc_d[e] == d;
         double sum = 0.0;
         i32 m = 0;
 #pragma unroll 1
         for (i32 c = lane; c < nc; c += 32) {
             const u32 code = staged ? (u32)s_code[(j << pitch_log) + c] : cell_code(T, s_row[c], d);
             float tf = s_tf[code];
-            if (code == 0u && forced) {
-                for (int e = 0; e < n_exc; e++)
-                    if (s_exc_c[e] == (u32)c && s_exc_d[e] == d) tf = tf_of(s_exc_f[e]);
+            if (code == 0u && s_exn[c]) {
+                const float f = exc_lookup(T, s_exa[c], s_exn[c], d);
+                if (f != 0.0f) tf = tf_of(f);
             }
             if (tf != 0.0f) {
                 sum += (double)__fmul_rn(__fmul_rn(tf, s_val[c]), nrm);          // TFIDFSimScorer#score
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         if (lane == 0) s_ckey[j] = m >= need ? cand_key(final_score(SIM_TFIDF, sum, m, nc), d) : 0ull;
     }
     __syncthreads();
-    // ---- top-10 among the candidates (duplicates carry equal keys and are removed together)
+    // ---- top-10 among the candidates
     if (warp == 0) {
         u64 loc[FK_CAND_CAP / 32];
 #pragma unroll
@@ -573,7 +576,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         }
         if (lane == 0) {
             part_n[pbase] = found;
-            if (stats) { atomicAdd(&stats->candidates, (unsigned long long)n_cand); atomicAdd(&stats->forced, (unsigned long long)n_exc); }
+            if (stats) { atomicAdd(&stats->candidates, (unsigned long long)n_cand); atomicAdd(&stats->forced, (unsigned long long)s_nexc); }
         }
     }
 }
