@@ -526,7 +526,7 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     const i64 filter_mode = env_i64("BSP_FILTER", -1);
     qp.filter_ok = qp.dense_ok && qp.sim == SIM_TFIDF && ix.d_pad <= 512 * FK_DOCS && filter_mode != 0 &&
                    (filter_mode == 1 || D >= 1024);
-    weights_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p,
+    weights_kernel<<<(unsigned)ceil_div((i64)n * 32, 256), 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p,
                                                                sc.tok_df.p, h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p,
                                                                sc.n_clauses.p, sc.msm.p, sc.route.p, sc.status_in.p, sc.vrange.p);
     CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));

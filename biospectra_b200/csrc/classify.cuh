@@ -270,9 +270,10 @@ __global__ void __launch_bounds__(256) token_df_kernel(const u64* __restrict__ t
     }
 }
 
-// Thread per read: msm, clause weights (A.5) and routing.
+// Warp per read: msm, clause weights (A.5) and routing.  Lanes work on clauses in parallel; the only order-dependent
+// step -- BooleanWeight#getValueForNormalization's float sum over the clauses -- is replayed in clause order.
 //   clause_val[tok_off[r] + c] = value_c ; clause_row[...] = dense-table row (dense route)
-__global__ void __launch_bounds__(128) weights_kernel(const u8* __restrict__ seq, const i64* __restrict__ seq_off, i32 n_reads,
+__global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq, const i64* __restrict__ seq_off, i32 n_reads,
                                                        const i64* __restrict__ tok_off, const i32* __restrict__ n_tok,
                                                        const u64* __restrict__ tok_key, const u32* __restrict__ tok_pos,
                                                        const u32* __restrict__ tok_df, const float* __restrict__ idf_by_df,
@@ -281,53 +282,65 @@ __global__ void __launch_bounds__(128) weights_kernel(const u8* __restrict__ seq
                                                        i32* __restrict__ n_clauses, i32* __restrict__ msm_out,
                                                        i32* __restrict__ route, i32* __restrict__ status,
                                                        float2* __restrict__ vrange /* per read: (max, min) clause value */) {
-    const i32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const i32 r = (i32)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
     if (r >= n_reads) return;
     const i64 base = tok_off[r];
     const i32 n = n_tok[r];
     const i32 nc = clause_count(qp.alg, n);
-    n_clauses[r] = nc;
     if (n <= 1 || nc > MAX_CLAUSES) {               // Classifier.java:223-227 / TooManyClauses
-        msm_out[r] = 0; route[r] = ROUTE_NONE; status[r] = ST_DROPPED;
+        if (lane == 0) { n_clauses[r] = nc; msm_out[r] = 0; route[r] = ROUTE_NONE; status[r] = ST_DROPPED; }
         return;
     }
-    msm_out[r] = (i32)(qp.msm_ratio * (double)nc);   // Classifier.java:257
     bool dense = qp.dense_ok != 0;
     float sum_sq = 0.0f;
-    for (i32 c = 0; c < nc; c++) {
-        i32 j0, j1;
-        clause_tokens(qp.alg, n, c, j0, j1);
-        float idf = idf_by_df[tok_df[base + j0]];
-        if (j1 >= 0) {
-            // TFIDFSimilarity#idfExplain(stats, TermStatistics[]): float sum, t0 first
-            idf = __fadd_rn(__fadd_rn(0.0f, idf), idf_by_df[tok_df[base + j1]]);
-            if (tok_pos[base + j1] - tok_pos[base + j0] != 1u) dense = false;      // slop != 2
+    for (i32 c0 = 0; c0 < nc; c0 += 32) {
+        const i32 c = c0 + lane;
+        float sq = 0.0f;
+        bool bad_slop = false;
+        if (c < nc) {
+            i32 j0, j1;
+            clause_tokens(qp.alg, n, c, j0, j1);
+            float idf = idf_by_df[tok_df[base + j0]];
+            if (j1 >= 0) {
+                // TFIDFSimilarity#idfExplain(stats, TermStatistics[]): float sum, t0 first
+                idf = __fadd_rn(__fadd_rn(0.0f, idf), idf_by_df[tok_df[base + j1]]);
+                bad_slop = tok_pos[base + j1] - tok_pos[base + j0] != 1u;          // slop != 2: not a dense-table row
+            }
+            clause_val[base + c] = idf;
+            const float qw = __fmul_rn(idf, 1.0f);
+            sq = __fmul_rn(qw, qw);
         }
-        clause_val[base + c] = idf;
-        float qw = __fmul_rn(idf, 1.0f);
-        sum_sq = __fadd_rn(sum_sq, __fmul_rn(qw, qw));
+        if (__any_sync(0xFFFFFFFFu, bad_slop)) dense = false;
+        const i32 lim = min(32, nc - c0);
+        for (i32 i = 0; i < lim; i++) sum_sq = __fadd_rn(sum_sq, __shfl_sync(0xFFFFFFFFu, sq, i));   // clause order
     }
     if (qp.sim == SIM_TFIDF) {
         sum_sq = __fmul_rn(sum_sq, 1.0f);                                           // BooleanWeight#getValueForNormalization
         float qn = __double2float_rn(__ddiv_rn(1.0, __dsqrt_rn((double)sum_sq)));   // DefaultSimilarity#queryNorm
         if (isinf(qn) || isnan(qn)) qn = 1.0f;                                      // IndexSearcher#createNormalizedWeight
         float vmax = 0.0f, vmin = 3.0e38f;
-        for (i32 c = 0; c < nc; c++) {
-            float idf = clause_val[base + c];
-            float qw = __fmul_rn(__fmul_rn(idf, 1.0f), __fmul_rn(qn, 1.0f));        // IDFStats#normalize
+        for (i32 c = lane; c < nc; c += 32) {
+            const float idf = clause_val[base + c];
+            const float qw = __fmul_rn(__fmul_rn(idf, 1.0f), __fmul_rn(qn, 1.0f));  // IDFStats#normalize
             const float v = __fmul_rn(qw, idf);
             clause_val[base + c] = v;
             vmax = fmaxf(vmax, v); vmin = fminf(vmin, v);
         }
-        vrange[r] = make_float2(vmax, vmin);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xFFFFFFFFu, vmax, o));
+            vmin = fminf(vmin, __shfl_xor_sync(0xFFFFFFFFu, vmin, o));
+        }
+        if (lane == 0) vrange[r] = make_float2(vmax, vmin);
     }   // BM25Stats#normalize: weight = idf * 1 * 1
     if (dense) {
         const u8* s = seq + seq_off[r];
-        for (i32 c = 0; c < nc; c++) {
+        for (i32 c = lane; c < nc; c += 32) {
             i32 j0, j1;
             clause_tokens(qp.alg, n, c, j0, j1);
             if (j1 >= 0) {      // pair row: the raw (k+1)-mer at the first token's offset
-                u32 off = tok_pos[base + j0];
+                const u32 off = tok_pos[base + j0];
                 u64 u = 0;
                 for (int i = 0; i <= qp.k; i++) u = (u << 2) | (u64)base_code_dev(s[off + i]);
                 clause_row[base + c] = (u32)(qp.pair_row0 + u);
@@ -336,12 +349,16 @@ __global__ void __launch_bounds__(128) weights_kernel(const u8* __restrict__ seq
             }
         }
     }
-    // u16 weight lanes / u8 count lanes of the filter kernel: <= 255 pair clauses, <= 181 term clauses
-    const bool fast = dense && qp.filter_ok && nc <= (qp.alg == ALG_NAIVE ? 181 : 255);
-    if (fast) { route[r] = ROUTE_FILTER; status[r] = ST_OK; }
-    else if (dense) { route[r] = ROUTE_DENSE; status[r] = ST_OK; }
-    else if (qp.positional_ok) { route[r] = ROUTE_POSITIONAL; status[r] = ST_OK; }
-    else { route[r] = ROUTE_NONE; status[r] = ST_ERROR; }
+    if (lane == 0) {
+        n_clauses[r] = nc;
+        msm_out[r] = (i32)(qp.msm_ratio * (double)nc);   // Classifier.java:257
+        // u16 weight lanes / u8 count lanes of the filter kernel: <= 255 pair clauses, <= 181 term clauses
+        const bool fast = dense && qp.filter_ok && nc <= (qp.alg == ALG_NAIVE ? 181 : 255);
+        if (fast) { route[r] = ROUTE_FILTER; status[r] = ST_OK; }
+        else if (dense) { route[r] = ROUTE_DENSE; status[r] = ST_OK; }
+        else if (qp.positional_ok) { route[r] = ROUTE_POSITIONAL; status[r] = ST_OK; }
+        else { route[r] = ROUTE_NONE; status[r] = ST_ERROR; }
+    }
 }
 
 // ------------------------------------------------------------------ scoring math
