@@ -265,7 +265,9 @@ def main():
     ix = Indexer(iconf)
     # every rank indexes the same reference (replica) but classifies its own reads (read_seed + rank)
     data = synth.build_reference_and_reads_cuda(ix, lengths, wl["reads"], wl["R"], wl["err"], wl["seed"], wl["read_seed"] + rank,
-                                                dev, keep_genomes=set(range(S)) if rank == 0 else ())
+                                                dev, keep_genomes=set(range(S)) if rank == 0 else (),
+                                                n_frac=float(os.environ.get("BSP_N_READ_FRAC", 0)))
+    torch.cuda.empty_cache()        # the generator's scratch goes back to the driver before the index is built
     torch.cuda.synchronize()
     t_gen = time.time() - t0
     t0 = time.time()

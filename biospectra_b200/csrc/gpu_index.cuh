@@ -350,12 +350,18 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
     i64 seg_tokens = std::min<i64>(opt.seg_tokens, ((i64)1 << 31) - 8192);
     u64 key_bytes = (2 * k <= 32) ? 4 : 8;
     u64 temp_bytes = (u64)std::min<i64>(std::max<i64>(total_tok, 1), seg_tokens) * (2 * key_bytes + 8 + 8 + 8);
-    u64 pos_est = (u64)total_tok * 12 + (ix.direct ? (1ull << (2 * k)) * 4 : 0);
+    // resident positional index: 4 B per token (positions) + 8 B per posting (doc, position offset; a posting needs a
+    // (term, doc) pair: at most docs * 4^k of them) + per segment the dictionary and the term arrays
+    const u64 n_seg_est = (u64)std::max<i64>(1, std::max<i64>(ceil_div(std::max<i64>(total_tok, 1), seg_tokens), ceil_div(D, SEG_MAX_DOCS)));
+    const u64 terms_per_seg = ix.direct ? (1ull << (2 * k)) : (u64)std::min<i64>(std::max<i64>(total_tok, 1), seg_tokens);
+    const u64 postings_est = ix.direct ? std::min<u64>((u64)total_tok, (u64)D * (1ull << (2 * k))) : (u64)total_tok;
+    u64 pos_est = (u64)total_tok * 4 + postings_est * 8 + n_seg_est * terms_per_seg * (ix.direct ? 16 : 36);
     bool positional = true;
     if (opt.want_positional == 2) positional = false;
     else if (opt.want_positional == 0) {
         u64 avail = free_b > (tables ? tf_bytes + pair_bytes : 0) ? free_b - (tables ? tf_bytes + pair_bytes : 0) : 0;
-        positional = (double)(pos_est + temp_bytes) <= 0.85 * (double)avail;
+        // (if the estimate turns out too low the build falls back to a non-resident positional index, see below)
+        positional = (double)(pos_est + temp_bytes) <= 0.92 * (double)avail;
     }
     if (!tables && !positional) {
         if (opt.want_positional == 2 && opt.want_tables == 2) throw BspError(-1, "both dense_tables and positional are forced off");
@@ -426,15 +432,32 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
     i64 postings = 0;
     std::vector<SegDev> views;
     DevBuf<SegDev> d_prev;
+    const bool may_drop_positional = positional && opt.want_positional == 0 && tables && ix.direct;
     for (size_t si = 0; si < ix.segs.size(); si++) {
         Segment& seg = ix.segs[si];
         u32 c0 = h_entries[seg.first_entry].first_chunk, c1 = h_entries[seg.first_entry + seg.n_entries].first_chunk;
-        if (2 * k <= 32)
-            build_segment<u32>(ix, seg, d_entries.p, d_chunk_entry.p, d_chunk_base.p, c0, c1, kbuf_a, kbuf_b, vbuf_a, vbuf_b,
-                               flags, rst, scan_tmp, d_total, st);
-        else
-            build_segment<u64>(ix, seg, d_entries.p, d_chunk_entry.p, d_chunk_base.p, c0, c1, kbuf_a, kbuf_b, vbuf_a, vbuf_b,
-                               flags, rst, scan_tmp, d_total, st);
+        try {
+            if (2 * k <= 32)
+                build_segment<u32>(ix, seg, d_entries.p, d_chunk_entry.p, d_chunk_base.p, c0, c1, kbuf_a, kbuf_b, vbuf_a, vbuf_b,
+                                   flags, rst, scan_tmp, d_total, st);
+            else
+                build_segment<u64>(ix, seg, d_entries.p, d_chunk_entry.p, d_chunk_base.p, c0, c1, kbuf_a, kbuf_b, vbuf_a, vbuf_b,
+                                   flags, rst, scan_tmp, d_total, st);
+        } catch (const BspError& e) {
+            // out of device memory with the positional index resident: give it up (the dense tables stay complete for
+            // the segments already processed) and redo this segment
+            if (e.code != -6 || !positional || !may_drop_positional) throw;
+            cudaGetLastError();
+            for (size_t j = 0; j < si; j++) {
+                Segment& o = ix.segs[j];
+                o.direct.release(); o.term_key.release(); o.term_off.release(); o.post_doc.release();
+                o.post_pos.release(); o.positions.release(); o.doc_tok.release();
+            }
+            positional = false; ix.positional = false; ix.positional_bytes = 0; views.clear();
+            ix.notes += "positional index dropped: out of device memory; ";
+            si--;
+            continue;
+        }
         postings += seg.n_post;
         SegDev v = seg.view();
         if (ix.direct) {

@@ -104,7 +104,7 @@ def make_small_workload(n_genomes=10, genome_len=2_000_000, n_reads=10_000, R=10
 
 # ------------------------------------------------------------------------ torch / CUDA
 def build_reference_and_reads_cuda(indexer, lengths, n_reads: int, R: int, err: float, seed: int, read_seed: int,
-                                   device, keep_genomes=(), rank_slice=None):
+                                   device, keep_genomes=(), rank_slice=None, n_frac: float = 0.0):
     """Generates every genome on `device`, adds it to `indexer` through the device-pointer entry
     point, and samples reads from it while it is alive.
 
@@ -176,6 +176,11 @@ def build_reference_and_reads_cuda(indexer, lengths, n_reads: int, R: int, err: 
     read_of_byte = torch.repeat_interleave(torch.arange(n, device=device), new_lens)
     within = torch.arange(flat.numel(), device=device) - new_off[read_of_byte]
     gathered = flat[off[perm][read_of_byte] + within]
+    if n_frac > 0:          # a fraction of the reads gets one 'N' (not part of the BASELINE workload: exercises the positional path)
+        pick = torch.rand(n, device=device, generator=gen) < n_frac
+        at = new_off[:-1] + (torch.rand(n, device=device, generator=gen) * new_lens.double()).long().clamp(max=int(new_lens.max()) - 1)
+        at = torch.minimum(at, new_off[1:] - 1)
+        gathered[at[pick]] = ord("N")
     seq_host = torch.empty(gathered.numel(), dtype=torch.uint8, pin_memory=True)
     seq_host.copy_(gathered)
     off_host = torch.empty(n + 1, dtype=torch.int64, pin_memory=True)
