@@ -202,6 +202,34 @@ __device__ __forceinline__ void pair_word2(u32 wa, u32 wb, const uint2 la, const
     add_fma_pipe(c1, prmt(0x01010100u, 0x01010101u, ha), one); add_fma_pipe(c1, prmt(0x01010100u, 0x01010101u, hb), one);
 }
 
+// Term rows hold codes 0..14: a 16-entry LUT out of two 8-entry PRMT lookups.  PRMT reads bit 3 of a selector nibble as
+// "replicate the sign of the selected byte": looking up the constant 0x80 therefore yields 0xFF for codes >= 8 and 0x80
+// otherwise -- a per-byte select mask for bits 0..6 (weights are kept <= 127 so bit 7 is never set).
+__device__ __forceinline__ u32 lut16(const uint4 t, u32 sel /* 4 codes in the low 16 bits */, u32& ge8) {
+    const u32 s7 = sel & 0x7777u;
+    const u32 lo = prmt(t.x, t.y, s7), hi = prmt(t.z, t.w, s7);
+    ge8 = prmt(0x80808080u, 0x80808080u, sel);
+    return (hi & ge8) | (lo & ~ge8);
+}
+__device__ __forceinline__ u32 cnt16(u32 sel, u32 ge8) {        // 1 per non-zero code
+    return prmt(0x01010100u, 0x01010101u, sel & 0x7777u) | (ge8 & 0x01010101u);
+}
+// one u32 (8 docs) of each of two term rows
+__device__ __forceinline__ void term_word2(u32 wa, u32 wb, const uint4 ta, const uint4 tb, u32& w0, u32& w1, u32& w2, u32& w3,
+                                           u32& c0, u32& c1, u32 one) {
+    const u32 ha = wa >> 16, hb = wb >> 16;
+    u32 ga0, ga1, gb0, gb1;
+    u32 s0 = lut16(ta, wa, ga0), s1 = lut16(ta, ha, ga1);
+    add_fma_pipe(s0, lut16(tb, wb, gb0), one);        // weights <= 127: the two rows' bytes add without carry
+    add_fma_pipe(s1, lut16(tb, hb, gb1), one);
+    add_fma_pipe(w0, prmt(s0, 0u, 0x4140u), one);
+    add_fma_pipe(w1, prmt(s0, 0u, 0x4342u), one);
+    add_fma_pipe(w2, prmt(s1, 0u, 0x4140u), one);
+    add_fma_pipe(w3, prmt(s1, 0u, 0x4342u), one);
+    add_fma_pipe(c0, cnt16(wa, ga0), one); add_fma_pipe(c0, cnt16(wb, gb0), one);
+    add_fma_pipe(c1, cnt16(ha, ga1), one); add_fma_pipe(c1, cnt16(hb, gb1), one);
+}
+
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {     // read-only path, do not keep in L1
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -289,7 +317,8 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score, i32* __restrict__ route,
         i32* __restrict__ overflow_list, i32* __restrict__ overflow_count, FilterStats* __restrict__ stats, int full_topn,
         u32 one /* = 1, see add_fma_pipe */) {
-    __shared__ uint2 s_lut[FK_MAX_CLAUSES + 1];          // pair clauses: q for codes 0..3 | 4..7
+    __shared__ uint2 s_lut[FK_MAX_CLAUSES + 1];          // q for codes 0..3 | 4..7
+    __shared__ uint2 s_lut_hi[FK_MAX_CLAUSES + 1];       // term rows (NAIVE_KMER): q for codes 8..11 | 12..15
     __shared__ u32 s_row[FK_MAX_CLAUSES + 1];
     __shared__ float s_val[FK_MAX_CLAUSES + 1];
     __shared__ u32 s_exa[FK_MAX_CLAUSES + 1], s_exn[FK_MAX_CLAUSES + 1];     // exception list of each clause's row
@@ -312,7 +341,9 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     // scale S: S * value_c * tf(7) <= 255 for every clause; q_min = smallest non-zero cell weight (weights_kernel
     // recorded the largest and smallest clause value of the read)
     const float2 vr = read_vrange[r];
-    const float S = FK_QMAX / (vr.x * tf16[T4_PAIR_MAX]);
+    // (NAIVE_KMER has term rows only: all 15 codes go through the byte LUT, weights <= 127)
+    const bool all_terms = n_pair == 0;
+    const float S = all_terms ? 127.0f / (vr.x * tf16[T4_TF_MAX]) : FK_QMAX / (vr.x * tf16[T4_PAIR_MAX]);
     if (threadIdx.x < 16) s_tf[threadIdx.x] = tf16[threadIdx.x];
     if (threadIdx.x == 0) { s_ncand = 0; s_nexrows = 0; s_over = 0; s_nexc = 0; s_qmin = (u32)__float2int_rn(S * vr.y); }
     __syncthreads();
@@ -328,6 +359,13 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
 #pragma unroll
             for (int j = 1; j < 8; j++) q[j] = min((u32)__float2int_rn(sv * tf16[j]), 255u);
             s_lut[c] = make_uint2(q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24), q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24));
+        } else if (all_terms) {
+            u32 q[16];
+            q[0] = 0; q[15] = 0;
+#pragma unroll
+            for (int j = 1; j < 15; j++) q[j] = min((u32)__float2int_rn(sv * tf16[j]), 127u);
+            s_lut[c] = make_uint2(q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24), q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24));
+            s_lut_hi[c] = make_uint2(q[8] | (q[9] << 8) | (q[10] << 16) | (q[11] << 24), q[12] | (q[13] << 8) | (q[14] << 16) | (q[15] << 24));
         }
         const u32 a = T.exc_off[row], b = T.exc_off[row + 1];
         s_exa[c] = a;
@@ -358,17 +396,27 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
             cp_async_commit();
         }
         i32 c = 0;
+        const i32 n_two = all_terms ? nc : n_pair;    // rows streamed two at a time through a byte LUT
 #pragma unroll 1
-        for (; c + 2 <= n_pair; c += 2) {             // two pair rows per iteration
+        for (; c + 2 <= n_two; c += 2) {
             cp_async_wait<FK_STAGES - 2>();
             uint4* my0 = slot + (c % FK_STAGES) * stride;
             uint4* my1 = slot + ((c + 1) % FK_STAGES) * stride;
             const uint4 q0 = *my0, q1 = *my1;
             const uint2 l0 = s_lut[c], l1 = s_lut[c + 1];
-            pair_word2(q0.x, q1.x, l0, l1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1], one);
-            pair_word2(q0.y, q1.y, l0, l1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3], one);
-            pair_word2(q0.z, q1.z, l0, l1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5], one);
-            pair_word2(q0.w, q1.w, l0, l1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7], one);
+            if (all_terms) {
+                const uint2 h0 = s_lut_hi[c], h1 = s_lut_hi[c + 1];
+                const uint4 t0 = make_uint4(l0.x, l0.y, h0.x, h0.y), t1 = make_uint4(l1.x, l1.y, h1.x, h1.y);
+                term_word2(q0.x, q1.x, t0, t1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1], one);
+                term_word2(q0.y, q1.y, t0, t1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3], one);
+                term_word2(q0.z, q1.z, t0, t1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5], one);
+                term_word2(q0.w, q1.w, t0, t1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7], one);
+            } else {
+                pair_word2(q0.x, q1.x, l0, l1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1], one);
+                pair_word2(q0.y, q1.y, l0, l1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3], one);
+                pair_word2(q0.z, q1.z, l0, l1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5], one);
+                pair_word2(q0.w, q1.w, l0, l1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7], one);
+            }
             if (c + FK_STAGES < nc) cp_async16(my0, tbase + (u64)s_row[c + FK_STAGES] * T.row_bytes);
             cp_async_commit();
             if (c + 1 + FK_STAGES < nc) cp_async16(my1, tbase + (u64)s_row[c + 1 + FK_STAGES] * T.row_bytes);
