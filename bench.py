@@ -228,6 +228,88 @@ def workload_config(args, wl):
             "l2": "inputs larger than L2: the dense index rows read per step span the whole table (>> 126 MB)"}
 
 
+def run_docpart(args, wl, lengths):
+    """Doc-partitioned mode (BASELINE configs[3] style): rank r holds the documents of a contiguous slice of the genomes,
+    every rank scores the SAME reads against its slice; build: all_gather of (docs, tokens) + all_reduce of the dense df
+    array; query: one all_gather of the per-rank hit lists + merge (biospectra_b200/partition.py).  value = reads/s of
+    the whole job against the whole (partitioned) index.  With --verify rank 0 also builds the whole index on its own
+    and requires the merged results to be identical to the single-index results."""
+    import torch
+    import torch.distributed as dist
+    from biospectra_b200 import Indexer, partition, synth
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    plan = partition.plan_entries(lengths, world)
+    e0, e1 = plan[rank]
+    qconf = shipped_config(device=local, query_algorithm=args.algorithm)
+    t0 = time.time()
+    ix = Indexer(shipped_config(device=local))
+    full = Indexer(shipped_config(device=local)) if (args.verify and rank == 0) else None
+
+    class Both:                      # rank 0 with --verify feeds the whole-index handle as well
+        def add_entry_device(self, *a):
+            g = int(a[0].split(".")[0])
+            if e0 <= g < e1:
+                ix.add_entry_device(*a)
+            if full is not None:
+                full.add_entry_device(*a)
+    data = synth.build_reference_and_reads_cuda(Both(), lengths, wl["reads"], wl["R"], wl["err"], wl["seed"], wl["read_seed"], dev)
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    t0 = time.time()
+    clf = ix.close_to_classifier(qconf)
+    dp = partition.DocPartitionedClassifier(partition.GpuPartitionEngine(clf, dev)).sync_statistics()
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
+    n = len(data["offsets"]) - 1
+
+    def step():
+        return dp.classify(data["seq_bytes"], data["offsets"])
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        res = step()
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t
+    tt = torch.tensor([el], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    el = float(tt[0])
+    verify = None
+    if full is not None:
+        fclf = full.close_to_classifier(qconf)
+        ref = fclf.classify_packed(data["seq_bytes"], data["offsets"])
+        got = {k: v.cpu().numpy() for k, v in res.items()}
+        same = (got["status"] == ref["status"]) & (got["label"] == ref["label"]) & (got["n_hits"] == ref["n_hits"])
+        for j in range(10):
+            live = ref["n_hits"] > j
+            same &= ~live | ((got["top_doc"][:, j] == ref["top_doc"][:, j]) &
+                             (got["top_score"][:, j].view(np.uint32) == ref["top_score"][:, j].view(np.uint32)))
+        verify = {"reads": n, "identical_to_single_index": int(same.sum())}
+        fclf.close()
+    if rank == 0:
+        print(json.dumps({"metric": "reads/sec classified", "mode": "doc-partitioned", "value": n * args.steps / el, "unit": "reads/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 scores, f64 accumulate",
+                          "data": "synthetic",
+                          "config": {"workload": "%s: %d genomes / %.2f Gbp split over %d GPUs by contiguous genome ranges, %d reads scored "
+                                                 "on every GPU, hit lists merged after one NCCL all_gather" %
+                                                 (args.workload, wl["genomes"], wl["total_bp"] / 1e9, world, n),
+                                     "parallelism": "doc-partitioned x%d" % world},
+                          "partition": {"plan": plan, "global_docs": dp.global_docs, "gen_seconds": t_gen, "build_seconds": t_build},
+                          "verify": verify}))
+    clf.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -237,6 +319,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("BSP_WORKLOAD", "C2"))
     ap.add_argument("--algorithm", default="PAIRED_PROXIMITY")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="replica", choices=["replica", "docpart"],
+                    help="replica: read-sharded index replicas (default, no collective); docpart: doc-partitioned index")
+    ap.add_argument("--verify", action="store_true", help="docpart: compare with a single-index run on rank 0")
     ap.add_argument("--profile", default="classify", choices=["classify", "build"],
                     help="which region cudaProfilerStart/Stop brackets (for ncu --profile-from-start off)")
     args = ap.parse_args()
@@ -245,6 +330,8 @@ def main():
     lengths = synth.genome_lengths(wl["genomes"], wl["total_bp"], wl["seed"], *((1, 1) if wl.get("equal") else (1.5e6, 6.5e6)))
     if args.impl == "reference":
         return run_reference(args, wl, lengths)
+    if args.mode == "docpart":
+        return run_docpart(args, wl, lengths)
 
     import torch
     import torch.distributed as dist
