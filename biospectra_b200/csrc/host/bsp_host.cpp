@@ -16,6 +16,9 @@
 #include <dirent.h>
 #include <sys/stat.h>
 #include <zlib.h>
+#include <condition_variable>
+#include <deque>
+#include <thread>
 
 namespace bsp {
 
@@ -184,6 +187,14 @@ bool FASTAReader::readLine(std::string& line) {      // BufferedReader#readLine:
 }
 
 bool FASTAReader::readNext(FASTAEntry& e) {
+    // org.yeastrc.fasta.FASTAReader#readNext, scanning the file image in place
+    static unsigned char UP[256];
+    static bool up_init = false;
+    if (!up_init) {
+        for (int c = 0; c < 256; c++) UP[c] = c >= 0x80 ? (unsigned char)'?'       // US-ASCII decoding: undecodable byte
+                                              : (unsigned char)toupper(c);          // String#toUpperCase
+        up_init = true;
+    }
     std::string line;
     if (!have_pending_) {
         if (!readLine(line)) return false;
@@ -193,16 +204,28 @@ bool FASTAReader::readNext(FASTAEntry& e) {
     e.headerLine = line;
     e.sequence.clear();
     bool any = false;
-    while (readLine(line)) {
-        if (!line.empty() && line[0] == '>') { pending_ = line; have_pending_ = true; break; }
-        if (!line.empty() && line[0] == ';') continue;
-        any = true;
-        for (char& c : line) {
-            unsigned char u = (unsigned char)c;
-            if (u >= 0x80) c = '?';                  // US-ASCII decoding: undecodable byte
-            else c = (char)toupper(u);               // String#toUpperCase
+    const char* d = data_.data();
+    const size_t n = data_.size();
+    while (pos_ < n) {
+        const char first = d[pos_];
+        if (first == '>') {                              // next entry: leave it for the next call
+            readLine(pending_);
+            have_pending_ = true;
+            break;
         }
-        e.sequence += line;
+        size_t st = pos_;                                // one line: up to \n, \r\n or \r (BufferedReader#readLine)
+        const char* nl = (const char*)memchr(d + st, '\n', n - st);
+        size_t end = nl ? (size_t)(nl - d) : n;
+        const char* cr = (const char*)memchr(d + st, '\r', end - st);
+        size_t stop = cr ? (size_t)(cr - d) : end;
+        if (stop < n) pos_ = (d[stop] == '\r' && stop + 1 < n && d[stop + 1] == '\n') ? stop + 2 : stop + 1;
+        else pos_ = n;
+        if (first == ';' && stop > st) continue;
+        any = true;
+        const size_t old = e.sequence.size();
+        e.sequence.resize(old + (stop - st));
+        char* o = &e.sequence[old];
+        for (size_t i = st; i < stop; i++) o[i - st] = (char)UP[(unsigned char)d[i]];
     }
     if (!any) throw FASTADataError("FASTADataErrorException: header without sequence");
     // String#trim: strip chars <= ' ' at both ends
@@ -362,6 +385,95 @@ Classifier::Classifier(const Configuration* conf) {
     if (!conf->hasIndexPath) throw IllegalArgument("indexPath is null");               // :76-78
     bsp_config c = conf->toStruct();
     check_rc(bsp_classifier_open(&c, conf->indexPath.c_str(), &h_));                   // validates k, skips, dir
+    workerThreads_ = conf->workerThreads > 0 ? conf->workerThreads : 1;
+    // stored fields of every document (IndexSearcher.doc, Classifier.java:361-363), rendered and parsed once
+    int64_t nDocs = 0;
+    check_rc(bsp_index_stats(h_, &nDocs, nullptr, nullptr, nullptr));
+    docs_.resize((size_t)nDocs);
+    for (int64_t d = 0; d < nDocs; d++) {
+        const char *fn, *hd, *dir, *tax;
+        check_rc(bsp_doc_fields(h_, (int32_t)d, &fn, &hd, &dir, &tax));
+        DocInfo& di = docs_[(size_t)d];
+        di.json = "\"filename\":"; jsonm::write_string(di.json, fn);
+        di.json += ",\"header\":"; jsonm::write_string(di.json, hd);
+        di.json += ",\"sequence_direction\":"; jsonm::write_string(di.json, dir);
+        di.json += ",\"taxon_hierarchy\":"; jsonm::write_string(di.json, tax);
+        di.hasTaxonomy = tax[0] != 0;
+        if (di.hasTaxonomy) {
+            try { di.ranked = TaxonTreeDescription::classifiable(TaxonTreeDescription::parse(tax)); }
+            catch (const std::exception&) { di.taxonomyBad = true; }
+        }
+    }
+}
+
+void Classifier::classifyPacked(const char* seqBytes, const int64_t* offsets, int32_t n, PackedResults& out) {
+    out.status.assign((size_t)n, BSP_READ_ERROR);
+    out.nHits.assign((size_t)n, 0);
+    out.topDoc.assign((size_t)n * BSP_TOPN, -1);
+    out.topScore.assign((size_t)n * BSP_TOPN, 0.0f);
+    if (n == 0) return;
+    check_rc(bsp_classify_packed(h_, n, seqBytes, offsets, out.status.data(), nullptr, out.nHits.data(), nullptr, out.topDoc.data(),
+                                 out.topScore.data()));
+    for (int32_t i = 0; i < n; i++)
+        if (offsets[i + 1] == offsets[i]) out.status[(size_t)i] = BSP_READ_ERROR;       // Classifier.java:342-344
+}
+
+// Classifier.classify's tail (Classifier.java:356-371) + makeClassificationResult (:263-339) + the Jackson layout of
+// ClassificationResult / SearchResultEntry, on the prepared per-document data
+bool Classifier::appendResultJson(std::string& o, const char* header, size_t headerLen, const char* seq, size_t seqLen,
+                                  const PackedResults& r, int32_t i, int* type) const {
+    const int nh = r.nHits[(size_t)i];
+    const int32_t* docs = &r.topDoc[(size_t)i * BSP_TOPN];
+    const float* scores = &r.topScore[(size_t)i * BSP_TOPN];
+    // label
+    int ty = 0;
+    const Taxonomy* tax = nullptr;
+    if (nh == 1) {
+        ty = 2;
+        const DocInfo& d = docs_[(size_t)docs[0]];
+        if (d.hasTaxonomy) { if (d.taxonomyBad) return false; if (!d.ranked.empty()) tax = &d.ranked[0]; }
+    } else if (nh >= 2) {
+        bool all = true;
+        for (int j = 0; j < nh && all; j++) {
+            const DocInfo& d = docs_[(size_t)docs[j]];
+            if (!d.hasTaxonomy) all = false;                 // quick fail: VAGUE (the earlier entries were already parsed)
+            else if (d.taxonomyBad) return false;
+        }
+        ty = 1;
+        if (all) {
+            for (const Taxonomy& t : docs_[(size_t)docs[0]].ranked) {
+                bool common = true;
+                for (int j = 1; j < nh && common; j++) {
+                    bool found = false;
+                    for (const Taxonomy& t2 : docs_[(size_t)docs[j]].ranked) if (t2.taxid == t.taxid) { found = true; break; }
+                    common = found;
+                }
+                if (common) { ty = 2; tax = &t; break; }
+            }
+        }
+    }
+    *type = ty;
+    o += "{\"query_header\":"; jsonm::write_string_n(o, header, headerLen);
+    o += ",\"query\":"; jsonm::write_string_n(o, seq, seqLen);
+    o += ",\"result\":[";
+    char num[48];
+    for (int j = 0; j < nh; j++) {
+        if (j) o.push_back(',');
+        int len = snprintf(num, sizeof num, "{\"docid\":%d,\"rank\":%d,", docs[j], j);
+        o.append(num, (size_t)len);
+        o += docs_[(size_t)docs[j]].json;
+        o += ",\"score\":";
+        o += jsonm::java_double((double)scores[j]);
+        o.push_back('}');
+    }
+    static const char* TYPE[3] = {"UNKNOWN", "VAGUE", "CLASSIFIED"};
+    o += "],\"type\":\""; o += TYPE[ty]; o += "\",\"taxon_rank\":";
+    if (tax) jsonm::write_string(o, tax->rank); else o += "\"unknown\"";
+    o += ",\"taxon_name\":";
+    if (tax) { if (tax->hasName) jsonm::write_string(o, tax->name); else o += "null"; }
+    else o += "\"\"";
+    o.push_back('}');
+    return true;
 }
 Classifier::~Classifier() { close(); }
 void Classifier::close() {
@@ -417,6 +529,49 @@ bool Classifier::classify(const std::string& header, const std::string& sequence
 // ------------------------------------------------------------------ LocalClassifier
 LocalClassifier::LocalClassifier(const Configuration* conf) : classifier_(conf) {}
 
+// One batch of reads, packed back to back (what bsp_classify_packed takes) plus its results.
+namespace {
+struct ReadBatch {
+    std::string headers, seqs;              // header lines (with '>') and sequences, concatenated
+    std::vector<size_t> hoff{0};
+    std::vector<int64_t> soff{0};
+    Classifier::PackedResults res;
+    size_t size() const { return soff.size() - 1; }
+};
+
+template <typename T>
+class BoundedQueue {                        // single producer / single consumer hand-off between pipeline stages
+public:
+    explicit BoundedQueue(size_t cap) : cap_(cap) {}
+    void push(T v) {
+        std::unique_lock<std::mutex> lk(mu_);
+        not_full_.wait(lk, [&] { return q_.size() < cap_; });
+        q_.push_back(std::move(v));
+        not_empty_.notify_one();
+    }
+    void close() { std::lock_guard<std::mutex> lk(mu_); closed_ = true; not_empty_.notify_all(); }
+    bool pop(T& v) {
+        std::unique_lock<std::mutex> lk(mu_);
+        not_empty_.wait(lk, [&] { return !q_.empty() || closed_; });
+        if (q_.empty()) return false;
+        v = std::move(q_.front());
+        q_.pop_front();
+        not_full_.notify_one();
+        return true;
+    }
+private:
+    std::mutex mu_;
+    std::condition_variable not_full_, not_empty_;
+    std::deque<T> q_;
+    size_t cap_;
+    bool closed_ = false;
+};
+}  // namespace
+
+// LocalClassifier.classify(File, File, File) (LocalClassifier.java:60-131).  The reference runs one Runnable per read on
+// `worker_threads` threads and serialises the writer; here three stages overlap: a reader thread parses FASTA into
+// batches, the calling thread classifies each batch on the GPU, a writer thread formats the JSON lines of a batch on
+// `worker_threads` threads and writes them in read order.
 void LocalClassifier::classify(const std::string& inputFasta, const std::string& classifyOutput, const std::string& summaryOutput) {
     if (inputFasta.empty()) throw IllegalArgument("inputFasta is null");               // LocalClassifier.java:61-63
     if (classifyOutput.empty()) throw IllegalArgument("classifyOutput is null");       // :65-67
@@ -426,40 +581,99 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
     FASTAReader reader(inputFasta);
     FILE* fw = fopen(classifyOutput.c_str(), "wb");
     if (!fw) throw IOError("cannot create " + classifyOutput);
-    std::vector<char> wbuf(1 << 20);
-    setvbuf(fw, wbuf.data(), _IOFBF, wbuf.size());
     ClassificationResultSummary summary;
     summary.queryFilename = base_name(inputFasta);
     summary.startTime = now_ms();
-    const size_t BATCH_READS = 262144, BATCH_BYTES = (size_t)128 << 20;
-    std::vector<std::string> headers, seqs;
-    size_t bytes = 0;
-    auto flush = [&]() {
-        if (seqs.empty()) return;
-        std::vector<ClassificationResult> res;
-        std::vector<int> st;
-        // reads with an empty sequence throw in Classifier.classify and are skipped (LocalClassifier.java:112-114)
-        classifier_.classifyBatch(headers, seqs, res, st);
-        for (size_t i = 0; i < res.size(); i++) {
-            if (st[i] != BSP_READ_OK) continue;
-            std::string js = res[i].toJson();
-            summary.report(res[i]);
-            fwrite(js.data(), 1, js.size(), fw);
-            fputc('\n', fw);
+    const size_t BATCH_READS = 262144, BATCH_BYTES = (size_t)64 << 20;
+    typedef std::unique_ptr<ReadBatch> BatchPtr;
+    BoundedQueue<BatchPtr> parsed(2), classified(2);
+    std::exception_ptr reader_error, writer_error;
+
+    std::thread reader_thread([&] {
+        try {
+            FASTAEntry read;
+            BatchPtr b(new ReadBatch());
+            while (reader.readNext(read)) {
+                b->headers += read.headerLine;                                         // header INCLUDING '>' (:94)
+                b->hoff.push_back(b->headers.size());
+                b->seqs += read.sequence;
+                b->soff.push_back((int64_t)b->seqs.size());
+                if (b->size() >= BATCH_READS || b->seqs.size() >= BATCH_BYTES) { parsed.push(std::move(b)); b.reset(new ReadBatch()); }
+            }
+            if (b->size()) parsed.push(std::move(b));
+        } catch (...) { reader_error = std::current_exception(); }
+        parsed.close();
+    });
+
+    const Classifier& cls = classifier_;
+    const int T = std::max(1, cls.workerThreads());
+    std::thread writer_thread([&] {
+        try {
+            BatchPtr b;
+            while (classified.pop(b)) {
+                const size_t n = b->size();
+                const int nt = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, n / 4096));
+                std::vector<std::string> chunk((size_t)nt);
+                std::vector<long long> counts((size_t)nt * 3, 0);
+                auto work = [&](int t) {
+                    const size_t i0 = n * (size_t)t / (size_t)nt, i1 = n * (size_t)(t + 1) / (size_t)nt;
+                    std::string& o = chunk[(size_t)t];
+                    o.reserve((i1 - i0) * 700);
+                    for (size_t i = i0; i < i1; i++) {
+                        // reads the reference's classify() throws on (empty sequence, < 2 k-mers, > 10000 clauses) are
+                        // logged and skipped: no line, not counted (LocalClassifier.java:112-114)
+                        if (b->res.status[i] != BSP_READ_OK) continue;
+                        const size_t mark = o.size();
+                        int type = 0;
+                        if (!cls.appendResultJson(o, b->headers.data() + b->hoff[i], b->hoff[i + 1] - b->hoff[i],
+                                                  b->seqs.data() + b->soff[i], (size_t)(b->soff[i + 1] - b->soff[i]), b->res,
+                                                  (int32_t)i, &type)) {
+                            o.resize(mark);
+                            fprintf(stderr, "ERROR Exception occurred during search: malformed taxonomy\n");
+                            continue;
+                        }
+                        o.push_back('\n');
+                        counts[(size_t)t * 3 + (size_t)type]++;
+                    }
+                };
+                std::vector<std::thread> pool;
+                for (int t = 1; t < nt; t++) pool.emplace_back(work, t);
+                work(0);
+                for (auto& th : pool) th.join();
+                for (int t = 0; t < nt; t++) {
+                    if (!chunk[(size_t)t].empty() && fwrite(chunk[(size_t)t].data(), 1, chunk[(size_t)t].size(), fw) != chunk[(size_t)t].size())
+                        throw IOError("write failed: " + classifyOutput);
+                    summary.unknown += counts[(size_t)t * 3]; summary.vague += counts[(size_t)t * 3 + 1];
+                    summary.classified += counts[(size_t)t * 3 + 2];
+                }
+            }
+        } catch (...) {
+            writer_error = std::current_exception();
+            BatchPtr drop;
+            while (classified.pop(drop)) {}
         }
-        headers.clear(); seqs.clear(); bytes = 0;
-    };
+    });
+
+    std::exception_ptr gpu_error;
     try {
-        FASTAEntry read;
-        while (reader.readNext(read)) {
-            bytes += read.sequence.size();
-            headers.push_back(read.headerLine);                                        // header INCLUDING '>' (:94)
-            seqs.push_back(std::move(read.sequence));
-            if (seqs.size() >= BATCH_READS || bytes >= BATCH_BYTES) flush();
+        BatchPtr b;
+        while (parsed.pop(b)) {
+            classifier_.classifyPacked(b->seqs.data(), b->soff.data(), (int32_t)b->size(), b->res);
+            classified.push(std::move(b));
         }
-        flush();
-    } catch (...) { fclose(fw); throw; }
+    } catch (...) {
+        gpu_error = std::current_exception();
+        BatchPtr drop;
+        while (parsed.pop(drop)) {}
+    }
+    classified.close();
+    reader_thread.join();
+    writer_thread.join();
     fclose(fw);
+    if (gpu_error) std::rethrow_exception(gpu_error);
+    if (writer_error) std::rethrow_exception(writer_error);
+    if (reader_error) std::rethrow_exception(reader_error);
+    summary.total = summary.unknown + summary.vague + summary.classified;
     summary.endTime = now_ms();
     if (!summaryOutput.empty()) {                                                      // :128-130
         FILE* fs = fopen(summaryOutput.c_str(), "wb");

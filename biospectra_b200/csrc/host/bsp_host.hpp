@@ -105,8 +105,28 @@ public:
                        std::vector<ClassificationResult>& out, std::vector<int>& status);
     void close();
     bsp_classifier* handle() { return h_; }
+
+    // ---- batch path used by LocalClassifier (the reference's per-read Runnable, LocalClassifier.java:96-118, as a batch)
+    // Stored fields of a document, prepared once: the JSON fragment of its SearchResultEntry and its ranked lineage
+    struct DocInfo {
+        std::string json;                 // "filename":..,"header":..,"sequence_direction":..,"taxon_hierarchy":..
+        bool hasTaxonomy = false, taxonomyBad = false;
+        std::vector<Taxonomy> ranked;     // TaxonTreeDescription#getClassifiableTaxonomyTree
+    };
+    struct PackedResults {                // per read, as bsp_classify_packed returns them
+        std::vector<int32_t> status, nHits, topDoc;
+        std::vector<float> topScore;
+    };
+    void classifyPacked(const char* seqBytes, const int64_t* offsets, int32_t n, PackedResults& out);
+    // JSON line of read i (no trailing newline) appended to `o`; returns false when the reference would have thrown
+    // (malformed taxonomy JSON); *type gets 0 UNKNOWN / 1 VAGUE / 2 CLASSIFIED
+    bool appendResultJson(std::string& o, const char* header, size_t headerLen, const char* seq, size_t seqLen,
+                          const PackedResults& r, int32_t i, int* type) const;
+    int workerThreads() const { return workerThreads_; }
 private:
     bsp_classifier* h_ = nullptr;
+    std::vector<DocInfo> docs_;
+    int workerThreads_ = 4;
 };
 
 class LocalClassifier {

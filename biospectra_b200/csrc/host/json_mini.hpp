@@ -1,6 +1,7 @@
 // json_mini.hpp -- minimal JSON value/parser/writer for the host-side mirror
 // (configuration.json, .taxd lineages, .result / .result.sum output).
 #pragma once
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -144,9 +145,17 @@ private:
 inline ValuePtr parse(const std::string& s) { return Parser(s).parse(); }
 
 // Jackson-style string escaping (JsonStringEncoder): ", \ and control chars
-inline void write_string(std::string& o, const std::string& s) {
+inline void write_string_n(std::string& o, const char* s, size_t n);
+inline void write_string(std::string& o, const std::string& s) { write_string_n(o, s.data(), s.size()); }
+inline void write_string_n(std::string& o, const char* sp, size_t n) {
     o.push_back('"');
-    for (unsigned char c : s) {
+    // fast path: runs of characters that need no escaping are appended in one go
+    size_t run = 0;
+    for (size_t i = 0; i < n; i++) {
+        const unsigned char c = (unsigned char)sp[i];
+        if (c >= 0x20 && c != '"' && c != '\\') continue;
+        o.append(sp + run, i - run);
+        run = i + 1;
         switch (c) {
             case '"': o += "\\\""; break;
             case '\\': o += "\\\\"; break;
@@ -155,11 +164,10 @@ inline void write_string(std::string& o, const std::string& s) {
             case '\n': o += "\\n"; break;
             case '\r': o += "\\r"; break;
             case '\t': o += "\\t"; break;
-            default:
-                if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04X", c); o += b; }
-                else o.push_back((char)c);
+            default: { char b[8]; snprintf(b, sizeof b, "\\u%04X", c); o += b; }
         }
     }
+    o.append(sp + run, n - run);
     o.push_back('"');
 }
 
@@ -170,11 +178,9 @@ inline std::string java_double(double d) {
     if (std::isinf(d)) return d > 0 ? "Infinity" : "-Infinity";
     if (d == 0) return std::signbit(d) ? "-0.0" : "0.0";
     char buf[64];
-    int prec = 1;
-    for (; prec <= 17; prec++) {
-        snprintf(buf, sizeof buf, "%.*e", prec - 1, d);
-        if (strtod(buf, nullptr) == d) break;
-    }
+    // shortest digits that round-trip (std::to_chars), scientific layout: [-]d.ddddde[+-]xx
+    auto tc = std::to_chars(buf, buf + sizeof buf - 1, d, std::chars_format::scientific);
+    *tc.ptr = 0;
     // buf = [-]d.ddddde[+-]xx
     std::string s(buf);
     bool neg = s[0] == '-';
