@@ -352,8 +352,8 @@ __global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq
     if (lane == 0) {
         n_clauses[r] = nc;
         msm_out[r] = (i32)(qp.msm_ratio * (double)nc);   // Classifier.java:257
-        // u16 weight lanes / u8 count lanes of the filter kernel: <= 255 pair clauses, <= 181 term clauses
-        const bool fast = dense && qp.filter_ok && nc <= (qp.alg == ALG_NAIVE ? 181 : 255);
+        // u8 count lanes of the filter kernel: <= 255 clauses (the u16 weight lanes then hold 255 * 255 at most)
+        const bool fast = dense && qp.filter_ok && nc <= 255;
         if (fast) { route[r] = ROUTE_FILTER; status[r] = ST_OK; }
         else if (dense) { route[r] = ROUTE_DENSE; status[r] = ST_OK; }
         else if (qp.positional_ok) { route[r] = ROUTE_POSITIONAL; status[r] = ST_OK; }

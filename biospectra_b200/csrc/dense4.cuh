@@ -478,8 +478,10 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
                 atomicMin(&s_qmin, qe);
             }
         }
-        // u16 lanes: pair-row weights <= 255, term-row weights <= 255*tf(14)/tf(7) < 362, plus this thread's exception cells
-        if (255u * (u32)n_pair + 362u * (u32)(nc - n_pair) + exc_sum > 65535u) s_over = 1;
+        // u16 lanes: pair-row weights <= 255 and term-row weights <= 255*tf(14)/tf(7) < 362 (all-term reads: <= 127 each),
+        // plus this thread's exception cells
+        const u32 lane_max = all_terms ? 127u * (u32)nc : 255u * (u32)n_pair + 362u * (u32)(nc - n_pair);
+        if (lane_max + exc_sum > 65535u) s_over = 1;
         if (exc_cnt) atomicAdd(&s_nexc, exc_cnt);
     }
     // ---- pass 2: per-thread best estimate, then the block's 10th best (full list) or best (result set only).

@@ -159,3 +159,32 @@ def test_filter_overflow_falls_back(oracle_lib, monkeypatch):
         assert cnt["filter_overflow_reads"] >= 2, cnt
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("alg", [0, 1, 2])
+def test_filter_long_reads_up_to_255_clauses(oracle_lib, monkeypatch, alg):
+    """Reads with up to 255 clauses stay on the packed-lane filter (u8 match counters, u16 weight lanes); longer ones are
+    handed to the exact scorer.  Both must agree with the oracle."""
+    ents = _many_docs_corpus(77, 300, 700, 5)
+    rng = random.Random(5)
+    reads = []
+    for i in range(120):
+        e = rng.choice(ents)
+        ln = rng.choice([150, 200, 254, 258, 259, 262, 300, 420, 520, 600])
+        a = rng.randint(0, max(0, len(e) - 10))
+        s = (e[a:] + common.rand_seq(rng, 700))[:ln]
+        reads.append("".join(c if rng.random() > 0.03 else rng.choice("ACGT") for c in s))
+    ox = common.build_oracle(oracle_lib, ents, 5, False)
+    res_o = ox.classify([r.encode() for r in reads], skips=0, algorithm=alg, scoring=0, msm=0.5, threads=4)
+    monkeypatch.setenv("BSP_FILTER", "1")
+    g = common.build_gpu(ents, 5, False, dict(kmer_skips=0, query_algorithm=["NAIVE_KMER", "CHAIN_PROXIMITY", "PAIRED_PROXIMITY"][alg],
+                                              scoring_algorithm="tfidf", dense_tables=1, positional=2))
+    try:
+        res_g = g.classify_batch(reads)
+        common.assert_classify_equal(res_g, res_o, reads, "long reads alg%d" % alg)
+        routes = g.last_routes(len(reads))
+        ncl = res_o["n_clauses"]
+        assert (ncl[routes == 3] <= 255).all() and (routes[ncl > 255] == 1).all()       # (a lane overflow also hands over)
+        assert ((routes == 3) & (ncl > 181)).sum() > 0 and (routes == 1).sum() > 0
+    finally:
+        g.close()
