@@ -116,50 +116,60 @@ static void exclusive_scan(const TI* in, TO* out, u64 n, TO* d_total, DevBuf<u8>
 }
 
 // ------------------------------------------------------------------ radix sort
-// Stable LSD radix sort of (key, u32 value) pairs by key bits [0, key_bits), 8 bits
-// per pass.  Three kernels per pass: per-tile digit histogram -> scan of the
-// digit-major [256][tiles] matrix -> stable scatter (warp match-any ranking).
+// Stable LSD radix sort of (key, u32 value) pairs by key bits [0, key_bits), <= 8 bits per pass (the passes split the
+// key evenly: 20 bits -> 7+7+6).  Three kernels per pass: per-tile digit histogram -> scan of the digit-major
+// [256][tiles] matrix -> stable scatter.  The scatter ranks its tile with warp match-any, orders the tile by digit in
+// shared memory and writes it out run by run, so that consecutive threads store to consecutive addresses.
 #define RS_WARPS 8
-#define RS_PER_WARP 512               // items per warp = 16 rows of 32 lanes
-#define RS_ROWS (RS_PER_WARP / 32)
-#define RS_TILE (RS_WARPS * RS_PER_WARP)
+#define RS_THREADS (RS_WARPS * 32)
+template <typename K> struct RsTile { static const int ROWS = sizeof(K) == 4 ? 16 : 8; };   // 32-item rows per warp
+#define RS_TILE_OF(K) (RS_WARPS * 32 * RsTile<K>::ROWS)
 
 template <typename K>
-__global__ void __launch_bounds__(RS_WARPS * 32) rs_hist_kernel(const K* __restrict__ keys, u32 n, int shift,
-                                                                 u32* __restrict__ hist, u32 tiles) {
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const K* __restrict__ keys, u32 n, int shift, u32 mask,
+                                                              u32* __restrict__ hist, u32 tiles) {
     __shared__ u32 h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
-    u32 base = blockIdx.x * RS_TILE;
+    const u32 TILE = RS_TILE_OF(K);
+    u32 base = blockIdx.x * TILE;
 #pragma unroll 4
-    for (int i = 0; i < RS_TILE / (RS_WARPS * 32); i++) {
-        u32 idx = base + i * (RS_WARPS * 32) + threadIdx.x;
-        if (idx < n) atomicAdd(&h[(u32)(keys[idx] >> shift) & 255u], 1u);
+    for (int i = 0; i < (int)(TILE / RS_THREADS); i++) {
+        u32 idx = base + i * RS_THREADS + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(u32)(keys[idx] >> shift) & mask], 1u);
     }
     __syncthreads();
     hist[(u64)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
 }
 
 template <typename K>
-__global__ void __launch_bounds__(RS_WARPS * 32) rs_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin,
-                                                                    K* __restrict__ kout, u32* __restrict__ vout, u32 n,
-                                                                    int shift, const u32* __restrict__ hist_scanned, u32 tiles) {
-    __shared__ u32 wcnt[RS_WARPS][256];
-    __shared__ u32 gbase[256];
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin,
+                                                                 K* __restrict__ kout, u32* __restrict__ vout, u32 n,
+                                                                 int shift, u32 mask, const u32* __restrict__ hist_scanned, u32 tiles) {
+    const int ROWS = RsTile<K>::ROWS;
+    const u32 TILE = RS_TILE_OF(K);
+    __shared__ u32 wcnt[RS_WARPS][256];      // per warp digit counts -> exclusive offsets inside the tile
+    __shared__ u32 dstart[257];              // first tile-local slot of every digit
+    __shared__ u32 gbase[256];               // first global slot of every digit for this tile
+    __shared__ u32 scan_sm[33];
+    __shared__ K s_key[RS_WARPS * 32 * RsTile<K>::ROWS];
+    __shared__ u32 s_val[RS_WARPS * 32 * RsTile<K>::ROWS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += blockDim.x) (&wcnt[0][0])[i] = 0;
     gbase[threadIdx.x] = hist_scanned[(u64)threadIdx.x * tiles + blockIdx.x];
     __syncthreads();
-    const u32 wbase = blockIdx.x * RS_TILE + warp * RS_PER_WARP;
-    K key[RS_ROWS];
-    u32 rank[RS_ROWS];
+    const u32 tbase = blockIdx.x * TILE;
+    const u32 wbase = tbase + warp * (32 * ROWS);
+    K key[ROWS];
+    u32 val[ROWS], rank[ROWS];
     const u32 lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int j = 0; j < RS_ROWS; j++) {
+    for (int j = 0; j < ROWS; j++) {
         u32 idx = wbase + j * 32 + lane;
         bool ok = idx < n;
         key[j] = ok ? kin[idx] : (K)0;
-        u32 d = ok ? ((u32)(key[j] >> shift) & 255u) : 256u;      // 256 = out-of-range sentinel group
+        val[j] = ok ? vin[idx] : 0u;
+        u32 d = ok ? ((u32)(key[j] >> shift) & mask) : 256u;      // 256 = out-of-range sentinel group
         u32 grp = __match_any_sync(0xFFFFFFFFu, d);
         int leader = __ffs(grp) - 1;
         u32 b = 0;
@@ -172,25 +182,37 @@ __global__ void __launch_bounds__(RS_WARPS * 32) rs_scatter_kernel(const K* __re
         __syncwarp();
     }
     __syncthreads();
-    {   // exclusive prefix over warps for digit = threadIdx.x (blockDim.x == 256)
-        u32 run = gbase[threadIdx.x];
+    {   // digit = threadIdx.x: exclusive prefix over warps, then over digits (tile-local layout: digit, warp, rank)
+        u32 tot = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
             u32 c = wcnt[w][threadIdx.x];
-            wcnt[w][threadIdx.x] = run;
-            run += c;
+            wcnt[w][threadIdx.x] = tot;
+            tot += c;
         }
+        u32 ex = block_exclusive_scan<u32>(tot, (u32*)nullptr, scan_sm);
+        dstart[threadIdx.x] = ex;
+        if (threadIdx.x == 255) dstart[256] = ex + tot;
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < RS_ROWS; j++) {
+    for (int j = 0; j < ROWS; j++) {
         u32 idx = wbase + j * 32 + lane;
         if (idx < n) {
-            u32 d = (u32)(key[j] >> shift) & 255u;
-            u32 dst = wcnt[warp][d] + rank[j];
-            kout[dst] = key[j];
-            vout[dst] = vin[idx];
+            u32 d = (u32)(key[j] >> shift) & mask;
+            u32 slot = dstart[d] + wcnt[warp][d] + rank[j];
+            s_key[slot] = key[j];
+            s_val[slot] = val[j];
         }
+    }
+    __syncthreads();
+    const u32 n_tile = dstart[256];
+    for (u32 i = threadIdx.x; i < n_tile; i += blockDim.x) {
+        const K k = s_key[i];
+        const u32 d = (u32)(k >> shift) & mask;
+        const u32 dst = gbase[d] + (i - dstart[d]);
+        kout[dst] = k;
+        vout[dst] = s_val[i];
     }
 }
 
@@ -204,15 +226,21 @@ struct RadixSortTemp {
 template <typename K>
 static void radix_sort_pairs(K** keys, u32** vals, K** keys_alt, u32** vals_alt, u32 n, int key_bits,
                              RadixSortTemp& t, cudaStream_t st) {
-    if (n == 0) return;
-    u32 tiles = (u32)ceil_div(n, RS_TILE);
+    if (n == 0 || key_bits <= 0) return;
+    const u32 TILE = RS_TILE_OF(K);
+    u32 tiles = (u32)ceil_div(n, TILE);
     t.hist.ensure((size_t)256 * tiles);
-    for (int shift = 0; shift < key_bits; shift += 8) {
-        rs_hist_kernel<K><<<tiles, RS_WARPS * 32, 0, st>>>(*keys, n, shift, t.hist.p, tiles);
+    const int passes = (key_bits + 7) / 8;
+    int shift = 0;
+    for (int p = 0; p < passes; p++) {
+        const int bits = (key_bits - shift + (passes - p) - 1) / (passes - p);     // spread the bits evenly over the passes
+        const u32 mask = (1u << bits) - 1u;
+        rs_hist_kernel<K><<<tiles, RS_THREADS, 0, st>>>(*keys, n, shift, mask, t.hist.p, tiles);
         exclusive_scan<u32, u32>(t.hist.p, t.hist.p, (u64)256 * tiles, (u32*)nullptr, t.scan_tmp, st);
-        rs_scatter_kernel<K><<<tiles, RS_WARPS * 32, 0, st>>>(*keys, *vals, *keys_alt, *vals_alt, n, shift, t.hist.p, tiles);
+        rs_scatter_kernel<K><<<tiles, RS_THREADS, 0, st>>>(*keys, *vals, *keys_alt, *vals_alt, n, shift, mask, t.hist.p, tiles);
         KERNEL_CHECK();
         K* tk = *keys; *keys = *keys_alt; *keys_alt = tk;
         u32* tv = *vals; *vals = *vals_alt; *vals_alt = tv;
+        shift += bits;
     }
 }
