@@ -40,7 +40,8 @@ struct Scratch {
     i32* h_counts = nullptr;            // pinned: [0..3] route counts, [4] filter overflow
     FilterStats* h_fstats = nullptr;    // pinned
     // state between the two phases of a sub-batch
-    i32 n = 0; int n_tiles = 1, parts_pos = 0, parts_stride = 1, dense_threads = 32; QueryParams qp; bool busy = false;
+    i32 n = 0; int n_tiles = 1, parts_pos = 0, parts_stride = 1, dense_threads = 32, filter_threads = 32, filter_tiles = 1;
+    QueryParams qp; bool busy = false;
     i32 r0 = 0;                         // first read of the sub-batch in the caller's arrays
     void init() {
         CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -520,12 +521,11 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     qp.dense_ok = ix.tables && (qp.alg == ALG_NAIVE || ix.has_pair) && env_i64("BSP_DISABLE_DENSE", 0) == 0;
     qp.positional_ok = ix.positional ? 1 : 0;
     qp.pair_row0 = ix.pair_row0;
-    // fast filter path: tf-idf, every doc of the handle inside one CTA (32 docs per thread, <= 512 threads).
+    // fast filter path: tf-idf; CTA per (doc tile, read), 32 docs per thread, <= 512 threads per tile.
     // BSP_FILTER: 0 off, 1 whenever usable, unset = only where it pays (enough docs to fill a CTA)
     const u32 D = (u32)ix.docs.size();
     const i64 filter_mode = env_i64("BSP_FILTER", -1);
-    qp.filter_ok = qp.dense_ok && qp.sim == SIM_TFIDF && ix.d_pad <= 512 * FK_DOCS && filter_mode != 0 &&
-                   (filter_mode == 1 || D >= 1024);
+    qp.filter_ok = qp.dense_ok && qp.sim == SIM_TFIDF && filter_mode != 0 && (filter_mode == 1 || D >= 1024);
     weights_kernel<<<(unsigned)ceil_div((i64)n * 32, 256), 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p,
                                                                sc.tok_df.p, h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p,
                                                                sc.n_clauses.p, sc.msm.p, sc.route.p, sc.status_in.p, sc.vrange.p);
@@ -538,7 +538,11 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     sc.dense_threads = (int)std::min<i64>(512, round_up(std::max<i64>(ceil_div(ix.d_pad, EX_DPT), 1), 32));
     sc.n_tiles = (int)std::max<i64>(1, ceil_div(ix.d_pad, (i64)sc.dense_threads * EX_DPT));
     sc.parts_pos = ix.positional ? (int)ix.segs.size() : 0;
-    sc.parts_stride = std::max(std::max(sc.n_tiles, sc.parts_pos), 1);
+    // filter tiles: BSP_FILTER_THREADS (multiple of 32, <= 512) caps the CTA size (tests use it to force several tiles)
+    const i64 ft_cap = std::min<i64>(512, std::max<i64>(32, round_up(env_i64("BSP_FILTER_THREADS", 512), 32)));
+    sc.filter_threads = (int)std::min<i64>(ft_cap, round_up(std::max<i64>(ceil_div(ix.d_pad, FK_DOCS), 1), 32));
+    sc.filter_tiles = (int)std::max<i64>(1, ceil_div(ix.d_pad, (i64)sc.filter_threads * FK_DOCS));
+    sc.parts_stride = std::max(std::max(std::max(sc.n_tiles, sc.parts_pos), sc.filter_tiles), 1);
     sc.part_n.ensure((size_t)n * sc.parts_stride);
     sc.part_doc.ensure((size_t)n * sc.parts_stride * TOPN);
     sc.part_score.ensure((size_t)n * sc.parts_stride * TOPN);
@@ -563,16 +567,17 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
     FilterStats fs = {0, 0, 0};
     if (counts[2] > 0) {
         CUDA_CHECK(cudaMemsetAsync(sc.fstats.p, 0, sizeof(FilterStats), st));
-        int threads = (int)round_up(std::max<i64>(ceil_div(ix.d_pad, FK_DOCS), 1), 32);
+        const int threads = sc.filter_threads;
         const size_t ring_bytes = (size_t)FK_STAGES * threads * 16;
         static bool attr_set[64] = {false};      // per device: allow the 512-thread ring (64 KB dynamic shared memory)
         if (!attr_set[h->conf.device & 63]) {
             CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
             attr_set[h->conf.device & 63] = true;
         }
-        filter_score_kernel<<<(unsigned)counts[2], threads, ring_bytes, st>>>(T, D, h->tf16.p, sc.list_filter.p, sc.tok_off.p, sc.n_tok.p,
+        if ((i64)counts[2] * sc.filter_tiles > 0x7FFFFFFF) throw BspError(BSP_ERR_UNSUPPORTED, "batch too large for the filter path");
+        filter_score_kernel<<<(unsigned)((i64)counts[2] * sc.filter_tiles), threads, ring_bytes, st>>>(T, D, h->tf16.p, sc.list_filter.p, sc.tok_off.p, sc.n_tok.p,
             sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.vrange.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n,
-            part_doc, part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p, full_topn, 1u);
+            part_doc, part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p, full_topn, 1u, sc.filter_tiles);
         KERNEL_CHECK();
         launches++;
         // reads the filter could not bound (exception or candidate overflow) were appended to the exact list
@@ -607,7 +612,7 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
     }
     KERNEL_CHECK();
     CUDA_CHECK(cudaEventRecord(sc.ev[2], st));
-    merge_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(n, sc.route.p, sc.status_in.p, n_tiles, parts_pos, parts_stride, part_n,
+    merge_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(n, sc.route.p, sc.status_in.p, n_tiles, parts_pos, sc.filter_tiles, parts_stride, part_n,
                                                              part_doc, part_score, out.status, out.label, out.n_hits, out.n_top,
                                                              out.top_doc, out.top_score, full_topn);
     KERNEL_CHECK();
@@ -971,7 +976,7 @@ BSP_API int bsp_merge_topk_device(bsp_classifier* h, int32_t n, int32_t parts, c
     API_TRY(h)
     CUDA_CHECK(cudaSetDevice(h->conf.device));
     // layout: [n][parts] lists; status is taken from part 0 (identical on every rank: it depends on the read only)
-    merge_kernel<<<(unsigned)ceil_div(std::max(n, 1), 128), 128, 0, h->st>>>(n, nullptr, (const i32*)d_part_status, parts, parts, parts,
+    merge_kernel<<<(unsigned)ceil_div(std::max(n, 1), 128), 128, 0, h->st>>>(n, nullptr, (const i32*)d_part_status, parts, parts, parts, parts,
         (const i32*)d_part_n_top, (const u32*)d_part_doc, (const float*)d_part_score, (i32*)d_status, (i32*)d_label, (i32*)d_n_hits,
         (i32*)d_n_top, (i32*)d_top_doc, (float*)d_top_score, (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0);
     KERNEL_CHECK();

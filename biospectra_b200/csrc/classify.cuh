@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
 // into the final list; n_hits = entries equal to the max (Classifier.java:358-366);
 // label by score tier (Classifier.java:263-339 without taxonomy).
 __global__ void __launch_bounds__(128) merge_kernel(i32 n_reads, const i32* __restrict__ route, const i32* __restrict__ status_in,
-                                                     int parts_dense, int parts_pos, int parts_stride,
+                                                     int parts_dense, int parts_pos, int parts_filter, int parts_stride,
                                                      const i32* __restrict__ part_n, const u32* __restrict__ part_doc,
                                                      const float* __restrict__ part_score,
                                                      i32* __restrict__ status, i32* __restrict__ label, i32* __restrict__ n_hits,
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(128) merge_kernel(i32 n_reads, const i32* __re
     u32 bd[TOPN];
     int nt = 0;
     const int rt = route ? route[r] : ROUTE_POSITIONAL;
-    const int parts = rt == ROUTE_DENSE ? parts_dense : (rt == ROUTE_POSITIONAL ? parts_pos : (rt == ROUTE_FILTER ? 1 : 0));
+    const int parts = rt == ROUTE_DENSE ? parts_dense : (rt == ROUTE_POSITIONAL ? parts_pos : (rt == ROUTE_FILTER ? parts_filter : 0));
     for (int p = 0; p < parts; p++) {
         const i64 pb = (i64)r * parts_stride + p;
         const int np = part_n[pb];

@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         const float2* __restrict__ read_vrange, const float* __restrict__ doc_w, int alg, u32 global_doc_base, int parts_stride,
         i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score, i32* __restrict__ route,
         i32* __restrict__ overflow_list, i32* __restrict__ overflow_count, FilterStats* __restrict__ stats, int full_topn,
-        u32 one /* = 1, see add_fma_pipe */) {
+        u32 one /* = 1, see add_fma_pipe */, int n_tiles /* doc tiles of blockDim.x * 32 docs; CTA per (tile, read) */) {
     __shared__ uint2 s_lut[FK_MAX_CLAUSES + 1];          // q for codes 0..3 | 4..7
     __shared__ uint2 s_lut_hi[FK_MAX_CLAUSES + 1];       // term rows (NAIVE_KMER): q for codes 8..11 | 12..15
     __shared__ u32 s_row[FK_MAX_CLAUSES + 1];
@@ -333,7 +333,8 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     __shared__ u32 s_qmin, s_nexc;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
-    const i32 r = read_list[blockIdx.x];
+    const int tile = blockIdx.x % n_tiles;
+    const i32 r = read_list[blockIdx.x / n_tiles];
     const i64 base = tok_off[r];
     const i32 n = n_tok[r], nc = n_clauses[r];
     const i32 n_pair = alg == ALG_NAIVE ? 0 : (alg == ALG_CHAIN ? nc : n / 2);
@@ -376,14 +377,14 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
 
     // ---- pass 1: stream the rows.  Thread owns docs [32t, 32t+32): wacc[i] = u16 lanes (doc 2i, 2i+1),
     //      cacc[j] = u8 lanes (docs 4j..4j+3)
-    const u32 d0 = threadIdx.x * FK_DOCS;
+    const u32 d0 = ((u32)tile * blockDim.x + threadIdx.x) * FK_DOCS;
     const bool active = (u64)d0 < T.row_bytes * 2;
     u32 wacc[16], cacc[8];
 #pragma unroll
     for (int i = 0; i < 16; i++) wacc[i] = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) cacc[i] = 0;
-    const u8* tbase = T.tab + (u64)threadIdx.x * 16;
+    const u8* tbase = T.tab + (u64)d0 / 2;
     if (active) {
         // Each thread prefetches its own 16-byte slice of the next FK_STAGES rows into its private slots of the
         // ring (no cross-thread hand-off, so no barriers): FK_STAGES x 16 B in flight per thread.
@@ -541,13 +542,14 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     }
     __syncthreads();
     const int n_cand = s_ncand;
-    const i64 pbase = (i64)r * parts_stride;
-    if (lane_overflow || n_cand > FK_CAND_CAP) {          // hand the read to exact_score_kernel
+    const i64 pbase = (i64)r * parts_stride + tile;
+    if (lane_overflow || n_cand > FK_CAND_CAP) {          // hand the read to exact_score_kernel (once, whichever tile asks)
         if (threadIdx.x == 0) {
-            overflow_list[atomicAdd(overflow_count, 1)] = r;
-            route[r] = ROUTE_DENSE;
             part_n[pbase] = 0;
-            if (stats) atomicAdd(&stats->overflow_reads, 1ull);
+            if (atomicExch(&route[r], ROUTE_DENSE) != ROUTE_DENSE) {
+                overflow_list[atomicAdd(overflow_count, 1)] = r;
+                if (stats) atomicAdd(&stats->overflow_reads, 1ull);
+            }
         }
         return;
     }

@@ -107,7 +107,7 @@ def _many_docs_corpus(seed, n_docs, length, k):
     return ents
 
 
-@pytest.mark.parametrize("k,alg,n_docs", [(5, 2, 700), (4, 1, 1300), (6, 0, 500), (5, 2, 90)])
+@pytest.mark.parametrize("k,alg,n_docs", [(5, 2, 700), (4, 1, 1300), (6, 0, 500), (5, 2, 90), (5, 2, 2600)])
 def test_filter_path_many_docs(oracle_lib, monkeypatch, k, alg, n_docs):
     """The bound-and-rescore kernel with CTAs of several warps (>= 10 threads hold valid docs, so the 10th-best
     lower bound really prunes), forced candidates from exception cells, and candidate overflow (many exact ties)
@@ -128,6 +128,17 @@ def test_filter_path_many_docs(oracle_lib, monkeypatch, k, alg, n_docs):
         assert cnt["filter_candidates"] > 0
     finally:
         g.close()
+    # several doc tiles per read (CTAs of 32 threads = 1,024 docs each): per-tile lists merged by merge_kernel
+    monkeypatch.setenv("BSP_FILTER_THREADS", "32")
+    for full in (1, 0):
+        g = common.build_gpu(ents, k, False, dict(kmer_skips=0, query_algorithm=alg_name, scoring_algorithm="tfidf",
+                                                  dense_tables=1, positional=2, full_topn=full))
+        try:
+            common.assert_classify_equal(g.classify_batch(reads), res_o, reads, "filter tiles k%d alg%d" % (k, alg), hits_only=not full)
+            assert g.last_counters()["filter_reads"] > 0
+        finally:
+            g.close()
+    monkeypatch.delenv("BSP_FILTER_THREADS")
     # result-set mode (the default): only the hits equal to the maximum are reported, from fewer rescored docs
     g = common.build_gpu(ents, k, False, dict(kmer_skips=0, query_algorithm=alg_name, scoring_algorithm="tfidf",
                                               dense_tables=1, positional=2, full_topn=0))
