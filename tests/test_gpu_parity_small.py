@@ -199,3 +199,36 @@ def test_filter_long_reads_up_to_255_clauses(oracle_lib, monkeypatch, alg):
         assert ((routes == 3) & (ncl > 181)).sum() > 0 and (routes == 1).sum() > 0
     finally:
         g.close()
+
+
+def test_edge_batches_and_clause_limits(oracle_lib, monkeypatch):
+    """Empty batch, reads shorter than k, exactly 2 tokens, and the reference's 10,000-clause limit
+    (Classifier.java:110 BooleanQuery.setMaxClauseCount(10000): longer reads throw and are skipped); reads with
+    thousands of clauses go through the multi-stage loops of the exact and positional scorers."""
+    rng = random.Random(12)
+    ents = [common.rand_seq(rng, rng.randint(3000, 12000)) for _ in range(9)] + ["ACGT" * 3000]
+    long_src = ents[2] + ents[5]
+    reads = ["ACGTA", "ACGTAC", "ACGTACG", ents[0][:5], ents[1][10:2000], ents[2][:9000], (long_src * 2)[:10004],
+             (long_src * 2)[:10005], (long_src * 2)[:10006], (long_src * 2)[:14000], "ACGT" * 2600, "N" * 30]
+    k = 6
+    ox = common.build_oracle(oracle_lib, ents, k, False)
+    for alg, sim in ((0, 0), (1, 0), (2, 1), (2, 0)):
+        res_o = ox.classify([r.encode() for r in reads], skips=0, algorithm=alg, scoring=sim, msm=0.5, threads=4)
+        assert res_o["status"][0] == 1 and res_o["status"][1] == 1 and res_o["status"][2] == 0
+        alg_name = ["NAIVE_KMER", "CHAIN_PROXIMITY", "PAIRED_PROXIMITY"][alg]
+        if alg == 0:
+            # NAIVE: n_clauses = n_tokens = len - k + 1: 10,005 bases -> 10,000 clauses (kept), 10,006 -> 10,001 (dropped)
+            assert res_o["n_clauses"][7] == 10000 and res_o["status"][7] == 0 and res_o["status"][8] == 1
+        for dense in (1, 2):
+            monkeypatch.setenv("BSP_FILTER", "1")
+            g = common.build_gpu(ents, k, False, dict(kmer_skips=0, query_algorithm=alg_name, scoring_algorithm="bm25" if sim else "tfidf",
+                                                      dense_tables=dense, positional=1))
+            try:
+                res_g = g.classify_batch(reads)
+                common.assert_classify_equal(res_g, res_o, reads, "edge alg%d sim%d dense%d" % (alg, sim, dense))
+                empty = g.classify_packed(np.zeros(0, np.uint8), np.zeros(1, np.int64))
+                assert len(empty["status"]) == 0
+                with pytest.raises(ValueError):
+                    g.classify_batch(["ACGTACGT", ""])          # Classifier.java:342-344: null/empty sequence
+            finally:
+                g.close()
