@@ -319,6 +319,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("BSP_WORKLOAD", "C2"))
     ap.add_argument("--algorithm", default="PAIRED_PROXIMITY")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skips", type=int, default=0, help="kmer_skips of the query side (shipped configuration.json: 0; code default: 5)")
+    ap.add_argument("--reads", type=int, default=0, help="override the number of reads per GPU")
     ap.add_argument("--mode", default="replica", choices=["replica", "docpart"],
                     help="replica: read-sharded index replicas (default, no collective); docpart: doc-partitioned index")
     ap.add_argument("--verify", action="store_true", help="docpart: compare with a single-index run on rank 0")
@@ -326,6 +328,8 @@ def main():
                     help="which region cudaProfilerStart/Stop brackets (for ncu --profile-from-start off)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
+    if args.reads:
+        wl["reads"] = args.reads
     from biospectra_b200 import synth
     lengths = synth.genome_lengths(wl["genomes"], wl["total_bp"], wl["seed"], *((1, 1) if wl.get("equal") else (1.5e6, 6.5e6)))
     if args.impl == "reference":
@@ -346,7 +350,7 @@ def main():
 
     # ---- build: synthetic reference generated in HBM, indexed on the GPU (not timed as part of the metric)
     iconf = shipped_config(device=local)
-    qconf = shipped_config(device=local, query_algorithm=args.algorithm)
+    qconf = shipped_config(device=local, query_algorithm=args.algorithm, kmer_skips=args.skips)
     S = sample_plan(wl, lengths)
     t0 = time.time()
     ix = Indexer(iconf)
