@@ -366,6 +366,8 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
         h->ref = ref;
         for (auto& sc : h->sc) sc.init();
         h->st = h->sc[0].st;
+        // the filter kernel's cp.async ring needs up to 64 KB of dynamic shared memory (512 threads x 8 stages x 16 B)
+        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
         BuildOptions opt;
         opt.want_tables = conf->dense_tables;
         opt.want_positional = conf->positional;
@@ -569,11 +571,6 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
         CUDA_CHECK(cudaMemsetAsync(sc.fstats.p, 0, sizeof(FilterStats), st));
         const int threads = sc.filter_threads;
         const size_t ring_bytes = (size_t)FK_STAGES * threads * 16;
-        static bool attr_set[64] = {false};      // per device: allow the 512-thread ring (64 KB dynamic shared memory)
-        if (!attr_set[h->conf.device & 63]) {
-            CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
-            attr_set[h->conf.device & 63] = true;
-        }
         if ((i64)counts[2] * sc.filter_tiles > 0x7FFFFFFF) throw BspError(BSP_ERR_UNSUPPORTED, "batch too large for the filter path");
         filter_score_kernel<<<(unsigned)((i64)counts[2] * sc.filter_tiles), threads, ring_bytes, st>>>(T, D, h->tf16.p, sc.list_filter.p, sc.tok_off.p, sc.n_tok.p,
             sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.vrange.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n,
@@ -605,9 +602,17 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
         i64 blocks = (i64)counts[1] * parts_pos;
         const i64 MAXG = 0x7FFFFFFF;
         if (blocks > MAXG) throw BspError(BSP_ERR_UNSUPPORTED, "batch too large for the positional path");
-        score_positional_kernel<<<(unsigned)blocks, POS_THREADS, smem, st>>>(ix.d_segs.p, parts_pos, sc.list_pos.p, counts[1], sc.tok_off.p,
-            sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p, sc.clause_val.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, qp, sp, gbase,
-            parts_stride, part_n, part_doc, part_score);
+        if (ix.max_seg_docs <= POSW_DOCS && env_i64("BSP_POS_BLOCK_KERNEL", 0) == 0) {
+            // few documents per segment (large genomes): one warp per (segment, read)
+            const i64 wblocks = ceil_div(blocks, POSW_WARPS);
+            score_positional_warp_kernel<<<(unsigned)wblocks, POSW_WARPS * 32, 0, st>>>(ix.d_segs.p, parts_pos, sc.list_pos.p, counts[1],
+                sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p, sc.clause_val.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, qp, sp, gbase,
+                parts_stride, part_n, part_doc, part_score);
+        } else {
+            score_positional_kernel<<<(unsigned)blocks, POS_THREADS, smem, st>>>(ix.d_segs.p, parts_pos, sc.list_pos.p, counts[1], sc.tok_off.p,
+                sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p, sc.clause_val.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, qp, sp, gbase,
+                parts_stride, part_n, part_doc, part_score);
+        }
         launches++;
     }
     KERNEL_CHECK();

@@ -517,6 +517,117 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
     if (threadIdx.x == 0) part_n[pbase] = found;
 }
 
+// Same scorer, one WARP per (segment, read), for segments of at most POSW_DOCS documents (large genomes: a 2^28-token
+// segment holds ~80 docs at 3 Mbp each).  No block barriers: the warp stages 32 clauses at a time, walks each clause's
+// postings 32 at a time (a doc occurs once per clause -> plain shared-memory updates), and selects its top 10 with
+// shuffles.  POSW_WARPS pairs per CTA.
+#define POSW_DOCS 256
+#define POSW_WARPS 8
+__global__ void __launch_bounds__(POSW_WARPS * 32) score_positional_warp_kernel(
+        const SegDev* __restrict__ segs, int n_segs, const i32* __restrict__ read_list, i32 n_list,
+        const i64* __restrict__ tok_off, const i32* __restrict__ n_tok, const u64* __restrict__ tok_key,
+        const u32* __restrict__ tok_pos, const float* __restrict__ clause_val, const i32* __restrict__ n_clauses,
+        const i32* __restrict__ msm, const float* __restrict__ doc_w, QueryParams qp, SimParams sp, u32 global_doc_base,
+        int parts_stride, i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score) {
+    __shared__ double s_acc[POSW_WARPS][POSW_DOCS];
+    __shared__ u16 s_cnt[POSW_WARPS][POSW_DOCS];
+    __shared__ ClauseStage s_stage[POSW_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 pair = (i64)blockIdx.x * POSW_WARPS + warp;
+    if (pair >= (i64)n_list * n_segs) return;
+    const int sidx = (int)(pair % n_segs);
+    const i32 r = read_list[pair / n_segs];
+    const SegDev s = segs[sidx];
+    double* acc = s_acc[warp];
+    u16* cnt = s_cnt[warp];
+    ClauseStage* stage = s_stage[warp];
+    for (u32 d = lane; d < s.n_docs; d += 32) { acc[d] = 0.0; cnt[d] = 0; }
+    const i64 base = tok_off[r];
+    const i32 n = n_tok[r], nc = n_clauses[r];
+    const float* dw = doc_w + s.doc_base;
+    for (i32 c0 = 0; c0 < nc; c0 += 32) {
+        __syncwarp();
+        const i32 c = c0 + lane;
+        if (c < nc) {
+            i32 j0, j1;
+            clause_tokens(qp.alg, n, c, j0, j1);
+            ClauseStage st;
+            st.val = clause_val[base + c];
+            const u64 k0 = tok_key[base + j0];
+            const u32 t0 = seg_find_term(s, k0);
+            st.a0 = st.b0 = st.a1 = st.b1 = 0; st.slop = 0;
+            if (t0 != NO_TERM) { st.a0 = s.term_off[t0]; st.b0 = s.term_off[t0 + 1]; }
+            if (j1 >= 0) {
+                const u64 k1 = tok_key[base + j1];
+                const int slop = (int)(tok_pos[base + j1] - tok_pos[base + j0]) + 1;     // Classifier.java:146,182
+                if (k1 == k0) { st.slop = -slop; st.a1 = st.a0; st.b1 = st.b0; }
+                else {
+                    st.slop = slop;
+                    const u32 t1 = seg_find_term(s, k1);
+                    if (t1 != NO_TERM) { st.a1 = s.term_off[t1]; st.b1 = s.term_off[t1 + 1]; }
+                    else st.b0 = st.a0;                                                  // conjunction is empty
+                }
+            }
+            stage[lane] = st;
+        }
+        __syncwarp();
+        const i32 lim = min(32, nc - c0);
+        for (i32 ci = 0; ci < lim; ci++) {
+            const ClauseStage st = stage[ci];
+            for (u32 i = st.a0 + lane; i < st.b0; i += 32) {
+                const u32 d = s.post_doc[i];
+                float f;
+                if (st.slop == 0) f = (float)(s.post_pos[i + 1] - s.post_pos[i]);       // TermScorer: freq as float
+                else {
+                    const bool same = st.slop < 0;
+                    f = phrase_freq_at(s, i, st.a1, st.b1, st.a1 + (i - st.a0), same ? -st.slop : st.slop, same);
+                }
+                if (f != 0.0f) {
+                    const float sc = clause_doc_score(sp.sim, sp.sim == SIM_TFIDF ? tf_of(f) : f, st.val, dw[d], sp.k1p1);
+                    acc[d] += (double)sc;                                                // BooleanScorer: double sum
+                    cnt[d] += 1;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    // final scores, msm filter, per-lane candidates (lane owns docs lane, lane+32, ...: at most 8)
+    const i32 need = max(1, msm[r]);
+    u64 keys[POSW_DOCS / 32];
+#pragma unroll
+    for (int j = 0; j < POSW_DOCS / 32; j++) {
+        const u32 d = lane + 32 * j;
+        keys[j] = 0;
+        if (d < s.n_docs) {
+            const i32 m = cnt[d];
+            if (m >= need) keys[j] = cand_key(final_score(sp.sim, acc[d], m, nc), d);
+        }
+    }
+    const i64 pbase = (i64)r * parts_stride + sidx;
+    i32 found = 0;
+    for (int round = 0; round < TOPN; round++) {
+        u64 lm = 0;
+#pragma unroll
+        for (int j = 0; j < POSW_DOCS / 32; j++) if (keys[j] > lm) lm = keys[j];
+        u64 best = lm;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const u64 x = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+            if (x > best) best = x;
+        }
+        if (best == 0) break;
+#pragma unroll
+        for (int j = 0; j < POSW_DOCS / 32; j++) if (keys[j] == best) keys[j] = 0;
+        if (lane == 0) {
+            part_doc[pbase * TOPN + round] = global_doc_base + s.doc_base + (0xFFFFFFFFu - (u32)(best & 0xFFFFFFFFu));
+            part_score[pbase * TOPN + round] = __uint_as_float((u32)(best >> 32));
+        }
+        found++;
+    }
+    if (lane == 0) part_n[pbase] = found;
+}
+
 // ------------------------------------------------------------------------ K8
 // Thread per read: merge the per-part top-10 lists (each sorted score desc, doc asc)
 // into the final list; n_hits = entries equal to the max (Classifier.java:358-366);

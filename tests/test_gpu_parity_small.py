@@ -29,13 +29,16 @@ def test_index_and_classify_bit_exact(case, oracle_lib, monkeypatch):
     alg_name = ["NAIVE_KMER", "CHAIN_PROXIMITY", "PAIRED_PROXIMITY"][case["alg"]]
     qkw = dict(kmer_skips=case["skips"], query_algorithm=alg_name, scoring_algorithm="bm25" if case["sim"] else "tfidf",
                query_term_min_should_match=case["msm"])
-    # positional (general) path only
+    # positional (general) path only: warp-per-(segment, read) kernel (few docs per segment) and the block kernel
     g = common.build_gpu(ents, k, ms, dict(qkw, dense_tables=2, positional=1))
     try:
         common.assert_index_equal(g, ox)
-        res_g = g.classify_batch(reads)
-        common.assert_classify_equal(res_g, res_o, reads, "positional")
-        assert set(g.last_routes(len(reads))[res_o["status"] == 0]) <= {2}
+        for block_kernel in ("0", "1"):
+            monkeypatch.setenv("BSP_POS_BLOCK_KERNEL", block_kernel)
+            res_g = g.classify_batch(reads)
+            common.assert_classify_equal(res_g, res_o, reads, "positional block_kernel=" + block_kernel)
+            assert set(g.last_routes(len(reads))[res_o["status"] == 0]) <= {2}
+        monkeypatch.delenv("BSP_POS_BLOCK_KERNEL")
     finally:
         g.close()
     # dense 4-bit tables on (small k): reads whose clauses all have slop 2 take a dense route --
@@ -76,6 +79,10 @@ def test_multi_segment_matches_single(oracle_lib, monkeypatch):
                     common.assert_index_equal(g, ox, sample_terms=[ox.term_at(i) for i in range(0, ox.stats()["n_terms"], 37)])
                 res_g = g.classify_batch(reads)
                 common.assert_classify_equal(res_g, res_o, reads, "k%d dense%d filter%s" % (k, dense, filt))
+                if dense == 2:
+                    monkeypatch.setenv("BSP_POS_BLOCK_KERNEL", "1")
+                    common.assert_classify_equal(g.classify_batch(reads), res_o, reads, "k%d block kernel" % k)
+                    monkeypatch.delenv("BSP_POS_BLOCK_KERNEL")
                 if dense == 1:
                     routes = g.last_routes(len(reads))
                     assert ((routes == 1) | (routes == 3)).sum() > 0
