@@ -30,8 +30,10 @@ struct bsp_indexer {
 struct Scratch {
     DevBuf<u8> seq, scan_tmp; DevBuf<i64> seq_off, tok_off, tok_cap;
     DevBuf<u64> tok_key; DevBuf<u32> tok_pos, tok_df, clause_row; DevBuf<float> clause_val;
-    DevBuf<i32> n_tok, n_clauses, msm, route, status_in, list_dense, list_pos, list_filter, counts;
+    DevBuf<i32> n_tok, n_clauses, msm, route, status_in, list_dense, list_pos, list_filter, counts, read_ngap;
     DevBuf<FilterStats> fstats; DevBuf<float2> vrange;
+    DevBuf<GapClause> gaps; DevBuf<u32> gap_cnt;       // gap clauses of the sub-batch; gap_cnt[GAP_CAP] matches, [GAP_CAP] = #clauses
+    int slot_index = 0;
     DevBuf<i32> part_n; DevBuf<u32> part_doc; DevBuf<float> part_score;
     DevBuf<i32> o_status, o_label, o_nhits, o_ntop, o_doc; DevBuf<float> o_score;
     cudaStream_t st = nullptr;
@@ -364,7 +366,7 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
     try {
         h->conf = *conf;
         h->ref = ref;
-        for (auto& sc : h->sc) sc.init();
+        for (int i = 0; i < 2; i++) { h->sc[i].init(); h->sc[i].slot_index = i; }
         h->st = h->sc[0].st;
         // the filter kernel's cp.async ring needs up to 64 KB of dynamic shared memory (512 threads x 8 stages x 16 B)
         CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
@@ -502,7 +504,7 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     sc.tok_df.ensure((size_t)tok_cap_total + 1); sc.clause_val.ensure((size_t)tok_cap_total + 1);
     sc.clause_row.ensure((size_t)tok_cap_total + 1);
     sc.n_tok.ensure(n); sc.n_clauses.ensure(n); sc.msm.ensure(n); sc.route.ensure(n); sc.status_in.ensure(n);
-    sc.list_dense.ensure(n); sc.list_pos.ensure(n); sc.list_filter.ensure(n); sc.counts.ensure(8); sc.vrange.ensure(n);
+    sc.list_dense.ensure(n); sc.list_pos.ensure(n); sc.list_filter.ensure(n); sc.counts.ensure(8); sc.vrange.ensure(n); sc.read_ngap.ensure(n);
     if (!sc.fstats.p) sc.fstats.alloc(1);
     sc.n = n; sc.busy = true;
     CUDA_CHECK(cudaEventRecord(sc.ev[0], st));
@@ -523,6 +525,10 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     qp.dense_ok = ix.tables && (qp.alg == ALG_NAIVE || ix.has_pair) && env_i64("BSP_DISABLE_DENSE", 0) == 0;
     qp.positional_ok = ix.positional ? 1 : 0;
     qp.pair_row0 = ix.pair_row0;
+    qp.gap_ok = qp.dense_ok && ix.has_pair && ix.positional && env_i64("BSP_DISABLE_GAP", 0) == 0;
+    qp.temp_row0 = (u32)ix.n_rows + 1;
+    if (!sc.gaps.p) { sc.gaps.alloc(GAP_CAP); sc.gap_cnt.alloc(GAP_CAP + 1); }
+    if (qp.gap_ok) CUDA_CHECK(cudaMemsetAsync(sc.gap_cnt.p, 0, (GAP_CAP + 1) * sizeof(u32), st));
     // fast filter path: tf-idf; CTA per (doc tile, read), 32 docs per thread, <= 512 threads per tile.
     // BSP_FILTER: 0 off, 1 whenever usable, unset = only where it pays (enough docs to fill a CTA)
     const u32 D = (u32)ix.docs.size();
@@ -530,12 +536,14 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     qp.filter_ok = qp.dense_ok && qp.sim == SIM_TFIDF && filter_mode != 0 && (filter_mode == 1 || D >= 1024);
     weights_kernel<<<(unsigned)ceil_div((i64)n * 32, 256), 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p,
                                                                sc.tok_df.p, h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p,
-                                                               sc.n_clauses.p, sc.msm.p, sc.route.p, sc.status_in.p, sc.vrange.p);
+                                                               sc.n_clauses.p, sc.msm.p, sc.route.p, sc.status_in.p, sc.vrange.p,
+                                                               sc.gaps.p, sc.gap_cnt.p + GAP_CAP, sc.read_ngap.p);
     CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));
     route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, n, sc.list_dense.p, sc.list_pos.p, sc.list_filter.p,
                                                                      sc.counts.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(sc.h_counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 5, sc.gap_cnt.p + GAP_CAP, 4, cudaMemcpyDeviceToHost, st));   // # gap clauses
     // partial top-10 buffers
     sc.dense_threads = (int)std::min<i64>(512, round_up(std::max<i64>(ceil_div(ix.d_pad, EX_DPT), 1), 32));
     sc.n_tiles = (int)std::max<i64>(1, ceil_div(ix.d_pad, (i64)sc.dense_threads * EX_DPT));
@@ -556,13 +564,31 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
     const i32 n = sc.n;
     const QueryParams& qp = sc.qp;
     CUDA_CHECK(cudaStreamSynchronize(st));                  // route counts have arrived
+    if (qp.gap_ok && sc.h_counts[5] > 0) {
+        // gap clauses (reads with an N, kmer_skips > 0): matches from the positional postings -> sorted lists in the tail
+        // of the exception arrays; a clause with too many matches sends its read to the positional scorer, so the route
+        // lists are rebuilt afterwards
+        const int n_segs = (int)ix.segs.size();
+        const i64 ng = std::min<i64>(sc.h_counts[5], GAP_CAP);
+        const u32 tmp_base = (u32)ix.n_exc + (u32)sc.slot_index * GAP_CAP * GAP_LIST;
+        gap_fill_kernel<<<(unsigned)ceil_div(ng * n_segs * 32, 256), 256, 0, st>>>(ix.d_segs.p, n_segs, sc.gaps.p,
+            sc.gap_cnt.p + GAP_CAP, sc.gap_cnt.p, ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base);
+        gap_sort_kernel<<<(unsigned)ceil_div(ng * 32, 256), 256, 0, st>>>(sc.gaps.p, sc.gap_cnt.p + GAP_CAP, sc.gap_cnt.p,
+            ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base, sc.route.p, sc.status_in.p, qp.positional_ok);
+        CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));
+        route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, n, sc.list_dense.p, sc.list_pos.p, sc.list_filter.p,
+                                                                         sc.counts.p);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaMemcpyAsync(sc.h_counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
     i32 counts[4] = {sc.h_counts[0], sc.h_counts[1], sc.h_counts[2], 0};
     const u32 D = (u32)ix.docs.size();
     const int n_tiles = sc.n_tiles, parts_pos = sc.parts_pos, parts_stride = sc.parts_stride;
     i32* part_n = sc.part_n.p; u32* part_doc = sc.part_doc.p; float* part_score = sc.part_score.p;
     SimParams sp; sp.sim = qp.sim; sp.k1p1 = 1.2f + 1.0f;
     const u32 gbase = (u32)h->doc_base_global;
-    const Tab4Dev T = ix.tab4_view();
+    const Tab4Dev T = ix.tab4_view(sc.slot_index, sc.gap_cnt.p);
     const int full_topn = (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0;
     CUDA_CHECK(cudaEventRecord(sc.ev[1], st));
     i64 launches = 6;
@@ -573,7 +599,7 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
         const size_t ring_bytes = (size_t)FK_STAGES * threads * 16;
         if ((i64)counts[2] * sc.filter_tiles > 0x7FFFFFFF) throw BspError(BSP_ERR_UNSUPPORTED, "batch too large for the filter path");
         filter_score_kernel<<<(unsigned)((i64)counts[2] * sc.filter_tiles), threads, ring_bytes, st>>>(T, D, h->tf16.p, sc.list_filter.p, sc.tok_off.p, sc.n_tok.p,
-            sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.vrange.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n,
+            sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.vrange.p, sc.read_ngap.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n,
             part_doc, part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p, full_topn, 1u, sc.filter_tiles);
         KERNEL_CHECK();
         launches++;

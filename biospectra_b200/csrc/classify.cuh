@@ -159,7 +159,17 @@ struct QueryParams {
     int positional_ok;      // positional segments resident
     int filter_ok;          // fast filter path usable (tf-idf, doc count within one CTA)
     u64 pair_row0;          // first pair row of the dense table (= 4^k)
+    int gap_ok;             // gap clauses can be evaluated sparsely (dense tables AND positional postings resident)
+    u32 temp_row0;          // row id of gap clause 0 of the sub-batch
 };
+
+// Gap clauses: a phrase clause whose two k-mers are not adjacent in the read (an N in between, or kmer_skips > 0) is
+// not a function of a (k+1)-mer, so no table row exists for it.  Its matches are sparse (two independent k-mers must
+// fall within the slop of each other: ~1 doc per clause at C2), so a pre-pass evaluates it against the positional
+// postings and stores the matches as the exception list of a virtual all-zero row (dense4.cuh).
+#define GAP_CAP 4096            // gap clauses per sub-batch
+#define GAP_LIST 64             // matches kept per gap clause (more: the read falls back to the positional scorer)
+struct GapClause { u64 k0, k1; i32 slop; i32 read; };
 
 __device__ __forceinline__ int base_code_dev(u8 c) {
     return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
@@ -281,7 +291,9 @@ __global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq
                                                        float* __restrict__ clause_val, u32* __restrict__ clause_row,
                                                        i32* __restrict__ n_clauses, i32* __restrict__ msm_out,
                                                        i32* __restrict__ route, i32* __restrict__ status,
-                                                       float2* __restrict__ vrange /* per read: (max, min) clause value */) {
+                                                       float2* __restrict__ vrange /* per read: (max, min) clause value */,
+                                                       GapClause* __restrict__ gaps, u32* __restrict__ gap_count,
+                                                       i32* __restrict__ read_ngap /* per read: # gap clauses registered */) {
     const int lane = threadIdx.x & 31;
     const i32 r = (i32)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
     if (r >= n_reads) return;
@@ -294,10 +306,11 @@ __global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq
     }
     bool dense = qp.dense_ok != 0;
     float sum_sq = 0.0f;
+    i32 n_gap = 0;
     for (i32 c0 = 0; c0 < nc; c0 += 32) {
         const i32 c = c0 + lane;
         float sq = 0.0f;
-        bool bad_slop = false;
+        bool bad_slop = false, is_gap = false;
         if (c < nc) {
             i32 j0, j1;
             clause_tokens(qp.alg, n, c, j0, j1);
@@ -305,13 +318,28 @@ __global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq
             if (j1 >= 0) {
                 // TFIDFSimilarity#idfExplain(stats, TermStatistics[]): float sum, t0 first
                 idf = __fadd_rn(__fadd_rn(0.0f, idf), idf_by_df[tok_df[base + j1]]);
-                bad_slop = tok_pos[base + j1] - tok_pos[base + j0] != 1u;          // slop != 2: not a dense-table row
+                const u32 delta = tok_pos[base + j1] - tok_pos[base + j0];
+                if (delta != 1u) {                                                  // slop != 2: not a dense-table row
+                    bad_slop = true;
+                    if (qp.gap_ok) {                                                // a gap clause: sparse pre-pass (dense4.cuh)
+                        const u32 g = atomicAdd(gap_count, 1u);
+                        if (g < (u32)GAP_CAP) {
+                            GapClause gc;
+                            gc.k0 = tok_key[base + j0]; gc.k1 = tok_key[base + j1]; gc.slop = (int)delta + 1; gc.read = r;
+                            gaps[g] = gc;
+                            clause_row[base + c] = qp.temp_row0 + g;
+                            bad_slop = false;
+                            is_gap = true;
+                        }
+                    }
+                }
             }
             clause_val[base + c] = idf;
             const float qw = __fmul_rn(idf, 1.0f);
             sq = __fmul_rn(qw, qw);
         }
         if (__any_sync(0xFFFFFFFFu, bad_slop)) dense = false;
+        n_gap += __popc(__ballot_sync(0xFFFFFFFFu, is_gap));
         const i32 lim = min(32, nc - c0);
         for (i32 i = 0; i < lim; i++) sum_sq = __fadd_rn(sum_sq, __shfl_sync(0xFFFFFFFFu, sq, i));   // clause order
     }
@@ -339,7 +367,9 @@ __global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq
         for (i32 c = lane; c < nc; c += 32) {
             i32 j0, j1;
             clause_tokens(qp.alg, n, c, j0, j1);
-            if (j1 >= 0) {      // pair row: the raw (k+1)-mer at the first token's offset
+            if (j1 >= 0 && tok_pos[base + j1] - tok_pos[base + j0] != 1u) {
+                // gap clause: its temporary row id was stored above
+            } else if (j1 >= 0) {      // pair row: the raw (k+1)-mer at the first token's offset
                 const u32 off = tok_pos[base + j0];
                 u64 u = 0;
                 for (int i = 0; i <= qp.k; i++) u = (u << 2) | (u64)base_code_dev(s[off + i]);
@@ -351,6 +381,7 @@ __global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq
     }
     if (lane == 0) {
         n_clauses[r] = nc;
+        read_ngap[r] = n_gap;
         msm_out[r] = (i32)(qp.msm_ratio * (double)nc);   // Classifier.java:257
         // u8 count lanes of the filter kernel: <= 255 clauses (the u16 weight lanes then hold 255 * 255 at most)
         const bool fast = dense && qp.filter_ok && nc <= 255;

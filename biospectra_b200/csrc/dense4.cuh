@@ -31,10 +31,21 @@ struct Tab4Dev {
     const u8* tab;
     u64 row_bytes;
     u64 pair_row0;          // 4^k
-    const u32* exc_off;     // [n_rows + 1]
+    const u32* exc_off;     // [n_rows + 2]
     const u32* exc_doc;     // handle-global doc ids, ascending within a row
     const float* exc_freq;
+    u32 zero_row;           // = n_rows: an all-zero row without exceptions
+    u32 temp_row0;          // = n_rows + 1: temporary rows of the current sub-batch's gap clauses
+    u32 tmp_base;           // their match lists live at exc_doc/exc_freq[tmp_base + g * GAP_LIST ...]
+    const u32* gap_cnt;     // [GAP_CAP] matches per gap clause
 };
+
+// exception list (first entry, count) and table row of a clause row id
+__device__ __forceinline__ void row_exceptions(const Tab4Dev& T, u32 row, u32& a, u32& n) {
+    if (row >= T.temp_row0) { const u32 g = row - T.temp_row0; a = T.tmp_base + g * GAP_LIST; n = min(T.gap_cnt[g], (u32)GAP_LIST); }
+    else { a = T.exc_off[row]; n = T.exc_off[row + 1] - a; }
+}
+__device__ __forceinline__ u32 row_data(const Tab4Dev& T, u32 row) { return row >= T.temp_row0 ? T.zero_row : row; }
 
 struct ExcBuild {           // append buffer used while the tables are built
     u32* row; u32* doc; float* freq;
@@ -139,6 +150,72 @@ __global__ void __launch_bounds__(256) exc_offsets_kernel(const u64* __restrict_
         if ((keys[mid] >> 32) < r) lo = mid + 1; else hi = mid;
     }
     exc_off[r] = lo;
+}
+
+// ---- gap clauses: evaluate against the positional postings, keep the (few) matching docs as a sorted list
+// warp per (gap clause, segment); idle warps (no such clause in this sub-batch) leave at once
+__global__ void __launch_bounds__(256) gap_fill_kernel(const SegDev* __restrict__ segs, int n_segs, const GapClause* __restrict__ gaps,
+                                                        const u32* __restrict__ gap_count, u32* __restrict__ gap_cnt,
+                                                        u32* __restrict__ tmp_doc, float* __restrict__ tmp_freq) {
+    const int lane = threadIdx.x & 31;
+    const u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 ng = min(*gap_count, (u32)GAP_CAP);
+    const u32 g = (u32)(w / (u64)n_segs);
+    if (g >= ng) return;
+    const SegDev s = segs[w % (u64)n_segs];
+    const GapClause gc = gaps[g];
+    const bool same = gc.k0 == gc.k1;
+    const u32 t0 = seg_find_term(s, gc.k0);
+    if (t0 == NO_TERM) return;
+    u32 a1 = 0, b1 = 0;
+    if (same) { a1 = s.term_off[t0]; b1 = s.term_off[t0 + 1]; }
+    else {
+        const u32 t1 = seg_find_term(s, gc.k1);
+        if (t1 == NO_TERM) return;
+        a1 = s.term_off[t1]; b1 = s.term_off[t1 + 1];
+    }
+    const u32 a0 = s.term_off[t0], b0 = s.term_off[t0 + 1];
+    for (u32 i = a0 + lane; i < b0; i += 32) {
+        const float f = phrase_freq_at(s, i, a1, b1, a1 + (i - a0), gc.slop, same);
+        if (f != 0.0f) {
+            const u32 pos = atomicAdd(&gap_cnt[g], 1u);
+            if (pos < GAP_LIST) {
+                tmp_doc[(u64)g * GAP_LIST + pos] = s.doc_base + s.post_doc[i];
+                tmp_freq[(u64)g * GAP_LIST + pos] = f;
+            }
+        }
+    }
+}
+
+// warp per gap clause: sort its matches by doc id (the filter and the exact scorer binary-search them); a clause with
+// more than GAP_LIST matches sends its read to the positional scorer instead
+__global__ void __launch_bounds__(256) gap_sort_kernel(const GapClause* __restrict__ gaps, const u32* __restrict__ gap_count,
+                                                        const u32* __restrict__ gap_cnt, u32* __restrict__ tmp_doc,
+                                                        float* __restrict__ tmp_freq, i32* __restrict__ route, i32* __restrict__ status,
+                                                        int positional_ok) {
+    __shared__ u32 sd[8][GAP_LIST];
+    __shared__ float sf[8][GAP_LIST];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= min(*gap_count, (u32)GAP_CAP)) return;
+    const u32 n = gap_cnt[g];
+    if (n > GAP_LIST) {
+        if (lane == 0) {
+            const i32 r = gaps[g].read;
+            route[r] = positional_ok ? ROUTE_POSITIONAL : ROUTE_NONE;
+            if (!positional_ok) status[r] = ST_ERROR;
+        }
+        return;
+    }
+    for (u32 i = lane; i < n; i += 32) { sd[warp][i] = tmp_doc[(u64)g * GAP_LIST + i]; sf[warp][i] = tmp_freq[(u64)g * GAP_LIST + i]; }
+    __syncwarp();
+    for (u32 i = lane; i < n; i += 32) {          // rank sort: a doc appears at most once per clause
+        const u32 d = sd[warp][i];
+        u32 rank = 0;
+        for (u32 j = 0; j < n; j++) rank += sd[warp][j] < d;
+        tmp_doc[(u64)g * GAP_LIST + rank] = d;
+        tmp_freq[(u64)g * GAP_LIST + rank] = sf[warp][i];
+    }
 }
 
 // ------------------------------------------------------------------ shared helpers
@@ -313,7 +390,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         Tab4Dev T, u32 n_docs, const float* __restrict__ tf16, const i32* __restrict__ read_list,
         const i64* __restrict__ tok_off, const i32* __restrict__ n_tok, const float* __restrict__ clause_val,
         const u32* __restrict__ clause_row, const i32* __restrict__ n_clauses, const i32* __restrict__ msm,
-        const float2* __restrict__ read_vrange, const float* __restrict__ doc_w, int alg, u32 global_doc_base, int parts_stride,
+        const float2* __restrict__ read_vrange, const i32* __restrict__ read_ngap, const float* __restrict__ doc_w, int alg, u32 global_doc_base, int parts_stride,
         i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score, i32* __restrict__ route,
         i32* __restrict__ overflow_list, i32* __restrict__ overflow_count, FilterStats* __restrict__ stats, int full_topn,
         u32 one /* = 1, see add_fma_pipe */, int n_tiles /* doc tiles of blockDim.x * 32 docs; CTA per (tile, read) */) {
@@ -329,7 +406,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     __shared__ u32 s_cand[FK_CAND_CAP];
     __shared__ u64 s_ckey[FK_CAND_CAP];
     __shared__ u8 s_code[FK_CODE_CAP];
-    __shared__ int s_ncand, s_nexrows, s_over;
+    __shared__ int s_ncand, s_nexrows, s_over, s_ndense, s_ngap;
     __shared__ u32 s_qmin, s_nexc;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
@@ -339,6 +416,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     const i32 n = n_tok[r], nc = n_clauses[r];
     const i32 n_pair = alg == ALG_NAIVE ? 0 : (alg == ALG_CHAIN ? nc : n / 2);
     const i32 need = max(1, msm[r]);
+    const i32 n_gap = read_ngap[r];                    // gap clauses of the read (all of them pair clauses)
     // scale S: S * value_c * tf(7) <= 255 for every clause; q_min = smallest non-zero cell weight (weights_kernel
     // recorded the largest and smallest clause value of the read)
     const float2 vr = read_vrange[r];
@@ -346,15 +424,27 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     const bool all_terms = n_pair == 0;
     const float S = all_terms ? 127.0f / (vr.x * tf16[T4_TF_MAX]) : FK_QMAX / (vr.x * tf16[T4_PAIR_MAX]);
     if (threadIdx.x < 16) s_tf[threadIdx.x] = tf16[threadIdx.x];
-    if (threadIdx.x == 0) { s_ncand = 0; s_nexrows = 0; s_over = 0; s_nexc = 0; s_qmin = (u32)__float2int_rn(S * vr.y); }
+    if (threadIdx.x == 0) {
+        s_ncand = 0; s_nexrows = 0; s_over = 0; s_nexc = 0; s_ndense = 0; s_ngap = 0;
+        s_qmin = (u32)__float2int_rn(S * vr.y);
+    }
     __syncthreads();
-    for (i32 c = threadIdx.x; c < nc; c += blockDim.x) {
-        const float v = clause_val[base + c];
-        const u32 row = clause_row[base + c];
+    // Clause order in shared memory: table-backed pair clauses [0, n_dense), term clauses, then the gap pair clauses
+    // (virtual all-zero rows, matches in their exception lists) at the end: rows [0, n_stream) are streamed.  The double
+    // sums are exact, so the order is free.
+    const i32 n_dense = n_pair - n_gap, n_stream = nc - n_gap;
+    for (i32 c0 = threadIdx.x; c0 < nc; c0 += blockDim.x) {
+        const float v = clause_val[base + c0];
+        const u32 row = clause_row[base + c0];
+        i32 c = c0;
+        if (n_gap) {
+            if (c0 >= n_pair) c = c0 - n_gap;
+            else c = row >= T.temp_row0 ? nc - 1 - atomicAdd(&s_ngap, 1) : atomicAdd(&s_ndense, 1);
+        }
         s_val[c] = v;
         s_row[c] = row;
         const float sv = S * v;
-        if (c < n_pair) {
+        if (c0 < n_pair) {
             u32 q[8];
             q[0] = 0;
 #pragma unroll
@@ -368,10 +458,11 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
             s_lut[c] = make_uint2(q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24), q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24));
             s_lut_hi[c] = make_uint2(q[8] | (q[9] << 8) | (q[10] << 16) | (q[11] << 24), q[12] | (q[13] << 8) | (q[14] << 16) | (q[15] << 24));
         }
-        const u32 a = T.exc_off[row], b = T.exc_off[row + 1];
+        u32 a, ne;
+        row_exceptions(T, row, a, ne);
         s_exa[c] = a;
-        s_exn[c] = b - a;
-        if (b > a) s_exrows[atomicAdd(&s_nexrows, 1)] = (u8)c;
+        s_exn[c] = ne;
+        if (ne) s_exrows[atomicAdd(&s_nexrows, 1)] = (u8)c;
     }
     __syncthreads();
 
@@ -393,20 +484,20 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         const u32 stride = blockDim.x;
 #pragma unroll
         for (int st = 0; st < FK_STAGES; st++) {
-            if (st < nc) cp_async16(slot + st * stride, tbase + (u64)s_row[st] * T.row_bytes);
+            if (st < n_stream) cp_async16(slot + st * stride, tbase + (u64)s_row[st] * T.row_bytes);
             cp_async_commit();
         }
-        i32 c = 0;
-        const i32 n_two = all_terms ? nc : n_pair;    // rows streamed two at a time through a byte LUT
+        i32 i = 0;
+        const i32 n_two = all_terms ? nc : n_dense;   // rows streamed two at a time through a byte LUT
 #pragma unroll 1
-        for (; c + 2 <= n_two; c += 2) {
+        for (; i + 2 <= n_two; i += 2) {
             cp_async_wait<FK_STAGES - 2>();
-            uint4* my0 = slot + (c % FK_STAGES) * stride;
-            uint4* my1 = slot + ((c + 1) % FK_STAGES) * stride;
+            uint4* my0 = slot + (i % FK_STAGES) * stride;
+            uint4* my1 = slot + ((i + 1) % FK_STAGES) * stride;
             const uint4 q0 = *my0, q1 = *my1;
-            const uint2 l0 = s_lut[c], l1 = s_lut[c + 1];
+            const uint2 l0 = s_lut[i], l1 = s_lut[i + 1];
             if (all_terms) {
-                const uint2 h0 = s_lut_hi[c], h1 = s_lut_hi[c + 1];
+                const uint2 h0 = s_lut_hi[i], h1 = s_lut_hi[i + 1];
                 const uint4 t0 = make_uint4(l0.x, l0.y, h0.x, h0.y), t1 = make_uint4(l1.x, l1.y, h1.x, h1.y);
                 term_word2(q0.x, q1.x, t0, t1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1], one);
                 term_word2(q0.y, q1.y, t0, t1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3], one);
@@ -418,17 +509,19 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
                 pair_word2(q0.z, q1.z, l0, l1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5], one);
                 pair_word2(q0.w, q1.w, l0, l1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7], one);
             }
-            if (c + FK_STAGES < nc) cp_async16(my0, tbase + (u64)s_row[c + FK_STAGES] * T.row_bytes);
+            // the slots' data now lives in registers: refill them with the rows FK_STAGES ahead
+            if (i + FK_STAGES < n_stream) cp_async16(my0, tbase + (u64)s_row[i + FK_STAGES] * T.row_bytes);
             cp_async_commit();
-            if (c + 1 + FK_STAGES < nc) cp_async16(my1, tbase + (u64)s_row[c + 1 + FK_STAGES] * T.row_bytes);
+            if (i + 1 + FK_STAGES < n_stream) cp_async16(my1, tbase + (u64)s_row[i + 1 + FK_STAGES] * T.row_bytes);
             cp_async_commit();
         }
 #pragma unroll 1
-        for (; c < nc; c++) {
+        for (; i < n_stream; i++) {
             cp_async_wait<FK_STAGES - 1>();
-            uint4* my = slot + (c % FK_STAGES) * stride;
+            uint4* my = slot + (i % FK_STAGES) * stride;
             const uint4 q = *my;
-            if (c < n_pair) {
+            const i32 c = i;
+            if (c < n_dense) {
                 const uint2 lut = s_lut[c];
                 pair_word(q.x, lut, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1]);
                 pair_word(q.y, lut, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3]);
@@ -449,7 +542,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
                 }
             }
             // the slot's data now lives in registers: refill it with the row FK_STAGES ahead
-            if (c + FK_STAGES < nc) cp_async16(my, tbase + (u64)s_row[c + FK_STAGES] * T.row_bytes);
+            if (i + FK_STAGES < n_stream) cp_async16(my, tbase + (u64)s_row[i + FK_STAGES] * T.row_bytes);
             cp_async_commit();
         }
         // ---- exception cells (stored as 0 in the table) of this thread's docs join their lanes with the same
@@ -568,7 +661,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
                 const int it = it0 + u * blockDim.x;
                 code[u] = 0;
                 const int j = it >> pitch_log, c = it & ((1 << pitch_log) - 1);
-                if (it < n_items && c < nc) code[u] = cell_code(T, s_row[c], s_cand[j]);
+                if (it < n_items && c < nc && s_row[c] < T.temp_row0) code[u] = cell_code(T, s_row[c], s_cand[j]);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -586,7 +679,8 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         i32 m = 0;
 #pragma unroll 1
         for (i32 c = lane; c < nc; c += 32) {
-            const u32 code = staged ? (u32)s_code[(j << pitch_log) + c] : cell_code(T, s_row[c], d);
+            const u32 code = staged ? (u32)s_code[(j << pitch_log) + c]
+                                    : (s_row[c] >= T.temp_row0 ? 0u : cell_code(T, s_row[c], d));
             float tf = s_tf[code];
             if (code == 0u && s_exn[c]) {
                 const float f = exc_lookup(T, s_exa[c], s_exn[c], d);
@@ -687,7 +781,7 @@ __global__ void __launch_bounds__(512) exact_score_kernel(
         if (active) {
 #pragma unroll 2
             for (i32 ci = 0; ci < lim; ci++) {
-                const uint2 q = ldg_stream8(tbase + (u64)s_row[ci] * T.row_bytes);
+                const uint2 q = ldg_stream8(tbase + (u64)row_data(T, s_row[ci]) * T.row_bytes);
                 const float val = SIM == SIM_TFIDF ? s_val[ci] : __fmul_rn(s_val[ci], k1p1);
 #pragma unroll
                 for (int i = 0; i < EX_DPT; i++) {
@@ -704,9 +798,7 @@ __global__ void __launch_bounds__(512) exact_score_kernel(
         // exception cells of this stage, in windows of EX_EXC_CAP
         u32 my_a = 0, my_n = 0;
         if ((int)threadIdx.x < lim) {
-            const u32 row = s_row[threadIdx.x];
-            my_a = T.exc_off[row];
-            my_n = T.exc_off[row + 1] - my_a;
+            row_exceptions(T, s_row[threadIdx.x], my_a, my_n);
         }
         u32 total;
         const u32 my_base = block_exclusive_scan<u32>(my_n, &total, s_scan);

@@ -159,10 +159,14 @@ struct GpuIndex {
     // dense 4-bit table
     DevBuf<u8> tab4; u64 d_pad = 0, row_bytes = 0, n_rows = 0, pair_row0 = 0;
     DevBuf<u32> exc_off, exc_doc; DevBuf<float> exc_freq; i64 n_exc = 0;
-    Tab4Dev tab4_view() const {
+    // slot: pipeline slot whose gap-clause lists (tail of the exception arrays) and counters the view refers to
+    Tab4Dev tab4_view(int slot, const u32* gap_cnt) const {
         Tab4Dev t;
         t.tab = tab4.p; t.row_bytes = row_bytes; t.pair_row0 = pair_row0;
         t.exc_off = exc_off.p; t.exc_doc = exc_doc.p; t.exc_freq = exc_freq.p;
+        t.zero_row = (u32)n_rows; t.temp_row0 = (u32)n_rows + 1;
+        t.tmp_base = (u32)n_exc + (u32)slot * GAP_CAP * GAP_LIST;
+        t.gap_cnt = gap_cnt;
         return t;
     }
     u32 max_seg_docs = 0;
@@ -341,7 +345,7 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
     ix.n_rows = can_tables ? (ix.pair_row0 + (opt.need_pair_table ? (1ull << (2 * (k + 1))) : 0ull)) : 0ull;
     u64 tf_bytes = can_tables ? ix.pair_row0 * ix.row_bytes : 0;
     u64 pair_bytes = (can_tables && opt.need_pair_table) ? ((1ull << (2 * (k + 1))) * ix.row_bytes) : 0;
-    if (ix.n_rows >= ((u64)1 << 32) - 1) throw BspError(-5, "dense table row count exceeds 2^32");
+    if (ix.n_rows + GAP_CAP + 2 >= ((u64)1 << 32)) throw BspError(-5, "dense table row count exceeds 2^32");
     bool tables = false;
     if (can_tables && opt.want_tables != 2) {
         if (opt.want_tables == 1) tables = true;
@@ -371,9 +375,9 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
     DevBuf<u32> ex_row, ex_doc; DevBuf<float> ex_freq; DevBuf<unsigned long long> ex_count;
     ExcBuild exb{nullptr, nullptr, nullptr, nullptr, 0};
     if (tables) {
-        ix.tab4.alloc(tf_bytes + pair_bytes);
-        CUDA_CHECK(cudaMemsetAsync(ix.tab4.p, 0, tf_bytes + pair_bytes, st));
-        ix.table_bytes = tf_bytes + pair_bytes;
+        ix.tab4.alloc(tf_bytes + pair_bytes + ix.row_bytes);          // + one all-zero row (index n_rows)
+        CUDA_CHECK(cudaMemsetAsync(ix.tab4.p, 0, tf_bytes + pair_bytes + ix.row_bytes, st));
+        ix.table_bytes = tf_bytes + pair_bytes + ix.row_bytes;
         // a cell can only be an exception where a term posting exists: <= tokens (term rows) + 4 * tokens (pair rows)
         exb.cap = (u64)std::min<i64>(opt.exc_cap, 5 * total_tok + 1024);
         ex_row.alloc((size_t)exb.cap); ex_doc.alloc((size_t)exb.cap); ex_freq.alloc((size_t)exb.cap);
@@ -511,7 +515,9 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
         ix.n_exc = (i64)ne;
         const u32 n = (u32)ne;
         ix.exc_off.alloc(ix.n_rows + 2);
-        ix.exc_doc.alloc(std::max<size_t>(n, 1)); ix.exc_freq.alloc(std::max<size_t>(n, 1));
+        // the tail of the exception arrays holds the gap-clause match lists of the two pipeline slots
+        const size_t tail = (size_t)2 * GAP_CAP * GAP_LIST;
+        ix.exc_doc.alloc((size_t)n + tail); ix.exc_freq.alloc((size_t)n + tail);
         DevBuf<u64> ka, kb; DevBuf<u32> va, vb;
         ka.alloc(std::max<size_t>(n, 1)); kb.alloc(std::max<size_t>(n, 1)); va.alloc(std::max<size_t>(n, 1)); vb.alloc(std::max<size_t>(n, 1));
         u64* keys = ka.p; u64* keys_alt = kb.p; u32* vals = va.p; u32* vals_alt = vb.p;
