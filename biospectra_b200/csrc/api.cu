@@ -369,7 +369,10 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
         for (int i = 0; i < 2; i++) { h->sc[i].init(); h->sc[i].slot_index = i; }
         h->st = h->sc[0].st;
         // the filter kernel's cp.async ring needs up to 64 KB of dynamic shared memory (512 threads x 8 stages x 16 B)
-        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
+        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
+        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
+        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
+        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
         BuildOptions opt;
         opt.want_tables = conf->dense_tables;
         opt.want_positional = conf->positional;
@@ -598,9 +601,14 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
         const int threads = sc.filter_threads;
         const size_t ring_bytes = (size_t)FK_STAGES * threads * 16;
         if ((i64)counts[2] * sc.filter_tiles > 0x7FFFFFFF) throw BspError(BSP_ERR_UNSUPPORTED, "batch too large for the filter path");
-        filter_score_kernel<<<(unsigned)((i64)counts[2] * sc.filter_tiles), threads, ring_bytes, st>>>(T, D, h->tf16.p, sc.list_filter.p, sc.tok_off.p, sc.n_tok.p,
-            sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.vrange.p, sc.read_ngap.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n,
-            part_doc, part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p, full_topn, 1u, sc.filter_tiles);
+        const bool tiled = sc.filter_tiles > 1, naive = qp.alg == ALG_NAIVE;
+        const unsigned fgrid = (unsigned)((i64)counts[2] * sc.filter_tiles);
+#define FK_LAUNCH(TI, AT) filter_score_kernel<TI, AT><<<fgrid, threads, ring_bytes, st>>>(T, D, h->tf16.p, sc.list_filter.p, sc.tok_off.p, sc.n_tok.p, \
+            sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.vrange.p, sc.read_ngap.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n, \
+            part_doc, part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p, full_topn, 1u, sc.filter_tiles)
+        if (tiled) { if (naive) FK_LAUNCH(true, true); else FK_LAUNCH(true, false); }
+        else { if (naive) FK_LAUNCH(false, true); else FK_LAUNCH(false, false); }
+#undef FK_LAUNCH
         KERNEL_CHECK();
         launches++;
         // reads the filter could not bound (exception or candidate overflow) were appended to the exact list

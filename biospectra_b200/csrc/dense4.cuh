@@ -386,6 +386,8 @@ __device__ __forceinline__ float exc_lookup(const Tab4Dev& T, u32 a, u32 n, u32 
     return (lo < n && __ldg(T.exc_doc + a + lo) == d) ? __ldg(T.exc_freq + a + lo) : 0.0f;
 }
 
+// TILED: several doc tiles per read (more than 16,384 docs, or a capped CTA size); ALLTERMS: NAIVE_KMER (term rows only)
+template <bool TILED, bool ALLTERMS>
 __global__ void __launch_bounds__(512) filter_score_kernel(
         Tab4Dev T, u32 n_docs, const float* __restrict__ tf16, const i32* __restrict__ read_list,
         const i64* __restrict__ tok_off, const i32* __restrict__ n_tok, const float* __restrict__ clause_val,
@@ -410,8 +412,8 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     __shared__ u32 s_qmin, s_nexc;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
-    const int tile = blockIdx.x % n_tiles;
-    const i32 r = read_list[blockIdx.x / n_tiles];
+    const int tile = TILED ? blockIdx.x % n_tiles : 0;
+    const i32 r = read_list[TILED ? blockIdx.x / n_tiles : blockIdx.x];
     const i64 base = tok_off[r];
     const i32 n = n_tok[r], nc = n_clauses[r];
     const i32 n_pair = alg == ALG_NAIVE ? 0 : (alg == ALG_CHAIN ? nc : n / 2);
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     // recorded the largest and smallest clause value of the read)
     const float2 vr = read_vrange[r];
     // (NAIVE_KMER has term rows only: all 15 codes go through the byte LUT, weights <= 127)
-    const bool all_terms = n_pair == 0;
+    const bool all_terms = ALLTERMS;
     const float S = all_terms ? 127.0f / (vr.x * tf16[T4_TF_MAX]) : FK_QMAX / (vr.x * tf16[T4_PAIR_MAX]);
     if (threadIdx.x < 16) s_tf[threadIdx.x] = tf16[threadIdx.x];
     if (threadIdx.x == 0) {
