@@ -32,7 +32,7 @@ struct Scratch {
     DevBuf<u64> tok_key; DevBuf<u32> tok_pos, tok_df, clause_row; DevBuf<float> clause_val;
     DevBuf<i32> n_tok, n_clauses, msm, route, status_in, list_dense, list_pos, list_filter, counts, read_ngap;
     DevBuf<FilterStats> fstats; DevBuf<float2> vrange;
-    DevBuf<GapClause> gaps; DevBuf<u32> gap_cnt;       // gap clauses of the sub-batch; gap_cnt[GAP_CAP] matches, [GAP_CAP] = #clauses
+    DevBuf<GapClause> gaps; DevBuf<u32> gap_cnt;       // gap clauses of the sub-batch; gap_cnt[cap] matches, [cap] = #clauses
     int slot_index = 0;
     DevBuf<i32> part_n; DevBuf<u32> part_doc; DevBuf<float> part_score;
     DevBuf<i32> o_status, o_label, o_nhits, o_ntop, o_doc; DevBuf<float> o_score;
@@ -379,6 +379,9 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
         opt.need_pair_table = conf->query_algorithm != BSP_NAIVE_KMER;
         opt.seg_tokens = env_i64("BSP_SEG_TOKENS", (i64)1 << 28);
         opt.exc_cap = std::max<i64>(env_i64("BSP_EXC_CAP", (i64)1 << 26), 1024);
+        // (kmer_skips > 0 turns every phrase clause into a gap clause; evaluating them all in the pre-pass costs what the
+        // positional scorer costs -- measured at C2 -- so those reads overflow this list on purpose and take that scorer)
+        opt.gap_cap = std::max<i64>(env_i64("BSP_GAP_CAP", GAP_CAP_DEFAULT), 1);
         if (opt.seg_tokens < 1024) opt.seg_tokens = 1024;
         build_gpu_index(h->ix, *ref, opt, h->st);
         h->global_docs = (i64)h->ix.docs.size();
@@ -530,8 +533,10 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     qp.pair_row0 = ix.pair_row0;
     qp.gap_ok = qp.dense_ok && ix.has_pair && ix.positional && env_i64("BSP_DISABLE_GAP", 0) == 0;
     qp.temp_row0 = (u32)ix.n_rows + 1;
-    if (!sc.gaps.p) { sc.gaps.alloc(GAP_CAP); sc.gap_cnt.alloc(GAP_CAP + 1); }
-    if (qp.gap_ok) CUDA_CHECK(cudaMemsetAsync(sc.gap_cnt.p, 0, (GAP_CAP + 1) * sizeof(u32), st));
+    const u32 GC = ix.gap_cap;
+    qp.gap_cap = GC;
+    if (!sc.gaps.p) { sc.gaps.alloc(GC); sc.gap_cnt.alloc((size_t)GC + 1); }
+    if (qp.gap_ok) CUDA_CHECK(cudaMemsetAsync(sc.gap_cnt.p, 0, ((size_t)GC + 1) * sizeof(u32), st));
     // fast filter path: tf-idf; CTA per (doc tile, read), 32 docs per thread, <= 512 threads per tile.
     // BSP_FILTER: 0 off, 1 whenever usable, unset = only where it pays (enough docs to fill a CTA)
     const u32 D = (u32)ix.docs.size();
@@ -540,13 +545,13 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     weights_kernel<<<(unsigned)ceil_div((i64)n * 32, 256), 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p,
                                                                sc.tok_df.p, h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p,
                                                                sc.n_clauses.p, sc.msm.p, sc.route.p, sc.status_in.p, sc.vrange.p,
-                                                               sc.gaps.p, sc.gap_cnt.p + GAP_CAP, sc.read_ngap.p);
+                                                               sc.gaps.p, sc.gap_cnt.p + GC, sc.read_ngap.p);
     CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));
     route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, n, sc.list_dense.p, sc.list_pos.p, sc.list_filter.p,
                                                                      sc.counts.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(sc.h_counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 5, sc.gap_cnt.p + GAP_CAP, 4, cudaMemcpyDeviceToHost, st));   // # gap clauses
+    CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 5, sc.gap_cnt.p + GC, 4, cudaMemcpyDeviceToHost, st));   // # gap clauses
     // partial top-10 buffers
     sc.dense_threads = (int)std::min<i64>(512, round_up(std::max<i64>(ceil_div(ix.d_pad, EX_DPT), 1), 32));
     sc.n_tiles = (int)std::max<i64>(1, ceil_div(ix.d_pad, (i64)sc.dense_threads * EX_DPT));
@@ -572,11 +577,12 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
         // of the exception arrays; a clause with too many matches sends its read to the positional scorer, so the route
         // lists are rebuilt afterwards
         const int n_segs = (int)ix.segs.size();
-        const i64 ng = std::min<i64>(sc.h_counts[5], GAP_CAP);
-        const u32 tmp_base = (u32)ix.n_exc + (u32)sc.slot_index * GAP_CAP * GAP_LIST;
+        const u32 GC = ix.gap_cap;
+        const i64 ng = std::min<i64>((u32)sc.h_counts[5], GC);
+        const u32 tmp_base = (u32)ix.n_exc + (u32)sc.slot_index * GC * GAP_LIST;
         gap_fill_kernel<<<(unsigned)ceil_div(ng * n_segs * 32, 256), 256, 0, st>>>(ix.d_segs.p, n_segs, sc.gaps.p,
-            sc.gap_cnt.p + GAP_CAP, sc.gap_cnt.p, ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base);
-        gap_sort_kernel<<<(unsigned)ceil_div(ng * 32, 256), 256, 0, st>>>(sc.gaps.p, sc.gap_cnt.p + GAP_CAP, sc.gap_cnt.p,
+            sc.gap_cnt.p + GC, GC, sc.gap_cnt.p, ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base);
+        gap_sort_kernel<<<(unsigned)ceil_div(ng * 32, 256), 256, 0, st>>>(sc.gaps.p, sc.gap_cnt.p + GC, GC, sc.gap_cnt.p,
             ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base, sc.route.p, sc.status_in.p, qp.positional_ok);
         CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));
         route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, n, sc.list_dense.p, sc.list_pos.p, sc.list_filter.p,

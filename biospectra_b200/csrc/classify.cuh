@@ -161,13 +161,14 @@ struct QueryParams {
     u64 pair_row0;          // first pair row of the dense table (= 4^k)
     int gap_ok;             // gap clauses can be evaluated sparsely (dense tables AND positional postings resident)
     u32 temp_row0;          // row id of gap clause 0 of the sub-batch
+    u32 gap_cap;            // capacity of the sub-batch's gap clause list
 };
 
 // Gap clauses: a phrase clause whose two k-mers are not adjacent in the read (an N in between, or kmer_skips > 0) is
 // not a function of a (k+1)-mer, so no table row exists for it.  Its matches are sparse (two independent k-mers must
 // fall within the slop of each other: ~1 doc per clause at C2), so a pre-pass evaluates it against the positional
 // postings and stores the matches as the exception list of a virtual all-zero row (dense4.cuh).
-#define GAP_CAP 4096            // gap clauses per sub-batch
+#define GAP_CAP_DEFAULT 4096    // gap clauses per sub-batch (reads with an N); BSP_GAP_CAP overrides
 #define GAP_LIST 64             // matches kept per gap clause (more: the read falls back to the positional scorer)
 struct GapClause { u64 k0, k1; i32 slop; i32 read; };
 
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq
                     bad_slop = true;
                     if (qp.gap_ok) {                                                // a gap clause: sparse pre-pass (dense4.cuh)
                         const u32 g = atomicAdd(gap_count, 1u);
-                        if (g < (u32)GAP_CAP) {
+                        if (g < qp.gap_cap) {
                             GapClause gc;
                             gc.k0 = tok_key[base + j0]; gc.k1 = tok_key[base + j1]; gc.slop = (int)delta + 1; gc.read = r;
                             gaps[g] = gc;

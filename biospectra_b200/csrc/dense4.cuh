@@ -37,7 +37,7 @@ struct Tab4Dev {
     u32 zero_row;           // = n_rows: an all-zero row without exceptions
     u32 temp_row0;          // = n_rows + 1: temporary rows of the current sub-batch's gap clauses
     u32 tmp_base;           // their match lists live at exc_doc/exc_freq[tmp_base + g * GAP_LIST ...]
-    const u32* gap_cnt;     // [GAP_CAP] matches per gap clause
+    const u32* gap_cnt;     // [gap_cap] matches per gap clause
 };
 
 // exception list (first entry, count) and table row of a clause row id
@@ -155,11 +155,11 @@ __global__ void __launch_bounds__(256) exc_offsets_kernel(const u64* __restrict_
 // ---- gap clauses: evaluate against the positional postings, keep the (few) matching docs as a sorted list
 // warp per (gap clause, segment); idle warps (no such clause in this sub-batch) leave at once
 __global__ void __launch_bounds__(256) gap_fill_kernel(const SegDev* __restrict__ segs, int n_segs, const GapClause* __restrict__ gaps,
-                                                        const u32* __restrict__ gap_count, u32* __restrict__ gap_cnt,
+                                                        const u32* __restrict__ gap_count, u32 gap_cap, u32* __restrict__ gap_cnt,
                                                         u32* __restrict__ tmp_doc, float* __restrict__ tmp_freq) {
     const int lane = threadIdx.x & 31;
     const u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const u32 ng = min(*gap_count, (u32)GAP_CAP);
+    const u32 ng = min(*gap_count, gap_cap);
     const u32 g = (u32)(w / (u64)n_segs);
     if (g >= ng) return;
     const SegDev s = segs[w % (u64)n_segs];
@@ -190,14 +190,14 @@ __global__ void __launch_bounds__(256) gap_fill_kernel(const SegDev* __restrict_
 // warp per gap clause: sort its matches by doc id (the filter and the exact scorer binary-search them); a clause with
 // more than GAP_LIST matches sends its read to the positional scorer instead
 __global__ void __launch_bounds__(256) gap_sort_kernel(const GapClause* __restrict__ gaps, const u32* __restrict__ gap_count,
-                                                        const u32* __restrict__ gap_cnt, u32* __restrict__ tmp_doc,
+                                                        u32 gap_cap, const u32* __restrict__ gap_cnt, u32* __restrict__ tmp_doc,
                                                         float* __restrict__ tmp_freq, i32* __restrict__ route, i32* __restrict__ status,
                                                         int positional_ok) {
     __shared__ u32 sd[8][GAP_LIST];
     __shared__ float sf[8][GAP_LIST];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= min(*gap_count, (u32)GAP_CAP)) return;
+    if (g >= min(*gap_count, gap_cap)) return;
     const u32 n = gap_cnt[g];
     if (n > GAP_LIST) {
         if (lane == 0) {

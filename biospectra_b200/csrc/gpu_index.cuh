@@ -142,6 +142,7 @@ struct BuildOptions {
     int need_pair_table = 1;      // query algorithm uses phrases
     i64 seg_tokens = (i64)1 << 28;
     i64 exc_cap = (i64)1 << 26;   // capacity of the exception append buffer (entries)
+    i64 gap_cap = GAP_CAP_DEFAULT; // gap clauses per sub-batch
 };
 
 struct GpuIndex {
@@ -158,14 +159,14 @@ struct GpuIndex {
     DevBuf<u32> df_dense; DevBuf<u32> ttf_dense;
     // dense 4-bit table
     DevBuf<u8> tab4; u64 d_pad = 0, row_bytes = 0, n_rows = 0, pair_row0 = 0;
-    DevBuf<u32> exc_off, exc_doc; DevBuf<float> exc_freq; i64 n_exc = 0;
+    DevBuf<u32> exc_off, exc_doc; DevBuf<float> exc_freq; i64 n_exc = 0; u32 gap_cap = GAP_CAP_DEFAULT;
     // slot: pipeline slot whose gap-clause lists (tail of the exception arrays) and counters the view refers to
     Tab4Dev tab4_view(int slot, const u32* gap_cnt) const {
         Tab4Dev t;
         t.tab = tab4.p; t.row_bytes = row_bytes; t.pair_row0 = pair_row0;
         t.exc_off = exc_off.p; t.exc_doc = exc_doc.p; t.exc_freq = exc_freq.p;
         t.zero_row = (u32)n_rows; t.temp_row0 = (u32)n_rows + 1;
-        t.tmp_base = (u32)n_exc + (u32)slot * GAP_CAP * GAP_LIST;
+        t.tmp_base = (u32)n_exc + (u32)slot * gap_cap * GAP_LIST;
         t.gap_cnt = gap_cnt;
         return t;
     }
@@ -345,7 +346,8 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
     ix.n_rows = can_tables ? (ix.pair_row0 + (opt.need_pair_table ? (1ull << (2 * (k + 1))) : 0ull)) : 0ull;
     u64 tf_bytes = can_tables ? ix.pair_row0 * ix.row_bytes : 0;
     u64 pair_bytes = (can_tables && opt.need_pair_table) ? ((1ull << (2 * (k + 1))) * ix.row_bytes) : 0;
-    if (ix.n_rows + GAP_CAP + 2 >= ((u64)1 << 32)) throw BspError(-5, "dense table row count exceeds 2^32");
+    ix.gap_cap = (u32)std::max<i64>(opt.gap_cap, 1);
+    if (ix.n_rows + ix.gap_cap + 2 >= ((u64)1 << 32)) throw BspError(-5, "dense table row count exceeds 2^32");
     bool tables = false;
     if (can_tables && opt.want_tables != 2) {
         if (opt.want_tables == 1) tables = true;
@@ -516,7 +518,8 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
         const u32 n = (u32)ne;
         ix.exc_off.alloc(ix.n_rows + 2);
         // the tail of the exception arrays holds the gap-clause match lists of the two pipeline slots
-        const size_t tail = (size_t)2 * GAP_CAP * GAP_LIST;
+        const size_t tail = (size_t)2 * ix.gap_cap * GAP_LIST;
+        if ((u64)n + tail >= ((u64)1 << 32)) throw BspError(-5, "exception + gap lists exceed 2^32 entries");
         ix.exc_doc.alloc((size_t)n + tail); ix.exc_freq.alloc((size_t)n + tail);
         DevBuf<u64> ka, kb; DevBuf<u32> va, vb;
         ka.alloc(std::max<size_t>(n, 1)); kb.alloc(std::max<size_t>(n, 1)); va.alloc(std::max<size_t>(n, 1)); vb.alloc(std::max<size_t>(n, 1));
