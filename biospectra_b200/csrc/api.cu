@@ -368,11 +368,13 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
         h->ref = ref;
         for (int i = 0; i < 2; i++) { h->sc[i].init(); h->sc[i].slot_index = i; }
         h->st = h->sc[0].st;
-        // the filter kernel's cp.async ring needs up to 64 KB of dynamic shared memory (512 threads x 8 stages x 16 B)
-        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
-        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
-        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
-        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * 512 * 16));
+        // the filter kernel's cp.async ring needs up to 64 KB of dynamic shared memory (512 threads x 8 stages x 16 B);
+        // its residency is bounded by shared memory: ask for the largest carve-out
+#define FK_ATTR(TI, AT)                                                                                                          \
+        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<TI, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * FK_MAXT * 16)); \
+        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<TI, AT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+        FK_ATTR(false, false); FK_ATTR(false, true); FK_ATTR(true, false); FK_ATTR(true, true);
+#undef FK_ATTR
         BuildOptions opt;
         opt.want_tables = conf->dense_tables;
         opt.want_positional = conf->positional;
@@ -541,7 +543,9 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     // BSP_FILTER: 0 off, 1 whenever usable, unset = only where it pays (enough docs to fill a CTA)
     const u32 D = (u32)ix.docs.size();
     const i64 filter_mode = env_i64("BSP_FILTER", -1);
-    qp.filter_ok = qp.dense_ok && qp.sim == SIM_TFIDF && filter_mode != 0 && (filter_mode == 1 || D >= 1024);
+    // (the filter kernel addresses rows by 32-bit offsets in 16-byte units: table below 64 GiB)
+    const bool tab_addressable = ((u64)ix.n_rows + 2) * ix.row_bytes < (64ull << 30);
+    qp.filter_ok = qp.dense_ok && tab_addressable && qp.sim == SIM_TFIDF && filter_mode != 0 && (filter_mode == 1 || D >= 1024);
     weights_kernel<<<(unsigned)ceil_div((i64)n * 32, 256), 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p,
                                                                sc.tok_df.p, h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p,
                                                                sc.n_clauses.p, sc.msm.p, sc.route.p, sc.status_in.p, sc.vrange.p,
@@ -557,7 +561,7 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     sc.n_tiles = (int)std::max<i64>(1, ceil_div(ix.d_pad, (i64)sc.dense_threads * EX_DPT));
     sc.parts_pos = ix.positional ? (int)ix.segs.size() : 0;
     // filter tiles: BSP_FILTER_THREADS (multiple of 32, <= 512) caps the CTA size (tests use it to force several tiles)
-    const i64 ft_cap = std::min<i64>(512, std::max<i64>(32, round_up(env_i64("BSP_FILTER_THREADS", 512), 32)));
+    const i64 ft_cap = std::min<i64>(FK_MAXT, std::max<i64>(32, round_up(env_i64("BSP_FILTER_THREADS", 512), 32)));
     sc.filter_threads = (int)std::min<i64>(ft_cap, round_up(std::max<i64>(ceil_div(ix.d_pad, FK_DOCS), 1), 32));
     sc.filter_tiles = (int)std::max<i64>(1, ceil_div(ix.d_pad, (i64)sc.filter_threads * FK_DOCS));
     sc.parts_stride = std::max(std::max(std::max(sc.n_tiles, sc.parts_pos), sc.filter_tiles), 1);

@@ -237,6 +237,18 @@ __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 c) {
     return d;
 }
 
+// build-time variants of the filter kernel
+#ifndef FK_UNROLL
+#define FK_UNROLL 2                // rows per iteration of the streaming loop (2, 4 or 8; measured at C2: 38.3 / 41.2 / 45.6 ms --
+                                   // the larger bodies lose more to instruction fetch than they save in address arithmetic)
+#endif
+#ifndef FK_MAXT
+#define FK_MAXT 512                // largest CTA of the filter kernel
+#endif
+#ifndef FK_MINB
+#define FK_MINB 2                  // 64 registers: 5 CTAs of 192 threads per SM (80 regs / 4 CTAs: 42.2 ms, 56 regs / 6 CTAs: 38.7 ms)
+#endif
+
 // one u32 of a pair row (8 docs) through the clause's 8-entry LUT into the u16 weight lanes and u8 count lanes
 __device__ __forceinline__ void pair_word(u32 word, const uint2 lut, u32& w0, u32& w1, u32& w2, u32& w3, u32& c0, u32& c1) {
     const u32 hi = word >> 16;
@@ -266,8 +278,10 @@ __device__ __forceinline__ void add_fma_pipe(u32& acc, u32 x, u32 one) {
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(x), "r"(one));
 }
 // two rows at once
+// (cnt_lo = 0x01010100 arrives in a register computed from a kernel argument: as a literal, ptxas re-materialises it
+// with a move in front of every count PRMT)
 __device__ __forceinline__ void pair_word2(u32 wa, u32 wb, const uint2 la, const uint2 lb, u32& w0, u32& w1, u32& w2, u32& w3,
-                                           u32& c0, u32& c1, u32 one) {
+                                           u32& c0, u32& c1, u32 one, u32 cnt_lo) {
     const u32 ha = wa >> 16, hb = wb >> 16;
     const u32 a0 = prmt(la.x, la.y, wa), a1 = prmt(la.x, la.y, ha);
     const u32 b0 = prmt(lb.x, lb.y, wb), b1 = prmt(lb.x, lb.y, hb);
@@ -275,8 +289,8 @@ __device__ __forceinline__ void pair_word2(u32 wa, u32 wb, const uint2 la, const
     add_fma_pipe(w1, prmt(a0, 0u, 0x4342u), one); add_fma_pipe(w1, prmt(b0, 0u, 0x4342u), one);
     add_fma_pipe(w2, prmt(a1, 0u, 0x4140u), one); add_fma_pipe(w2, prmt(b1, 0u, 0x4140u), one);
     add_fma_pipe(w3, prmt(a1, 0u, 0x4342u), one); add_fma_pipe(w3, prmt(b1, 0u, 0x4342u), one);
-    add_fma_pipe(c0, prmt(0x01010100u, 0x01010101u, wa), one); add_fma_pipe(c0, prmt(0x01010100u, 0x01010101u, wb), one);
-    add_fma_pipe(c1, prmt(0x01010100u, 0x01010101u, ha), one); add_fma_pipe(c1, prmt(0x01010100u, 0x01010101u, hb), one);
+    add_fma_pipe(c0, prmt(cnt_lo, 0x01010101u, wa), one); add_fma_pipe(c0, prmt(cnt_lo, 0x01010101u, wb), one);
+    add_fma_pipe(c1, prmt(cnt_lo, 0x01010101u, ha), one); add_fma_pipe(c1, prmt(cnt_lo, 0x01010101u, hb), one);
 }
 
 // Term rows hold codes 0..14: a 16-entry LUT out of two 8-entry PRMT lookups.  PRMT reads bit 3 of a selector nibble as
@@ -327,7 +341,6 @@ __device__ __forceinline__ u32 cell_code(const Tab4Dev& T, u32 row, u32 doc) {
 #define FK_DOCS 32                 // docs per thread: one 16-byte vector per row
 #define FK_MAX_CLAUSES 255         // u8 match counters
 #define FK_CAND_CAP 128
-#define FK_CODE_CAP 6144           // candidate x clause cells staged in shared memory for the exact pass
 #define FK_STAGES 8                // rows in flight per thread (cp.async ring in shared memory)
 #define FK_QMAX 255.0f
 #define FK_ROUND_SLACK 0.51f       // |q - S*tf*value| <= 0.5 (+ float rounding of the product)
@@ -388,7 +401,7 @@ __device__ __forceinline__ float exc_lookup(const Tab4Dev& T, u32 a, u32 n, u32 
 
 // TILED: several doc tiles per read (more than 16,384 docs, or a capped CTA size); ALLTERMS: NAIVE_KMER (term rows only)
 template <bool TILED, bool ALLTERMS>
-__global__ void __launch_bounds__(512) filter_score_kernel(
+__global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
         Tab4Dev T, u32 n_docs, const float* __restrict__ tf16, const i32* __restrict__ read_list,
         const i64* __restrict__ tok_off, const i32* __restrict__ n_tok, const float* __restrict__ clause_val,
         const u32* __restrict__ clause_row, const i32* __restrict__ n_clauses, const i32* __restrict__ msm,
@@ -397,8 +410,9 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         i32* __restrict__ overflow_list, i32* __restrict__ overflow_count, FilterStats* __restrict__ stats, int full_topn,
         u32 one /* = 1, see add_fma_pipe */, int n_tiles /* doc tiles of blockDim.x * 32 docs; CTA per (tile, read) */) {
     __shared__ uint2 s_lut[FK_MAX_CLAUSES + 1];          // q for codes 0..3 | 4..7
-    __shared__ uint2 s_lut_hi[FK_MAX_CLAUSES + 1];       // term rows (NAIVE_KMER): q for codes 8..11 | 12..15
+    __shared__ uint2 s_lut_hi[ALLTERMS ? FK_MAX_CLAUSES + 1 : 1];       // term rows (NAIVE_KMER): q for codes 8..11 | 12..15
     __shared__ u32 s_row[FK_MAX_CLAUSES + 1];
+    __shared__ u32 s_off[FK_MAX_CLAUSES + 1];           // row offset in the table, in 16-byte units (table < 64 GiB)
     __shared__ float s_val[FK_MAX_CLAUSES + 1];
     __shared__ u32 s_exa[FK_MAX_CLAUSES + 1], s_exn[FK_MAX_CLAUSES + 1];     // exception list of each clause's row
     __shared__ u8 s_exrows[FK_MAX_CLAUSES + 1];          // the clauses whose row has exceptions
@@ -407,10 +421,10 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     __shared__ u32 s_wmax[16];
     __shared__ u32 s_cand[FK_CAND_CAP];
     __shared__ u64 s_ckey[FK_CAND_CAP];
-    __shared__ u8 s_code[FK_CODE_CAP];
     __shared__ int s_ncand, s_nexrows, s_over, s_ndense, s_ngap;
-    __shared__ u32 s_qmin, s_nexc;
+    __shared__ u32 s_qmin, s_nexc, s_cntlo;
 
+    extern __shared__ __align__(16) uint4 ring[];         // FK_STAGES x blockDim.x x 16 B: row ring of pass 1, then the staged cell codes
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
     const int tile = TILED ? blockIdx.x % n_tiles : 0;
     const i32 r = read_list[TILED ? blockIdx.x / n_tiles : blockIdx.x];
@@ -429,6 +443,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     if (threadIdx.x == 0) {
         s_ncand = 0; s_nexrows = 0; s_over = 0; s_nexc = 0; s_ndense = 0; s_ngap = 0;
         s_qmin = (u32)__float2int_rn(S * vr.y);
+        s_cntlo = 0x01010100u * one;
     }
     __syncthreads();
     // Clause order in shared memory: table-backed pair clauses [0, n_dense), term clauses, then the gap pair clauses
@@ -445,6 +460,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
         }
         s_val[c] = v;
         s_row[c] = row;
+        s_off[c] = row < T.temp_row0 ? row * (u32)(T.row_bytes >> 4) : 0u;
         const float sv = S * v;
         if (c0 < n_pair) {
             u32 q[8];
@@ -478,45 +494,59 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
 #pragma unroll
     for (int i = 0; i < 8; i++) cacc[i] = 0;
     const u8* tbase = T.tab + (u64)d0 / 2;
+    asm volatile("" : "+l"(tbase));          // keep the thread's table base in a register pair (one IMAD.WIDE per row address)
     if (active) {
         // Each thread prefetches its own 16-byte slice of the next FK_STAGES rows into its private slots of the
         // ring (no cross-thread hand-off, so no barriers): FK_STAGES x 16 B in flight per thread.
-        extern __shared__ __align__(16) uint4 ring[];
         uint4* slot = ring + threadIdx.x;
         const u32 stride = blockDim.x;
 #pragma unroll
         for (int st = 0; st < FK_STAGES; st++) {
-            if (st < n_stream) cp_async16(slot + st * stride, tbase + (u64)s_row[st] * T.row_bytes);
+            if (st < n_stream) cp_async16(slot + st * stride, tbase + (u64)s_off[st] * 16);
             cp_async_commit();
         }
         i32 i = 0;
         const i32 n_two = all_terms ? nc : n_dense;   // rows streamed two at a time through a byte LUT
-#pragma unroll 1
-        for (; i + 2 <= n_two; i += 2) {
-            cp_async_wait<FK_STAGES - 2>();
-            uint4* my0 = slot + (i % FK_STAGES) * stride;
-            uint4* my1 = slot + ((i + 1) % FK_STAGES) * stride;
-            const uint4 q0 = *my0, q1 = *my1;
-            const uint2 l0 = s_lut[i], l1 = s_lut[i + 1];
-            if (all_terms) {
-                const uint2 h0 = s_lut_hi[i], h1 = s_lut_hi[i + 1];
-                const uint4 t0 = make_uint4(l0.x, l0.y, h0.x, h0.y), t1 = make_uint4(l1.x, l1.y, h1.x, h1.y);
-                term_word2(q0.x, q1.x, t0, t1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1], one);
-                term_word2(q0.y, q1.y, t0, t1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3], one);
-                term_word2(q0.z, q1.z, t0, t1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5], one);
-                term_word2(q0.w, q1.w, t0, t1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7], one);
-            } else {
-                pair_word2(q0.x, q1.x, l0, l1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1], one);
-                pair_word2(q0.y, q1.y, l0, l1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3], one);
-                pair_word2(q0.z, q1.z, l0, l1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5], one);
-                pair_word2(q0.w, q1.w, l0, l1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7], one);
-            }
-            // the slots' data now lives in registers: refill them with the rows FK_STAGES ahead
-            if (i + FK_STAGES < n_stream) cp_async16(my0, tbase + (u64)s_row[i + FK_STAGES] * T.row_bytes);
-            cp_async_commit();
-            if (i + 1 + FK_STAGES < n_stream) cp_async16(my1, tbase + (u64)s_row[i + 1 + FK_STAGES] * T.row_bytes);
-            cp_async_commit();
+        // count LUT low word, read from shared memory so that it lives in a vector register: as a literal (or a
+        // uniform value) ptxas re-materialises it with a move in front of every count PRMT
+        const u32 cnt_lo = s_cntlo;
+        // two rows per step: wait for them, pull them into registers, refill their slots with the rows FK_STAGES
+        // ahead, then the LUT arithmetic
+#define FK_STEP2(I)                                                                                                       \
+        {                                                                                                                 \
+            cp_async_wait<FK_STAGES - 2>();                                                                               \
+            uint4* my0 = slot + ((I) % FK_STAGES) * stride;                                                               \
+            uint4* my1 = slot + (((I) + 1) % FK_STAGES) * stride;                                                         \
+            const uint4 q0 = *my0, q1 = *my1;                                                                             \
+            const uint2 l0 = s_lut[(I)], l1 = s_lut[(I) + 1];                                                             \
+            if (all_terms) {                                                                                              \
+                const uint2 h0 = s_lut_hi[(I)], h1 = s_lut_hi[(I) + 1];                                                   \
+                const uint4 t0 = make_uint4(l0.x, l0.y, h0.x, h0.y), t1 = make_uint4(l1.x, l1.y, h1.x, h1.y);             \
+                term_word2(q0.x, q1.x, t0, t1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1], one);                \
+                term_word2(q0.y, q1.y, t0, t1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3], one);                \
+                term_word2(q0.z, q1.z, t0, t1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5], one);              \
+                term_word2(q0.w, q1.w, t0, t1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7], one);            \
+            } else {                                                                                                      \
+                pair_word2(q0.x, q1.x, l0, l1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1], one, cnt_lo);        \
+                pair_word2(q0.y, q1.y, l0, l1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3], one, cnt_lo);        \
+                pair_word2(q0.z, q1.z, l0, l1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5], one, cnt_lo);      \
+                pair_word2(q0.w, q1.w, l0, l1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7], one, cnt_lo);    \
+            }                                                                                                             \
+            if ((I) + FK_STAGES < n_stream) cp_async16(my0, tbase + (u64)s_off[(I) + FK_STAGES] * 16);                    \
+            cp_async_commit();                                                                                            \
+            if ((I) + 1 + FK_STAGES < n_stream) cp_async16(my1, tbase + (u64)s_off[(I) + 1 + FK_STAGES] * 16);            \
+            cp_async_commit();                                                                                            \
         }
+#if FK_UNROLL > 2
+#pragma unroll 1
+        for (; i + FK_UNROLL <= n_two; i += FK_UNROLL) {
+#pragma unroll
+            for (int u = 0; u < FK_UNROLL; u += 2) FK_STEP2(i + u)
+        }
+#endif
+#pragma unroll 1
+        for (; i + 2 <= n_two; i += 2) FK_STEP2(i)
+#undef FK_STEP2
 #pragma unroll 1
         for (; i < n_stream; i++) {
             cp_async_wait<FK_STAGES - 1>();
@@ -544,7 +574,7 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
                 }
             }
             // the slot's data now lives in registers: refill it with the row FK_STAGES ahead
-            if (i + FK_STAGES < n_stream) cp_async16(my, tbase + (u64)s_row[i + FK_STAGES] * T.row_bytes);
+            if (i + FK_STAGES < n_stream) cp_async16(my, tbase + (u64)s_off[i + FK_STAGES] * 16);
             cp_async_commit();
         }
         // ---- exception cells (stored as 0 in the table) of this thread's docs join their lanes with the same
@@ -583,7 +613,18 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     // ---- pass 2: per-thread best estimate, then the block's 10th best (full list) or best (result set only).
     //      Padded docs have no cells (m = 0).
     float e_best = 0.0f;
-    if (active) {
+    // Only docs with m >= need have an estimate, and a read matches few of them that often: test the 32 count bytes of
+    // the thread at once.  byte >= need  <=>  bit 7 of ((byte | 0x80) - need) | byte, for need <= 128 (no borrow
+    // crosses a byte: byte | 0x80 >= need).
+    bool any_m = active;
+    if (active && need <= 128) {
+        const u32 need4 = (u32)need * 0x01010101u;
+        u32 f = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) f |= ((cacc[j] | 0x80808080u) - need4) | cacc[j];
+        any_m = (f & 0x80808080u) != 0u;
+    }
+    if (any_m) {
 #pragma unroll
         for (int i4 = 0; i4 < FK_DOCS; i4 += 4) {
             const float4 nv = *reinterpret_cast<const float4*>(doc_w + d0 + i4);
@@ -653,7 +694,8 @@ __global__ void __launch_bounds__(512) filter_score_kernel(
     int pitch_log = 5;                                    // clause pitch of the staging buffer: power of two >= nc
     while ((1 << pitch_log) < nc) pitch_log++;
     const int n_items = n_cand << pitch_log;
-    const bool staged = n_cand > nw && n_items <= FK_CODE_CAP;
+    u8* s_code = reinterpret_cast<u8*>(ring);             // pass 1 is over in every warp (barriers above): the ring is free
+    const bool staged = n_cand > nw && n_items <= FK_STAGES * (int)blockDim.x * 16;
     if (staged) {
 #pragma unroll 1
         for (int it0 = threadIdx.x; it0 < n_items; it0 += 4 * blockDim.x) {
