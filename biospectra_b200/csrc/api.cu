@@ -4,6 +4,8 @@
 
 #include <dirent.h>
 #include <errno.h>
+#include <chrono>
+#include <condition_variable>
 #include <mutex>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -60,8 +62,31 @@ struct Scratch {
     }
 };
 
+// bsp_classify_one: one pending request per blocked caller
+struct OneRead {
+    const char* seq; i32 len;
+    i32 status = BSP_READ_ERROR, label = 0, n_hits = 0, n_top = 0;
+    i32 doc[TOPN]; float score[TOPN];
+    int rc = BSP_OK; std::string err;
+    bool done = false;
+};
+// Leader/follower micro-batcher: the first caller of a batch collects company, runs the GPU batch for everybody and
+// hands the results back; no background thread.
+struct MicroBatcher {
+    std::mutex mu;
+    std::condition_variable cv_collect, cv_done;
+    std::vector<OneRead*> pending;
+    bool leader = false;
+    int gpu_busy = 0;                       // micro-batches that left the queue and have not finished
+    i32 max_reads = 4096;
+    i64 wait_us = 200;
+    i32 last_size = 0;                      // size of the previous micro-batch
+    i64 batches = 0, reads = 0;
+};
+
 struct bsp_classifier {
     std::mutex mu;
+    MicroBatcher mb;
     bsp_config conf;
     RefStore* ref = nullptr;
     GpuIndex ix;
@@ -368,6 +393,8 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
         h->ref = ref;
         for (int i = 0; i < 2; i++) { h->sc[i].init(); h->sc[i].slot_index = i; }
         h->st = h->sc[0].st;
+        h->mb.max_reads = (i32)std::max<i64>(1, env_i64("BSP_MICROBATCH_MAX", 4096));
+        h->mb.wait_us = std::max<i64>(0, env_i64("BSP_MICROBATCH_US", 200));
         // the filter kernel's cp.async ring needs up to 64 KB of dynamic shared memory (512 threads x 8 stages x 16 B);
         // its residency is bounded by shared memory: ask for the largest carve-out
 #define FK_ATTR(TI, AT)                                                                                                          \
@@ -375,6 +402,8 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
         CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<TI, AT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
         FK_ATTR(false, false); FK_ATTR(false, true); FK_ATTR(true, false); FK_ATTR(true, true);
 #undef FK_ATTR
+        CUDA_CHECK(cudaFuncSetAttribute(score_positional_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(POSW_WARPS * posw_warp_bytes(POSW_DOCS, PW_POS))));
+        CUDA_CHECK(cudaFuncSetAttribute(score_positional_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         BuildOptions opt;
         opt.want_tables = conf->dense_tables;
         opt.want_positional = conf->positional;
@@ -649,9 +678,10 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
         if (ix.max_seg_docs <= POSW_DOCS && env_i64("BSP_POS_BLOCK_KERNEL", 0) == 0) {
             // few documents per segment (large genomes): one warp per (segment, read)
             const i64 wblocks = ceil_div(blocks, POSW_WARPS);
-            score_positional_warp_kernel<<<(unsigned)wblocks, POSW_WARPS * 32, 0, st>>>(ix.d_segs.p, parts_pos, sc.list_pos.p, counts[1],
+            const int dcap = (int)round_up(std::max<i64>(ix.max_seg_docs, 1), 32);
+            score_positional_warp_kernel<<<(unsigned)wblocks, POSW_WARPS * 32, POSW_WARPS * posw_warp_bytes(dcap, PW_POS), st>>>(ix.d_segs.p, parts_pos, sc.list_pos.p, counts[1],
                 sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p, sc.clause_val.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, qp, sp, gbase,
-                parts_stride, part_n, part_doc, part_score);
+                parts_stride, part_n, part_doc, part_score, (int)env_i64("BSP_POS_STAGE", 1), dcap, PW_POS);
         } else {
             score_positional_kernel<<<(unsigned)blocks, POS_THREADS, smem, st>>>(ix.d_segs.p, parts_pos, sc.list_pos.p, counts[1], sc.tok_off.p,
                 sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p, sc.clause_val.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, qp, sp, gbase,
@@ -791,6 +821,95 @@ BSP_API int bsp_classify_batch(bsp_classifier* h, int32_t n, const char* const* 
     std::string bytes((size_t)off[n], '\0');
     for (i32 i = 0; i < n; i++) if (seq_lens[i]) memcpy(&bytes[off[i]], seqs[i], (size_t)seq_lens[i]);
     return classify_packed_impl(h, n, bytes.data(), off.data(), status, label, n_hits, n_top, top_doc, top_score);
+}
+
+BSP_API int bsp_classifier_set_microbatch(bsp_classifier* h, int32_t max_reads, int64_t max_wait_us) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    if (max_reads < 1 || max_wait_us < 0) return fail(&h->last_error, BSP_ERR_ARG, "micro-batch: max_reads >= 1 and max_wait_us >= 0");
+    std::lock_guard<std::mutex> lk(h->mb.mu);
+    h->mb.max_reads = max_reads;
+    h->mb.wait_us = max_wait_us;
+    return BSP_OK;
+}
+
+BSP_API int bsp_microbatch_stats(bsp_classifier* h, int64_t* batches, int64_t* reads) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    std::lock_guard<std::mutex> lk(h->mb.mu);
+    if (batches) *batches = h->mb.batches;
+    if (reads) *reads = h->mb.reads;
+    return BSP_OK;
+}
+
+// the leader's part: pack the batch, one bsp_classify_packed, scatter the results
+static void microbatch_run(bsp_classifier* h, std::vector<OneRead*>& batch) {
+    const i32 n = (i32)batch.size();
+    std::vector<i64> off((size_t)n + 1, 0);
+    for (i32 i = 0; i < n; i++) off[i + 1] = off[i] + batch[i]->len;
+    std::string bytes((size_t)off[n], '\0');
+    for (i32 i = 0; i < n; i++) memcpy(&bytes[off[i]], batch[i]->seq, (size_t)batch[i]->len);
+    std::vector<i32> st(n, BSP_READ_ERROR), label(n, 0), nh(n, 0), nt(n, 0), doc((size_t)n * TOPN, -1);
+    std::vector<float> score((size_t)n * TOPN, 0.0f);
+    const int rc = classify_packed_impl(h, n, bytes.data(), off.data(), st.data(), label.data(), nh.data(), nt.data(), doc.data(), score.data());
+    const std::string err = rc == BSP_OK ? std::string() : g_last_error;
+    for (i32 i = 0; i < n; i++) {
+        OneRead& q = *batch[i];
+        q.rc = rc; q.err = err;
+        q.status = st[i]; q.label = label[i]; q.n_hits = nh[i]; q.n_top = nt[i];
+        memcpy(q.doc, &doc[(size_t)i * TOPN], sizeof q.doc);
+        memcpy(q.score, &score[(size_t)i * TOPN], sizeof q.score);
+    }
+}
+
+BSP_API int bsp_classify_one(bsp_classifier* h, const char* seq, int32_t seq_len, int32_t* status, int32_t* label,
+                             int32_t* n_hits, int32_t* n_top, int32_t* top_doc, float* top_score) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    if (!seq || seq_len <= 0) return fail(&h->last_error, BSP_ERR_ARG, "sequence is null or empty");     // Classifier.java:342-344
+    if (!status) return fail(&h->last_error, BSP_ERR_ARG, "null argument");
+    MicroBatcher& mb = h->mb;
+    OneRead rq;
+    rq.seq = seq; rq.len = seq_len;
+    std::unique_lock<std::mutex> lk(mb.mu);
+    mb.pending.push_back(&rq);
+    if (!mb.leader) {
+        // Leader of this batch: wait for company until the window closes, and for as long as the previous batch
+        // still owns the GPU (those reads would only queue on the handle's lock one by one otherwise).
+        mb.leader = true;
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(mb.wait_us);
+        while ((i32)mb.pending.size() < mb.max_reads) {
+            // a closed loop of T callers comes back T at a time: once as many reads wait as the previous batch held,
+            // the window would only add latency
+            if (!mb.gpu_busy && mb.last_size > 0 && (i32)mb.pending.size() >= mb.last_size) break;
+            if (mb.gpu_busy) mb.cv_collect.wait(lk);
+            else if (mb.cv_collect.wait_until(lk, deadline) == std::cv_status::timeout) { if (!mb.gpu_busy) break; }
+        }
+        std::vector<OneRead*> batch;
+        batch.swap(mb.pending);
+        mb.last_size = (i32)batch.size();
+        mb.leader = false;                 // the next arrival leads the next batch and collects while this one runs
+        mb.gpu_busy++;
+        lk.unlock();
+        try { microbatch_run(h, batch); }
+        catch (const std::exception& e) { for (OneRead* q : batch) { q->rc = BSP_ERR_NOMEM; q->err = e.what(); } }
+        lk.lock();
+        mb.gpu_busy--;
+        mb.batches++;
+        mb.reads += (i64)batch.size();
+        for (OneRead* q : batch) q->done = true;
+        mb.cv_done.notify_all();
+        mb.cv_collect.notify_all();        // a leader that waited for the GPU may go now
+    } else {
+        if ((i32)mb.pending.size() >= mb.max_reads || (i32)mb.pending.size() == mb.last_size) mb.cv_collect.notify_all();
+        mb.cv_done.wait(lk, [&] { return rq.done; });
+    }
+    lk.unlock();
+    if (rq.rc != BSP_OK) return fail(&h->last_error, rq.rc, rq.err);
+    *status = rq.status;
+    if (label) *label = rq.label;
+    if (n_hits) *n_hits = rq.n_hits;
+    if (n_top) *n_top = rq.n_top;
+    if (top_doc) memcpy(top_doc, rq.doc, sizeof rq.doc);
+    if (top_score) memcpy(top_score, rq.score, sizeof rq.score);
+    return BSP_OK;
 }
 
 BSP_API int bsp_classify_device(bsp_classifier* h, int32_t n, const void* d_seq_bytes, const void* d_seq_offsets,

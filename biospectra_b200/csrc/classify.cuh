@@ -71,6 +71,25 @@ __device__ __forceinline__ float sloppy_freq_distinct(const u32* __restrict__ A,
     return freq;
 }
 
+// Can the phrase (t0@0, t1@1) match at all?  Every matchLength the sweep above tests is |(b - 1) - a| of an actual pair
+// (a in A, b in B), so freq = 0 whenever no pair is within the slop.  Branch-light two-pointer scan; no false negatives.
+__device__ __forceinline__ bool sloppy_may_match(const u32* __restrict__ A, int nA, const u32* __restrict__ B, int nB, int slop) {
+    int i = 0, j = 0;
+    int a = (int)A[0], b = (int)B[0] - 1;                // nA, nB >= 1: a posting has at least one position
+    const unsigned w = 2u * (unsigned)slop;
+    while (true) {
+        const int d = b - a;
+        if ((unsigned)(d + slop) <= w) return true;
+        const bool adv_a = d > 0;                         // a is behind: advance it (selects, no divergence inside a step)
+        i += adv_a ? 1 : 0;
+        j += adv_a ? 0 : 1;
+        if ((adv_a ? i : j) >= (adv_a ? nA : nB)) return false;
+        const int v = (int)*(adv_a ? A + i : B + j);
+        a = adv_a ? v : a;
+        b = adv_a ? b : v - 1;
+    }
+}
+
 // Same-term phrase (t0 == t1): the repeat-group path, restated literally
 // (#initComplex/#advanceRepeatGroups/#advanceRpts/#collide/#lesser).
 struct PPd { const u32* pl; int n, idx, count, position, offset; };
@@ -460,8 +479,10 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
     extern __shared__ __align__(16) u8 smem_raw[];
     __shared__ ClauseStage stage[POS_CHUNK];
     __shared__ u64 red[33];
-    const int sidx = blockIdx.x % n_segs;
-    const i32 r = read_list[blockIdx.x / n_segs];
+    // segment-major: the CTAs resident at any moment work on one or two segments, so their postings, term tables and
+    // page translations stay hot (read-major order touched all of the 100+ GB index at once)
+    const int sidx = blockIdx.x / n_list;
+    const i32 r = read_list[blockIdx.x % n_list];
     const SegDev s = segs[sidx];
     double* acc = reinterpret_cast<double*>(smem_raw);
     u16* cnt = reinterpret_cast<u16*>(smem_raw + (size_t)s.n_docs * 8);
@@ -555,25 +576,47 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
 // shuffles.  POSW_WARPS pairs per CTA.
 #define POSW_DOCS 256
 #define POSW_WARPS 8
-__global__ void __launch_bounds__(POSW_WARPS * 32) score_positional_warp_kernel(
+#ifndef POSW_MINB
+#define POSW_MINB 4                // 64 registers, 4 CTAs per SM (3 CTAs at 80 registers: 0.75 M reads/s against 0.87 M at C2, skips 5)
+#endif
+// Phrase clauses are staged: the warp copies both terms' posting slices of the segment (doc ids, position offsets)
+// and then their position ranges -- each one contiguous in the term-major layout -- into shared memory with coalesced
+// loads, and the per-doc conjunction + sloppy sweep run out of shared memory.  Three dependent rounds of wide loads per
+// clause instead of a dozen dependent scalar loads per (clause, doc).  Slices beyond the caps take the direct path.
+// Shared memory per warp (all dynamic, sized by the host from the largest segment): double acc[dcap] | u32 pos[2][pcap]
+// | u32 doc[2][dcap] | u32 pp[2][dcap + 4] | ClauseStage stage[32] | u16 cnt[dcap] | u8 inv[dcap];  dcap = docs per
+// segment rounded up to 32 (a term has at most one posting per doc), pcap = PW_POS positions per term and segment.
+// inv[doc] = index of the doc's posting in the second term's slice (possibly stale: always verified).
+#define PW_POS 384               // 2^28 tokens / 4^10 terms = 256 on average
+__host__ __device__ inline size_t posw_warp_bytes(int dcap, int pcap) {
+    return (size_t)dcap * 8 + (size_t)pcap * 8 + (size_t)dcap * 8 + (size_t)(dcap + 4) * 8 + 32 * 24 + (size_t)dcap * 2 + (size_t)dcap;
+}
+__global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_warp_kernel(
         const SegDev* __restrict__ segs, int n_segs, const i32* __restrict__ read_list, i32 n_list,
         const i64* __restrict__ tok_off, const i32* __restrict__ n_tok, const u64* __restrict__ tok_key,
         const u32* __restrict__ tok_pos, const float* __restrict__ clause_val, const i32* __restrict__ n_clauses,
         const i32* __restrict__ msm, const float* __restrict__ doc_w, QueryParams qp, SimParams sp, u32 global_doc_base,
-        int parts_stride, i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score) {
-    __shared__ double s_acc[POSW_WARPS][POSW_DOCS];
-    __shared__ u16 s_cnt[POSW_WARPS][POSW_DOCS];
-    __shared__ ClauseStage s_stage[POSW_WARPS][32];
+        int parts_stride, i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score, int stage_ok,
+        int dcap /* >= docs of any segment, multiple of 32 */, int pcap) {
+    extern __shared__ __align__(16) u8 pw_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u8* wbase = pw_raw + (size_t)warp * posw_warp_bytes(dcap, pcap);
+    double* acc = reinterpret_cast<double*>(wbase);
+    u32* w_pos0 = reinterpret_cast<u32*>(wbase + (size_t)dcap * 8);
+    u32* w_pos1 = w_pos0 + pcap;
+    u32* w_doc0 = w_pos1 + pcap;
+    u32* w_doc1 = w_doc0 + dcap;
+    u32* w_pp0 = w_doc1 + dcap;
+    u32* w_pp1 = w_pp0 + dcap + 4;
+    ClauseStage* stage = reinterpret_cast<ClauseStage*>(w_pp1 + dcap + 4);
+    u16* cnt = reinterpret_cast<u16*>(stage + 32);
+    u8* inv = reinterpret_cast<u8*>(cnt + dcap);
     const i64 pair = (i64)blockIdx.x * POSW_WARPS + warp;
     if (pair >= (i64)n_list * n_segs) return;
-    const int sidx = (int)(pair % n_segs);
-    const i32 r = read_list[pair / n_segs];
+    const int sidx = (int)(pair / n_list);              // segment-major, see score_positional_kernel
+    const i32 r = read_list[pair % n_list];
     const SegDev s = segs[sidx];
-    double* acc = s_acc[warp];
-    u16* cnt = s_cnt[warp];
-    ClauseStage* stage = s_stage[warp];
-    for (u32 d = lane; d < s.n_docs; d += 32) { acc[d] = 0.0; cnt[d] = 0; }
+    for (u32 d = lane; d < s.n_docs; d += 32) { acc[d] = 0.0; cnt[d] = 0; inv[d] = 0; }
     const i64 base = tok_off[r];
     const i32 n = n_tok[r], nc = n_clauses[r];
     const float* dw = doc_w + s.doc_base;
@@ -606,18 +649,87 @@ __global__ void __launch_bounds__(POSW_WARPS * 32) score_positional_warp_kernel(
         const i32 lim = min(32, nc - c0);
         for (i32 ci = 0; ci < lim; ci++) {
             const ClauseStage st = stage[ci];
-            for (u32 i = st.a0 + lane; i < st.b0; i += 32) {
-                const u32 d = s.post_doc[i];
-                float f;
-                if (st.slop == 0) f = (float)(s.post_pos[i + 1] - s.post_pos[i]);       // TermScorer: freq as float
-                else {
-                    const bool same = st.slop < 0;
-                    f = phrase_freq_at(s, i, st.a1, st.b1, st.a1 + (i - st.a0), same ? -st.slop : st.slop, same);
+            const u32 n0 = st.b0 - st.a0, n1 = st.b1 - st.a1;
+            bool staged = false;
+            if (stage_ok && st.slop > 0 && n0 && n1) {                          // (n0, n1 <= docs of the segment <= dcap)
+                // all loads of a round are issued before the first store: one memory round trip per round, not per load
+                const u32 nmax = max(n0, n1) + 1;
+#pragma unroll 1
+                for (u32 i0 = lane; i0 < nmax; i0 += 64) {
+                    u32 vd0[2], vp0[2], vd1[2], vp1[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const u32 i = i0 + 32 * u;
+                        vd0[u] = i < n0 ? s.post_doc[st.a0 + i] : 0u;
+                        vp0[u] = i <= n0 ? s.post_pos[st.a0 + i] : 0u;
+                        vd1[u] = i < n1 ? s.post_doc[st.a1 + i] : 0u;
+                        vp1[u] = i <= n1 ? s.post_pos[st.a1 + i] : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const u32 i = i0 + 32 * u;
+                        if (i < n0) w_doc0[i] = vd0[u];
+                        if (i <= n0) w_pp0[i] = vp0[u];
+                        if (i < n1) { w_doc1[i] = vd1[u]; inv[vd1[u]] = (u8)i; }
+                        if (i <= n1) w_pp1[i] = vp1[u];
+                    }
                 }
-                if (f != 0.0f) {
-                    const float sc = clause_doc_score(sp.sim, sp.sim == SIM_TFIDF ? tf_of(f) : f, st.val, dw[d], sp.k1p1);
-                    acc[d] += (double)sc;                                                // BooleanScorer: double sum
-                    cnt[d] += 1;
+                __syncwarp();
+                const u32 p0 = w_pp0[0], m0 = w_pp0[n0] - p0, p1 = w_pp1[0], m1 = w_pp1[n1] - p1;
+                if (m0 <= (u32)pcap && m1 <= (u32)pcap) {
+                    const u32 mmax = max(m0, m1);
+#pragma unroll 1
+                    for (u32 i0 = lane; i0 < mmax; i0 += 256) {
+                        u32 va[8], vb[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const u32 i = i0 + 32 * u;
+                            va[u] = i < m0 ? s.positions[p0 + i] : 0u;
+                            vb[u] = i < m1 ? s.positions[p1 + i] : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const u32 i = i0 + 32 * u;
+                            if (i < m0) w_pos0[i] = va[u];
+                            if (i < m1) w_pos1[i] = vb[u];
+                        }
+                    }
+                    __syncwarp();
+                    for (u32 i = lane; i < n0; i += 32) {
+                        const u32 d = w_doc0[i];
+                        const u32 j = inv[d];                                            // verified: may be a stale entry
+                        if (j < n1 && w_doc1[j] == d) {
+                            const u32 q0 = w_pp0[i], q1 = w_pp1[j];
+                            const u32* A = w_pos0 + (q0 - p0);
+                            const u32* B = w_pos1 + (q1 - p1);
+                            const int nA = (int)(w_pp0[i + 1] - q0), nB = (int)(w_pp1[j + 1] - q1);
+                            // two independent k-mers within the slop of each other: rare, so the cheap test comes first
+                            const float f = sloppy_may_match(A, nA, B, nB, st.slop) ? sloppy_freq_distinct(A, nA, B, nB, st.slop) : 0.0f;
+                            if (f != 0.0f) {
+                                const float sc = clause_doc_score(sp.sim, sp.sim == SIM_TFIDF ? tf_of(f) : f, st.val, dw[d], sp.k1p1);
+                                acc[d] += (double)sc;                                    // BooleanScorer: double sum
+                                cnt[d] += 1;
+                            }
+                        }
+                    }
+                    staged = true;
+                }
+                __syncwarp();
+            }
+            if (!staged) {
+                for (u32 i = st.a0 + lane; i < st.b0; i += 32) {
+                    const u32 d = s.post_doc[i];
+                    float f;
+                    if (st.slop == 0) f = (float)(s.post_pos[i + 1] - s.post_pos[i]);   // TermScorer: freq as float
+                    else {
+                        const bool same = st.slop < 0;
+                        f = phrase_freq_at(s, i, st.a1, st.b1, st.a1 + (i - st.a0), same ? -st.slop : st.slop, same);
+                    }
+                    if (f != 0.0f) {
+                        const float sc = clause_doc_score(sp.sim, sp.sim == SIM_TFIDF ? tf_of(f) : f, st.val, dw[d], sp.k1p1);
+                        acc[d] += (double)sc;                                            // BooleanScorer: double sum
+                        cnt[d] += 1;
+                    }
                 }
             }
             __syncwarp();

@@ -516,13 +516,29 @@ void Classifier::classifyBatch(const std::vector<std::string>& headers, const st
     }
 }
 
+// Thread-safe like the reference's (LocalClassifier.java:96-118 and ClassifierServer.java:70-98 call it from
+// worker_threads pool threads at once): concurrent calls are coalesced into GPU micro-batches by bsp_classify_one.
 bool Classifier::classify(const std::string& header, const std::string& sequence, ClassificationResult& out) {
     if (sequence.empty()) throw IllegalArgument("sequence is null or empty");           // Classifier.java:342-344
-    std::vector<ClassificationResult> r;
-    std::vector<int> st;
-    classifyBatch({header}, {sequence}, r, st);
-    if (st[0] != BSP_READ_OK) return false;      // the reference throws (NPE / TooManyClauses); callers log + skip
-    out = std::move(r[0]);
+    int32_t st = BSP_READ_ERROR, label = 0, nhits = 0, ntop = 0, tdoc[BSP_TOPN];
+    float tscore[BSP_TOPN];
+    check_rc(bsp_classify_one(h_, sequence.data(), (int32_t)sequence.size(), &st, &label, &nhits, &ntop, tdoc, tscore));
+    if (st != BSP_READ_OK) return false;         // the reference throws (NPE / TooManyClauses); callers log + skip
+    ClassificationResult r;
+    r.queryHeader = header;
+    r.query = sequence;
+    for (int j = 0; j < nhits; j++) {                                   // Classifier.java:358-366: hits equal to the max
+        SearchResultEntry e;
+        e.docId = tdoc[j];
+        e.rank = j;
+        e.score = (double)tscore[j];
+        const char *fn, *hd, *dir, *tax;
+        check_rc(bsp_doc_fields(h_, e.docId, &fn, &hd, &dir, &tax));
+        e.filename = fn; e.header = hd; e.sequenceDirection = dir; e.taxonHierarchy = tax;
+        r.result.push_back(std::move(e));
+    }
+    makeClassificationResult(r);
+    out = std::move(r);
     return true;
 }
 
@@ -540,7 +556,7 @@ struct ReadBatch {
 };
 
 template <typename T>
-class BoundedQueue {                        // single producer / single consumer hand-off between pipeline stages
+class BoundedQueue {                        // bounded hand-off between pipeline stages (any number of producers / consumers)
 public:
     explicit BoundedQueue(size_t cap) : cap_(cap) {}
     void push(T v) {
@@ -685,6 +701,67 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
     lastSummary_ = summary;
 }
 
+// The reference's LocalClassifier.classify as written (LocalClassifier.java:88-120): the calling thread reads FASTA
+// entries and hands one task per read to a pool of `threads` workers behind a queue of 2 x threads (BlockingExecutor);
+// a worker calls Classifier.classify(header, sequence), serialises the result and writes the line under a lock, so the
+// line order is the completion order, as in the reference.  Nothing here batches: bsp_classify_one coalesces the
+// workers' concurrent calls on the GPU side.
+void LocalClassifier::classifyPerRead(const std::string& inputFasta, const std::string& classifyOutput, const std::string& summaryOutput,
+                                      int threads) {
+    if (inputFasta.empty()) throw IllegalArgument("inputFasta is null");
+    if (classifyOutput.empty()) throw IllegalArgument("classifyOutput is null");
+    std::string pd = parent_dir(classifyOutput);
+    if (!pd.empty() && !file_exists(pd)) make_dirs(pd);
+    if (!summaryOutput.empty()) { std::string sd = parent_dir(summaryOutput); if (!sd.empty() && !file_exists(sd)) make_dirs(sd); }
+    FASTAReader reader(inputFasta);
+    FILE* fw = fopen(classifyOutput.c_str(), "wb");
+    if (!fw) throw IOError("cannot create " + classifyOutput);
+    ClassificationResultSummary summary;
+    summary.queryFilename = base_name(inputFasta);
+    summary.startTime = now_ms();
+    const int T = std::max(1, threads > 0 ? threads : classifier_.workerThreads());
+    typedef std::pair<std::string, std::string> Task;              // (header line, sequence)
+    BoundedQueue<Task> tasks((size_t)T * 2);
+    std::mutex out_mu;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; t++) pool.emplace_back([&] {
+        Task task;
+        std::string line;
+        while (tasks.pop(task)) {
+            try {
+                ClassificationResult result;
+                if (!classifier_.classify(task.first, task.second, result)) continue;   // the reference logs + skips
+                line = result.toJson();
+                line.push_back('\n');
+                std::lock_guard<std::mutex> lk(out_mu);
+                summary.report(result);
+                fwrite(line.data(), 1, line.size(), fw);
+            } catch (const std::exception& ex) {
+                fprintf(stderr, "ERROR Exception occurred during search: %s\n", ex.what());
+            }
+        }
+    });
+    std::exception_ptr reader_error;
+    try {
+        FASTAEntry read;
+        while (reader.readNext(read)) tasks.push(Task(read.headerLine, read.sequence));
+    } catch (...) { reader_error = std::current_exception(); }
+    tasks.close();
+    for (auto& th : pool) th.join();
+    fclose(fw);
+    if (reader_error) std::rethrow_exception(reader_error);
+    summary.total = summary.unknown + summary.vague + summary.classified;
+    summary.endTime = now_ms();
+    if (!summaryOutput.empty()) {
+        FILE* fs = fopen(summaryOutput.c_str(), "wb");
+        if (!fs) throw IOError("cannot create " + summaryOutput);
+        std::string js = summary.toJson();
+        fwrite(js.data(), 1, js.size(), fs);
+        fclose(fs);
+    }
+    lastSummary_ = summary;
+}
+
 // ------------------------------------------------------------------ drivers (BioSpectra.java:110-161)
 void runIndex(const std::string& jsonConfiguration, const std::string& indexDir, const std::string& referenceDir, int device) {
     Configuration conf;
@@ -701,7 +778,7 @@ void runIndex(const std::string& jsonConfiguration, const std::string& indexDir,
 }
 
 void runClassifyLocal(const std::string& jsonConfiguration, const std::string& indexDir, const std::string& inputDir,
-                      const std::string& outputDir, int device) {
+                      const std::string& outputDir, int device, int perReadThreads) {
     Configuration conf;
     if (!jsonConfiguration.empty()) conf = Configuration::createInstanceFromFile(jsonConfiguration);
     else { conf.indexPath = indexDir; conf.hasIndexPath = !indexDir.empty(); }
@@ -710,7 +787,8 @@ void runClassifyLocal(const std::string& jsonConfiguration, const std::string& i
     if (!file_exists(outputDir)) make_dirs(outputDir);
     for (auto& f : FastaFileHelper::findFastaDocs(inputDir)) {
         std::string name = base_name(f);
-        classifier.classify(f, outputDir + "/" + name + ".result", outputDir + "/" + name + ".result.sum");
+        if (perReadThreads >= 0) classifier.classifyPerRead(f, outputDir + "/" + name + ".result", outputDir + "/" + name + ".result.sum", perReadThreads);
+        else classifier.classify(f, outputDir + "/" + name + ".result", outputDir + "/" + name + ".result.sum");
         fprintf(stderr, "INFO classifying %s finished in %lld millisec\n", name.c_str(),
                 classifier.lastSummary().endTime - classifier.lastSummary().startTime);
     }
@@ -741,6 +819,20 @@ HOST_API int bsp_host_classify_local(const char* json_conf, const char* index_di
     try {
         bsp::runClassifyLocal(json_conf ? json_conf : "", index_dir ? index_dir : "", input_dir ? input_dir : "",
                               output_dir ? output_dir : "", device);
+        return BSP_OK;
+    } catch (const bsp::IllegalArgument& e) { g_host_error = e.what(); return BSP_ERR_ARG; }
+    catch (const bsp::IOError& e) { g_host_error = e.what(); return BSP_ERR_IO; }
+    catch (const std::exception& e) { g_host_error = e.what(); return BSP_ERR_STATE; }
+}
+
+// Same job with the reference's control flow: `threads` pool threads (0 = conf.worker_threads) each call
+// Classifier.classify(header, sequence) per read (LocalClassifier.java:88-120); lines are written in completion order.
+HOST_API int bsp_host_classify_local_per_read(const char* json_conf, const char* index_dir, const char* input_dir,
+                                              const char* output_dir, int32_t device, int32_t threads) {
+    try {
+        if (threads < 0) throw bsp::IllegalArgument("threads must be >= 0");
+        bsp::runClassifyLocal(json_conf ? json_conf : "", index_dir ? index_dir : "", input_dir ? input_dir : "",
+                              output_dir ? output_dir : "", device, threads);
         return BSP_OK;
     } catch (const bsp::IllegalArgument& e) { g_host_error = e.what(); return BSP_ERR_ARG; }
     catch (const bsp::IOError& e) { g_host_error = e.what(); return BSP_ERR_IO; }

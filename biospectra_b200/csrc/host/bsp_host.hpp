@@ -136,6 +136,10 @@ public:
         return classifier_.classify(header, sequence, out);
     }
     void classify(const std::string& inputFasta, const std::string& classifyOutput, const std::string& summaryOutput);
+    // the reference's own control flow: one task per read on `threads` pool threads, each calling
+    // Classifier.classify(header, sequence) (LocalClassifier.java:88-120); the GPU sees micro-batches
+    void classifyPerRead(const std::string& inputFasta, const std::string& classifyOutput, const std::string& summaryOutput,
+                         int threads /* 0 = conf.worker_threads */);
     void close() { classifier_.close(); }
     const ClassificationResultSummary& lastSummary() const { return lastSummary_; }
 private:
@@ -145,6 +149,6 @@ private:
 
 void runIndex(const std::string& jsonConfiguration, const std::string& indexDir, const std::string& referenceDir, int device);
 void runClassifyLocal(const std::string& jsonConfiguration, const std::string& indexDir, const std::string& inputDir,
-                      const std::string& outputDir, int device);
+                      const std::string& outputDir, int device, int perReadThreads = -1);
 
 }  // namespace bsp

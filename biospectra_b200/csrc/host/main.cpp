@@ -14,13 +14,15 @@
 
 static void print_help() {
     printf("usage: biospectra_gpu i|index [-j conf.json | -i indexdir] -r refdir [--device N]\n"
-           "       biospectra_gpu lc|lclassify [-j conf.json | -i indexdir] -in reads -out outdir [--device N]\n");
+           "       biospectra_gpu lc|lclassify [-j conf.json | -i indexdir] -in reads -out outdir [--device N]\n"
+           "                 [--per-read THREADS]   one Classifier.classify call per read from THREADS pool threads, like the\n"
+           "                                        reference's LocalClassifier (0 = worker_threads of the configuration)\n");
 }
 
 int main(int argc, char** argv) {
     if (argc < 2) { print_help(); return 0; }
     std::string mode = argv[1], json, index, ref, in, out;
-    int device = 0;
+    int device = 0, per_read = -1;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];
         auto val = [&](std::string& dst) { if (i + 1 < argc) dst = argv[++i]; };
@@ -30,6 +32,7 @@ int main(int argc, char** argv) {
         else if (a == "-in" || a == "--input") val(in);
         else if (a == "-out" || a == "--output") val(out);
         else if (a == "--device") { std::string d; val(d); device = atoi(d.c_str()); }
+        else if (a == "--per-read") { std::string d; val(d); per_read = atoi(d.c_str()); }
         else if (a == "-h" || a == "--help") { print_help(); return 0; }
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); print_help(); return 1; }
     }
@@ -41,7 +44,8 @@ int main(int argc, char** argv) {
         rc = bsp_host_index(j, ix, ref.c_str(), device);
     } else if (!strcasecmp(mode.c_str(), "lc") || !strcasecmp(mode.c_str(), "lclassify")) {
         printf("Classifying (LOCAL mode)...\n");
-        rc = bsp_host_classify_local(j, ix, in.c_str(), out.c_str(), device);
+        rc = per_read >= 0 ? bsp_host_classify_local_per_read(j, ix, in.c_str(), out.c_str(), device, per_read)
+                           : bsp_host_classify_local(j, ix, in.c_str(), out.c_str(), device);
     } else { print_help(); }
     if (rc != 0) { fprintf(stderr, "Exception: %s\n", bsp_host_last_error()); return 2; }
     return 0;

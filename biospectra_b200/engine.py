@@ -116,6 +116,26 @@ class Classifier:
         data, off = self.pack_reads(seqs)
         return self.classify_packed(data, off)
 
+    def classify_one(self, seq: bytes):
+        """One read, blocking; safe to call from many threads at once (the GIL is released inside the call): concurrent
+        calls are coalesced into GPU micro-batches.  Mirrors Classifier.classify(header, sequence), Classifier.java:341-366."""
+        if seq is None or len(seq) == 0:
+            raise ValueError("sequence is null or empty")      # Classifier.java:342-344
+        st, label, nh, nt = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        doc = (C.c_int32 * 10)()
+        score = (C.c_float * 10)()
+        _lib.check(self.L.bsp_classify_one(self.h, seq, len(seq), C.byref(st), C.byref(label), C.byref(nh), C.byref(nt), doc, score), self.h)
+        return {"status": st.value, "label": label.value, "n_hits": nh.value, "n_top": nt.value,
+                "top_doc": np.array(doc[:], np.int32), "top_score": np.array(score[:], np.float32)}
+
+    def set_microbatch(self, max_reads: int, max_wait_us: int):
+        _lib.check(self.L.bsp_classifier_set_microbatch(self.h, max_reads, max_wait_us), self.h)
+
+    def microbatch_stats(self):
+        b, r = C.c_int64(), C.c_int64()
+        _lib.check(self.L.bsp_microbatch_stats(self.h, C.byref(b), C.byref(r)), self.h)
+        return {"batches": b.value, "reads": r.value}
+
     def classify_device(self, n, d_bytes, d_offsets, total_bytes, d_status, d_label, d_n_hits, d_n_top, d_top_doc, d_top_score):
         vp = C.c_void_p
         _lib.check(self.L.bsp_classify_device(self.h, n, vp(d_bytes), vp(d_offsets), total_bytes, 0, vp(d_status), vp(d_label),

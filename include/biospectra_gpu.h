@@ -127,6 +127,24 @@ int bsp_classify_batch(bsp_classifier* h, int32_t n, const char* const* seqs, co
 int bsp_classify_packed(bsp_classifier* h, int32_t n, const char* seq_bytes, const int64_t* seq_offsets,
                         int32_t* status, int32_t* label, int32_t* n_hits, int32_t* n_top,
                         int32_t* top_doc, float* top_score);
+/* One read, blocking, for concurrent callers: replaces the body of
+ * Classifier.classify(header, sequence) (classify/Classifier.java:341-366), which the
+ * reference calls from `worker_threads` pool threads at once (LocalClassifier.java:96-118,
+ * ClassifierServer.java:70-98).  Calls that arrive within the micro-batch window of each
+ * other -- or while the GPU is busy with the previous micro-batch -- are coalesced into one
+ * bsp_classify_packed; every caller gets exactly its own read's result.  top_doc / top_score
+ * point at 10 entries each (may be NULL).  seq == NULL or seq_len <= 0 returns BSP_ERR_ARG
+ * (IllegalArgumentException, Classifier.java:342-344). */
+int bsp_classify_one(bsp_classifier* h, const char* seq, int32_t seq_len,
+                     int32_t* status, int32_t* label, int32_t* n_hits, int32_t* n_top,
+                     int32_t* top_doc, float* top_score);
+/* micro-batch window of bsp_classify_one: at most max_reads per GPU batch (default 4096),
+ * the first caller of a batch waits at most max_wait_us for company (default 200; 0 = no
+ * waiting, reads still coalesce while the GPU is busy).  Environment BSP_MICROBATCH_MAX /
+ * BSP_MICROBATCH_US give the defaults. */
+int bsp_classifier_set_microbatch(bsp_classifier* h, int32_t max_reads, int64_t max_wait_us);
+/* counters since open: GPU batches run and reads served by bsp_classify_one */
+int bsp_microbatch_stats(bsp_classifier* h, int64_t* batches, int64_t* reads);
 /* Device-resident variant: d_seq_bytes / d_seq_offsets and all outputs are device
  * pointers; nothing crosses PCIe.  total_bytes = seq_offsets[n]. */
 int bsp_classify_device(bsp_classifier* h, int32_t n, const void* d_seq_bytes, const void* d_seq_offsets,
@@ -197,6 +215,13 @@ int bsp_merge_topk_device(bsp_classifier* h, int32_t n, int32_t parts,
 int bsp_host_index(const char* json_conf, const char* index_dir, const char* reference_dir, int32_t device);
 int bsp_host_classify_local(const char* json_conf, const char* index_dir, const char* input_dir,
                             const char* output_dir, int32_t device);
+/* bsp_host_classify_local keeps the files but batches reads itself (reader thread -> GPU ->
+ * formatter threads, lines in read order).  The _per_read variant keeps the reference's control
+ * flow too: `threads` pool threads (0 = conf.worker_threads) call Classifier.classify(header,
+ * sequence) once per read (LocalClassifier.java:88-120) and write lines in completion order;
+ * the concurrent calls meet in bsp_classify_one's micro-batches. */
+int bsp_host_classify_local_per_read(const char* json_conf, const char* index_dir, const char* input_dir,
+                                     const char* output_dir, int32_t device, int32_t threads);
 const char* bsp_host_last_error(void);
 /* pure host helpers (no GPU): used by the CPU-side tests */
 int bsp_host_label_json(const char* const* taxon_hierarchies, int32_t n, char* out, int32_t cap);

@@ -52,10 +52,19 @@ def main():
     t_cls = time.time() - t0
     summ = json.load(open(os.path.join(out, "sample.fa.result.sum")))
     first = open(os.path.join(out, "sample.fa.result")).readline()
+    # the reference's control flow: T pool threads, one Classifier.classify call per read (micro-batched on the GPU side)
+    per_read = {}
+    for threads in [int(x) for x in os.environ.get("PER_READ_THREADS", "16,256").split(",") if x]:
+        out_t = out + "_pr%d" % threads
+        subprocess.check_call([cli, "lclassify", "-j", conf, "-in", reads_dir, "-out", out_t, "--per-read", str(threads)],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        st = json.load(open(os.path.join(out_t, "sample.fa.result.sum")))
+        assert {k: st[k] for k in ("total", "unknown", "vague", "classified")} == {k: summ[k] for k in ("total", "unknown", "vague", "classified")}
+        per_read[str(threads)] = n_reads / ((st["end_time"] - st["start_time"]) / 1e3)
     print(json.dumps({"reads": n_reads, "index_seconds": t_index, "index_mbp_per_s": n_genomes * glen / 1e6 / t_index,
                       "lclassify_seconds_process": t_cls, "lclassify_ms_in_summary": summ["end_time"] - summ["start_time"],
                       "reads_per_s_file_to_file": n_reads / ((summ["end_time"] - summ["start_time"]) / 1e3),
-                      "summary": summ, "result_bytes": os.path.getsize(os.path.join(out, "sample.fa.result")),
+                      "reads_per_s_per_read_calls_by_threads": per_read, "summary": summ, "result_bytes": os.path.getsize(os.path.join(out, "sample.fa.result")),
                       "first_line": first[:300]}))
 
 

@@ -239,3 +239,33 @@ def test_edge_batches_and_clause_limits(oracle_lib, monkeypatch):
                     g.classify_batch(["ACGTACGT", ""])          # Classifier.java:342-344: null/empty sequence
             finally:
                 g.close()
+
+
+@pytest.mark.parametrize("alg,skips", [(2, 0), (1, 2), (2, 5)])
+def test_positional_warp_kernel_staged_and_direct_paths(oracle_lib, monkeypatch, alg, skips):
+    """The warp-per-(segment, read) scorer stages a phrase clause in shared memory when both terms' slices fit
+    (<= 128 postings, <= 384 positions per term and segment) and walks global memory otherwise.  200 docs that share a
+    stretch (terms with df = 200 > 128), one periodic doc (a term with hundreds of positions) and unrelated docs put
+    clauses on both sides of both caps; every read is compared bit for bit."""
+    rng = random.Random(91)
+    shared = common.rand_seq(rng, 60)
+    ents = []
+    for i in range(100):
+        ents.append(common.rand_seq(rng, rng.randint(20, 120)) + shared + common.rand_seq(rng, rng.randint(0, 80)))
+    ents[7] = ("ACGGTC" * 400) + shared                      # ~400 positions per term of the period
+    ents[8] = "A" * 500 + shared[:30]                        # same-term phrases (repeat path)
+    k = 5
+    reads = common.make_reads(1091, ents, n=96, max_len=140, n_frac=0.1)
+    reads += [shared[5:55], ("ACGGTC" * 20), "A" * 40, shared[:20] + "N" + shared[21:50]]
+    ox = common.build_oracle(oracle_lib, ents, k, False)
+    res_o = ox.classify([r.encode() for r in reads], skips=skips, algorithm=alg, scoring=0, msm=0.3, threads=2)
+    alg_name = ["NAIVE_KMER", "CHAIN_PROXIMITY", "PAIRED_PROXIMITY"][alg]
+    g = common.build_gpu(ents, k, False, dict(kmer_skips=skips, query_algorithm=alg_name, query_term_min_should_match=0.3,
+                                              dense_tables=2, positional=1))
+    try:
+        monkeypatch.setenv("BSP_POS_BLOCK_KERNEL", "0")
+        res_g = g.classify_batch(reads)
+        common.assert_classify_equal(res_g, res_o, reads, "warp positional alg=%d skips=%d" % (alg, skips))
+        assert set(g.last_routes(len(reads))[res_o["status"] == 0]) <= {2}
+    finally:
+        g.close()
