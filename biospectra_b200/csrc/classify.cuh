@@ -36,14 +36,15 @@
 // A = positions of t0, B = positions of t1 (ascending, non-empty).  With two phrase
 // positions the priority queue degenerates to "the other one": after pp passes `next`
 // the other pp is strictly smaller, so pop() always returns it.
+// (boff = 1: B holds positions; boff = 0: B already holds position - 1, the staged form)
 __device__ __forceinline__ float sloppy_freq_distinct(const u32* __restrict__ A, int nA, const u32* __restrict__ B, int nB,
-                                                      int slop) {
-    int pa = (int)A[0], pb = (int)B[0] - 1;
+                                                      int slop, int boff = 1) {
+    int pa = (int)A[0], pb = (int)B[0] - boff;
     int end = pa > pb ? pa : pb;
     // PhraseQueue#lessThan: smaller position first, ties -> smaller offset (t0)
     bool cur_is_a = pa <= pb;
-    const u32* cl = cur_is_a ? A : B; int cn = cur_is_a ? nA : nB; int co = cur_is_a ? 0 : 1; int cp = cur_is_a ? pa : pb;
-    const u32* ol = cur_is_a ? B : A; int on = cur_is_a ? nB : nA; int oo = cur_is_a ? 1 : 0; int op = cur_is_a ? pb : pa;
+    const u32* cl = cur_is_a ? A : B; int cn = cur_is_a ? nA : nB; int co = cur_is_a ? 0 : boff; int cp = cur_is_a ? pa : pb;
+    const u32* ol = cur_is_a ? B : A; int on = cur_is_a ? nB : nA; int oo = cur_is_a ? boff : 0; int op = cur_is_a ? pb : pa;
     int ci = 1, oi = 1;
     int ml = end - cp;
     int next = op;
@@ -72,21 +73,28 @@ __device__ __forceinline__ float sloppy_freq_distinct(const u32* __restrict__ A,
 }
 
 // Can the phrase (t0@0, t1@1) match at all?  Every matchLength the sweep above tests is |(b - 1) - a| of an actual pair
-// (a in A, b in B), so freq = 0 whenever no pair is within the slop.  Branch-light two-pointer scan; no false negatives.
-__device__ __forceinline__ bool sloppy_may_match(const u32* __restrict__ A, int nA, const u32* __restrict__ B, int nB, int slop) {
-    int i = 0, j = 0;
-    int a = (int)A[0], b = (int)B[0] - 1;                // nA, nB >= 1: a posting has at least one position
+// (a in A, b in B), so freq = 0 whenever no pair is within the slop.  Two-pointer scan over the staged lists (shared
+// memory byte addresses; Bm1 holds b - 1); selects instead of branches inside a step.  No false negatives.
+__device__ __forceinline__ int lds_s32(u32 addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ bool sloppy_may_match_staged(u32 sa, int nA, u32 sb, int nB, int slop) {
+    const u32 ea = sa + 4u * (u32)nA, eb = sb + 4u * (u32)nB;  // nA, nB >= 1: a posting has at least one position
+    int a = lds_s32(sa), b = lds_s32(sb);
     const unsigned w = 2u * (unsigned)slop;
     while (true) {
         const int d = b - a;
         if ((unsigned)(d + slop) <= w) return true;
-        const bool adv_a = d > 0;                         // a is behind: advance it (selects, no divergence inside a step)
-        i += adv_a ? 1 : 0;
-        j += adv_a ? 0 : 1;
-        if ((adv_a ? i : j) >= (adv_a ? nA : nB)) return false;
-        const int v = (int)*(adv_a ? A + i : B + j);
+        const bool adv_a = d > 0;                         // a is behind: advance it
+        sa += adv_a ? 4u : 0u;
+        sb += adv_a ? 0u : 4u;
+        const u32 ptr = adv_a ? sa : sb;
+        if (ptr >= (adv_a ? ea : eb)) return false;
+        const int v = lds_s32(ptr);
         a = adv_a ? v : a;
-        b = adv_a ? b : v - 1;
+        b = adv_a ? b : v;
     }
 }
 
@@ -691,7 +699,7 @@ __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_w
                         for (int u = 0; u < 8; u++) {
                             const u32 i = i0 + 32 * u;
                             if (i < m0) w_pos0[i] = va[u];
-                            if (i < m1) w_pos1[i] = vb[u];
+                            if (i < m1) w_pos1[i] = vb[u] - 1u;                          // staged as position - 1 (phrase offset of t1)
                         }
                     }
                     __syncwarp();
@@ -704,7 +712,8 @@ __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_w
                             const u32* B = w_pos1 + (q1 - p1);
                             const int nA = (int)(w_pp0[i + 1] - q0), nB = (int)(w_pp1[j + 1] - q1);
                             // two independent k-mers within the slop of each other: rare, so the cheap test comes first
-                            const float f = sloppy_may_match(A, nA, B, nB, st.slop) ? sloppy_freq_distinct(A, nA, B, nB, st.slop) : 0.0f;
+                            const float f = sloppy_may_match_staged((u32)__cvta_generic_to_shared(A), nA, (u32)__cvta_generic_to_shared(B), nB, st.slop)
+                                                ? sloppy_freq_distinct(A, nA, B, nB, st.slop, 0) : 0.0f;
                             if (f != 0.0f) {
                                 const float sc = clause_doc_score(sp.sim, sp.sim == SIM_TFIDF ? tf_of(f) : f, st.val, dw[d], sp.k1p1);
                                 acc[d] += (double)sc;                                    // BooleanScorer: double sum
