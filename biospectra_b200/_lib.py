@@ -43,7 +43,7 @@ EXPORTS = [
     "bsp_config_default", "bsp_last_error", "bsp_version", "bsp_index_create", "bsp_index_add_entry",
     "bsp_index_add_entry_device", "bsp_index_close", "bsp_index_close_to_classifier", "bsp_classifier_open",
     "bsp_classify_batch", "bsp_classify_packed", "bsp_classify_device", "bsp_classify_one",
-    "bsp_classifier_set_microbatch", "bsp_microbatch_stats", "bsp_doc_fields", "bsp_classifier_close",
+    "bsp_classifier_set_microbatch", "bsp_microbatch_stats", "bsp_classifier_set_lineages", "bsp_classify_packed_tax", "bsp_doc_fields", "bsp_classifier_close",
     "bsp_index_stats", "bsp_doc_info", "bsp_term_postings", "bsp_tokenize", "bsp_last_routes", "bsp_last_counters",
     "bsp_last_timings", "bsp_memory_info", "bsp_partition_df_buffer", "bsp_partition_local_stats",
     "bsp_partition_set_global", "bsp_merge_topk_device", "bsp_read_cost",
@@ -77,6 +77,8 @@ def lib():
     L.bsp_classifier_open.argtypes = [cfgp, C.c_char_p, C.POINTER(vp)]
     L.bsp_classify_batch.argtypes = [vp, C.c_int32, C.POINTER(C.c_char_p), vp, vp, vp, vp, vp, vp, vp]
     L.bsp_classify_packed.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.bsp_classifier_set_lineages.argtypes = [vp, C.c_int32, vp, vp, vp]
+    L.bsp_classify_packed_tax.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.bsp_classify_one.argtypes = [vp, C.c_char_p, C.c_int32, i32p, i32p, i32p, i32p, vp, vp]
     L.bsp_classifier_set_microbatch.argtypes = [vp, C.c_int32, C.c_int64]
     L.bsp_microbatch_stats.argtypes = [vp, i64p, i64p]

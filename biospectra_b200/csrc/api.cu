@@ -38,6 +38,7 @@ struct Scratch {
     int slot_index = 0;
     DevBuf<i32> part_n; DevBuf<u32> part_doc; DevBuf<float> part_score;
     DevBuf<i32> o_status, o_label, o_nhits, o_ntop, o_doc; DevBuf<float> o_score;
+    DevBuf<i32> o_taxlabel, o_taxidx;
     cudaStream_t st = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     u8* pin_in = nullptr; size_t pin_in_bytes = 0;
@@ -95,6 +96,8 @@ struct bsp_classifier {
     Scratch sc[2];                      // two sub-batches in flight: copies of one overlap the kernels of the other
     // scoring constants
     DevBuf<float> idf_by_df, doc_w, tf16;
+    // interned ranked lineages (bsp_classifier_set_lineages)
+    DevBuf<i64> lin_off; DevBuf<i32> lin_tax; DevBuf<u8> lin_flags; i64 lin_docs = 0;
     i64 global_docs = 0, global_sum_ttf = 0, doc_base_global = 0;
     // last batch
     std::vector<i32> last_routes;
@@ -736,12 +739,25 @@ static void enqueue_outputs(bsp_classifier* h, Scratch& sc, i32* status, i32* la
     CUDA_CHECK(cudaMemcpyAsync(h->last_routes.data() + r0, sc.route.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
 }
 
+// taxonomy labels of a finished sub-batch (its merged hit lists are on the device): one more small kernel + two copies
+static void enqueue_taxonomy(bsp_classifier* h, Scratch& sc, i32* tax_label, i32* tax_index) {
+    const i32 m = sc.n;
+    sc.o_taxlabel.ensure(m); sc.o_taxidx.ensure(m);
+    taxonomy_label_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, sc.st>>>(m, sc.o_nhits.p, sc.o_doc.p, h->lin_off.p, h->lin_tax.p, h->lin_flags.p,
+                                                                         h->lin_docs, sc.o_taxlabel.p, sc.o_taxidx.p);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(tax_label + sc.r0, sc.o_taxlabel.p, (size_t)m * 4, cudaMemcpyDeviceToHost, sc.st));
+    if (tax_index) CUDA_CHECK(cudaMemcpyAsync(tax_index + sc.r0, sc.o_taxidx.p, (size_t)m * 4, cudaMemcpyDeviceToHost, sc.st));
+}
+
 static int classify_packed_impl(bsp_classifier* h, i32 n, const char* seq_bytes, const i64* seq_offsets,
-                                i32* status, i32* label, i32* n_hits, i32* n_top, i32* top_doc, float* top_score) {
+                                i32* status, i32* label, i32* n_hits, i32* n_top, i32* top_doc, float* top_score,
+                                i32* tax_label = nullptr, i32* tax_index = nullptr) {
     if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
     std::lock_guard<std::mutex> lk(h->mu);
     API_TRY(h)
     if (n < 0 || (n > 0 && (!seq_bytes || !seq_offsets || !status))) return fail(&h->last_error, BSP_ERR_ARG, "null argument");
+    if (tax_label && h->lin_docs == 0) return fail(&h->last_error, BSP_ERR_STATE, "taxonomy labels requested before bsp_classifier_set_lineages");
     CUDA_CHECK(cudaSetDevice(h->conf.device));
     for (auto& c : h->counters) c = 0;
     h->score_ms = 0; h->pipe_ms = 0;
@@ -781,6 +797,7 @@ static int classify_packed_impl(bsp_classifier* h, i32 n, const char* seq_bytes,
                 BatchOut bo{prev->o_status.p, prev->o_label.p, prev->o_nhits.p, prev->o_ntop.p, prev->o_doc.p, prev->o_score.p};
                 pipeline_phase2(h, *prev, bo);
                 enqueue_outputs(h, *prev, status, label, n_hits, n_top, top_doc, top_score);
+                if (tax_label) enqueue_taxonomy(h, *prev, tax_label, tax_index);
             }
             prev = &sc;
             slot ^= 1;
@@ -789,6 +806,7 @@ static int classify_packed_impl(bsp_classifier* h, i32 n, const char* seq_bytes,
             BatchOut bo{prev->o_status.p, prev->o_label.p, prev->o_nhits.p, prev->o_ntop.p, prev->o_doc.p, prev->o_score.p};
             pipeline_phase2(h, *prev, bo);
             enqueue_outputs(h, *prev, status, label, n_hits, n_top, top_doc, top_score);
+            if (tax_label) enqueue_taxonomy(h, *prev, tax_label, tax_index);
         }
         for (auto& sc : h->sc) {
             CUDA_CHECK(cudaStreamSynchronize(sc.st));
@@ -806,6 +824,37 @@ BSP_API int bsp_classify_packed(bsp_classifier* h, int32_t n, const char* seq_by
                                 int32_t* status, int32_t* label, int32_t* n_hits, int32_t* n_top,
                                 int32_t* top_doc, float* top_score) {
     return classify_packed_impl(h, n, seq_bytes, seq_offsets, status, label, n_hits, n_top, top_doc, top_score);
+}
+
+BSP_API int bsp_classify_packed_tax(bsp_classifier* h, int32_t n, const char* seq_bytes, const int64_t* seq_offsets,
+                                    int32_t* status, int32_t* label, int32_t* n_hits, int32_t* n_top,
+                                    int32_t* top_doc, float* top_score, int32_t* tax_label, int32_t* tax_index) {
+    if (h && !tax_label) return fail(&h->last_error, BSP_ERR_ARG, "tax_label is null");
+    return classify_packed_impl(h, n, seq_bytes, seq_offsets, status, label, n_hits, n_top, top_doc, top_score, tax_label, tax_index);
+}
+
+BSP_API int bsp_classifier_set_lineages(bsp_classifier* h, int32_t n_docs, const int64_t* lineage_off, const int32_t* taxid,
+                                        const uint8_t* flags) {
+    if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
+    std::lock_guard<std::mutex> lk(h->mu);
+    API_TRY(h)
+    const i64 expect = h->global_docs > 0 ? h->global_docs : (i64)h->ix.docs.size();
+    if (n_docs <= 0 || !lineage_off || !flags || (lineage_off[n_docs] > 0 && !taxid)) return fail(&h->last_error, BSP_ERR_ARG, "null argument");
+    if ((i64)n_docs != expect) return fail(&h->last_error, BSP_ERR_ARG, "lineages must cover every document of the index (global ids)");
+    if (lineage_off[0] != 0) return fail(&h->last_error, BSP_ERR_ARG, "lineage_off[0] must be 0");
+    for (i32 d = 0; d < n_docs; d++) if (lineage_off[d + 1] < lineage_off[d]) return fail(&h->last_error, BSP_ERR_ARG, "lineage_off must be non-decreasing");
+    CUDA_CHECK(cudaSetDevice(h->conf.device));
+    const i64 total = lineage_off[n_docs];
+    h->lin_off.alloc((size_t)n_docs + 1);
+    h->lin_tax.alloc((size_t)std::max<i64>(total, 1));
+    h->lin_flags.alloc((size_t)n_docs);
+    CUDA_CHECK(cudaMemcpyAsync(h->lin_off.p, lineage_off, ((size_t)n_docs + 1) * 8, cudaMemcpyHostToDevice, h->st));
+    if (total) CUDA_CHECK(cudaMemcpyAsync(h->lin_tax.p, taxid, (size_t)total * 4, cudaMemcpyHostToDevice, h->st));
+    CUDA_CHECK(cudaMemcpyAsync(h->lin_flags.p, flags, (size_t)n_docs, cudaMemcpyHostToDevice, h->st));
+    CUDA_CHECK(cudaStreamSynchronize(h->st));
+    h->lin_docs = n_docs;
+    return BSP_OK;
+    API_CATCH(h)
 }
 
 BSP_API int bsp_classify_batch(bsp_classifier* h, int32_t n, const char* const* seqs, const int32_t* seq_lens,

@@ -827,6 +827,55 @@ __global__ void __launch_bounds__(128) merge_kernel(i32 n_reads, const i32* __re
     }
 }
 
+// Taxonomy-aware label of a read from its hit list (Classifier.java:263-339, after the hits equal to the maximum are
+// known).  lin_off/lin_tax: per document the taxids of TaxonTreeDescription#getClassifiableTaxonomyTree (the entries
+// with a rank, leaf -> root); flags bit0 = the document has a taxonomy string, bit1 = it is malformed (the reference
+// throws while parsing it and the caller skips the read: label -1).  tax_index = position in hit 0's ranked lineage of
+// the taxon the read is classified at, -1 = ("unknown", "").  Thread per read.
+__global__ void __launch_bounds__(128) taxonomy_label_kernel(i32 n_reads, const i32* __restrict__ n_hits, const i32* __restrict__ top_doc,
+                                                              const i64* __restrict__ lin_off, const i32* __restrict__ lin_tax,
+                                                              const u8* __restrict__ flags, i64 n_docs, i32* __restrict__ tax_label,
+                                                              i32* __restrict__ tax_index) {
+    const i32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const i32 nh = min(max(n_hits[r], 0), TOPN);
+    const i32* hd = top_doc + (i64)r * TOPN;
+    i32 tl = 0, ti = -1;                                      // no hit: UNKNOWN
+    bool bad = false;
+    for (int j = 0; j < nh; j++) if (hd[j] < 0 || hd[j] >= n_docs) bad = true;
+    if (bad) tl = -1;
+    else if (nh == 1) {                                       // one hit: CLASSIFIED at its lowest ranked taxon (:266-279)
+        tl = 2;
+        const i32 d = hd[0];
+        const u8 f = flags[d];
+        if (f & 1) { if (f & 2) tl = -1; else if (lin_off[d + 1] > lin_off[d]) ti = 0; }
+    } else if (nh >= 2) {                                     // several: first taxon of hit 0 common to all (:280-338)
+        bool all = true;
+        for (int j = 0; j < nh; j++) {                        // entries are parsed in order; a missing string fails quickly
+            const u8 f = flags[hd[j]];
+            if (!(f & 1)) { all = false; break; }
+            if (f & 2) { bad = true; break; }
+        }
+        tl = 1;
+        if (bad) tl = -1;
+        else if (all) {
+            const i64 a0 = lin_off[hd[0]], b0 = lin_off[hd[0] + 1];
+            for (i64 x = a0; x < b0 && tl == 1; x++) {
+                const i32 t = lin_tax[x];
+                bool common = true;
+                for (int j = 1; j < nh && common; j++) {
+                    bool found = false;
+                    for (i64 y = lin_off[hd[j]]; y < lin_off[hd[j] + 1]; y++) if (lin_tax[y] == t) { found = true; break; }
+                    common = found;
+                }
+                if (common) { tl = 2; ti = (i32)(x - a0); }
+            }
+        }
+    }
+    tax_label[r] = tl;
+    tax_index[r] = ti;
+}
+
 // ------------------------------------------------------------- cost model (8d)
 // Warp per read.  out[0] reads, [1] tokens, [2] unique terms (= probes), [3] sum df,
 // [4] sum ttf, [5] A_read (CSR formula of SURVEY.md 8d), [6] dense-layout bytes, [7] clauses.

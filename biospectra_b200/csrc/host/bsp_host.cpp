@@ -404,6 +404,22 @@ Classifier::Classifier(const Configuration* conf) {
             catch (const std::exception&) { di.taxonomyBad = true; }
         }
     }
+    // ranked lineages interned for the device: makeClassificationResult's taxid comparisons
+    // (Classifier.java:296-327) then run next to the merge kernel and the formatter only looks names up
+    const char* hostLca = getenv("BSP_HOST_LCA");
+    deviceLca_ = !(hostLca && atoi(hostLca) != 0) && nDocs > 0;
+    if (deviceLca_) {
+        std::vector<int64_t> off((size_t)nDocs + 1, 0);
+        std::vector<int32_t> tax;
+        std::vector<uint8_t> flags((size_t)nDocs, 0);
+        for (int64_t d = 0; d < nDocs; d++) {
+            const DocInfo& di = docs_[(size_t)d];
+            flags[(size_t)d] = (uint8_t)((di.hasTaxonomy ? 1 : 0) | (di.taxonomyBad ? 2 : 0));
+            for (const Taxonomy& t : di.ranked) tax.push_back((int32_t)t.taxid);
+            off[(size_t)d + 1] = (int64_t)tax.size();
+        }
+        check_rc(bsp_classifier_set_lineages(h_, (int32_t)nDocs, off.data(), tax.empty() ? nullptr : tax.data(), flags.data()));
+    }
 }
 
 void Classifier::classifyPacked(const char* seqBytes, const int64_t* offsets, int32_t n, PackedResults& out) {
@@ -412,8 +428,16 @@ void Classifier::classifyPacked(const char* seqBytes, const int64_t* offsets, in
     out.topDoc.assign((size_t)n * BSP_TOPN, -1);
     out.topScore.assign((size_t)n * BSP_TOPN, 0.0f);
     if (n == 0) return;
-    check_rc(bsp_classify_packed(h_, n, seqBytes, offsets, out.status.data(), nullptr, out.nHits.data(), nullptr, out.topDoc.data(),
-                                 out.topScore.data()));
+    if (deviceLca_) {
+        out.taxLabel.assign((size_t)n, 0);
+        out.taxIndex.assign((size_t)n, -1);
+        check_rc(bsp_classify_packed_tax(h_, n, seqBytes, offsets, out.status.data(), nullptr, out.nHits.data(), nullptr,
+                                         out.topDoc.data(), out.topScore.data(), out.taxLabel.data(), out.taxIndex.data()));
+    } else {
+        out.taxLabel.clear(); out.taxIndex.clear();
+        check_rc(bsp_classify_packed(h_, n, seqBytes, offsets, out.status.data(), nullptr, out.nHits.data(), nullptr, out.topDoc.data(),
+                                     out.topScore.data()));
+    }
     for (int32_t i = 0; i < n; i++)
         if (offsets[i + 1] == offsets[i]) out.status[(size_t)i] = BSP_READ_ERROR;       // Classifier.java:342-344
 }
@@ -428,7 +452,12 @@ bool Classifier::appendResultJson(std::string& o, const char* header, size_t hea
     // label
     int ty = 0;
     const Taxonomy* tax = nullptr;
-    if (nh == 1) {
+    if (!r.taxLabel.empty()) {                               // computed on the device (taxonomy_label_kernel)
+        ty = r.taxLabel[(size_t)i];
+        if (ty < 0) return false;                            // malformed taxonomy among the hits: the reference throws
+        const int ti = r.taxIndex[(size_t)i];
+        if (ti >= 0 && nh > 0) tax = &docs_[(size_t)docs[0]].ranked[(size_t)ti];
+    } else if (nh == 1) {
         ty = 2;
         const DocInfo& d = docs_[(size_t)docs[0]];
         if (d.hasTaxonomy) { if (d.taxonomyBad) return false; if (!d.ranked.empty()) tax = &d.ranked[0]; }

@@ -116,6 +116,7 @@ public:
     struct PackedResults {                // per read, as bsp_classify_packed returns them
         std::vector<int32_t> status, nHits, topDoc;
         std::vector<float> topScore;
+        std::vector<int32_t> taxLabel, taxIndex;   // bsp_classify_packed_tax: label with taxonomy, index into hit 0's ranked lineage
     };
     void classifyPacked(const char* seqBytes, const int64_t* offsets, int32_t n, PackedResults& out);
     // JSON line of read i (no trailing newline) appended to `o`; returns false when the reference would have thrown
@@ -127,6 +128,7 @@ private:
     bsp_classifier* h_ = nullptr;
     std::vector<DocInfo> docs_;
     int workerThreads_ = 4;
+    bool deviceLca_ = true;               // labels with taxonomy computed on the device (BSP_HOST_LCA=1: on the host)
 };
 
 class LocalClassifier {

@@ -116,6 +116,27 @@ class Classifier:
         data, off = self.pack_reads(seqs)
         return self.classify_packed(data, off)
 
+    def set_lineages(self, lineage_off, taxids, flags):
+        """interned ranked lineages per document (leaf -> root taxids of the entries with a rank); flags bit0 = has a
+        taxonomy string, bit1 = malformed.  Enables classify_packed_tax (Classifier.java:263-339 on the device)."""
+        off = np.ascontiguousarray(lineage_off, np.int64)
+        tax = np.ascontiguousarray(taxids, np.int32)
+        fl = np.ascontiguousarray(flags, np.uint8)
+        _lib.check(self.L.bsp_classifier_set_lineages(self.h, len(fl), off.ctypes.data, tax.ctypes.data if tax.size else None,
+                                                      fl.ctypes.data), self.h)
+
+    def classify_packed_tax(self, seq_bytes: np.ndarray, offsets: np.ndarray):
+        n = len(offsets) - 1
+        out = self.alloc_outputs(n)
+        out["tax_label"] = np.zeros(n, np.int32)
+        out["tax_index"] = np.full(n, -1, np.int32)
+        seq_bytes = np.ascontiguousarray(seq_bytes, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        _lib.check(self.L.bsp_classify_packed_tax(self.h, n, seq_bytes.ctypes.data if seq_bytes.size else None, offsets.ctypes.data,
+                                                  *[out[k].ctypes.data for k in ("status", "label", "n_hits", "n_top", "top_doc",
+                                                                                 "top_score", "tax_label", "tax_index")]), self.h)
+        return out
+
     def classify_one(self, seq: bytes):
         """One read, blocking; safe to call from many threads at once (the GIL is released inside the call): concurrent
         calls are coalesced into GPU micro-batches.  Mirrors Classifier.classify(header, sequence), Classifier.java:341-366."""

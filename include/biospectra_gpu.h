@@ -127,6 +127,20 @@ int bsp_classify_batch(bsp_classifier* h, int32_t n, const char* const* seqs, co
 int bsp_classify_packed(bsp_classifier* h, int32_t n, const char* seq_bytes, const int64_t* seq_offsets,
                         int32_t* status, int32_t* label, int32_t* n_hits, int32_t* n_top,
                         int32_t* top_doc, float* top_score);
+/* Taxonomy-aware labels on the device: Classifier.makeClassificationResult (classify/Classifier.java:263-339) with
+ * the lineages interned once.  The host parses each document's taxon_hierarchy JSON and passes the taxids of
+ * TaxonTreeDescription#getClassifiableTaxonomyTree (beans/TaxonTreeDescription.java:33-98: the entries with a rank,
+ * leaf -> root): lineage_off[n_docs + 1] into taxid[]; flags[d] bit0 = the document has a taxonomy string, bit1 = the
+ * string is malformed (the reference throws while parsing it and its caller skips the read).  n_docs must equal the
+ * document count of the index (the global count in doc-partitioned mode). */
+int bsp_classifier_set_lineages(bsp_classifier* h, int32_t n_docs, const int64_t* lineage_off,
+                                const int32_t* taxid, const uint8_t* flags);
+/* bsp_classify_packed plus, per read: tax_label = BSP_UNKNOWN / BSP_VAGUE / BSP_CLASSIFIED as the reference labels the
+ * read with taxonomy (-1: a hit's taxonomy is malformed, the reference throws), tax_index = position in hit 0's ranked
+ * lineage of the taxon the read is classified at (-1: taxon ("unknown", "")).  tax_index may be NULL. */
+int bsp_classify_packed_tax(bsp_classifier* h, int32_t n, const char* seq_bytes, const int64_t* seq_offsets,
+                            int32_t* status, int32_t* label, int32_t* n_hits, int32_t* n_top,
+                            int32_t* top_doc, float* top_score, int32_t* tax_label, int32_t* tax_index);
 /* One read, blocking, for concurrent callers: replaces the body of
  * Classifier.classify(header, sequence) (classify/Classifier.java:341-366), which the
  * reference calls from `worker_threads` pool threads at once (LocalClassifier.java:96-118,
