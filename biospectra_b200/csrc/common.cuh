@@ -1,6 +1,7 @@
 // common.cuh -- shared device/host helpers for libbiospectra_gpu (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <chrono>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -36,24 +37,43 @@ static inline i64 round_up(i64 a, i64 b) { return ceil_div(a, b) * b; }
 
 // ---------------------------------------------------------------- device buffer
 // RAII device allocation (no torch: plain cudaMalloc).
+// host time spent in cudaMalloc / cudaFree (reported by the build when BSP_BUILD_TIMING is set)
+struct AllocStats { double alloc_ms = 0, free_ms = 0; long allocs = 0, frees = 0; };
+static AllocStats g_alloc_stats;
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool owned = true;                  // false: a view into another allocation (adopt)
     DevBuf() {}
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), owned(o.owned) { o.p = nullptr; o.n = 0; o.owned = true; }
     DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        if (this != &o) { release(); p = o.p; n = o.n; owned = o.owned; o.p = nullptr; o.n = 0; o.owned = true; }
         return *this;
     }
     ~DevBuf() { release(); }
-    void release() { if (p) { cudaFree(p); p = nullptr; n = 0; } }
+    // view of `count` elements at `ptr` inside a block somebody else owns
+    void adopt(T* ptr, size_t count) { release(); p = ptr; n = count; owned = false; }
+    void release() {
+        if (p && !owned) { p = nullptr; n = 0; owned = true; return; }
+        if (p) {
+            const auto t0 = std::chrono::steady_clock::now();
+            cudaFree(p);
+            g_alloc_stats.free_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            g_alloc_stats.frees++;
+            p = nullptr; n = 0;
+        }
+    }
     void alloc(size_t count) {
         release();
         if (count == 0) count = 1;
+        const auto t0 = std::chrono::steady_clock::now();
         CUDA_CHECK(cudaMalloc((void**)&p, count * sizeof(T)));
+        g_alloc_stats.alloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        g_alloc_stats.allocs++;
         n = count;
     }
     void ensure(size_t count) { if (count > n) alloc(count + count / 8); }

@@ -124,6 +124,117 @@ __global__ void __launch_bounds__(256) pair_table4_kernel(SegDev s, int k, int m
     }
 }
 
+// Same rows, staged: warp per first k-mer t0 (segments of at most 256 docs).  The four (k+1)-mers t0+A/C/G/T share
+// t0's postings, so its slice of the segment (docs, position offsets, positions) is copied to shared memory once with
+// batched coalesced loads; each second k-mer's slice follows, a doc -> posting byte map replaces the binary search and
+// the literal sweep runs out of shared memory.  Slices beyond the position cap and same-term rows take the direct path.
+#define PT_WARPS 8
+__host__ __device__ inline size_t pair_stage_warp_bytes(int dcap, int pcap) {
+    return 2 * ((size_t)dcap * 4 + (size_t)(dcap + 4) * 4 + (size_t)pcap * 4) + (size_t)dcap;
+}
+__device__ __forceinline__ void stage_slice(const SegDev& s, u32 a, u32 n, u32* __restrict__ w_doc, u32* __restrict__ w_pp,
+                                            u8* __restrict__ inv, int lane) {
+#pragma unroll 1
+    for (u32 i0 = lane; i0 <= n; i0 += 128) {
+        u32 vd[4], vp[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const u32 i = i0 + 32 * u;
+            vd[u] = i < n ? s.post_doc[a + i] : 0u;
+            vp[u] = i <= n ? s.post_pos[a + i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const u32 i = i0 + 32 * u;
+            if (i < n) { w_doc[i] = vd[u]; if (inv) inv[vd[u]] = (u8)i; }
+            if (i <= n) w_pp[i] = vp[u];
+        }
+    }
+}
+__device__ __forceinline__ void stage_positions(const SegDev& s, u32 p, u32 m, u32* __restrict__ w_pos, u32 dec, int lane) {
+#pragma unroll 1
+    for (u32 i0 = lane; i0 < m; i0 += 256) {
+        u32 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const u32 i = i0 + 32 * u; v[u] = i < m ? s.positions[p + i] : 0u; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const u32 i = i0 + 32 * u; if (i < m) w_pos[i] = v[u] - dec; }
+    }
+}
+__global__ void __launch_bounds__(PT_WARPS * 32) pair_table4_staged_kernel(SegDev s, int k, int min_strand, u32* __restrict__ tab32,
+                                                                            u64 row_words, u64 pair_row0, ExcBuild ex, u64 n_kmers,
+                                                                            int dcap, int pcap) {
+    extern __shared__ __align__(16) u8 pt_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u64 t0raw = (u64)blockIdx.x * PT_WARPS + warp;
+    if (t0raw >= n_kmers) return;
+    u8* wbase = pt_raw + (size_t)warp * pair_stage_warp_bytes(dcap, pcap);
+    u32* w_pos0 = reinterpret_cast<u32*>(wbase);
+    u32* w_pos1 = w_pos0 + pcap;
+    u32* w_doc0 = w_pos1 + pcap;
+    u32* w_doc1 = w_doc0 + dcap;
+    u32* w_pp0 = w_doc1 + dcap;
+    u32* w_pp1 = w_pp0 + dcap + 4;
+    u8* inv = reinterpret_cast<u8*>(w_pp1 + dcap + 4);
+    const u64 kmask = (1ull << (2 * k)) - 1ull;
+    const u64 t0 = canon_kmer(t0raw, k, min_strand);
+    const u32 lt0 = s.direct[t0];
+    if (lt0 == NO_TERM) return;
+    const u32 a0 = s.term_off[lt0], n0 = s.term_off[lt0 + 1] - a0;
+    for (u32 d = lane; d < s.n_docs; d += 32) inv[d] = 0;
+    stage_slice(s, a0, n0, w_doc0, w_pp0, nullptr, lane);
+    __syncwarp();
+    const u32 p0 = w_pp0[0], m0 = w_pp0[n0] - p0;
+    const bool fit0 = m0 <= (u32)pcap;
+    if (fit0) stage_positions(s, p0, m0, w_pos0, 0u, lane);
+    __syncwarp();
+#pragma unroll 1
+    for (u32 c = 0; c < 4; c++) {
+        const u64 u = (t0raw << 2) | c;
+        const u64 t1 = canon_kmer(u & kmask, k, min_strand);
+        const u32 lt1 = s.direct[t1];
+        if (lt1 == NO_TERM) continue;
+        const bool same = t0 == t1;
+        const u32 a1 = s.term_off[lt1], n1 = s.term_off[lt1 + 1] - a1;
+        u32* row = tab32 + (pair_row0 + u) * row_words;
+        bool staged = false;
+        u32 p1 = 0;
+        if (fit0 && !same) {
+            stage_slice(s, a1, n1, w_doc1, w_pp1, inv, lane);
+            __syncwarp();
+            p1 = w_pp1[0];
+            const u32 m1 = w_pp1[n1] - p1;
+            if (m1 <= (u32)pcap) { stage_positions(s, p1, m1, w_pos1, 1u, lane); staged = true; }   // staged as position - 1
+            __syncwarp();
+        }
+        for (u32 i0 = 0; i0 < n0; i0 += 32) {
+            const u32 i = i0 + lane;
+            bool has = false;
+            u32 doc = 0, code = 0;
+            if (i < n0) {
+                float f = 0.0f;
+                if (staged) {
+                    const u32 d = w_doc0[i], j = inv[d];                  // verified: may be a stale entry
+                    if (j < n1 && w_doc1[j] == d) {
+                        const u32 q0 = w_pp0[i], q1 = w_pp1[j];
+                        f = sloppy_freq_distinct(w_pos0 + (q0 - p0), (int)(w_pp0[i + 1] - q0), w_pos1 + (q1 - p1), (int)(w_pp1[j + 1] - q1), 2, 0);
+                    }
+                } else {
+                    f = phrase_freq_at(s, a0 + i, a1, a1 + n1, a1 + i, 2, same);
+                }
+                if (f != 0.0f) {
+                    doc = s.doc_base + (staged ? w_doc0[i] : s.post_doc[a0 + i]);
+                    const u32 cc = (u32)f;
+                    if ((float)cc == f && cc >= 1u && cc <= T4_PAIR_MAX) { code = cc; has = true; }
+                    else exc_append(ex, (u32)(pair_row0 + u), doc, f);
+                }
+            }
+            nibble_or(row, doc, code, has, lane);
+        }
+        __syncwarp();
+    }
+}
+
 // ---- exception list finalisation: sort by (row, doc), then per-row offsets
 __global__ void __launch_bounds__(256) exc_keys_kernel(const u32* __restrict__ row, const u32* __restrict__ doc, u32 n,
                                                         u64* __restrict__ keys, u32* __restrict__ vals) {

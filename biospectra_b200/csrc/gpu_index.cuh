@@ -145,6 +145,30 @@ struct BuildOptions {
     i64 gap_cap = GAP_CAP_DEFAULT; // gap clauses per sub-batch
 };
 
+// Slab allocator of the positional index: the segments' arrays are carved out of a few large allocations (first fit over
+// the slabs' tails) instead of two cudaMallocs per segment.
+struct DevArena {
+    struct Slab { DevBuf<u8> buf; size_t used = 0; };
+    std::vector<Slab> slabs;
+    size_t slab_bytes = (size_t)8 << 30;
+    u8* take(size_t bytes) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        for (Slab& sl : slabs)
+            if (sl.buf.n - sl.used >= bytes) { u8* p = sl.buf.p + sl.used; sl.used += bytes; return p; }
+        slabs.emplace_back();
+        Slab& sl = slabs.back();
+        try { sl.buf.alloc(std::max(slab_bytes, bytes)); }
+        catch (const BspError&) {                      // not enough room for a whole slab: exactly what is asked for
+            cudaGetLastError();
+            try { sl.buf.alloc(bytes); } catch (...) { slabs.pop_back(); throw; }
+        }
+        sl.used = bytes;
+        return sl.buf.p;
+    }
+    void release_all() { slabs.clear(); }
+    void reset() { for (Slab& sl : slabs) sl.used = 0; }          // reuse the slabs (segment arrays not kept)
+};
+
 struct GpuIndex {
     int k = 10, min_strand = 0;
     bool direct = true;
@@ -152,6 +176,8 @@ struct GpuIndex {
     std::vector<DocMeta> docs;
     std::vector<u32> doc_ntok; std::vector<u8> doc_norm;
     std::vector<Segment> segs;
+    DevArena arena;                    // backing store of the segments' arrays
+    DevBuf<u32> doc_tok_all;           // every segment's doc_tok array
     DevBuf<SegDev> d_segs;
     bool positional = false, tables = false, has_pair = false;
     i64 n_terms = 0, n_postings = 0, n_positions = 0, sum_ttf = 0;
@@ -206,25 +232,44 @@ __global__ void __launch_bounds__(256) count_nonzero_kernel(const u32* __restric
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(counter, (unsigned long long)__popc(bal));
 }
 
+// BSP_BUILD_TIMING: wall time per build phase (adds a stream synchronize at every phase boundary)
+struct BuildPhases {
+    bool on = false;
+    double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::chrono::steady_clock::time_point t;
+    void start(cudaStream_t st) { if (on) { cudaStreamSynchronize(st); t = std::chrono::steady_clock::now(); } }
+    void tick(int i, cudaStream_t st) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto n = std::chrono::steady_clock::now();
+        ms[i] += std::chrono::duration<double, std::milli>(n - t).count();
+        t = n;
+    }
+};
+static BuildPhases g_phases;
+
 template <typename K>
 static void build_segment(GpuIndex& ix, Segment& seg, const EntryDev* d_entries, const u32* d_chunk_entry,
                           const u64* d_chunk_base, u32 c0, u32 c1, DevBuf<u8>& kbuf_a, DevBuf<u8>& kbuf_b,
                           DevBuf<u32>& vbuf_a, DevBuf<u32>& vbuf_b, DevBuf<u64>& flags, RadixSortTemp& rst,
-                          DevBuf<u8>& scan_tmp, DevBuf<u64>& d_total, cudaStream_t st) {
+                          DevBuf<u8>& scan_tmp, DevBuf<u64>& d_total, DevBuf<u64>& scanned_buf, cudaStream_t st) {
     const u32 n = seg.n_tok;
     RefStore& ref = *ix.ref;
     kbuf_a.ensure((size_t)n * sizeof(K)); kbuf_b.ensure((size_t)n * sizeof(K));
     vbuf_a.ensure(n); vbuf_b.ensure(n);
     K* keys = (K*)kbuf_a.p; K* keys_alt = (K*)kbuf_b.p;
     u32* vals = vbuf_a.p; u32* vals_alt = vbuf_b.p;
+    g_phases.start(st);
     if (c1 > c0) {
         extract_kernel<K><<<c1 - c0, CHUNK_THREADS, 0, st>>>(ref.packed.p, ref.mask.p, d_entries, d_chunk_entry, d_chunk_base,
                                                              c0, ix.k, ix.min_strand, keys, vals);
         KERNEL_CHECK();
     }
+    g_phases.tick(0, st);
     radix_sort_pairs<K>(&keys, &vals, &keys_alt, &vals_alt, n, 2 * ix.k, rst, st);
+    g_phases.tick(1, st);
     // CSR
-    seg.positions.alloc(n);
+    seg.positions.adopt((u32*)ix.arena.take((size_t)std::max<u32>(n, 1) * 4), n);
     flags.ensure((size_t)n + 1);
     if (n) {
         mark_heads_kernel<K><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(keys, vals, n, seg.doc_tok.p, seg.n_docs,
@@ -232,20 +277,28 @@ static void build_segment(GpuIndex& ix, Segment& seg, const EntryDev* d_entries,
         KERNEL_CHECK();
     }
     // scanned flags go to the alternate key buffer when it is wide enough, else a fresh one
-    DevBuf<u64> scanned_own;
     u64* scanned;
     if (sizeof(K) == 8) scanned = (u64*)keys_alt;
-    else { scanned_own.alloc((size_t)n + 1); scanned = scanned_own.p; }
+    else { scanned_buf.ensure((size_t)n + 1); scanned = scanned_buf.p; }      // kept across segments (2 GB at 2^28 tokens)
     exclusive_scan<u64, u64>(flags.p, scanned, n, d_total.p, scan_tmp, st);
     u64 tot = 0;
     CUDA_CHECK(cudaMemcpyAsync(&tot, d_total.p, 8, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     seg.n_post = (u32)(tot & 0xFFFFFFFFu);
     seg.n_terms = (u32)(tot >> 32);
-    seg.term_key.alloc(seg.n_terms + 1);
-    seg.term_off.alloc(seg.n_terms + 1);
-    seg.post_doc.alloc(seg.n_post + 1);
-    seg.post_pos.alloc(seg.n_post + 1);
+    // one allocation for the segment's dictionary and postings (a cudaMalloc costs ~2 ms with 100+ GB mapped)
+    {
+        auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t b_key = pad(((size_t)seg.n_terms + 1) * 8), b_off = pad(((size_t)seg.n_terms + 1) * 4);
+        const size_t b_post = pad(((size_t)seg.n_post + 1) * 4);
+        const size_t b_dir = ix.direct ? pad((size_t)4 << (2 * ix.k)) : 0;
+        u8* q = ix.arena.take(b_key + b_off + 2 * b_post + b_dir);
+        seg.term_key.adopt((u64*)q, (size_t)seg.n_terms + 1); q += b_key;
+        seg.term_off.adopt((u32*)q, (size_t)seg.n_terms + 1); q += b_off;
+        seg.post_doc.adopt((u32*)q, (size_t)seg.n_post + 1); q += b_post;
+        seg.post_pos.adopt((u32*)q, (size_t)seg.n_post + 1); q += b_post;
+        if (ix.direct) seg.direct.adopt((u32*)q, (size_t)1 << (2 * ix.k));
+    }
     if (n) {
         write_csr_kernel<K><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(keys, vals_alt, n, flags.p, scanned, seg.term_key.p,
                                                                         seg.term_off.p, seg.post_doc.p, seg.post_pos.p);
@@ -253,10 +306,10 @@ static void build_segment(GpuIndex& ix, Segment& seg, const EntryDev* d_entries,
     }
     set_u32_kernel<<<1, 1, 0, st>>>(seg.term_off.p + seg.n_terms, seg.n_post);
     set_u32_kernel<<<1, 1, 0, st>>>(seg.post_pos.p + seg.n_post, n);
+    g_phases.tick(2, st);
     // dictionary
     if (ix.direct) {
         u64 sz = 1ull << (2 * ix.k);
-        seg.direct.alloc(sz);
         fill_u32_kernel<<<(unsigned)std::min<u64>(ceil_div(sz, 256), 4096), 256, 0, st>>>(seg.direct.p, sz, NO_TERM);
         if (seg.n_terms)
             direct_table_kernel<<<(unsigned)ceil_div(seg.n_terms, 256), 256, 0, st>>>(seg.term_key.p, seg.n_terms, seg.direct.p);
@@ -271,10 +324,15 @@ static void build_segment(GpuIndex& ix, Segment& seg, const EntryDev* d_entries,
     }
     KERNEL_CHECK();
     CUDA_CHECK(cudaStreamSynchronize(st));
+    g_phases.tick(3, st);
 }
 
 // Build everything for the entries of `ref` (which the index keeps a pointer to).
 static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt, cudaStream_t st) {
+    const auto build_t0 = std::chrono::steady_clock::now();
+    const AllocStats alloc0 = g_alloc_stats;
+    g_phases = BuildPhases();
+    g_phases.on = getenv("BSP_BUILD_TIMING") != nullptr;
     ix.ref = &ref;
     ix.k = ref.k; ix.min_strand = ref.min_strand;
     const int k = ix.k;
@@ -415,8 +473,13 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
         }
     }
     // per-entry token starts (segment-relative) + per-segment doc_tok arrays
+    size_t dt_total = 0;
+    for (Segment& seg : ix.segs) dt_total += (size_t)seg.n_docs + 1;
+    ix.doc_tok_all.alloc(dt_total);                    // one allocation + one copy for all segments
+    std::vector<u32> dt_all(dt_total);
+    size_t dt_at = 0;
     for (Segment& seg : ix.segs) {
-        std::vector<u32> dt(seg.n_docs + 1);
+        u32* dt = dt_all.data() + dt_at;
         u32 run = 0, dl = 0;
         for (i32 e = seg.first_entry; e < seg.first_entry + seg.n_entries; e++) {
             const EntryMeta& m = ref.entries[e];
@@ -424,15 +487,15 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
             if (m.doc_rev >= 0) { h_entries[e].tok_rev = run; dt[dl++] = run; run += (u32)m.ntok; }
         }
         dt[dl] = run;
-        seg.doc_tok.alloc(seg.n_docs + 1);
-        CUDA_CHECK(cudaMemcpyAsync(seg.doc_tok.p, dt.data(), (seg.n_docs + 1) * 4, cudaMemcpyHostToDevice, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        seg.doc_tok.adopt(ix.doc_tok_all.p + dt_at, (size_t)seg.n_docs + 1);
+        dt_at += (size_t)seg.n_docs + 1;
         ix.max_seg_docs = std::max(ix.max_seg_docs, seg.n_docs);
     }
+    CUDA_CHECK(cudaMemcpyAsync(ix.doc_tok_all.p, dt_all.data(), dt_total * 4, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(d_entries.p, h_entries.data(), (nE + 1) * sizeof(EntryDev), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     // ---- per segment: extract -> sort -> CSR -> dictionary -> (tables) -> (drop)
-    DevBuf<u8> kbuf_a, kbuf_b; DevBuf<u32> vbuf_a, vbuf_b; DevBuf<u64> flags; RadixSortTemp rst;
+    DevBuf<u8> kbuf_a, kbuf_b; DevBuf<u32> vbuf_a, vbuf_b; DevBuf<u64> flags, scanned_buf; RadixSortTemp rst;
     DevBuf<unsigned long long> d_counter; d_counter.alloc(1);
     CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 8, st));
     i64 postings = 0;
@@ -445,10 +508,10 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
         try {
             if (2 * k <= 32)
                 build_segment<u32>(ix, seg, d_entries.p, d_chunk_entry.p, d_chunk_base.p, c0, c1, kbuf_a, kbuf_b, vbuf_a, vbuf_b,
-                                   flags, rst, scan_tmp, d_total, st);
+                                   flags, rst, scan_tmp, d_total, scanned_buf, st);
             else
                 build_segment<u64>(ix, seg, d_entries.p, d_chunk_entry.p, d_chunk_base.p, c0, c1, kbuf_a, kbuf_b, vbuf_a, vbuf_b,
-                                   flags, rst, scan_tmp, d_total, st);
+                                   flags, rst, scan_tmp, d_total, scanned_buf, st);
         } catch (const BspError& e) {
             // out of device memory with the positional index resident: give it up (the dense tables stay complete for
             // the segments already processed) and redo this segment
@@ -459,6 +522,7 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
                 o.direct.release(); o.term_key.release(); o.term_off.release(); o.post_doc.release();
                 o.post_pos.release(); o.positions.release(); o.doc_tok.release();
             }
+            ix.arena.release_all();
             positional = false; ix.positional = false; ix.positional_bytes = 0; views.clear();
             ix.notes += "positional index dropped: out of device memory; ";
             si--;
@@ -466,6 +530,7 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
         }
         postings += seg.n_post;
         SegDev v = seg.view();
+        g_phases.start(st);
         if (ix.direct) {
             if (seg.n_terms) accumulate_df_kernel<<<(unsigned)ceil_div(seg.n_terms, 256), 256, 0, st>>>(v, ix.df_dense.p, ix.ttf_dense.p);
         } else {
@@ -480,19 +545,32 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
             tf_table4_kernel<<<(unsigned)ceil_div((u64)seg.n_terms * 32, 256), 256, 0, st>>>(v, (u32*)ix.tab4.p, ix.row_bytes / 4, exb);
             if (ix.has_pair) {
                 u64 rows = 1ull << (2 * (k + 1));
-                pair_table4_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(v, k, ix.min_strand, (u32*)ix.tab4.p,
-                                                                                      ix.row_bytes / 4, ix.pair_row0, exb, rows);
+                if (seg.n_docs <= POSW_DOCS && !getenv("BSP_PAIR_TABLE_DIRECT")) {
+                    // few docs per segment: warp per first k-mer, slices staged in shared memory
+                    const int dcap = (int)round_up(std::max<i64>(seg.n_docs, 1), 32);
+                    const size_t smem = PT_WARPS * pair_stage_warp_bytes(dcap, PW_POS);
+                    CUDA_CHECK(cudaFuncSetAttribute(pair_table4_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)(PT_WARPS * pair_stage_warp_bytes(POSW_DOCS, PW_POS))));
+                    pair_table4_staged_kernel<<<(unsigned)ceil_div(rows / 4, PT_WARPS), PT_WARPS * 32, smem, st>>>(
+                        v, k, ix.min_strand, (u32*)ix.tab4.p, ix.row_bytes / 4, ix.pair_row0, exb, rows / 4, dcap, PW_POS);
+                } else {
+                    pair_table4_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(v, k, ix.min_strand, (u32*)ix.tab4.p,
+                                                                                          ix.row_bytes / 4, ix.pair_row0, exb, rows);
+                }
             }
         }
         KERNEL_CHECK();
         CUDA_CHECK(cudaStreamSynchronize(st));
+        g_phases.tick(4, st);
         if (positional) { views.push_back(v); ix.positional_bytes += seg.bytes(); }
         else {
             if (!ix.direct) throw BspError(-5, "hash-mode index (k > 12) requires the positional index");
             seg.direct.release(); seg.term_key.release(); seg.term_off.release(); seg.post_doc.release();
             seg.post_pos.release(); seg.positions.release(); seg.doc_tok.release();
+            ix.arena.reset();
         }
     }
+    if (!positional) ix.arena.release_all();
     ix.n_postings = postings;
     if (ix.direct) {
         u64 sz = 1ull << (2 * k);
@@ -537,4 +615,11 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
         ix.table_bytes += ix.exc_off.bytes() + ix.exc_doc.bytes() + ix.exc_freq.bytes();
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
+    if (g_phases.on)
+        fprintf(stderr, "[bsp build] %.1f ms total; cudaMalloc %.1f ms in %ld calls, cudaFree %.1f ms in %ld calls; %zu segments; "
+                "phases: extract %.1f, sort %.1f, csr %.1f, dictionary %.1f, tables %.1f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - build_t0).count(),
+                g_alloc_stats.alloc_ms - alloc0.alloc_ms, g_alloc_stats.allocs - alloc0.allocs,
+                g_alloc_stats.free_ms - alloc0.free_ms, g_alloc_stats.frees - alloc0.frees, ix.segs.size(),
+                g_phases.ms[0], g_phases.ms[1], g_phases.ms[2], g_phases.ms[3], g_phases.ms[4]);
 }
