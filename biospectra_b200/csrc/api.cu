@@ -1043,7 +1043,14 @@ BSP_API int bsp_term_postings(bsp_classifier* h, uint64_t packed_kmer, int64_t* 
         CUDA_CHECK(cudaMemcpy(pp.data(), seg.post_pos.p + a, (np + 1) * 4, cudaMemcpyDeviceToHost));
         u32 npos = pp[np] - pp[0];
         if (docs && tfs) for (u32 i = 0; i < np; i++) { docs[ndf + i] = (i32)(seg.doc_base + pd[i]); tfs[ndf + i] = (i32)(pp[i + 1] - pp[i]); }
-        if (positions) CUDA_CHECK(cudaMemcpy(positions + nttf, seg.positions.p + pp[0], (size_t)npos * 4, cudaMemcpyDeviceToHost));
+        if (positions) {
+            // the device keeps segment ordinals: Lucene's position = ordinal - first ordinal of the doc
+            CUDA_CHECK(cudaMemcpy(positions + nttf, seg.positions.p + pp[0], (size_t)npos * 4, cudaMemcpyDeviceToHost));
+            std::vector<u32> dtok((size_t)seg.n_docs + 1);
+            CUDA_CHECK(cudaMemcpy(dtok.data(), seg.doc_tok.p, dtok.size() * 4, cudaMemcpyDeviceToHost));
+            for (u32 i = 0; i < np; i++)
+                for (u32 q = pp[i] - pp[0]; q < pp[i + 1] - pp[0]; q++) positions[nttf + q] -= (i32)dtok[pd[i]];
+        }
         ndf += np; nttf += npos;
     }
     if (df) *df = ndf;

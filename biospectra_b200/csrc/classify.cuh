@@ -72,32 +72,6 @@ __device__ __forceinline__ float sloppy_freq_distinct(const u32* __restrict__ A,
     return freq;
 }
 
-// Can the phrase (t0@0, t1@1) match at all?  Every matchLength the sweep above tests is |(b - 1) - a| of an actual pair
-// (a in A, b in B), so freq = 0 whenever no pair is within the slop.  Two-pointer scan over the staged lists (shared
-// memory byte addresses; Bm1 holds b - 1); selects instead of branches inside a step.  No false negatives.
-__device__ __forceinline__ int lds_s32(u32 addr) {
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ bool sloppy_may_match_staged(u32 sa, int nA, u32 sb, int nB, int slop) {
-    const u32 ea = sa + 4u * (u32)nA, eb = sb + 4u * (u32)nB;  // nA, nB >= 1: a posting has at least one position
-    int a = lds_s32(sa), b = lds_s32(sb);
-    const unsigned w = 2u * (unsigned)slop;
-    while (true) {
-        const int d = b - a;
-        if ((unsigned)(d + slop) <= w) return true;
-        const bool adv_a = d > 0;                         // a is behind: advance it
-        sa += adv_a ? 4u : 0u;
-        sb += adv_a ? 0u : 4u;
-        const u32 ptr = adv_a ? sa : sb;
-        if (ptr >= (adv_a ? ea : eb)) return false;
-        const int v = lds_s32(ptr);
-        a = adv_a ? v : a;
-        b = adv_a ? b : v;
-    }
-}
-
 // Same-term phrase (t0 == t1): the repeat-group path, restated literally
 // (#initComplex/#advanceRepeatGroups/#advanceRpts/#collide/#lesser).
 struct PPd { const u32* pl; int n, idx, count, position, offset; };
@@ -477,6 +451,15 @@ __device__ __forceinline__ u64 block_max_u64(u64 v, u64* sm /* [33] */) {
 #define POS_THREADS 256
 #define POS_CHUNK 128            // clauses staged per round
 struct ClauseStage { u32 a0, b0, a1, b1; float val; int slop; };   // slop 0 = Term, <0 = same-term phrase (-slop)
+// the warp kernel also keeps each term's position range of the segment: with it every copy of a clause can be issued at once
+struct ClauseStageW { u32 a0, b0, a1, b1; float val; int slop; u32 p0, m0, p1, m1; };
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    const u32 sa = (u32)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
         const SegDev* __restrict__ segs, int n_segs, const i32* __restrict__ read_list, i32 n_list,
@@ -592,12 +575,19 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
 // loads, and the per-doc conjunction + sloppy sweep run out of shared memory.  Three dependent rounds of wide loads per
 // clause instead of a dozen dependent scalar loads per (clause, doc).  Slices beyond the caps take the direct path.
 // Shared memory per warp (all dynamic, sized by the host from the largest segment): double acc[dcap] | u32 pos[2][pcap]
-// | u32 doc[2][dcap] | u32 pp[2][dcap + 4] | ClauseStage stage[32] | u16 cnt[dcap] | u8 inv[dcap];  dcap = docs per
-// segment rounded up to 32 (a term has at most one posting per doc), pcap = PW_POS positions per term and segment.
-// inv[doc] = index of the doc's posting in the second term's slice (possibly stale: always verified).
+// | u32 doc[2][dcap] | u32 pp[2][dcap + 4] | ClauseStageW stage[32] | u16 cnt[dcap] | u8 inv[dcap] | u8 hit[dcap];  dcap =
+// docs per segment rounded up to 32 (a term has at most one posting per doc), pcap = PW_POS positions per term and
+// segment.  inv[doc] = index of the doc's posting in the second term's slice (possibly stale: always verified);
+// hit[i] = posting i of the first term has a position within the slop of one of the second term's.
+//
+// Which docs can match at all?  Every matchLength the SloppyPhraseScorer sweep tests is |(b - 1) - a| of an actual
+// pair (a in A, b in B), so freq = 0 unless some pair is within the slop.  Positions are segment ordinals
+// (mark_heads_kernel), hence both staged slices ascend across docs and ONE scan per clause finds all close pairs: each
+// lane takes a contiguous chunk of the first term's positions and walks the second term's from a binary-searched start.
+// No false negatives; a pair straddling two docs is a false positive the exact sweep discards.
 #define PW_POS 384               // 2^28 tokens / 4^10 terms = 256 on average
 __host__ __device__ inline size_t posw_warp_bytes(int dcap, int pcap) {
-    return (size_t)dcap * 8 + (size_t)pcap * 8 + (size_t)dcap * 8 + (size_t)(dcap + 4) * 8 + 32 * 24 + (size_t)dcap * 2 + (size_t)dcap;
+    return (size_t)dcap * 8 + (size_t)pcap * 8 + (size_t)dcap * 8 + (size_t)(dcap + 4) * 8 + 32 * sizeof(ClauseStageW) + (size_t)dcap * 2 + (size_t)dcap * 2;
 }
 __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_warp_kernel(
         const SegDev* __restrict__ segs, int n_segs, const i32* __restrict__ read_list, i32 n_list,
@@ -616,15 +606,16 @@ __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_w
     u32* w_doc1 = w_doc0 + dcap;
     u32* w_pp0 = w_doc1 + dcap;
     u32* w_pp1 = w_pp0 + dcap + 4;
-    ClauseStage* stage = reinterpret_cast<ClauseStage*>(w_pp1 + dcap + 4);
+    ClauseStageW* stage = reinterpret_cast<ClauseStageW*>(w_pp1 + dcap + 4);
     u16* cnt = reinterpret_cast<u16*>(stage + 32);
     u8* inv = reinterpret_cast<u8*>(cnt + dcap);
+    u8* hit = inv + dcap;
     const i64 pair = (i64)blockIdx.x * POSW_WARPS + warp;
     if (pair >= (i64)n_list * n_segs) return;
     const int sidx = (int)(pair / n_list);              // segment-major, see score_positional_kernel
     const i32 r = read_list[pair % n_list];
     const SegDev s = segs[sidx];
-    for (u32 d = lane; d < s.n_docs; d += 32) { acc[d] = 0.0; cnt[d] = 0; inv[d] = 0; }
+    for (u32 d = lane; d < (u32)dcap; d += 32) { acc[d] = 0.0; cnt[d] = 0; inv[d] = 0; hit[d] = 0; }
     const i64 base = tok_off[r];
     const i32 n = n_tok[r], nc = n_clauses[r];
     const float* dw = doc_w + s.doc_base;
@@ -634,7 +625,7 @@ __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_w
         if (c < nc) {
             i32 j0, j1;
             clause_tokens(qp.alg, n, c, j0, j1);
-            ClauseStage st;
+            ClauseStageW st;
             st.val = clause_val[base + c];
             const u64 k0 = tok_key[base + j0];
             const u32 t0 = seg_find_term(s, k0);
@@ -651,69 +642,73 @@ __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_w
                     else st.b0 = st.a0;                                                  // conjunction is empty
                 }
             }
+            // position ranges of both slices, so that the clause loop can issue every copy of a clause in one batch
+            st.p0 = st.m0 = st.p1 = st.m1 = 0;
+            if (st.slop > 0 && st.b0 > st.a0 && st.b1 > st.a1) {
+                st.p0 = s.post_pos[st.a0]; st.m0 = s.post_pos[st.b0] - st.p0;
+                st.p1 = s.post_pos[st.a1]; st.m1 = s.post_pos[st.b1] - st.p1;
+            }
             stage[lane] = st;
         }
         __syncwarp();
         const i32 lim = min(32, nc - c0);
         for (i32 ci = 0; ci < lim; ci++) {
-            const ClauseStage st = stage[ci];
+            const ClauseStageW st = stage[ci];
             const u32 n0 = st.b0 - st.a0, n1 = st.b1 - st.a1;
             bool staged = false;
-            if (stage_ok && st.slop > 0 && n0 && n1) {                          // (n0, n1 <= docs of the segment <= dcap)
-                // all loads of a round are issued before the first store: one memory round trip per round, not per load
-                const u32 nmax = max(n0, n1) + 1;
-#pragma unroll 1
-                for (u32 i0 = lane; i0 < nmax; i0 += 64) {
-                    u32 vd0[2], vp0[2], vd1[2], vp1[2];
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const u32 i = i0 + 32 * u;
-                        vd0[u] = i < n0 ? s.post_doc[st.a0 + i] : 0u;
-                        vp0[u] = i <= n0 ? s.post_pos[st.a0 + i] : 0u;
-                        vd1[u] = i < n1 ? s.post_doc[st.a1 + i] : 0u;
-                        vp1[u] = i <= n1 ? s.post_pos[st.a1 + i] : 0u;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 2; u++) {
-                        const u32 i = i0 + 32 * u;
-                        if (i < n0) w_doc0[i] = vd0[u];
-                        if (i <= n0) w_pp0[i] = vp0[u];
-                        if (i < n1) { w_doc1[i] = vd1[u]; inv[vd1[u]] = (u8)i; }
-                        if (i <= n1) w_pp1[i] = vp1[u];
-                    }
-                }
-                __syncwarp();
-                const u32 p0 = w_pp0[0], m0 = w_pp0[n0] - p0, p1 = w_pp1[0], m1 = w_pp1[n1] - p1;
-                if (m0 <= (u32)pcap && m1 <= (u32)pcap) {
-                    const u32 mmax = max(m0, m1);
-#pragma unroll 1
-                    for (u32 i0 = lane; i0 < mmax; i0 += 256) {
-                        u32 va[8], vb[8];
-#pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            const u32 i = i0 + 32 * u;
-                            va[u] = i < m0 ? s.positions[p0 + i] : 0u;
-                            vb[u] = i < m1 ? s.positions[p1 + i] : 0u;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            const u32 i = i0 + 32 * u;
-                            if (i < m0) w_pos0[i] = va[u];
-                            if (i < m1) w_pos1[i] = vb[u] - 1u;                          // staged as position - 1 (phrase offset of t1)
+            if (stage_ok && st.slop > 0 && n0 && n1 && st.m0 <= (u32)pcap && st.m1 <= (u32)pcap) {   // (n0, n1 <= docs <= dcap)
+                {
+                    const u32 p0 = st.p0, m0 = st.m0, p1 = st.p1, m1 = st.m1;
+                    // one batch of asynchronous 4-byte copies (LDGSTS) for the whole clause: one memory round trip
+                    for (u32 i = lane; i <= n0; i += 32) { if (i < n0) cp_async4(w_doc0 + i, s.post_doc + st.a0 + i); cp_async4(w_pp0 + i, s.post_pos + st.a0 + i); }
+                    for (u32 i = lane; i <= n1; i += 32) { if (i < n1) cp_async4(w_doc1 + i, s.post_doc + st.a1 + i); cp_async4(w_pp1 + i, s.post_pos + st.a1 + i); }
+                    for (u32 i = lane; i < m0; i += 32) cp_async4(w_pos0 + i, s.positions + p0 + i);
+                    for (u32 i = lane; i < m1; i += 32) cp_async4(w_pos1 + i, s.positions + p1 + i);
+                    cp_async_commit_wait_all();
+                    __syncwarp();
+                    for (u32 i = lane; i < n1; i += 32) inv[w_doc1[i]] = (u8)i;
+                    __syncwarp();
+                    // ---- close pairs: lane takes positions [ia, ia1) of the first term
+                    {
+                        const int slop = st.slop;
+                        const u32 ca = (m0 + 31) >> 5;
+                        u32 ia = (u32)lane * ca;
+                        const u32 ia1 = min(m0, ia + ca);
+                        if (ia < ia1) {
+                            const int lo = (int)w_pos0[ia] - slop;
+                            u32 jb = 0, hi = m1;                                         // first b' >= lo (signed: b' may be -1)
+                            while (jb < hi) {
+                                const u32 mid = (jb + hi) >> 1;
+                                if ((int)w_pos1[mid] - 1 < lo) jb = mid + 1; else hi = mid;
+                            }
+                            while (ia < ia1 && jb < m1) {
+                                const int d = (int)w_pos1[jb] - 1 - (int)w_pos0[ia];         // b' = b - 1 (phrase offset of t1)
+                                if (d > slop) ia++;                                      // b' beyond this a: next a
+                                else if (d < -slop) jb++;                                // b' behind: next b'
+                                else {                                                   // within the slop: flag a's posting
+                                    const u32 target = p0 + ia;
+                                    u32 l = 0, h2 = n0;                                  // last posting with pp <= target
+                                    while (h2 - l > 1) {
+                                        const u32 mid = (l + h2) >> 1;
+                                        if (w_pp0[mid] <= target) l = mid; else h2 = mid;
+                                    }
+                                    hit[l] = 1;
+                                    ia++;
+                                }
+                            }
                         }
                     }
                     __syncwarp();
+                    // ---- the literal sweep for the flagged docs
                     for (u32 i = lane; i < n0; i += 32) {
+                        if (!hit[i]) continue;
+                        hit[i] = 0;
                         const u32 d = w_doc0[i];
                         const u32 j = inv[d];                                            // verified: may be a stale entry
                         if (j < n1 && w_doc1[j] == d) {
                             const u32 q0 = w_pp0[i], q1 = w_pp1[j];
-                            const u32* A = w_pos0 + (q0 - p0);
-                            const u32* B = w_pos1 + (q1 - p1);
-                            const int nA = (int)(w_pp0[i + 1] - q0), nB = (int)(w_pp1[j + 1] - q1);
-                            // two independent k-mers within the slop of each other: rare, so the cheap test comes first
-                            const float f = sloppy_may_match_staged((u32)__cvta_generic_to_shared(A), nA, (u32)__cvta_generic_to_shared(B), nB, st.slop)
-                                                ? sloppy_freq_distinct(A, nA, B, nB, st.slop, 0) : 0.0f;
+                            const float f = sloppy_freq_distinct(w_pos0 + (q0 - p0), (int)(w_pp0[i + 1] - q0),
+                                                                 w_pos1 + (q1 - p1), (int)(w_pp1[j + 1] - q1), st.slop);
                             if (f != 0.0f) {
                                 const float sc = clause_doc_score(sp.sim, sp.sim == SIM_TFIDF ? tf_of(f) : f, st.val, dw[d], sp.k1p1);
                                 acc[d] += (double)sc;                                    // BooleanScorer: double sum

@@ -153,7 +153,11 @@ __device__ __forceinline__ u32 find_doc(const u32* __restrict__ doc_tok, u32 n_d
     return lo;
 }
 
-// positions[i] = ordinal - doc start; docs[i] = local doc; flags[i] = head_post | head_term<<32
+// positions[i] = token ordinal within the SEGMENT (= doc_tok[doc] + Lucene's position); docs[i] = local doc;
+// flags[i] = head_post | head_term<<32.  Every consumer of positions is a sloppy sweep over two lists of the same doc,
+// which only looks at differences, so the per-doc offset is never subtracted on the device (bsp_term_postings does it
+// for the tests); keeping the segment ordinal makes a term's position slice ascending across docs, which is what lets
+// the warp scorer look for close (t0, t1) pairs with one balanced scan per clause.
 template <typename K>
 __global__ void __launch_bounds__(256) mark_heads_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, u32 n,
                                                           const u32* __restrict__ doc_tok, u32 n_docs,
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(256) mark_heads_kernel(const K* __restrict__ k
     if (i >= n) return;
     u32 ord = vals[i];
     u32 d = find_doc(doc_tok, n_docs, ord);
-    positions[i] = ord - doc_tok[d];
+    positions[i] = ord;
     docs[i] = d;
     u64 f = 0;
     if (i == 0) f = 1ull | (1ull << 32);
