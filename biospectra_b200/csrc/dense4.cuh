@@ -132,34 +132,11 @@ __global__ void __launch_bounds__(256) pair_table4_kernel(SegDev s, int k, int m
 __host__ __device__ inline size_t pair_stage_warp_bytes(int dcap, int pcap) {
     return 2 * ((size_t)dcap * 4 + (size_t)(dcap + 4) * 4 + (size_t)pcap * 4) + (size_t)dcap;
 }
-__device__ __forceinline__ void stage_slice(const SegDev& s, u32 a, u32 n, u32* __restrict__ w_doc, u32* __restrict__ w_pp,
-                                            u8* __restrict__ inv, int lane) {
-#pragma unroll 1
-    for (u32 i0 = lane; i0 <= n; i0 += 128) {
-        u32 vd[4], vp[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const u32 i = i0 + 32 * u;
-            vd[u] = i < n ? s.post_doc[a + i] : 0u;
-            vp[u] = i <= n ? s.post_pos[a + i] : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const u32 i = i0 + 32 * u;
-            if (i < n) { w_doc[i] = vd[u]; if (inv) inv[vd[u]] = (u8)i; }
-            if (i <= n) w_pp[i] = vp[u];
-        }
-    }
-}
-__device__ __forceinline__ void stage_positions(const SegDev& s, u32 p, u32 m, u32* __restrict__ w_pos, u32 dec, int lane) {
-#pragma unroll 1
-    for (u32 i0 = lane; i0 < m; i0 += 256) {
-        u32 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) { const u32 i = i0 + 32 * u; v[u] = i < m ? s.positions[p + i] : 0u; }
-#pragma unroll
-        for (int u = 0; u < 8; u++) { const u32 i = i0 + 32 * u; if (i < m) w_pos[i] = v[u] - dec; }
-    }
+// all copies of one term's slice (docs, position offsets, positions) as asynchronous 4-byte copies; the caller waits
+__device__ __forceinline__ void stage_term_async(const SegDev& s, u32 a, u32 n, u32 p, u32 m, u32* __restrict__ w_doc,
+                                                 u32* __restrict__ w_pp, u32* __restrict__ w_pos, int lane) {
+    for (u32 i = lane; i <= n; i += 32) { if (i < n) cp_async4(w_doc + i, s.post_doc + a + i); cp_async4(w_pp + i, s.post_pos + a + i); }
+    for (u32 i = lane; i < m; i += 32) cp_async4(w_pos + i, s.positions + p + i);
 }
 __global__ void __launch_bounds__(PT_WARPS * 32) pair_table4_staged_kernel(SegDev s, int k, int min_strand, u32* __restrict__ tab32,
                                                                             u64 row_words, u64 pair_row0, ExcBuild ex, u64 n_kmers,
@@ -180,31 +157,35 @@ __global__ void __launch_bounds__(PT_WARPS * 32) pair_table4_staged_kernel(SegDe
     const u64 t0 = canon_kmer(t0raw, k, min_strand);
     const u32 lt0 = s.direct[t0];
     if (lt0 == NO_TERM) return;
-    const u32 a0 = s.term_off[lt0], n0 = s.term_off[lt0 + 1] - a0;
-    for (u32 d = lane; d < s.n_docs; d += 32) inv[d] = 0;
-    stage_slice(s, a0, n0, w_doc0, w_pp0, nullptr, lane);
-    __syncwarp();
-    const u32 p0 = w_pp0[0], m0 = w_pp0[n0] - p0;
+    // lanes 0..3 look up the four second k-mers (term, posting slice, position range), lane 4 the first one's range
+    u32 my_a = 0, my_n = 0, my_p = 0, my_m = 0;
+    u64 my_t = 0;
+    if (lane < 4) {
+        my_t = canon_kmer(((t0raw << 2) | (u64)lane) & kmask, k, min_strand);
+        const u32 lt1 = s.direct[my_t];
+        if (lt1 != NO_TERM) { my_a = s.term_off[lt1]; my_n = s.term_off[lt1 + 1] - my_a; }
+    } else if (lane == 4) { my_a = s.term_off[lt0]; my_n = s.term_off[lt0 + 1] - my_a; }
+    if (lane < 5 && my_n) { my_p = s.post_pos[my_a]; my_m = s.post_pos[my_a + my_n] - my_p; }
+    const u32 a0 = __shfl_sync(0xFFFFFFFFu, my_a, 4), n0 = __shfl_sync(0xFFFFFFFFu, my_n, 4);
+    const u32 p0 = __shfl_sync(0xFFFFFFFFu, my_p, 4), m0 = __shfl_sync(0xFFFFFFFFu, my_m, 4);
+    for (u32 d = lane; d < (u32)dcap; d += 32) inv[d] = 0;
     const bool fit0 = m0 <= (u32)pcap;
-    if (fit0) stage_positions(s, p0, m0, w_pos0, 0u, lane);
-    __syncwarp();
+    if (fit0) stage_term_async(s, a0, n0, p0, m0, w_doc0, w_pp0, w_pos0, lane);     // waited for together with the first t1
 #pragma unroll 1
     for (u32 c = 0; c < 4; c++) {
         const u64 u = (t0raw << 2) | c;
-        const u64 t1 = canon_kmer(u & kmask, k, min_strand);
-        const u32 lt1 = s.direct[t1];
-        if (lt1 == NO_TERM) continue;
+        const u64 t1 = __shfl_sync(0xFFFFFFFFu, my_t, (int)c);
+        const u32 a1 = __shfl_sync(0xFFFFFFFFu, my_a, (int)c), n1 = __shfl_sync(0xFFFFFFFFu, my_n, (int)c);
+        const u32 p1 = __shfl_sync(0xFFFFFFFFu, my_p, (int)c), m1 = __shfl_sync(0xFFFFFFFFu, my_m, (int)c);
+        if (n1 == 0) continue;
         const bool same = t0 == t1;
-        const u32 a1 = s.term_off[lt1], n1 = s.term_off[lt1 + 1] - a1;
         u32* row = tab32 + (pair_row0 + u) * row_words;
-        bool staged = false;
-        u32 p1 = 0;
-        if (fit0 && !same) {
-            stage_slice(s, a1, n1, w_doc1, w_pp1, inv, lane);
-            __syncwarp();
-            p1 = w_pp1[0];
-            const u32 m1 = w_pp1[n1] - p1;
-            if (m1 <= (u32)pcap) { stage_positions(s, p1, m1, w_pos1, 1u, lane); staged = true; }   // staged as position - 1
+        const bool staged = fit0 && !same && m1 <= (u32)pcap;
+        if (staged) stage_term_async(s, a1, n1, p1, m1, w_doc1, w_pp1, w_pos1, lane);
+        cp_async_commit_wait_all();
+        __syncwarp();
+        if (staged) {
+            for (u32 i = lane; i < n1; i += 32) inv[w_doc1[i]] = (u8)i;
             __syncwarp();
         }
         for (u32 i0 = 0; i0 < n0; i0 += 32) {
@@ -217,7 +198,7 @@ __global__ void __launch_bounds__(PT_WARPS * 32) pair_table4_staged_kernel(SegDe
                     const u32 d = w_doc0[i], j = inv[d];                  // verified: may be a stale entry
                     if (j < n1 && w_doc1[j] == d) {
                         const u32 q0 = w_pp0[i], q1 = w_pp1[j];
-                        f = sloppy_freq_distinct(w_pos0 + (q0 - p0), (int)(w_pp0[i + 1] - q0), w_pos1 + (q1 - p1), (int)(w_pp1[j + 1] - q1), 2, 0);
+                        f = sloppy_freq_distinct(w_pos0 + (q0 - p0), (int)(w_pp0[i + 1] - q0), w_pos1 + (q1 - p1), (int)(w_pp1[j + 1] - q1), 2);
                     }
                 } else {
                     f = phrase_freq_at(s, a0 + i, a1, a1 + n1, a1 + i, 2, same);
@@ -233,6 +214,7 @@ __global__ void __launch_bounds__(PT_WARPS * 32) pair_table4_staged_kernel(SegDe
         }
         __syncwarp();
     }
+    cp_async_commit_wait_all();            // (nothing pending unless all four rows were empty)
 }
 
 // ---- exception list finalisation: sort by (row, doc), then per-row offsets
