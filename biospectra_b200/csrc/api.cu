@@ -939,6 +939,7 @@ BSP_API int bsp_classify_one(bsp_classifier* h, const char* seq, int32_t seq_len
         lk.unlock();
         try { microbatch_run(h, batch); }
         catch (const std::exception& e) { for (OneRead* q : batch) { q->rc = BSP_ERR_NOMEM; q->err = e.what(); } }
+        catch (...) { for (OneRead* q : batch) { q->rc = BSP_ERR_STATE; q->err = "micro-batch failed"; } }    // followers must wake up
         lk.lock();
         mb.gpu_busy--;
         mb.batches++;

@@ -36,15 +36,14 @@
 // A = positions of t0, B = positions of t1 (ascending, non-empty).  With two phrase
 // positions the priority queue degenerates to "the other one": after pp passes `next`
 // the other pp is strictly smaller, so pop() always returns it.
-// (boff = 1: B holds positions; boff = 0: B already holds position - 1, the staged form)
 __device__ __forceinline__ float sloppy_freq_distinct(const u32* __restrict__ A, int nA, const u32* __restrict__ B, int nB,
-                                                      int slop, int boff = 1) {
-    int pa = (int)A[0], pb = (int)B[0] - boff;
+                                                      int slop) {
+    int pa = (int)A[0], pb = (int)B[0] - 1;
     int end = pa > pb ? pa : pb;
     // PhraseQueue#lessThan: smaller position first, ties -> smaller offset (t0)
     bool cur_is_a = pa <= pb;
-    const u32* cl = cur_is_a ? A : B; int cn = cur_is_a ? nA : nB; int co = cur_is_a ? 0 : boff; int cp = cur_is_a ? pa : pb;
-    const u32* ol = cur_is_a ? B : A; int on = cur_is_a ? nB : nA; int oo = cur_is_a ? boff : 0; int op = cur_is_a ? pb : pa;
+    const u32* cl = cur_is_a ? A : B; int cn = cur_is_a ? nA : nB; int co = cur_is_a ? 0 : 1; int cp = cur_is_a ? pa : pb;
+    const u32* ol = cur_is_a ? B : A; int on = cur_is_a ? nB : nA; int oo = cur_is_a ? 1 : 0; int op = cur_is_a ? pb : pa;
     int ci = 1, oi = 1;
     int ml = end - cp;
     int next = op;
@@ -657,67 +656,69 @@ __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_w
             const u32 n0 = st.b0 - st.a0, n1 = st.b1 - st.a1;
             bool staged = false;
             if (stage_ok && st.slop > 0 && n0 && n1 && st.m0 <= (u32)pcap && st.m1 <= (u32)pcap) {   // (n0, n1 <= docs <= dcap)
-                {
-                    const u32 p0 = st.p0, m0 = st.m0, p1 = st.p1, m1 = st.m1;
-                    // one batch of asynchronous 4-byte copies (LDGSTS) for the whole clause: one memory round trip
-                    for (u32 i = lane; i <= n0; i += 32) { if (i < n0) cp_async4(w_doc0 + i, s.post_doc + st.a0 + i); cp_async4(w_pp0 + i, s.post_pos + st.a0 + i); }
-                    for (u32 i = lane; i <= n1; i += 32) { if (i < n1) cp_async4(w_doc1 + i, s.post_doc + st.a1 + i); cp_async4(w_pp1 + i, s.post_pos + st.a1 + i); }
-                    for (u32 i = lane; i < m0; i += 32) cp_async4(w_pos0 + i, s.positions + p0 + i);
-                    for (u32 i = lane; i < m1; i += 32) cp_async4(w_pos1 + i, s.positions + p1 + i);
-                    cp_async_commit_wait_all();
-                    __syncwarp();
-                    for (u32 i = lane; i < n1; i += 32) inv[w_doc1[i]] = (u8)i;
-                    __syncwarp();
-                    // ---- close pairs: lane takes positions [ia, ia1) of the first term
-                    {
-                        const int slop = st.slop;
-                        const u32 ca = (m0 + 31) >> 5;
-                        u32 ia = (u32)lane * ca;
-                        const u32 ia1 = min(m0, ia + ca);
-                        if (ia < ia1) {
-                            const int lo = (int)w_pos0[ia] - slop;
-                            u32 jb = 0, hi = m1;                                         // first b' >= lo (signed: b' may be -1)
-                            while (jb < hi) {
-                                const u32 mid = (jb + hi) >> 1;
-                                if ((int)w_pos1[mid] - 1 < lo) jb = mid + 1; else hi = mid;
-                            }
-                            while (ia < ia1 && jb < m1) {
-                                const int d = (int)w_pos1[jb] - 1 - (int)w_pos0[ia];         // b' = b - 1 (phrase offset of t1)
-                                if (d > slop) ia++;                                      // b' beyond this a: next a
-                                else if (d < -slop) jb++;                                // b' behind: next b'
-                                else {                                                   // within the slop: flag a's posting
-                                    const u32 target = p0 + ia;
-                                    u32 l = 0, h2 = n0;                                  // last posting with pp <= target
-                                    while (h2 - l > 1) {
-                                        const u32 mid = (l + h2) >> 1;
-                                        if (w_pp0[mid] <= target) l = mid; else h2 = mid;
-                                    }
-                                    hit[l] = 1;
-                                    ia++;
-                                }
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    // ---- the literal sweep for the flagged docs
-                    for (u32 i = lane; i < n0; i += 32) {
-                        if (!hit[i]) continue;
-                        hit[i] = 0;
-                        const u32 d = w_doc0[i];
-                        const u32 j = inv[d];                                            // verified: may be a stale entry
-                        if (j < n1 && w_doc1[j] == d) {
-                            const u32 q0 = w_pp0[i], q1 = w_pp1[j];
-                            const float f = sloppy_freq_distinct(w_pos0 + (q0 - p0), (int)(w_pp0[i + 1] - q0),
-                                                                 w_pos1 + (q1 - p1), (int)(w_pp1[j + 1] - q1), st.slop);
-                            if (f != 0.0f) {
-                                const float sc = clause_doc_score(sp.sim, sp.sim == SIM_TFIDF ? tf_of(f) : f, st.val, dw[d], sp.k1p1);
-                                acc[d] += (double)sc;                                    // BooleanScorer: double sum
-                                cnt[d] += 1;
-                            }
-                        }
-                    }
-                    staged = true;
+                const u32 p0 = st.p0, m0 = st.m0, p1 = st.p1, m1 = st.m1;
+                // one batch of asynchronous 4-byte copies (LDGSTS) for the whole clause: one memory round trip
+                for (u32 i = lane; i <= n0; i += 32) {
+                    if (i < n0) cp_async4(w_doc0 + i, s.post_doc + st.a0 + i);
+                    cp_async4(w_pp0 + i, s.post_pos + st.a0 + i);
                 }
+                for (u32 i = lane; i <= n1; i += 32) {
+                    if (i < n1) cp_async4(w_doc1 + i, s.post_doc + st.a1 + i);
+                    cp_async4(w_pp1 + i, s.post_pos + st.a1 + i);
+                }
+                for (u32 i = lane; i < m0; i += 32) cp_async4(w_pos0 + i, s.positions + p0 + i);
+                for (u32 i = lane; i < m1; i += 32) cp_async4(w_pos1 + i, s.positions + p1 + i);
+                cp_async_commit_wait_all();
+                __syncwarp();
+                for (u32 i = lane; i < n1; i += 32) inv[w_doc1[i]] = (u8)i;
+                __syncwarp();
+                // ---- close pairs: lane takes positions [ia, ia1) of the first term
+                const int slop = st.slop;
+                const u32 ca = (m0 + 31) >> 5;
+                u32 ia = (u32)lane * ca;
+                const u32 ia1 = min(m0, ia + ca);
+                if (ia < ia1) {
+                    const int lo = (int)w_pos0[ia] - slop;
+                    u32 jb = 0, hi = m1;                                                 // first b' >= lo, b' = b - 1 (phrase offset of t1)
+                    while (jb < hi) {
+                        const u32 mid = (jb + hi) >> 1;
+                        if ((int)w_pos1[mid] - 1 < lo) jb = mid + 1; else hi = mid;
+                    }
+                    while (ia < ia1 && jb < m1) {
+                        const int d = (int)w_pos1[jb] - 1 - (int)w_pos0[ia];
+                        if (d > slop) ia++;                                              // b' beyond this a: next a
+                        else if (d < -slop) jb++;                                        // b' behind: next b'
+                        else {                                                           // within the slop: flag a's posting
+                            const u32 target = p0 + ia;
+                            u32 l = 0, h2 = n0;                                          // last posting with pp <= target
+                            while (h2 - l > 1) {
+                                const u32 mid = (l + h2) >> 1;
+                                if (w_pp0[mid] <= target) l = mid; else h2 = mid;
+                            }
+                            hit[l] = 1;
+                            ia++;
+                        }
+                    }
+                }
+                __syncwarp();
+                // ---- the literal sweep for the flagged docs
+                for (u32 i = lane; i < n0; i += 32) {
+                    if (!hit[i]) continue;
+                    hit[i] = 0;
+                    const u32 d = w_doc0[i];
+                    const u32 j = inv[d];                                                // verified: may be a stale entry
+                    if (j < n1 && w_doc1[j] == d) {
+                        const u32 q0 = w_pp0[i], q1 = w_pp1[j];
+                        const float f = sloppy_freq_distinct(w_pos0 + (q0 - p0), (int)(w_pp0[i + 1] - q0),
+                                                             w_pos1 + (q1 - p1), (int)(w_pp1[j + 1] - q1), st.slop);
+                        if (f != 0.0f) {
+                            const float sc = clause_doc_score(sp.sim, sp.sim == SIM_TFIDF ? tf_of(f) : f, st.val, dw[d], sp.k1p1);
+                            acc[d] += (double)sc;                                        // BooleanScorer: double sum
+                            cnt[d] += 1;
+                        }
+                    }
+                }
+                staged = true;
                 __syncwarp();
             }
             if (!staged) {

@@ -39,7 +39,7 @@ static inline i64 round_up(i64 a, i64 b) { return ceil_div(a, b) * b; }
 // RAII device allocation (no torch: plain cudaMalloc).
 // host time spent in cudaMalloc / cudaFree (reported by the build when BSP_BUILD_TIMING is set)
 struct AllocStats { double alloc_ms = 0, free_ms = 0; long allocs = 0, frees = 0; };
-static AllocStats g_alloc_stats;
+static thread_local AllocStats g_alloc_stats;     // per thread: builds of different handles may run concurrently
 
 template <typename T>
 struct DevBuf {

@@ -246,7 +246,7 @@ struct BuildPhases {
         t = n;
     }
 };
-static BuildPhases g_phases;
+static thread_local BuildPhases g_phases;
 
 template <typename K>
 static void build_segment(GpuIndex& ix, Segment& seg, const EntryDev* d_entries, const u32* d_chunk_entry,

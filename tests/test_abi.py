@@ -69,6 +69,14 @@ def test_argument_validation_without_gpu(tmp_path):
     assert L.bsp_classifier_open(C.byref(c), None, C.byref(h)) == -1
     assert L.bsp_classifier_open(C.byref(c), str(tmp_path / "missing").encode(), C.byref(h)) == -1
     assert b"does not exist" in L.bsp_last_error(None)
+    # entry points added for the per-read seam and the taxonomy labels: a null handle is an argument error, not a crash
+    st = C.c_int32()
+    assert L.bsp_classify_one(None, b"ACGT", 4, C.byref(st), None, None, None, None, None) == -1
+    assert L.bsp_classifier_set_microbatch(None, 16, 100) == -1
+    assert L.bsp_microbatch_stats(None, None, None) == -1
+    assert L.bsp_classifier_set_lineages(None, 1, None, None, None) == -1
+    assert L.bsp_classify_packed_tax(None, 0, None, None, None, None, None, None, None, None, None, None) == -1
+    assert L.bsp_host_classify_local_per_read(None, None, b"", b"", 0, -1) == -1
 
 
 def test_no_oracle_in_product():
