@@ -636,7 +636,7 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
     const Tab4Dev T = ix.tab4_view(sc.slot_index, sc.gap_cnt.p);
     const int full_topn = (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0;
     CUDA_CHECK(cudaEventRecord(sc.ev[1], st));
-    i64 launches = 6;
+    i64 launches = 9;     // tok_capacity, 4 scan kernels, tokenize, token_df, weights, route_compact
     FilterStats fs = {0, 0, 0};
     if (counts[2] > 0) {
         CUDA_CHECK(cudaMemsetAsync(sc.fstats.p, 0, sizeof(FilterStats), st));
