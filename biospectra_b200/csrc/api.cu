@@ -28,6 +28,22 @@ struct bsp_indexer {
     ~bsp_indexer() { delete ref; if (st) cudaStreamDestroy(st); }
 };
 
+// page-locked host buffer that only grows (copies from / to it are truly asynchronous)
+struct PinBuf {
+    u8* p = nullptr; size_t bytes = 0;
+    PinBuf() {}
+    PinBuf(const PinBuf&) = delete;
+    PinBuf& operator=(const PinBuf&) = delete;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    void ensure(size_t need) {
+        if (need <= bytes) return;
+        if (p) { cudaFreeHost(p); p = nullptr; bytes = 0; }
+        const size_t want = need + need / 4 + 256;
+        CUDA_CHECK(cudaMallocHost((void**)&p, want));
+        bytes = want;
+    }
+};
+
 // Per pipeline slot: device scratch of one sub-batch, its stream, events and pinned host mailboxes.
 struct Scratch {
     DevBuf<u8> seq, scan_tmp; DevBuf<i64> seq_off, tok_off, tok_cap;
@@ -42,6 +58,8 @@ struct Scratch {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     u8* pin_in = nullptr; size_t pin_in_bytes = 0;
+    PinBuf pin_routes;                  // routes of the sub-batch on their way to bsp_last_routes
+    bool routes_pending = false;
     i32* h_counts = nullptr;            // pinned: [0..3] route counts, [4] filter overflow
     FilterStats* h_fstats = nullptr;    // pinned
     // state between the two phases of a sub-batch
@@ -79,6 +97,8 @@ struct MicroBatcher {
     std::vector<OneRead*> pending;
     bool leader = false;
     int gpu_busy = 0;                       // micro-batches that left the queue and have not finished
+    std::mutex run_mu;                      // one micro-batch at a time owns the pinned staging below
+    PinBuf pin_seq, pin_off, pin_i32, pin_f32;
     i32 max_reads = 4096;
     i64 wait_us = 200;
     i32 last_size = 0;                      // size of the previous micro-batch
@@ -711,6 +731,9 @@ static void pipeline_collect(bsp_classifier* h, Scratch& sc) {
     cudaEventElapsedTime(&ms_score, sc.ev[1], sc.ev[2]);
     cudaEventElapsedTime(&ms_pipe, sc.ev[0], sc.ev[3]);
     h->score_ms += ms_score; h->pipe_ms += ms_pipe;
+    if (sc.routes_pending && (size_t)sc.r0 + (size_t)sc.n <= h->last_routes.size())
+        memcpy(h->last_routes.data() + sc.r0, sc.pin_routes.p, (size_t)sc.n * 4);
+    sc.routes_pending = false;
     sc.busy = false;
 }
 
@@ -736,7 +759,9 @@ static void enqueue_outputs(bsp_classifier* h, Scratch& sc, i32* status, i32* la
     if (n_top) CUDA_CHECK(cudaMemcpyAsync(n_top + r0, sc.o_ntop.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
     if (top_doc) CUDA_CHECK(cudaMemcpyAsync(top_doc + (i64)r0 * TOPN, sc.o_doc.p, (size_t)m * TOPN * 4, cudaMemcpyDeviceToHost, st));
     if (top_score) CUDA_CHECK(cudaMemcpyAsync(top_score + (i64)r0 * TOPN, sc.o_score.p, (size_t)m * TOPN * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaMemcpyAsync(h->last_routes.data() + r0, sc.route.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    sc.pin_routes.ensure((size_t)m * 4);
+    CUDA_CHECK(cudaMemcpyAsync(sc.pin_routes.p, sc.route.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    sc.routes_pending = true;
 }
 
 // taxonomy labels of a finished sub-batch (its merged hit lists are on the device): one more small kernel + two copies
@@ -889,24 +914,41 @@ BSP_API int bsp_microbatch_stats(bsp_classifier* h, int64_t* batches, int64_t* r
     return BSP_OK;
 }
 
-// the leader's part: pack the batch, one bsp_classify_packed, scatter the results
+// the leader's part: pack the batch into page-locked staging, one bsp_classify_packed, scatter the results
 static void microbatch_run(bsp_classifier* h, std::vector<OneRead*>& batch) {
+    MicroBatcher& mb = h->mb;
+    std::lock_guard<std::mutex> run(mb.run_mu);
     const i32 n = (i32)batch.size();
-    std::vector<i64> off((size_t)n + 1, 0);
-    for (i32 i = 0; i < n; i++) off[i + 1] = off[i] + batch[i]->len;
-    std::string bytes((size_t)off[n], '\0');
-    for (i32 i = 0; i < n; i++) memcpy(&bytes[off[i]], batch[i]->seq, (size_t)batch[i]->len);
-    std::vector<i32> st(n, BSP_READ_ERROR), label(n, 0), nh(n, 0), nt(n, 0), doc((size_t)n * TOPN, -1);
-    std::vector<float> score((size_t)n * TOPN, 0.0f);
-    const int rc = classify_packed_impl(h, n, bytes.data(), off.data(), st.data(), label.data(), nh.data(), nt.data(), doc.data(), score.data());
-    const std::string err = rc == BSP_OK ? std::string() : g_last_error;
-    for (i32 i = 0; i < n; i++) {
-        OneRead& q = *batch[i];
-        q.rc = rc; q.err = err;
-        q.status = st[i]; q.label = label[i]; q.n_hits = nh[i]; q.n_top = nt[i];
-        memcpy(q.doc, &doc[(size_t)i * TOPN], sizeof q.doc);
-        memcpy(q.score, &score[(size_t)i * TOPN], sizeof q.score);
-    }
+    int rc = BSP_OK;
+    std::string err;
+    try {
+        CUDA_CHECK(cudaSetDevice(h->conf.device));
+        i64 total = 0;
+        for (i32 i = 0; i < n; i++) total += batch[i]->len;
+        mb.pin_off.ensure(((size_t)n + 1) * 8);
+        mb.pin_seq.ensure((size_t)total + 1);
+        mb.pin_i32.ensure((size_t)n * (4 + TOPN) * 4);
+        mb.pin_f32.ensure((size_t)n * TOPN * 4);
+        i64* off = (i64*)mb.pin_off.p;
+        char* bytes = (char*)mb.pin_seq.p;
+        off[0] = 0;
+        for (i32 i = 0; i < n; i++) {
+            memcpy(bytes + off[i], batch[i]->seq, (size_t)batch[i]->len);
+            off[i + 1] = off[i] + batch[i]->len;
+        }
+        i32* st = (i32*)mb.pin_i32.p; i32* label = st + n; i32* nh = label + n; i32* nt = nh + n; i32* doc = nt + n;
+        float* score = (float*)mb.pin_f32.p;
+        rc = classify_packed_impl(h, n, bytes, off, st, label, nh, nt, doc, score);
+        if (rc != BSP_OK) err = g_last_error;
+        else
+            for (i32 i = 0; i < n; i++) {
+                OneRead& q = *batch[i];
+                q.status = st[i]; q.label = label[i]; q.n_hits = nh[i]; q.n_top = nt[i];
+                memcpy(q.doc, doc + (size_t)i * TOPN, sizeof q.doc);
+                memcpy(q.score, score + (size_t)i * TOPN, sizeof q.score);
+            }
+    } catch (const BspError& e) { rc = e.code; err = e.what(); }
+    for (i32 i = 0; i < n; i++) { batch[i]->rc = rc; batch[i]->err = err; }
 }
 
 BSP_API int bsp_classify_one(bsp_classifier* h, const char* seq, int32_t seq_len, int32_t* status, int32_t* label,
