@@ -66,6 +66,8 @@ struct Scratch {
     i32 n = 0; int n_tiles = 1, parts_pos = 0, parts_stride = 1, dense_threads = 32, filter_threads = 32, filter_tiles = 1;
     QueryParams qp; bool busy = false;
     i32 r0 = 0;                         // first read of the sub-batch in the caller's arrays
+    i32 cnt[4] = {0, 0, 0, 0};          // route counts between the two halves of phase 2: dense, positional, filter, overflow
+    i64 launches = 0; bool filter_launched = false;
     void init() {
         CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
@@ -113,7 +115,7 @@ struct bsp_classifier {
     GpuIndex ix;
     cudaStream_t st = nullptr;          // build / introspection stream (= slot 0's stream)
     std::string last_error;
-    Scratch sc[2];                      // two sub-batches in flight: copies of one overlap the kernels of the other
+    Scratch sc[BSP_SLOTS];              // sub-batches in flight: the next one's scorer is queued before the current one ends
     // scoring constants
     DevBuf<float> idf_by_df, doc_w, tf16;
     // interned ranked lineages (bsp_classifier_set_lineages)
@@ -414,7 +416,7 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
     try {
         h->conf = *conf;
         h->ref = ref;
-        for (int i = 0; i < 2; i++) { h->sc[i].init(); h->sc[i].slot_index = i; }
+        for (int i = 0; i < BSP_SLOTS; i++) { h->sc[i].init(); h->sc[i].slot_index = i; }
         h->st = h->sc[0].st;
         h->mb.max_reads = (i32)std::max<i64>(1, env_i64("BSP_MICROBATCH_MAX", 4096));
         h->mb.wait_us = std::max<i64>(0, env_i64("BSP_MICROBATCH_US", 200));
@@ -622,7 +624,9 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     sc.part_score.ensure((size_t)n * sc.parts_stride * TOPN);
 }
 
-static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out) {
+// phase 2a: wait for the route counts, (gap pre-pass), launch the filter scorer and queue the read-back of what it hands
+// over -- no wait for it.  phase 2b: wait, then the exact / positional scorers, merge, on the same stream.
+static void pipeline_phase2a(bsp_classifier* h, Scratch& sc) {
     GpuIndex& ix = h->ix;
     cudaStream_t st = sc.st;
     const i32 n = sc.n;
@@ -647,17 +651,17 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
         CUDA_CHECK(cudaMemcpyAsync(sc.h_counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
     }
-    i32 counts[4] = {sc.h_counts[0], sc.h_counts[1], sc.h_counts[2], 0};
+    i32* counts = sc.cnt;
+    counts[0] = sc.h_counts[0]; counts[1] = sc.h_counts[1]; counts[2] = sc.h_counts[2]; counts[3] = 0;
     const u32 D = (u32)ix.docs.size();
-    const int n_tiles = sc.n_tiles, parts_pos = sc.parts_pos, parts_stride = sc.parts_stride;
+    const int parts_stride = sc.parts_stride;
     i32* part_n = sc.part_n.p; u32* part_doc = sc.part_doc.p; float* part_score = sc.part_score.p;
-    SimParams sp; sp.sim = qp.sim; sp.k1p1 = 1.2f + 1.0f;
     const u32 gbase = (u32)h->doc_base_global;
     const Tab4Dev T = ix.tab4_view(sc.slot_index, sc.gap_cnt.p);
     const int full_topn = (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0;
     CUDA_CHECK(cudaEventRecord(sc.ev[1], st));
-    i64 launches = 9;     // tok_capacity, 4 scan kernels, tokenize, token_df, weights, route_compact
-    FilterStats fs = {0, 0, 0};
+    sc.launches = 9;      // tok_capacity, 4 scan kernels, tokenize, token_df, weights, route_compact
+    sc.filter_launched = false;
     if (counts[2] > 0) {
         CUDA_CHECK(cudaMemsetAsync(sc.fstats.p, 0, sizeof(FilterStats), st));
         const int threads = sc.filter_threads;
@@ -672,10 +676,30 @@ static void pipeline_phase2(bsp_classifier* h, Scratch& sc, const BatchOut& out)
         else { if (naive) FK_LAUNCH(false, true); else FK_LAUNCH(false, false); }
 #undef FK_LAUNCH
         KERNEL_CHECK();
-        launches++;
+        sc.launches++;
+        sc.filter_launched = true;
         // reads the filter could not bound (exception or candidate overflow) were appended to the exact list
         CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 4, sc.counts.p + 3, 4, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaMemcpyAsync(sc.h_fstats, sc.fstats.p, sizeof(FilterStats), cudaMemcpyDeviceToHost, st));
+    }
+}
+
+static void pipeline_phase2b(bsp_classifier* h, Scratch& sc, const BatchOut& out) {
+    GpuIndex& ix = h->ix;
+    cudaStream_t st = sc.st;
+    const i32 n = sc.n;
+    const QueryParams& qp = sc.qp;
+    i32* counts = sc.cnt;
+    const u32 D = (u32)ix.docs.size();
+    const int n_tiles = sc.n_tiles, parts_pos = sc.parts_pos, parts_stride = sc.parts_stride;
+    i32* part_n = sc.part_n.p; u32* part_doc = sc.part_doc.p; float* part_score = sc.part_score.p;
+    SimParams sp; sp.sim = qp.sim; sp.k1p1 = 1.2f + 1.0f;
+    const u32 gbase = (u32)h->doc_base_global;
+    const Tab4Dev T = ix.tab4_view(sc.slot_index, sc.gap_cnt.p);
+    const int full_topn = (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0;
+    i64 launches = sc.launches;
+    FilterStats fs = {0, 0, 0};
+    if (sc.filter_launched) {
         CUDA_CHECK(cudaStreamSynchronize(st));
         counts[3] = sc.h_counts[4];
         fs = *sc.h_fstats;
@@ -742,7 +766,8 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
                                const BatchOut& out) {
     Scratch& sc = h->sc[0];
     pipeline_phase1(h, sc, n, d_seq, d_seq_off, total_bytes);
-    pipeline_phase2(h, sc, out);
+    pipeline_phase2a(h, sc);
+    pipeline_phase2b(h, sc, out);
     CUDA_CHECK(cudaStreamSynchronize(sc.st));
     pipeline_collect(h, sc);
 }
@@ -788,14 +813,21 @@ static int classify_packed_impl(bsp_classifier* h, i32 n, const char* seq_bytes,
     h->score_ms = 0; h->pipe_ms = 0;
     h->last_routes.assign(n, 0);
     const i32 SUB = (i32)std::max<i64>(1, env_i64("BSP_SUB_BATCH", 131072));
-    // Software pipeline over sub-batches, two slots: while slot A's scorers run, slot B's reads are copied in and
-    // tokenised and slot A's previous results are copied out.
-    int slot = 0;
-    Scratch* prev = nullptr;
+    // Software pipeline over sub-batches, BSP_SLOTS slots.  Iteration i copies sub-batch i in and queues its tokenizer /
+    // weights (phase 1), launches the scorer of sub-batch i-1 (phase 2a: its route counts arrived while sub-batch i-2
+    // was being scored) and only then waits for the scorer of sub-batch i-2 to finish, merges and copies it out (phase
+    // 2b): the GPU always has the next scoring kernel queued behind the running one.
+    auto finish = [&](Scratch& sc) {
+        BatchOut bo{sc.o_status.p, sc.o_label.p, sc.o_nhits.p, sc.o_ntop.p, sc.o_doc.p, sc.o_score.p};
+        pipeline_phase2b(h, sc, bo);
+        enqueue_outputs(h, sc, status, label, n_hits, n_top, top_doc, top_score);
+        if (tax_label) enqueue_taxonomy(h, sc, tax_label, tax_index);
+    };
     try {
-        for (i32 r0 = 0; r0 < n; r0 += SUB) {
-            Scratch& sc = h->sc[slot];
-            if (sc.busy) {          // the slot's previous sub-batch (two iterations ago) must be completely done
+        i32 i = 0;                                        // sub-batch index
+        for (i32 r0 = 0; r0 < n; r0 += SUB, i++) {
+            Scratch& sc = h->sc[i % BSP_SLOTS];
+            if (sc.busy) {          // the slot's previous sub-batch (BSP_SLOTS iterations ago) must be completely done
                 CUDA_CHECK(cudaStreamSynchronize(sc.st));
                 pipeline_collect(h, sc);
             }
@@ -811,28 +843,19 @@ static int classify_packed_impl(bsp_classifier* h, i32 n, const char* seq_bytes,
                 sc.pin_in_bytes = in_need + in_need / 4;
             }
             i64* po = (i64*)sc.pin_in;
-            for (i32 i = 0; i <= m; i++) po[i] = seq_offsets[r0 + i] - b0;
+            for (i32 j = 0; j <= m; j++) po[j] = seq_offsets[r0 + j] - b0;
             CUDA_CHECK(cudaMemcpyAsync(sc.seq_off.p, po, (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, sc.st));
             if (bytes) CUDA_CHECK(cudaMemcpyAsync(sc.seq.p, seq_bytes + b0, (size_t)bytes, cudaMemcpyHostToDevice, sc.st));
             sc.o_status.ensure(m); sc.o_label.ensure(m); sc.o_nhits.ensure(m); sc.o_ntop.ensure(m);
             sc.o_doc.ensure((size_t)m * TOPN); sc.o_score.ensure((size_t)m * TOPN);
             sc.r0 = r0;
             pipeline_phase1(h, sc, m, sc.seq.p, sc.seq_off.p, bytes);
-            if (prev) {             // the other slot: scorers + merge + copy-out, queued behind this slot's phase 1
-                BatchOut bo{prev->o_status.p, prev->o_label.p, prev->o_nhits.p, prev->o_ntop.p, prev->o_doc.p, prev->o_score.p};
-                pipeline_phase2(h, *prev, bo);
-                enqueue_outputs(h, *prev, status, label, n_hits, n_top, top_doc, top_score);
-                if (tax_label) enqueue_taxonomy(h, *prev, tax_label, tax_index);
-            }
-            prev = &sc;
-            slot ^= 1;
+            if (i >= 1) pipeline_phase2a(h, h->sc[(i - 1) % BSP_SLOTS]);
+            if (i >= 2) finish(h->sc[(i - 2) % BSP_SLOTS]);
         }
-        if (prev) {
-            BatchOut bo{prev->o_status.p, prev->o_label.p, prev->o_nhits.p, prev->o_ntop.p, prev->o_doc.p, prev->o_score.p};
-            pipeline_phase2(h, *prev, bo);
-            enqueue_outputs(h, *prev, status, label, n_hits, n_top, top_doc, top_score);
-            if (tax_label) enqueue_taxonomy(h, *prev, tax_label, tax_index);
-        }
+        if (i >= 1) pipeline_phase2a(h, h->sc[(i - 1) % BSP_SLOTS]);
+        if (i >= 2) finish(h->sc[(i - 2) % BSP_SLOTS]);
+        if (i >= 1) finish(h->sc[(i - 1) % BSP_SLOTS]);
         for (auto& sc : h->sc) {
             CUDA_CHECK(cudaStreamSynchronize(sc.st));
             pipeline_collect(h, sc);

@@ -147,6 +147,8 @@ struct BuildOptions {
 
 // Slab allocator of the positional index: the segments' arrays are carved out of a few large allocations (first fit over
 // the slabs' tails) instead of two cudaMallocs per segment.
+#define BSP_SLOTS 3              // sub-batches in flight in bsp_classify_packed (api.cu)
+
 struct DevArena {
     struct Slab { DevBuf<u8> buf; size_t used = 0; };
     std::vector<Slab> slabs;
@@ -596,7 +598,7 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
         const u32 n = (u32)ne;
         ix.exc_off.alloc(ix.n_rows + 2);
         // the tail of the exception arrays holds the gap-clause match lists of the two pipeline slots
-        const size_t tail = (size_t)2 * ix.gap_cap * GAP_LIST;
+        const size_t tail = (size_t)BSP_SLOTS * ix.gap_cap * GAP_LIST;      // one gap-list region per pipeline slot
         if ((u64)n + tail >= ((u64)1 << 32)) throw BspError(-5, "exception + gap lists exceed 2^32 entries");
         ix.exc_doc.alloc((size_t)n + tail); ix.exc_freq.alloc((size_t)n + tail);
         DevBuf<u64> ka, kb; DevBuf<u32> va, vb;
