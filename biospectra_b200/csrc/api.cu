@@ -433,7 +433,8 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
         opt.want_tables = conf->dense_tables;
         opt.want_positional = conf->positional;
         opt.need_pair_table = conf->query_algorithm != BSP_NAIVE_KMER;
-        opt.seg_tokens = env_i64("BSP_SEG_TOKENS", (i64)1 << 28);
+        // positions are segment ordinals compared as int: a segment never holds more than 2^30 tokens (one longer doc gets its own)
+        opt.seg_tokens = std::min<i64>(std::max<i64>(env_i64("BSP_SEG_TOKENS", (i64)1 << 28), 1), (i64)1 << 30);
         opt.exc_cap = std::max<i64>(env_i64("BSP_EXC_CAP", (i64)1 << 26), 1024);
         // (kmer_skips > 0 turns every phrase clause into a gap clause; evaluating them all in the pre-pass costs what the
         // positional scorer costs -- measured at C2 -- so those reads overflow this list on purpose and take that scorer)
