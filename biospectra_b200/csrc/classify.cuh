@@ -570,9 +570,10 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
 #define POSW_MINB 4                // 64 registers, 4 CTAs per SM (3 CTAs at 80 registers: 0.75 M reads/s against 0.87 M at C2, skips 5)
 #endif
 // Phrase clauses are staged: the warp copies both terms' posting slices of the segment (doc ids, position offsets)
-// and then their position ranges -- each one contiguous in the term-major layout -- into shared memory with coalesced
-// loads, and the per-doc conjunction + sloppy sweep run out of shared memory.  Three dependent rounds of wide loads per
-// clause instead of a dozen dependent scalar loads per (clause, doc).  Slices beyond the caps take the direct path.
+// and their position ranges -- each one contiguous in the term-major layout -- into shared memory as one batch of
+// asynchronous 4-byte copies (the ranges are looked up when the clauses are set up), and the conjunction + sloppy sweep
+// run out of shared memory: one memory round trip per clause instead of a dozen dependent scalar loads per
+// (clause, doc).  Slices beyond the position cap take the direct path.
 // Shared memory per warp (all dynamic, sized by the host from the largest segment): double acc[dcap] | u32 pos[2][pcap]
 // | u32 doc[2][dcap] | u32 pp[2][dcap + 4] | ClauseStageW stage[32] | u16 cnt[dcap] | u8 inv[dcap] | u8 hit[dcap];  dcap =
 // docs per segment rounded up to 32 (a term has at most one posting per doc), pcap = PW_POS positions per term and

@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(256) pair_table4_kernel(SegDev s, int k, int m
 }
 
 // Same rows, staged: warp per first k-mer t0 (segments of at most 256 docs).  The four (k+1)-mers t0+A/C/G/T share
-// t0's postings, so its slice of the segment (docs, position offsets, positions) is copied to shared memory once with
-// batched coalesced loads; each second k-mer's slice follows, a doc -> posting byte map replaces the binary search and
-// the literal sweep runs out of shared memory.  Slices beyond the position cap and same-term rows take the direct path.
+// t0's postings, so its slice of the segment (docs, position offsets, positions) is copied to shared memory once (one
+// batch of asynchronous 4-byte copies); each second k-mer's slice follows, a doc -> posting byte map replaces the
+// binary search and the literal sweep runs out of shared memory.  Slices beyond the position cap and same-term rows take the direct path.
 #define PT_WARPS 8
 __host__ __device__ inline size_t pair_stage_warp_bytes(int dcap, int pcap) {
     return 2 * ((size_t)dcap * 4 + (size_t)(dcap + 4) * 4 + (size_t)pcap * 4) + (size_t)dcap;
