@@ -387,31 +387,30 @@ __device__ __forceinline__ void pair_word2(u32 wa, u32 wb, const uint2 la, const
 }
 
 // Term rows hold codes 0..14: a 16-entry LUT out of two 8-entry PRMT lookups.  PRMT reads bit 3 of a selector nibble as
-// "replicate the sign of the selected byte": looking up the constant 0x80 therefore yields 0xFF for codes >= 8 and 0x80
-// otherwise -- a per-byte select mask for bits 0..6 (weights are kept <= 127 so bit 7 is never set).
-__device__ __forceinline__ u32 lut16(const uint4 t, u32 sel /* 4 codes in the low 16 bits */, u32& ge8) {
-    const u32 s7 = sel & 0x7777u;
-    const u32 lo = prmt(t.x, t.y, s7), hi = prmt(t.z, t.w, s7);
-    ge8 = prmt(0x80808080u, 0x80808080u, sel);
-    return (hi & ge8) | (lo & ~ge8);
+// "replicate the sign (bit 7) of the selected byte".  Weights are kept <= 127, so a lookup with the raw code yields
+// LUT_lo[code] for codes < 8 and 0x00 for codes >= 8, and with bit 3 of the code flipped LUT_hi[code - 8] for codes >= 8
+// and 0x00 below: the two results are disjoint and simply add (on the FMA pipe).
+__device__ __forceinline__ u32 lut16(const uint4 t, u32 sel /* 4 codes in the low 16 bits */, u32 one) {
+    u32 r = prmt(t.x, t.y, sel);
+    add_fma_pipe(r, prmt(t.z, t.w, sel ^ 0x8888u), one);
+    return r;
 }
-__device__ __forceinline__ u32 cnt16(u32 sel, u32 ge8) {        // 1 per non-zero code
-    return prmt(0x01010100u, 0x01010101u, sel & 0x7777u) | (ge8 & 0x01010101u);
-}
+// 1 per non-zero code.  Looked up in the bytes {0x80, 0x81 x 7}: code 0 -> 0x80, 1..7 -> 0x81, 8 -> sign of 0x80 = 0xFF,
+// 9..15 -> sign of 0x81 = 0xFF: bit 0 is the flag.
+__device__ __forceinline__ u32 cnt16(u32 sel) { return prmt(0x81818180u, 0x81818181u, sel) & 0x01010101u; }
 // one u32 (8 docs) of each of two term rows
 __device__ __forceinline__ void term_word2(u32 wa, u32 wb, const uint4 ta, const uint4 tb, u32& w0, u32& w1, u32& w2, u32& w3,
                                            u32& c0, u32& c1, u32 one) {
     const u32 ha = wa >> 16, hb = wb >> 16;
-    u32 ga0, ga1, gb0, gb1;
-    u32 s0 = lut16(ta, wa, ga0), s1 = lut16(ta, ha, ga1);
-    add_fma_pipe(s0, lut16(tb, wb, gb0), one);        // weights <= 127: the two rows' bytes add without carry
-    add_fma_pipe(s1, lut16(tb, hb, gb1), one);
+    u32 s0 = lut16(ta, wa, one), s1 = lut16(ta, ha, one);
+    add_fma_pipe(s0, lut16(tb, wb, one), one);        // weights <= 127: the two rows' bytes add without carry
+    add_fma_pipe(s1, lut16(tb, hb, one), one);
     add_fma_pipe(w0, prmt(s0, 0u, 0x4140u), one);
     add_fma_pipe(w1, prmt(s0, 0u, 0x4342u), one);
     add_fma_pipe(w2, prmt(s1, 0u, 0x4140u), one);
     add_fma_pipe(w3, prmt(s1, 0u, 0x4342u), one);
-    add_fma_pipe(c0, cnt16(wa, ga0), one); add_fma_pipe(c0, cnt16(wb, gb0), one);
-    add_fma_pipe(c1, cnt16(ha, ga1), one); add_fma_pipe(c1, cnt16(hb, gb1), one);
+    add_fma_pipe(c0, cnt16(wa), one); add_fma_pipe(c0, cnt16(wb), one);
+    add_fma_pipe(c1, cnt16(ha), one); add_fma_pipe(c1, cnt16(hb), one);
 }
 
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {     // read-only path, do not keep in L1
