@@ -33,6 +33,8 @@ WORKLOADS = {
     "C2": dict(genomes=3000, total_bp=10_000_000_000, reads=1_000_000, R=100, err=0.04, seed=2, read_seed=12),
     "C1": dict(genomes=10, total_bp=20_000_000, reads=10_000, R=100, err=0.04, seed=1, read_seed=11, equal=True),
     "mid": dict(genomes=300, total_bp=1_000_000_000, reads=200_000, R=100, err=0.04, seed=4, read_seed=14),
+    # BASELINE configs[3]: larger than one GPU; only with --mode docpart on 8 GPUs (7.5 Gbp per GPU)
+    "C4": dict(genomes=18000, total_bp=60_000_000_000, reads=1_000_000, R=100, err=0.04, seed=3, read_seed=13),
 }
 
 
