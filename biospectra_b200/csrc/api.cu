@@ -429,6 +429,7 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
 #undef FK_ATTR
         CUDA_CHECK(cudaFuncSetAttribute(score_positional_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(POSW_WARPS * posw_warp_bytes(POSW_DOCS, PW_POS))));
         CUDA_CHECK(cudaFuncSetAttribute(score_positional_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_CHECK(cudaFuncSetAttribute(gap_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * phrase_stage_bytes(POSW_DOCS, PW_POS))));
         BuildOptions opt;
         opt.want_tables = conf->dense_tables;
         opt.want_positional = conf->positional;
@@ -641,8 +642,10 @@ static void pipeline_phase2a(bsp_classifier* h, Scratch& sc) {
         const u32 GC = ix.gap_cap;
         const i64 ng = std::min<i64>((u32)sc.h_counts[5], GC);
         const u32 tmp_base = (u32)ix.n_exc + (u32)sc.slot_index * GC * GAP_LIST;
-        gap_fill_kernel<<<(unsigned)ceil_div(ng * n_segs * 32, 256), 256, 0, st>>>(ix.d_segs.p, n_segs, sc.gaps.p,
-            sc.gap_cnt.p + GC, GC, sc.gap_cnt.p, ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base);
+        const int gf_dcap = ix.max_seg_docs <= POSW_DOCS ? (int)round_up(std::max<i64>(ix.max_seg_docs, 1), 32) : 0;
+        gap_fill_kernel<<<(unsigned)ceil_div(ng * n_segs * 32, 256), 256, gf_dcap ? 8 * phrase_stage_bytes(gf_dcap, PW_POS) : 0, st>>>(
+            ix.d_segs.p, n_segs, sc.gaps.p, sc.gap_cnt.p + GC, GC, sc.gap_cnt.p, ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base,
+            gf_dcap, PW_POS);
         gap_sort_kernel<<<(unsigned)ceil_div(ng * 32, 256), 256, 0, st>>>(sc.gaps.p, sc.gap_cnt.p + GC, GC, sc.gap_cnt.p,
             ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base, sc.route.p, sc.status_in.p, qp.positional_ok);
         CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));

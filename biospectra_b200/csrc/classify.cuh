@@ -574,10 +574,10 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
 // asynchronous 4-byte copies (the ranges are looked up when the clauses are set up), and the conjunction + sloppy sweep
 // run out of shared memory: one memory round trip per clause instead of a dozen dependent scalar loads per
 // (clause, doc).  Slices beyond the position cap take the direct path.
-// Shared memory per warp (all dynamic, sized by the host from the largest segment): double acc[dcap] | u32 pos[2][pcap]
-// | u32 doc[2][dcap] | u32 pp[2][dcap + 4] | ClauseStageW stage[32] | u16 cnt[dcap] | u8 inv[dcap] | u8 hit[dcap];  dcap =
-// docs per segment rounded up to 32 (a term has at most one posting per doc), pcap = PW_POS positions per term and
-// segment.  inv[doc] = index of the doc's posting in the second term's slice (possibly stale: always verified);
+// Shared memory per warp (all dynamic, sized by the host from the largest segment): double acc[dcap] | PhraseStage
+// {u32 pos[2][pcap] | u32 doc[2][dcap] | u32 pp[2][dcap + 4] | u8 inv[dcap] | u8 hit[dcap]} | ClauseStageW stage[32] |
+// u16 cnt[dcap];  dcap = docs per segment rounded up to 32 (a term has at most one posting per doc), pcap = PW_POS
+// positions per term and segment.  inv[doc] = index of the doc's posting in the second term's slice (possibly stale: always verified);
 // hit[i] = posting i of the first term has a position within the slop of one of the second term's.
 //
 // Which docs can match at all?  Every matchLength the SloppyPhraseScorer sweep tests is |(b - 1) - a| of an actual
@@ -586,8 +586,90 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
 // lane takes a contiguous chunk of the first term's positions and walks the second term's from a binary-searched start.
 // No false negatives; a pair straddling two docs is a false positive the exact sweep discards.
 #define PW_POS 384               // 2^28 tokens / 4^10 terms = 256 on average
+// per-warp staging buffers of one phrase clause
+struct PhraseStage { u32 *pos0, *pos1, *doc0, *doc1, *pp0, *pp1; u8 *inv, *hit; };
+__host__ __device__ inline size_t phrase_stage_bytes(int dcap, int pcap) {
+    return (size_t)pcap * 8 + (size_t)dcap * 8 + (size_t)(dcap + 4) * 8 + (size_t)dcap * 2;
+}
+__device__ __forceinline__ PhraseStage phrase_stage_at(u8* base /* 4-byte aligned */, int dcap, int pcap) {
+    PhraseStage W;
+    W.pos0 = reinterpret_cast<u32*>(base);
+    W.pos1 = W.pos0 + pcap;
+    W.doc0 = W.pos1 + pcap;
+    W.doc1 = W.doc0 + dcap;
+    W.pp0 = W.doc1 + dcap;
+    W.pp1 = W.pp0 + dcap + 4;
+    W.inv = reinterpret_cast<u8*>(W.pp1 + dcap + 4);
+    W.hit = W.inv + dcap;
+    return W;
+}
+// The docs of the segment in which the phrase (t0@0, t1@1, slop) with t0 != t1 has a non-zero sloppy frequency:
+// on_match(local doc, freq) is called once per such doc (by whichever lane owns the posting).  Postings [a0, a0+n0) /
+// [a1, a1+n1) with position ranges [p0, p0+m0) / [p1, p1+m1); n0, n1 <= dcap, m0, m1 <= pcap, inv[] and hit[] hold
+// anything / zeros on entry and are left that way.  All 32 lanes call it.
+template <typename F>
+__device__ __forceinline__ void phrase_matches_staged(const SegDev& s, const PhraseStage& W, u32 a0, u32 n0, u32 p0, u32 m0,
+                                                      u32 a1, u32 n1, u32 p1, u32 m1, int slop, int lane, F&& on_match) {
+    // one batch of asynchronous 4-byte copies (LDGSTS) for the whole clause: one memory round trip
+    for (u32 i = lane; i <= n0; i += 32) {
+        if (i < n0) cp_async4(W.doc0 + i, s.post_doc + a0 + i);
+        cp_async4(W.pp0 + i, s.post_pos + a0 + i);
+    }
+    for (u32 i = lane; i <= n1; i += 32) {
+        if (i < n1) cp_async4(W.doc1 + i, s.post_doc + a1 + i);
+        cp_async4(W.pp1 + i, s.post_pos + a1 + i);
+    }
+    for (u32 i = lane; i < m0; i += 32) cp_async4(W.pos0 + i, s.positions + p0 + i);
+    for (u32 i = lane; i < m1; i += 32) cp_async4(W.pos1 + i, s.positions + p1 + i);
+    cp_async_commit_wait_all();
+    __syncwarp();
+    for (u32 i = lane; i < n1; i += 32) W.inv[W.doc1[i]] = (u8)i;
+    __syncwarp();
+    // ---- close pairs: lane takes positions [ia, ia1) of the first term
+    const u32 ca = (m0 + 31) >> 5;
+    u32 ia = (u32)lane * ca;
+    const u32 ia1 = min(m0, ia + ca);
+    if (ia < ia1) {
+        const int lo = (int)W.pos0[ia] - slop;
+        u32 jb = 0, hi = m1;                                                 // first b' >= lo, b' = b - 1 (phrase offset of t1)
+        while (jb < hi) {
+            const u32 mid = (jb + hi) >> 1;
+            if ((int)W.pos1[mid] - 1 < lo) jb = mid + 1; else hi = mid;
+        }
+        while (ia < ia1 && jb < m1) {
+            const int d = (int)W.pos1[jb] - 1 - (int)W.pos0[ia];
+            if (d > slop) ia++;                                              // b' beyond this a: next a
+            else if (d < -slop) jb++;                                        // b' behind: next b'
+            else {                                                           // within the slop: flag a's posting
+                const u32 target = p0 + ia;
+                u32 l = 0, h2 = n0;                                          // last posting with pp <= target
+                while (h2 - l > 1) {
+                    const u32 mid = (l + h2) >> 1;
+                    if (W.pp0[mid] <= target) l = mid; else h2 = mid;
+                }
+                W.hit[l] = 1;
+                ia++;
+            }
+        }
+    }
+    __syncwarp();
+    // ---- the literal sweep for the flagged docs
+    for (u32 i = lane; i < n0; i += 32) {
+        if (!W.hit[i]) continue;
+        W.hit[i] = 0;
+        const u32 d = W.doc0[i];
+        const u32 j = W.inv[d];                                              // verified: may be a stale entry
+        if (j < n1 && W.doc1[j] == d) {
+            const u32 q0 = W.pp0[i], q1 = W.pp1[j];
+            const float f = sloppy_freq_distinct(W.pos0 + (q0 - p0), (int)(W.pp0[i + 1] - q0),
+                                                 W.pos1 + (q1 - p1), (int)(W.pp1[j + 1] - q1), slop);
+            if (f != 0.0f) on_match(d, f);
+        }
+    }
+    __syncwarp();
+}
 __host__ __device__ inline size_t posw_warp_bytes(int dcap, int pcap) {
-    return (size_t)dcap * 8 + (size_t)pcap * 8 + (size_t)dcap * 8 + (size_t)(dcap + 4) * 8 + 32 * sizeof(ClauseStageW) + (size_t)dcap * 2 + (size_t)dcap * 2;
+    return (size_t)dcap * 8 + phrase_stage_bytes(dcap, pcap) + 32 * sizeof(ClauseStageW) + (size_t)dcap * 2;
 }
 __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_warp_kernel(
         const SegDev* __restrict__ segs, int n_segs, const i32* __restrict__ read_list, i32 n_list,
@@ -600,22 +682,15 @@ __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_w
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u8* wbase = pw_raw + (size_t)warp * posw_warp_bytes(dcap, pcap);
     double* acc = reinterpret_cast<double*>(wbase);
-    u32* w_pos0 = reinterpret_cast<u32*>(wbase + (size_t)dcap * 8);
-    u32* w_pos1 = w_pos0 + pcap;
-    u32* w_doc0 = w_pos1 + pcap;
-    u32* w_doc1 = w_doc0 + dcap;
-    u32* w_pp0 = w_doc1 + dcap;
-    u32* w_pp1 = w_pp0 + dcap + 4;
-    ClauseStageW* stage = reinterpret_cast<ClauseStageW*>(w_pp1 + dcap + 4);
+    const PhraseStage W = phrase_stage_at(wbase + (size_t)dcap * 8, dcap, pcap);
+    ClauseStageW* stage = reinterpret_cast<ClauseStageW*>(wbase + (size_t)dcap * 8 + phrase_stage_bytes(dcap, pcap));
     u16* cnt = reinterpret_cast<u16*>(stage + 32);
-    u8* inv = reinterpret_cast<u8*>(cnt + dcap);
-    u8* hit = inv + dcap;
     const i64 pair = (i64)blockIdx.x * POSW_WARPS + warp;
     if (pair >= (i64)n_list * n_segs) return;
     const int sidx = (int)(pair / n_list);              // segment-major, see score_positional_kernel
     const i32 r = read_list[pair % n_list];
     const SegDev s = segs[sidx];
-    for (u32 d = lane; d < (u32)dcap; d += 32) { acc[d] = 0.0; cnt[d] = 0; inv[d] = 0; hit[d] = 0; }
+    for (u32 d = lane; d < (u32)dcap; d += 32) { acc[d] = 0.0; cnt[d] = 0; W.inv[d] = 0; W.hit[d] = 0; }
     const i64 base = tok_off[r];
     const i32 n = n_tok[r], nc = n_clauses[r];
     const float* dw = doc_w + s.doc_base;
@@ -657,70 +732,12 @@ __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_w
             const u32 n0 = st.b0 - st.a0, n1 = st.b1 - st.a1;
             bool staged = false;
             if (stage_ok && st.slop > 0 && n0 && n1 && st.m0 <= (u32)pcap && st.m1 <= (u32)pcap) {   // (n0, n1 <= docs <= dcap)
-                const u32 p0 = st.p0, m0 = st.m0, p1 = st.p1, m1 = st.m1;
-                // one batch of asynchronous 4-byte copies (LDGSTS) for the whole clause: one memory round trip
-                for (u32 i = lane; i <= n0; i += 32) {
-                    if (i < n0) cp_async4(w_doc0 + i, s.post_doc + st.a0 + i);
-                    cp_async4(w_pp0 + i, s.post_pos + st.a0 + i);
-                }
-                for (u32 i = lane; i <= n1; i += 32) {
-                    if (i < n1) cp_async4(w_doc1 + i, s.post_doc + st.a1 + i);
-                    cp_async4(w_pp1 + i, s.post_pos + st.a1 + i);
-                }
-                for (u32 i = lane; i < m0; i += 32) cp_async4(w_pos0 + i, s.positions + p0 + i);
-                for (u32 i = lane; i < m1; i += 32) cp_async4(w_pos1 + i, s.positions + p1 + i);
-                cp_async_commit_wait_all();
-                __syncwarp();
-                for (u32 i = lane; i < n1; i += 32) inv[w_doc1[i]] = (u8)i;
-                __syncwarp();
-                // ---- close pairs: lane takes positions [ia, ia1) of the first term
-                const int slop = st.slop;
-                const u32 ca = (m0 + 31) >> 5;
-                u32 ia = (u32)lane * ca;
-                const u32 ia1 = min(m0, ia + ca);
-                if (ia < ia1) {
-                    const int lo = (int)w_pos0[ia] - slop;
-                    u32 jb = 0, hi = m1;                                                 // first b' >= lo, b' = b - 1 (phrase offset of t1)
-                    while (jb < hi) {
-                        const u32 mid = (jb + hi) >> 1;
-                        if ((int)w_pos1[mid] - 1 < lo) jb = mid + 1; else hi = mid;
-                    }
-                    while (ia < ia1 && jb < m1) {
-                        const int d = (int)w_pos1[jb] - 1 - (int)w_pos0[ia];
-                        if (d > slop) ia++;                                              // b' beyond this a: next a
-                        else if (d < -slop) jb++;                                        // b' behind: next b'
-                        else {                                                           // within the slop: flag a's posting
-                            const u32 target = p0 + ia;
-                            u32 l = 0, h2 = n0;                                          // last posting with pp <= target
-                            while (h2 - l > 1) {
-                                const u32 mid = (l + h2) >> 1;
-                                if (w_pp0[mid] <= target) l = mid; else h2 = mid;
-                            }
-                            hit[l] = 1;
-                            ia++;
-                        }
-                    }
-                }
-                __syncwarp();
-                // ---- the literal sweep for the flagged docs
-                for (u32 i = lane; i < n0; i += 32) {
-                    if (!hit[i]) continue;
-                    hit[i] = 0;
-                    const u32 d = w_doc0[i];
-                    const u32 j = inv[d];                                                // verified: may be a stale entry
-                    if (j < n1 && w_doc1[j] == d) {
-                        const u32 q0 = w_pp0[i], q1 = w_pp1[j];
-                        const float f = sloppy_freq_distinct(w_pos0 + (q0 - p0), (int)(w_pp0[i + 1] - q0),
-                                                             w_pos1 + (q1 - p1), (int)(w_pp1[j + 1] - q1), st.slop);
-                        if (f != 0.0f) {
-                            const float sc = clause_doc_score(sp.sim, sp.sim == SIM_TFIDF ? tf_of(f) : f, st.val, dw[d], sp.k1p1);
-                            acc[d] += (double)sc;                                        // BooleanScorer: double sum
-                            cnt[d] += 1;
-                        }
-                    }
-                }
+                phrase_matches_staged(s, W, st.a0, n0, st.p0, st.m0, st.a1, n1, st.p1, st.m1, st.slop, lane, [&](u32 d, float f) {
+                    const float sc = clause_doc_score(sp.sim, sp.sim == SIM_TFIDF ? tf_of(f) : f, st.val, dw[d], sp.k1p1);
+                    acc[d] += (double)sc;                                            // BooleanScorer: double sum
+                    cnt[d] += 1;
+                });
                 staged = true;
-                __syncwarp();
             }
             if (!staged) {
                 for (u32 i = st.a0 + lane; i < st.b0; i += 32) {

@@ -249,8 +249,10 @@ __global__ void __launch_bounds__(256) exc_offsets_kernel(const u64* __restrict_
 // warp per (gap clause, segment); idle warps (no such clause in this sub-batch) leave at once
 __global__ void __launch_bounds__(256) gap_fill_kernel(const SegDev* __restrict__ segs, int n_segs, const GapClause* __restrict__ gaps,
                                                         const u32* __restrict__ gap_count, u32 gap_cap, u32* __restrict__ gap_cnt,
-                                                        u32* __restrict__ tmp_doc, float* __restrict__ tmp_freq) {
-    const int lane = threadIdx.x & 31;
+                                                        u32* __restrict__ tmp_doc, float* __restrict__ tmp_freq,
+                                                        int dcap /* 0: no staging (segments of more than 256 docs) */, int pcap) {
+    extern __shared__ __align__(16) u8 gf_raw[];          // PhraseStage per warp (classify.cuh)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u32 ng = min(*gap_count, gap_cap);
     const u32 g = (u32)(w / (u64)n_segs);
@@ -268,15 +270,28 @@ __global__ void __launch_bounds__(256) gap_fill_kernel(const SegDev* __restrict_
         a1 = s.term_off[t1]; b1 = s.term_off[t1 + 1];
     }
     const u32 a0 = s.term_off[t0], b0 = s.term_off[t0 + 1];
+    auto keep = [&](u32 local_doc, float f) {
+        const u32 pos = atomicAdd(&gap_cnt[g], 1u);
+        if (pos < GAP_LIST) {
+            tmp_doc[(u64)g * GAP_LIST + pos] = s.doc_base + local_doc;
+            tmp_freq[(u64)g * GAP_LIST + pos] = f;
+        }
+    };
+    // staged like the warp scorer: both slices in shared memory, one scan for the docs that can match at all
+    const u32 n0 = b0 - a0, n1 = b1 - a1;
+    if (!same && n0 && n1 && dcap > 0 && s.n_docs <= (u32)dcap) {
+        const u32 p0 = s.post_pos[a0], m0 = s.post_pos[b0] - p0, p1 = s.post_pos[a1], m1 = s.post_pos[b1] - p1;
+        if (m0 <= (u32)pcap && m1 <= (u32)pcap) {
+            const PhraseStage W = phrase_stage_at(gf_raw + (size_t)warp * phrase_stage_bytes(dcap, pcap), dcap, pcap);
+            for (u32 d = lane; d < (u32)dcap; d += 32) { W.inv[d] = 0; W.hit[d] = 0; }
+            __syncwarp();
+            phrase_matches_staged(s, W, a0, n0, p0, m0, a1, n1, p1, m1, gc.slop, lane, keep);
+            return;
+        }
+    }
     for (u32 i = a0 + lane; i < b0; i += 32) {
         const float f = phrase_freq_at(s, i, a1, b1, a1 + (i - a0), gc.slop, same);
-        if (f != 0.0f) {
-            const u32 pos = atomicAdd(&gap_cnt[g], 1u);
-            if (pos < GAP_LIST) {
-                tmp_doc[(u64)g * GAP_LIST + pos] = s.doc_base + s.post_doc[i];
-                tmp_freq[(u64)g * GAP_LIST + pos] = f;
-            }
-        }
+        if (f != 0.0f) keep(s.post_doc[i], f);
     }
 }
 
