@@ -269,3 +269,23 @@ def test_positional_warp_kernel_staged_and_direct_paths(oracle_lib, monkeypatch,
         assert set(g.last_routes(len(reads))[res_o["status"] == 0]) <= {2}
     finally:
         g.close()
+
+
+def test_pipeline_slots_with_tiny_sub_batches(oracle_lib, monkeypatch):
+    """bsp_classify_packed runs sub-batches through three pipeline slots (phase 1 of sub-batch i, scorer launch of i-1,
+    completion of i-2 per iteration).  Sub-batches of 1, 2, 3, 5 and 7 reads over 61 reads exercise every fill / drain
+    shape and the reuse of every slot; each setting must reproduce the oracle bit for bit."""
+    ents = common.make_corpus(77, n_entries=(6, 7), length=(150, 300))
+    reads = common.make_reads(1077, ents, n=61, n_frac=0.3)
+    ox = common.build_oracle(oracle_lib, ents, 5, False)
+    res_o = ox.classify([r.encode() for r in reads], skips=0, algorithm=2, scoring=0, msm=0.4, threads=2)
+    g = common.build_gpu(ents, 5, False, dict(kmer_skips=0, query_algorithm="PAIRED_PROXIMITY", query_term_min_should_match=0.4))
+    try:
+        for sub in ("1", "2", "3", "5", "7", "64"):
+            monkeypatch.setenv("BSP_SUB_BATCH", sub)
+            res_g = g.classify_batch(reads)
+            common.assert_classify_equal(res_g, res_o, reads, "sub-batch " + sub)
+            routes = g.last_routes(len(reads))
+            assert (routes[res_o["status"] == 0] > 0).all() and (routes[res_o["status"] != 0] == 0).all()
+    finally:
+        g.close()
