@@ -456,6 +456,11 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     const u32 sa = (u32)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
 }
+// 16-byte copy global -> shared, bypassing L1 (both addresses 16-byte aligned)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const u32 sa = (u32)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
@@ -605,8 +610,10 @@ __device__ __forceinline__ PhraseStage phrase_stage_at(u8* base /* 4-byte aligne
 }
 // The docs of the segment in which the phrase (t0@0, t1@1, slop) with t0 != t1 has a non-zero sloppy frequency:
 // on_match(local doc, freq) is called once per such doc (by whichever lane owns the posting).  Postings [a0, a0+n0) /
-// [a1, a1+n1) with position ranges [p0, p0+m0) / [p1, p1+m1); n0, n1 <= dcap, m0, m1 <= pcap, inv[] and hit[] hold
-// anything / zeros on entry and are left that way.  All 32 lanes call it.
+// [a1, a1+n1) with position ranges [p0, p0+m0) / [p1, p1+m1); n0, n1 <= dcap, m0 + 3, m1 + 3 <= pcap, inv[] and hit[]
+// hold anything / zeros on entry and are left that way.  All 32 lanes call it.  The position ranges travel as 16-byte
+// copies from the enclosing aligned range (the arrays are 256-byte aligned and padded), so they start up to 3 elements
+// into their buffers.
 template <typename F>
 __device__ __forceinline__ void phrase_matches_staged(const SegDev& s, const PhraseStage& W, u32 a0, u32 n0, u32 p0, u32 m0,
                                                       u32 a1, u32 n1, u32 p1, u32 m1, int slop, int lane, F&& on_match) {
@@ -619,8 +626,11 @@ __device__ __forceinline__ void phrase_matches_staged(const SegDev& s, const Phr
         if (i < n1) cp_async4(W.doc1 + i, s.post_doc + a1 + i);
         cp_async4(W.pp1 + i, s.post_pos + a1 + i);
     }
-    for (u32 i = lane; i < m0; i += 32) cp_async4(W.pos0 + i, s.positions + p0 + i);
-    for (u32 i = lane; i < m1; i += 32) cp_async4(W.pos1 + i, s.positions + p1 + i);
+    const u32 o0 = p0 & 3u, o1 = p1 & 3u;
+    for (u32 i = 4u * (u32)lane; i < m0 + o0; i += 128) cp_async16(W.pos0 + i, s.positions + (p0 - o0) + i);
+    for (u32 i = 4u * (u32)lane; i < m1 + o1; i += 128) cp_async16(W.pos1 + i, s.positions + (p1 - o1) + i);
+    const u32* A = W.pos0 + o0;
+    const u32* B = W.pos1 + o1;
     cp_async_commit_wait_all();
     __syncwarp();
     for (u32 i = lane; i < n1; i += 32) W.inv[W.doc1[i]] = (u8)i;
@@ -630,14 +640,14 @@ __device__ __forceinline__ void phrase_matches_staged(const SegDev& s, const Phr
     u32 ia = (u32)lane * ca;
     const u32 ia1 = min(m0, ia + ca);
     if (ia < ia1) {
-        const int lo = (int)W.pos0[ia] - slop;
+        const int lo = (int)A[ia] - slop;
         u32 jb = 0, hi = m1;                                                 // first b' >= lo, b' = b - 1 (phrase offset of t1)
         while (jb < hi) {
             const u32 mid = (jb + hi) >> 1;
-            if ((int)W.pos1[mid] - 1 < lo) jb = mid + 1; else hi = mid;
+            if ((int)B[mid] - 1 < lo) jb = mid + 1; else hi = mid;
         }
         while (ia < ia1 && jb < m1) {
-            const int d = (int)W.pos1[jb] - 1 - (int)W.pos0[ia];
+            const int d = (int)B[jb] - 1 - (int)A[ia];
             if (d > slop) ia++;                                              // b' beyond this a: next a
             else if (d < -slop) jb++;                                        // b' behind: next b'
             else {                                                           // within the slop: flag a's posting
@@ -661,8 +671,8 @@ __device__ __forceinline__ void phrase_matches_staged(const SegDev& s, const Phr
         const u32 j = W.inv[d];                                              // verified: may be a stale entry
         if (j < n1 && W.doc1[j] == d) {
             const u32 q0 = W.pp0[i], q1 = W.pp1[j];
-            const float f = sloppy_freq_distinct(W.pos0 + (q0 - p0), (int)(W.pp0[i + 1] - q0),
-                                                 W.pos1 + (q1 - p1), (int)(W.pp1[j + 1] - q1), slop);
+            const float f = sloppy_freq_distinct(A + (q0 - p0), (int)(W.pp0[i + 1] - q0),
+                                                 B + (q1 - p1), (int)(W.pp1[j + 1] - q1), slop);
             if (f != 0.0f) on_match(d, f);
         }
     }
@@ -731,7 +741,7 @@ __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_w
             const ClauseStageW st = stage[ci];
             const u32 n0 = st.b0 - st.a0, n1 = st.b1 - st.a1;
             bool staged = false;
-            if (stage_ok && st.slop > 0 && n0 && n1 && st.m0 <= (u32)pcap && st.m1 <= (u32)pcap) {   // (n0, n1 <= docs <= dcap)
+            if (stage_ok && st.slop > 0 && n0 && n1 && st.m0 + 3 <= (u32)pcap && st.m1 + 3 <= (u32)pcap) {   // (n0, n1 <= docs <= dcap)
                 phrase_matches_staged(s, W, st.a0, n0, st.p0, st.m0, st.a1, n1, st.p1, st.m1, st.slop, lane, [&](u32 d, float f) {
                     const float sc = clause_doc_score(sp.sim, sp.sim == SIM_TFIDF ? tf_of(f) : f, st.val, dw[d], sp.k1p1);
                     acc[d] += (double)sc;                                            // BooleanScorer: double sum

@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) gap_fill_kernel(const SegDev* __restrict_
     const u32 n0 = b0 - a0, n1 = b1 - a1;
     if (!same && n0 && n1 && dcap > 0 && s.n_docs <= (u32)dcap) {
         const u32 p0 = s.post_pos[a0], m0 = s.post_pos[b0] - p0, p1 = s.post_pos[a1], m1 = s.post_pos[b1] - p1;
-        if (m0 <= (u32)pcap && m1 <= (u32)pcap) {
+        if (m0 + 3 <= (u32)pcap && m1 + 3 <= (u32)pcap) {
             const PhraseStage W = phrase_stage_at(gf_raw + (size_t)warp * phrase_stage_bytes(dcap, pcap), dcap, pcap);
             for (u32 d = lane; d < (u32)dcap; d += 32) { W.inv[d] = 0; W.hit[d] = 0; }
             __syncwarp();
@@ -371,10 +371,7 @@ __device__ __forceinline__ void pair_word(u32 word, const uint2 lut, u32& w0, u3
 }
 
 // cp.async (LDGSTS) 16-byte copy global -> shared, bypassing L1; one commit group per table row
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    const u32 sa = (u32)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
+// (cp_async16 lives in classify.cuh)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
