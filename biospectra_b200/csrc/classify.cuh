@@ -594,15 +594,15 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
 // per-warp staging buffers of one phrase clause
 struct PhraseStage { u32 *pos0, *pos1, *doc0, *doc1, *pp0, *pp1; u8 *inv, *hit; };
 __host__ __device__ inline size_t phrase_stage_bytes(int dcap, int pcap) {
-    return (size_t)pcap * 8 + (size_t)dcap * 8 + (size_t)(dcap + 4) * 8 + (size_t)dcap * 2;
+    return (size_t)pcap * 8 + (size_t)(dcap + 4) * 8 + (size_t)(dcap + 4) * 8 + (size_t)dcap * 2;
 }
 __device__ __forceinline__ PhraseStage phrase_stage_at(u8* base /* 4-byte aligned */, int dcap, int pcap) {
     PhraseStage W;
     W.pos0 = reinterpret_cast<u32*>(base);
     W.pos1 = W.pos0 + pcap;
     W.doc0 = W.pos1 + pcap;
-    W.doc1 = W.doc0 + dcap;
-    W.pp0 = W.doc1 + dcap;
+    W.doc1 = W.doc0 + dcap + 4;
+    W.pp0 = W.doc1 + dcap + 4;
     W.pp1 = W.pp0 + dcap + 4;
     W.inv = reinterpret_cast<u8*>(W.pp1 + dcap + 4);
     W.hit = W.inv + dcap;
@@ -617,15 +617,19 @@ __device__ __forceinline__ PhraseStage phrase_stage_at(u8* base /* 4-byte aligne
 template <typename F>
 __device__ __forceinline__ void phrase_matches_staged(const SegDev& s, const PhraseStage& W, u32 a0, u32 n0, u32 p0, u32 m0,
                                                       u32 a1, u32 n1, u32 p1, u32 m1, int slop, int lane, F&& on_match) {
-    // one batch of asynchronous 4-byte copies (LDGSTS) for the whole clause: one memory round trip
-    for (u32 i = lane; i <= n0; i += 32) {
-        if (i < n0) cp_async4(W.doc0 + i, s.post_doc + a0 + i);
-        cp_async4(W.pp0 + i, s.post_pos + a0 + i);
+    // one batch of asynchronous 16-byte copies (LDGSTS) for the whole clause: one memory round trip.  Every slice is
+    // copied from its enclosing 16-byte aligned range, so it starts up to 3 elements into its buffer.
+    const u32 s0 = a0 & 3u, s1 = a1 & 3u;
+    for (u32 i = 4u * (u32)lane; i < n0 + 1 + s0; i += 128) {
+        cp_async16(W.doc0 + i, s.post_doc + (a0 - s0) + i);
+        cp_async16(W.pp0 + i, s.post_pos + (a0 - s0) + i);
     }
-    for (u32 i = lane; i <= n1; i += 32) {
-        if (i < n1) cp_async4(W.doc1 + i, s.post_doc + a1 + i);
-        cp_async4(W.pp1 + i, s.post_pos + a1 + i);
+    for (u32 i = 4u * (u32)lane; i < n1 + 1 + s1; i += 128) {
+        cp_async16(W.doc1 + i, s.post_doc + (a1 - s1) + i);
+        cp_async16(W.pp1 + i, s.post_pos + (a1 - s1) + i);
     }
+    const u32* doc0 = W.doc0 + s0; const u32* pp0 = W.pp0 + s0;
+    const u32* doc1 = W.doc1 + s1; const u32* pp1 = W.pp1 + s1;
     const u32 o0 = p0 & 3u, o1 = p1 & 3u;
     for (u32 i = 4u * (u32)lane; i < m0 + o0; i += 128) cp_async16(W.pos0 + i, s.positions + (p0 - o0) + i);
     for (u32 i = 4u * (u32)lane; i < m1 + o1; i += 128) cp_async16(W.pos1 + i, s.positions + (p1 - o1) + i);
@@ -633,7 +637,7 @@ __device__ __forceinline__ void phrase_matches_staged(const SegDev& s, const Phr
     const u32* B = W.pos1 + o1;
     cp_async_commit_wait_all();
     __syncwarp();
-    for (u32 i = lane; i < n1; i += 32) W.inv[W.doc1[i]] = (u8)i;
+    for (u32 i = lane; i < n1; i += 32) W.inv[doc1[i]] = (u8)i;
     __syncwarp();
     // ---- close pairs: lane takes positions [ia, ia1) of the first term
     const u32 ca = (m0 + 31) >> 5;
@@ -655,7 +659,7 @@ __device__ __forceinline__ void phrase_matches_staged(const SegDev& s, const Phr
                 u32 l = 0, h2 = n0;                                          // last posting with pp <= target
                 while (h2 - l > 1) {
                     const u32 mid = (l + h2) >> 1;
-                    if (W.pp0[mid] <= target) l = mid; else h2 = mid;
+                    if (pp0[mid] <= target) l = mid; else h2 = mid;
                 }
                 W.hit[l] = 1;
                 ia++;
@@ -667,12 +671,12 @@ __device__ __forceinline__ void phrase_matches_staged(const SegDev& s, const Phr
     for (u32 i = lane; i < n0; i += 32) {
         if (!W.hit[i]) continue;
         W.hit[i] = 0;
-        const u32 d = W.doc0[i];
+        const u32 d = doc0[i];
         const u32 j = W.inv[d];                                              // verified: may be a stale entry
-        if (j < n1 && W.doc1[j] == d) {
-            const u32 q0 = W.pp0[i], q1 = W.pp1[j];
-            const float f = sloppy_freq_distinct(A + (q0 - p0), (int)(W.pp0[i + 1] - q0),
-                                                 B + (q1 - p1), (int)(W.pp1[j + 1] - q1), slop);
+        if (j < n1 && doc1[j] == d) {
+            const u32 q0 = pp0[i], q1 = pp1[j];
+            const float f = sloppy_freq_distinct(A + (q0 - p0), (int)(pp0[i + 1] - q0),
+                                                 B + (q1 - p1), (int)(pp1[j + 1] - q1), slop);
             if (f != 0.0f) on_match(d, f);
         }
     }
