@@ -700,10 +700,19 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
     });
 
     std::exception_ptr gpu_error;
+    int64_t gpu_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double gpu_score_ms = 0, gpu_pipe_ms = 0, gpu_wall_ms = 0;
+    long long gpu_batches = 0;
     try {
         BatchPtr b;
         while (parsed.pop(b)) {
+            const auto t0 = std::chrono::steady_clock::now();
             classifier_.classifyPacked(b->seqs.data(), b->soff.data(), (int32_t)b->size(), b->res);
+            gpu_wall_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            int64_t c[8]; double sm = 0, pm = 0;
+            if (bsp_last_counters(classifier_.handle(), c) == BSP_OK) for (int i = 0; i < 8; i++) gpu_counters[i] += c[i];
+            if (bsp_last_timings(classifier_.handle(), &sm, &pm) == BSP_OK) { gpu_score_ms += sm; gpu_pipe_ms += pm; }
+            gpu_batches++;
             classified.push(std::move(b));
         }
     } catch (...) {
@@ -728,6 +737,20 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
         fclose(fs);
     }
     lastSummary_ = summary;
+    // GPU-side counters next to the reference's files (not a reference output; SURVEY.md section 5 "metrics")
+    {
+        FILE* fm = fopen((classifyOutput + ".gpu_metrics.json").c_str(), "wb");
+        if (fm) {
+            fprintf(fm, "{\"reads\":%lld,\"gpu_batches\":%lld,\"reads_filter_kernel\":%lld,\"reads_exact_dense_kernel\":%lld,"
+                        "\"reads_positional_kernel\":%lld,\"reads_handed_over_by_filter\":%lld,\"docs_rescored_exactly\":%lld,"
+                        "\"exception_cells\":%lld,\"kernel_launches\":%lld,\"score_kernel_ms\":%.3f,\"device_pipeline_ms\":%.3f,"
+                        "\"classify_call_wall_ms\":%.3f,\"file_to_file_ms\":%lld}\n",
+                    (long long)gpu_counters[0], gpu_batches, (long long)gpu_counters[3], (long long)gpu_counters[1],
+                    (long long)gpu_counters[2], (long long)gpu_counters[7], (long long)gpu_counters[5], (long long)gpu_counters[6],
+                    (long long)gpu_counters[4], gpu_score_ms, gpu_pipe_ms, gpu_wall_ms, summary.endTime - summary.startTime);
+            fclose(fm);
+        }
+    }
 }
 
 // The reference's LocalClassifier.classify as written (LocalClassifier.java:88-120): the calling thread reads FASTA
