@@ -84,3 +84,28 @@ def test_parity_corpus_and_script_without_jvm(tmp_path):
         p = subprocess.run(["bash", os.path.join(ROOT, "tools", "ref_lucene_run.sh"), "/nonexistent", str(tmp_path / "x")],
                            capture_output=True, text=True)
         assert p.returncode == 3 and "unpinned" in p.stderr
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_parity_corpus_through_the_cli_and_comparator(tmp_path):
+    """Steps 4-5 of tools/ref_lucene_run.sh (this library's side): the CLI indexes and classifies the parity corpus, the
+    comparator reads its .result file (compared with itself: full agreement), and the corpus produces both CLASSIFIED
+    and VAGUE reads so that a run against the real reference exercises the tie handling."""
+    w = tmp_path / "w"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "make_parity_corpus.py"), str(w), "--genomes", "8",
+                           "--genome-bp", "60000", "--reads", "600"], stdout=subprocess.DEVNULL)
+    cli = os.path.join(ROOT, "biospectra_b200", "biospectra_gpu")
+    subprocess.check_call([cli, "index", "-j", str(w / "conf_gpu.json"), "-r", str(w / "ref")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.check_call([cli, "lclassify", "-j", str(w / "conf_gpu.json"), "-in", str(w / "reads"), "-out", str(w / "out_gpu")],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    res = w / "out_gpu" / "sample.fa.result"
+    got = cr.load(str(res))
+    assert len(got) == 600
+    types = {d["type"] for d in got.values()}
+    assert "CLASSIFIED" in types and "VAGUE" in types, types
+    assert any(d["type"] == "CLASSIFIED" and len(d["result"]) >= 2 and d["taxon_rank"] == "species" for d in got.values())
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "compare_results.py"), str(res), str(res)], capture_output=True, text=True)
+    assert p.returncode == 0 and json.loads(p.stdout.splitlines()[0])["agreement"] == 1.0

@@ -30,14 +30,21 @@ def main():
     for d in (ref, reads_dir):
         os.makedirs(d, exist_ok=True)
     genomes = [synth.genome_numpy(1, g, a.genome_bp) for g in range(a.genomes)]
-    # related strains: every third genome is a 98 % identity copy of its predecessor, so that ties and VAGUE labels occur
+    # related strains, 99.9 % identical (most 100 bp windows are shared, so their reads tie exactly): every third genome
+    # copies its predecessor (same species: the tie classifies at the species through the common-taxon rule), and the
+    # last genome copies genome 0 (another genus once there are more than 6 genomes: nothing ranked in common -> VAGUE)
     import numpy as np
     rng = np.random.default_rng(7)
-    for g in range(2, a.genomes, 3):
-        s = genomes[g - 1].copy()
-        pos = rng.choice(len(s), len(s) // 50, replace=False)
+
+    def near_copy(src):
+        s = src.copy()
+        pos = rng.choice(len(s), max(1, len(s) // 1000), replace=False)
         s[pos] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, len(pos))]
-        genomes[g] = s
+        return s
+    for g in range(2, a.genomes - 1, 3):
+        genomes[g] = near_copy(genomes[g - 1])
+    if a.genomes > 1:
+        genomes[a.genomes - 1] = near_copy(genomes[0])
     for g, seq in enumerate(genomes):
         with open(os.path.join(ref, "%02d.fna" % g), "wb") as f:
             f.write(b">syn|%d| synthetic genome %d\n" % (g, g))
