@@ -323,6 +323,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skips", type=int, default=0, help="kmer_skips of the query side (shipped configuration.json: 0; code default: 5)")
     ap.add_argument("--reads", type=int, default=0, help="override the number of reads per GPU")
+    ap.add_argument("--read-len", type=int, default=0, help="override the mean read length (BASELINE configs[4] sweep: 100-250)")
+    ap.add_argument("--err", type=float, default=-1.0, help="override the substitution rate (configs[4] sweep: 0-0.08)")
     ap.add_argument("--mode", default="replica", choices=["replica", "docpart"],
                     help="replica: read-sharded index replicas (default, no collective); docpart: doc-partitioned index")
     ap.add_argument("--verify", action="store_true", help="docpart: compare with a single-index run on rank 0")
@@ -332,6 +334,10 @@ def main():
     wl = dict(WORKLOADS[args.workload])
     if args.reads:
         wl["reads"] = args.reads
+    if args.read_len:
+        wl["R"] = args.read_len
+    if args.err >= 0:
+        wl["err"] = args.err
     from biospectra_b200 import synth
     lengths = synth.genome_lengths(wl["genomes"], wl["total_bp"], wl["seed"], *((1, 1) if wl.get("equal") else (1.5e6, 6.5e6)))
     if args.impl == "reference":
