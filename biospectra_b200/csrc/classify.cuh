@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
 //
 // Which docs can match at all?  Every matchLength the SloppyPhraseScorer sweep tests is |(b - 1) - a| of an actual
 // pair (a in A, b in B), so freq = 0 unless some pair is within the slop.  Positions are segment ordinals
-// (mark_heads_kernel), hence both staged slices ascend across docs and ONE scan per clause finds all close pairs: each
+// (index_build.cuh), hence both staged slices ascend across docs and ONE scan per clause finds all close pairs: each
 // lane takes a contiguous chunk of the first term's positions and walks the second term's from a binary-searched start.
 // No false negatives; a pair straddling two docs is a false positive the exact sweep discards.
 #define PW_POS 384               // 2^28 tokens / 4^10 terms = 256 on average

@@ -253,14 +253,19 @@ static thread_local BuildPhases g_phases;
 template <typename K>
 static void build_segment(GpuIndex& ix, Segment& seg, const EntryDev* d_entries, const u32* d_chunk_entry,
                           const u64* d_chunk_base, u32 c0, u32 c1, DevBuf<u8>& kbuf_a, DevBuf<u8>& kbuf_b,
-                          DevBuf<u32>& vbuf_a, DevBuf<u32>& vbuf_b, DevBuf<u64>& flags, RadixSortTemp& rst,
-                          DevBuf<u8>& scan_tmp, DevBuf<u64>& d_total, DevBuf<u64>& scanned_buf, cudaStream_t st) {
+                          DevBuf<u32>& vbuf_a, DevBuf<u64>& flags, RadixSortTemp& rst,
+                          DevBuf<u8>& scan_tmp, DevBuf<u64>& d_total, cudaStream_t st) {
     const u32 n = seg.n_tok;
     RefStore& ref = *ix.ref;
     kbuf_a.ensure((size_t)n * sizeof(K)); kbuf_b.ensure((size_t)n * sizeof(K));
-    vbuf_a.ensure(n); vbuf_b.ensure(n);
+    vbuf_a.ensure(n);
     K* keys = (K*)kbuf_a.p; K* keys_alt = (K*)kbuf_b.p;
-    u32* vals = vbuf_a.p; u32* vals_alt = vbuf_b.p;
+    // The sorted ordinals are the segment's positions array: the sort ping-pongs between a scratch buffer and the array
+    // itself, arranged so that the last pass lands in the array.
+    seg.positions.adopt((u32*)ix.arena.take((size_t)std::max<u32>(n, 1) * 4), n);
+    const int sort_passes = (2 * ix.k + 7) / 8;
+    u32* vals = (sort_passes & 1) ? vbuf_a.p : seg.positions.p;
+    u32* vals_alt = (sort_passes & 1) ? seg.positions.p : vbuf_a.p;
     g_phases.start(st);
     if (c1 > c0) {
         extract_kernel<K><<<c1 - c0, CHUNK_THREADS, 0, st>>>(ref.packed.p, ref.mask.p, d_entries, d_chunk_entry, d_chunk_base,
@@ -270,19 +275,17 @@ static void build_segment(GpuIndex& ix, Segment& seg, const EntryDev* d_entries,
     g_phases.tick(0, st);
     radix_sort_pairs<K>(&keys, &vals, &keys_alt, &vals_alt, n, 2 * ix.k, rst, st);
     g_phases.tick(1, st);
-    // CSR
-    seg.positions.adopt((u32*)ix.arena.take((size_t)std::max<u32>(n, 1) * 4), n);
-    flags.ensure((size_t)n + 1);
+    // CSR, pass 1: how many postings / terms start in every tile of the sorted tuples
+    if (n && vals != seg.positions.p) throw BspError(-3, "radix sort ended in the scratch buffer");
+    const u32 csr_tiles = (u32)ceil_div(n, CSR_TILE);
+    flags.ensure((size_t)2 * csr_tiles + 2);              // tile counts | their exclusive scan
+    u64* tile_counts = flags.p;
+    u64* tile_offs = flags.p + csr_tiles + 1;
     if (n) {
-        mark_heads_kernel<K><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(keys, vals, n, seg.doc_tok.p, seg.n_docs,
-                                                                         seg.positions.p, vals_alt, flags.p);
+        csr_count_kernel<K><<<csr_tiles, 256, 0, st>>>(keys, vals, n, seg.doc_tok.p, seg.n_docs, tile_counts);
         KERNEL_CHECK();
     }
-    // scanned flags go to the alternate key buffer when it is wide enough, else a fresh one
-    u64* scanned;
-    if (sizeof(K) == 8) scanned = (u64*)keys_alt;
-    else { scanned_buf.ensure((size_t)n + 1); scanned = scanned_buf.p; }      // kept across segments (2 GB at 2^28 tokens)
-    exclusive_scan<u64, u64>(flags.p, scanned, n, d_total.p, scan_tmp, st);
+    exclusive_scan<u64, u64>(tile_counts, tile_offs, csr_tiles, d_total.p, scan_tmp, st);
     u64 tot = 0;
     CUDA_CHECK(cudaMemcpyAsync(&tot, d_total.p, 8, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
@@ -302,8 +305,8 @@ static void build_segment(GpuIndex& ix, Segment& seg, const EntryDev* d_entries,
         if (ix.direct) seg.direct.adopt((u32*)q, (size_t)1 << (2 * ix.k));
     }
     if (n) {
-        write_csr_kernel<K><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(keys, vals_alt, n, flags.p, scanned, seg.term_key.p,
-                                                                        seg.term_off.p, seg.post_doc.p, seg.post_pos.p);
+        csr_write_kernel<K><<<csr_tiles, 256, 0, st>>>(keys, vals, n, seg.doc_tok.p, seg.n_docs, tile_offs, seg.term_key.p,
+                                                       seg.term_off.p, seg.post_doc.p, seg.post_pos.p);
         KERNEL_CHECK();
     }
     set_u32_kernel<<<1, 1, 0, st>>>(seg.term_off.p + seg.n_terms, seg.n_post);
@@ -497,7 +500,7 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
     CUDA_CHECK(cudaMemcpyAsync(d_entries.p, h_entries.data(), (nE + 1) * sizeof(EntryDev), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     // ---- per segment: extract -> sort -> CSR -> dictionary -> (tables) -> (drop)
-    DevBuf<u8> kbuf_a, kbuf_b; DevBuf<u32> vbuf_a, vbuf_b; DevBuf<u64> flags, scanned_buf; RadixSortTemp rst;
+    DevBuf<u8> kbuf_a, kbuf_b; DevBuf<u32> vbuf_a; DevBuf<u64> flags; RadixSortTemp rst;
     DevBuf<unsigned long long> d_counter; d_counter.alloc(1);
     CUDA_CHECK(cudaMemsetAsync(d_counter.p, 0, 8, st));
     i64 postings = 0;
@@ -509,11 +512,11 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
         u32 c0 = h_entries[seg.first_entry].first_chunk, c1 = h_entries[seg.first_entry + seg.n_entries].first_chunk;
         try {
             if (2 * k <= 32)
-                build_segment<u32>(ix, seg, d_entries.p, d_chunk_entry.p, d_chunk_base.p, c0, c1, kbuf_a, kbuf_b, vbuf_a, vbuf_b,
-                                   flags, rst, scan_tmp, d_total, scanned_buf, st);
+                build_segment<u32>(ix, seg, d_entries.p, d_chunk_entry.p, d_chunk_base.p, c0, c1, kbuf_a, kbuf_b, vbuf_a,
+                                   flags, rst, scan_tmp, d_total, st);
             else
-                build_segment<u64>(ix, seg, d_entries.p, d_chunk_entry.p, d_chunk_base.p, c0, c1, kbuf_a, kbuf_b, vbuf_a, vbuf_b,
-                                   flags, rst, scan_tmp, d_total, scanned_buf, st);
+                build_segment<u64>(ix, seg, d_entries.p, d_chunk_entry.p, d_chunk_base.p, c0, c1, kbuf_a, kbuf_b, vbuf_a,
+                                   flags, rst, scan_tmp, d_total, st);
         } catch (const BspError& e) {
             // out of device memory with the positional index resident: give it up (the dense tables stay complete for
             // the segments already processed) and redo this segment

@@ -153,50 +153,77 @@ __device__ __forceinline__ u32 find_doc(const u32* __restrict__ doc_tok, u32 n_d
     return lo;
 }
 
-// positions[i] = token ordinal within the SEGMENT (= doc_tok[doc] + Lucene's position); docs[i] = local doc;
-// flags[i] = head_post | head_term<<32.  Every consumer of positions is a sloppy sweep over two lists of the same doc,
-// which only looks at differences, so the per-doc offset is never subtracted on the device (bsp_term_postings does it
-// for the tests); keeping the segment ordinal makes a term's position slice ascending across docs, which is what lets
-// the warp scorer look for close (t0, t1) pairs with one balanced scan per clause.
+// ---- sorted (term, segment ordinal) tuples -> CSR, two passes over the tuples and no per-token scratch.
+// The sorted ordinals ARE the positions array: positions[i] = token ordinal within the SEGMENT (= doc_tok[doc] +
+// Lucene's position).  Every consumer of positions is a sloppy sweep over two lists of the same doc, which only looks at
+// differences, so the per-doc offset is never subtracted on the device (bsp_term_postings does it for the tests);
+// keeping the segment ordinal makes a term's position slice ascending across docs, which is what lets the warp scorer
+// look for close (t0, t1) pairs with one balanced scan per clause.
+// Tuple i starts a posting when its (term, doc) differs from tuple i-1's, and a term when its term does.
+#define CSR_ROUNDS 8
+#define CSR_TILE (256 * CSR_ROUNDS)
 template <typename K>
-__global__ void __launch_bounds__(256) mark_heads_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, u32 n,
-                                                          const u32* __restrict__ doc_tok, u32 n_docs,
-                                                          u32* __restrict__ positions, u32* __restrict__ docs,
-                                                          u64* __restrict__ flags) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    u32 ord = vals[i];
-    u32 d = find_doc(doc_tok, n_docs, ord);
-    positions[i] = ord;
-    docs[i] = d;
-    u64 f = 0;
-    if (i == 0) f = 1ull | (1ull << 32);
-    else {
-        bool nk = keys[i] != keys[i - 1];
-        u32 dp = find_doc(doc_tok, n_docs, vals[i - 1]);
-        if (nk) f = 1ull | (1ull << 32);
-        else if (dp != d) f = 1ull;
-    }
-    flags[i] = f;
+__device__ __forceinline__ void csr_heads(const K* __restrict__ keys, const u32* __restrict__ vals, u32 i,
+                                          const u32* __restrict__ doc_tok, u32 n_docs, u32& doc, bool& head_post, bool& head_term) {
+    doc = find_doc(doc_tok, n_docs, vals[i]);
+    if (i == 0) { head_post = head_term = true; return; }
+    head_term = keys[i] != keys[i - 1];
+    head_post = head_term || find_doc(doc_tok, n_docs, vals[i - 1]) != doc;
 }
-
+// pass 1: postings | terms << 32 that start in every tile
 template <typename K>
-__global__ void __launch_bounds__(256) write_csr_kernel(const K* __restrict__ keys, const u32* __restrict__ docs, u32 n,
-                                                         const u64* __restrict__ flags, const u64* __restrict__ scanned,
+__global__ void __launch_bounds__(256) csr_count_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, u32 n,
+                                                         const u32* __restrict__ doc_tok, u32 n_docs, u64* __restrict__ tile_counts) {
+    __shared__ u32 s_cnt[2];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 base = blockIdx.x * CSR_TILE;
+    u32 np = 0, nt = 0;
+#pragma unroll
+    for (int j = 0; j < CSR_ROUNDS; j++) {
+        const u32 i = base + j * 256 + threadIdx.x;
+        if (i < n) {
+            u32 d; bool hp, ht;
+            csr_heads<K>(keys, vals, i, doc_tok, n_docs, d, hp, ht);
+            np += hp ? 1u : 0u; nt += ht ? 1u : 0u;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { np += __shfl_xor_sync(0xFFFFFFFFu, np, o); nt += __shfl_xor_sync(0xFFFFFFFFu, nt, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_cnt[0], np); atomicAdd(&s_cnt[1], nt); }
+    __syncthreads();
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = (u64)s_cnt[0] | ((u64)s_cnt[1] << 32);
+}
+// pass 2: with the exclusive scan of the tile counts, every head writes its posting (doc, first position) / term
+template <typename K>
+__global__ void __launch_bounds__(256) csr_write_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, u32 n,
+                                                         const u32* __restrict__ doc_tok, u32 n_docs, const u64* __restrict__ tile_offs,
                                                          u64* __restrict__ term_key, u32* __restrict__ term_off,
                                                          u32* __restrict__ post_doc, u32* __restrict__ post_pos) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    u64 f = flags[i];
-    if (f == 0) return;
-    u64 s = scanned[i];
-    u32 pi = (u32)(s & 0xFFFFFFFFu);
-    post_doc[pi] = docs[i];
-    post_pos[pi] = i;
-    if (f >> 32) {
-        u32 ti = (u32)(s >> 32);
-        term_key[ti] = (u64)keys[i];
-        term_off[ti] = pi;
+    __shared__ u32 sm[33];
+    const u64 off = tile_offs[blockIdx.x];
+    u32 pbase = (u32)(off & 0xFFFFFFFFu), tbase = (u32)(off >> 32);
+    const u32 base = blockIdx.x * CSR_TILE;
+#pragma unroll 1
+    for (int j = 0; j < CSR_ROUNDS; j++) {
+        const u32 i = base + j * 256 + threadIdx.x;
+        u32 d = 0; bool hp = false, ht = false;
+        if (i < n) csr_heads<K>(keys, vals, i, doc_tok, n_docs, d, hp, ht);
+        const u32 v = (hp ? 1u : 0u) | (ht ? 0x10000u : 0u);                  // at most 256 of each per round
+        u32 tot;
+        const u32 ex = block_exclusive_scan<u32>(v, &tot, sm);
+        if (hp) {
+            const u32 pi = pbase + (ex & 0xFFFFu);
+            post_doc[pi] = d;
+            post_pos[pi] = i;
+            if (ht) {
+                const u32 ti = tbase + (ex >> 16);
+                term_key[ti] = (u64)keys[i];
+                term_off[ti] = pi;
+            }
+        }
+        pbase += tot & 0xFFFFu;
+        tbase += tot >> 16;
     }
 }
 
