@@ -346,10 +346,6 @@ __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 c) {
 }
 
 // build-time variants of the filter kernel
-#ifndef FK_UNROLL
-#define FK_UNROLL 2                // rows per iteration of the streaming loop (2, 4 or 8; measured at C2: 38.3 / 41.2 / 45.6 ms --
-                                   // the larger bodies lose more to instruction fetch than they save in address arithmetic)
-#endif
 #ifndef FK_MAXT
 #define FK_MAXT 512                // largest CTA of the filter kernel
 #endif
@@ -376,26 +372,47 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// shared-window forms of the ring accesses (32-bit shared addresses: no generic-to-shared conversion in the loop)
+__device__ __forceinline__ void cp_async16_sa(u32 sa, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(u32 sa) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa) : "memory");
+    return v;
+}
+
 // acc += x on the FMA pipe (IMAD x*1+acc): PRMT/SHF/IADD3 all issue on the ALU pipe, which runs at half the
 // warp-issue rate, so the lane adds are moved to the otherwise idle pipe
 // (`one` is a kernel argument equal to 1: with a literal 1 ptxas folds the multiply back into IADD3)
 __device__ __forceinline__ void add_fma_pipe(u32& acc, u32 x, u32 one) {
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(x), "r"(one));
 }
-// two rows at once
+// Two rows at once, weights kept in a packed form that needs one PRMT per four docs instead of two: with p = the four
+// LUT bytes (b3 b2 b1 b0) of docs 4j..4j+3 read as one integer,
+//   x += p                      -> B0 + 2^8 B1 + 2^16 B2 + 2^24 B3  (mod 2^32),  Bi = the doc's running sum
+//   y += (b3 << 16) | b1        -> (B3 << 16) | B1                  (exact while the sums stay below 2^16)
+// and after the loop x - (y << 8) = (B2 << 16) | B0 (mod 2^32, exact for the same reason): unpack_xy turns the pair
+// back into the u16 lanes of the single-row path.
 // (cnt_lo = 0x01010100 arrives in a register computed from a kernel argument: as a literal, ptxas re-materialises it
 // with a move in front of every count PRMT)
-__device__ __forceinline__ void pair_word2(u32 wa, u32 wb, const uint2 la, const uint2 lb, u32& w0, u32& w1, u32& w2, u32& w3,
+__device__ __forceinline__ void pair_word2(u32 wa, u32 wb, const uint2 la, const uint2 lb, u32& x0, u32& y0, u32& x1, u32& y1,
                                            u32& c0, u32& c1, u32 one, u32 cnt_lo) {
     const u32 ha = wa >> 16, hb = wb >> 16;
     const u32 a0 = prmt(la.x, la.y, wa), a1 = prmt(la.x, la.y, ha);
     const u32 b0 = prmt(lb.x, lb.y, wb), b1 = prmt(lb.x, lb.y, hb);
-    add_fma_pipe(w0, prmt(a0, 0u, 0x4140u), one); add_fma_pipe(w0, prmt(b0, 0u, 0x4140u), one);
-    add_fma_pipe(w1, prmt(a0, 0u, 0x4342u), one); add_fma_pipe(w1, prmt(b0, 0u, 0x4342u), one);
-    add_fma_pipe(w2, prmt(a1, 0u, 0x4140u), one); add_fma_pipe(w2, prmt(b1, 0u, 0x4140u), one);
-    add_fma_pipe(w3, prmt(a1, 0u, 0x4342u), one); add_fma_pipe(w3, prmt(b1, 0u, 0x4342u), one);
+    add_fma_pipe(x0, a0, one); add_fma_pipe(x0, b0, one);
+    add_fma_pipe(y0, prmt(a0, 0u, 0x4341u), one); add_fma_pipe(y0, prmt(b0, 0u, 0x4341u), one);
+    add_fma_pipe(x1, a1, one); add_fma_pipe(x1, b1, one);
+    add_fma_pipe(y1, prmt(a1, 0u, 0x4341u), one); add_fma_pipe(y1, prmt(b1, 0u, 0x4341u), one);
     add_fma_pipe(c0, prmt(cnt_lo, 0x01010101u, wa), one); add_fma_pipe(c0, prmt(cnt_lo, 0x01010101u, wb), one);
     add_fma_pipe(c1, prmt(cnt_lo, 0x01010101u, ha), one); add_fma_pipe(c1, prmt(cnt_lo, 0x01010101u, hb), one);
+}
+// packed (x, y) of docs 4j..4j+3 -> u16 lanes (doc 4j, 4j+1) and (doc 4j+2, 4j+3)
+__device__ __forceinline__ void unpack_xy(u32 x, u32 y, u32& w0, u32& w1) {
+    const u32 e = x - (y << 8);                        // (B2 << 16) | B0
+    w0 = prmt(e, y, 0x5410u);                          // (B1 << 16) | B0
+    w1 = prmt(e, y, 0x7632u);                          // (B3 << 16) | B2
 }
 
 // Term rows hold codes 0..14: a 16-entry LUT out of two 8-entry PRMT lookups.  PRMT reads bit 3 of a selector nibble as
@@ -410,17 +427,17 @@ __device__ __forceinline__ u32 lut16(const uint4 t, u32 sel /* 4 codes in the lo
 // 1 per non-zero code.  Looked up in the bytes {0x80, 0x81 x 7}: code 0 -> 0x80, 1..7 -> 0x81, 8 -> sign of 0x80 = 0xFF,
 // 9..15 -> sign of 0x81 = 0xFF: bit 0 is the flag.
 __device__ __forceinline__ u32 cnt16(u32 sel) { return prmt(0x81818180u, 0x81818181u, sel) & 0x01010101u; }
-// one u32 (8 docs) of each of two term rows
-__device__ __forceinline__ void term_word2(u32 wa, u32 wb, const uint4 ta, const uint4 tb, u32& w0, u32& w1, u32& w2, u32& w3,
+// one u32 (8 docs) of each of two term rows, into the packed (x, y) lanes of pair_word2
+__device__ __forceinline__ void term_word2(u32 wa, u32 wb, const uint4 ta, const uint4 tb, u32& x0, u32& y0, u32& x1, u32& y1,
                                            u32& c0, u32& c1, u32 one) {
     const u32 ha = wa >> 16, hb = wb >> 16;
     u32 s0 = lut16(ta, wa, one), s1 = lut16(ta, ha, one);
     add_fma_pipe(s0, lut16(tb, wb, one), one);        // weights <= 127: the two rows' bytes add without carry
     add_fma_pipe(s1, lut16(tb, hb, one), one);
-    add_fma_pipe(w0, prmt(s0, 0u, 0x4140u), one);
-    add_fma_pipe(w1, prmt(s0, 0u, 0x4342u), one);
-    add_fma_pipe(w2, prmt(s1, 0u, 0x4140u), one);
-    add_fma_pipe(w3, prmt(s1, 0u, 0x4342u), one);
+    add_fma_pipe(x0, s0, one);
+    add_fma_pipe(y0, prmt(s0, 0u, 0x4341u), one);
+    add_fma_pipe(x1, s1, one);
+    add_fma_pipe(y1, prmt(s1, 0u, 0x4341u), one);
     add_fma_pipe(c0, cnt16(wa), one); add_fma_pipe(c0, cnt16(wb), one);
     add_fma_pipe(c1, cnt16(ha), one); add_fma_pipe(c1, cnt16(hb), one);
 }
@@ -513,7 +530,9 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
         i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score, i32* __restrict__ route,
         i32* __restrict__ overflow_list, i32* __restrict__ overflow_count, FilterStats* __restrict__ stats, int full_topn,
         u32 one /* = 1, see add_fma_pipe */, int n_tiles /* doc tiles of blockDim.x * 32 docs; CTA per (tile, read) */) {
-    __shared__ uint2 s_lut[FK_MAX_CLAUSES + 1];          // q for codes 0..3 | 4..7
+    // per clause: q for codes 0..3 | 4..7, and in .z the table offset of the row FK_STAGES clauses further on (the row the
+    // streaming loop prefetches while it works on this one): one 16-byte shared load per row
+    __shared__ __align__(16) uint4 s_lo[FK_MAX_CLAUSES + 1];
     __shared__ uint2 s_lut_hi[ALLTERMS ? FK_MAX_CLAUSES + 1 : 1];       // term rows (NAIVE_KMER): q for codes 8..11 | 12..15
     __shared__ u32 s_row[FK_MAX_CLAUSES + 1];
     __shared__ u32 s_off[FK_MAX_CLAUSES + 1];           // row offset in the table, in 16-byte units (table < 64 GiB)
@@ -564,20 +583,24 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
         }
         s_val[c] = v;
         s_row[c] = row;
-        s_off[c] = row < T.temp_row0 ? row * (u32)(T.row_bytes >> 4) : 0u;
+        const u32 off16 = row < T.temp_row0 ? row * (u32)(T.row_bytes >> 4) : 0u;
+        s_off[c] = off16;
+        if (c >= FK_STAGES) s_lo[c - FK_STAGES].z = off16;
         const float sv = S * v;
         if (c0 < n_pair) {
             u32 q[8];
             q[0] = 0;
 #pragma unroll
             for (int j = 1; j < 8; j++) q[j] = min((u32)__float2int_rn(sv * tf16[j]), 255u);
-            s_lut[c] = make_uint2(q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24), q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24));
+            s_lo[c].x = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+            s_lo[c].y = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
         } else if (all_terms) {
             u32 q[16];
             q[0] = 0; q[15] = 0;
 #pragma unroll
             for (int j = 1; j < 15; j++) q[j] = min((u32)__float2int_rn(sv * tf16[j]), 127u);
-            s_lut[c] = make_uint2(q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24), q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24));
+            s_lo[c].x = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+            s_lo[c].y = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
             s_lut_hi[c] = make_uint2(q[8] | (q[9] << 8) | (q[10] << 16) | (q[11] << 24), q[12] | (q[13] << 8) | (q[14] << 16) | (q[15] << 24));
         }
         u32 a, ne;
@@ -601,64 +624,66 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     asm volatile("" : "+l"(tbase));          // keep the thread's table base in a register pair (one IMAD.WIDE per row address)
     if (active) {
         // Each thread prefetches its own 16-byte slice of the next FK_STAGES rows into its private slots of the
-        // ring (no cross-thread hand-off, so no barriers): FK_STAGES x 16 B in flight per thread.
+        // ring (no cross-thread hand-off, so no barriers): FK_STAGES x 16 B in flight per thread.  Slots are
+        // addressed in the shared window directly; one commit group per pair of rows.
         uint4* slot = ring + threadIdx.x;
         const u32 stride = blockDim.x;
+        const u32 slot_sa = (u32)__cvta_generic_to_shared(slot), stride_b = stride * 16u, ring_end = slot_sa + FK_STAGES * stride_b;
 #pragma unroll
         for (int st = 0; st < FK_STAGES; st++) {
-            if (st < n_stream) cp_async16(slot + st * stride, tbase + (u64)s_off[st] * 16);
-            cp_async_commit();
+            if (st < n_stream) cp_async16_sa(slot_sa + st * stride_b, tbase + (u64)s_off[st] * 16);
+            if (st & 1) cp_async_commit();
         }
         i32 i = 0;
         const i32 n_two = all_terms ? nc : n_dense;   // rows streamed two at a time through a byte LUT
         // count LUT low word, read from shared memory so that it lives in a vector register: as a literal (or a
         // uniform value) ptxas re-materialises it with a move in front of every count PRMT
         const u32 cnt_lo = s_cntlo;
-        // two rows per step: wait for them, pull them into registers, refill their slots with the rows FK_STAGES
-        // ahead, then the LUT arithmetic
-#define FK_STEP2(I)                                                                                                       \
-        {                                                                                                                 \
-            cp_async_wait<FK_STAGES - 2>();                                                                               \
-            uint4* my0 = slot + ((I) % FK_STAGES) * stride;                                                               \
-            uint4* my1 = slot + (((I) + 1) % FK_STAGES) * stride;                                                         \
-            const uint4 q0 = *my0, q1 = *my1;                                                                             \
-            const uint2 l0 = s_lut[(I)], l1 = s_lut[(I) + 1];                                                             \
-            if (all_terms) {                                                                                              \
-                const uint2 h0 = s_lut_hi[(I)], h1 = s_lut_hi[(I) + 1];                                                   \
-                const uint4 t0 = make_uint4(l0.x, l0.y, h0.x, h0.y), t1 = make_uint4(l1.x, l1.y, h1.x, h1.y);             \
-                term_word2(q0.x, q1.x, t0, t1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1], one);                \
-                term_word2(q0.y, q1.y, t0, t1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3], one);                \
-                term_word2(q0.z, q1.z, t0, t1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5], one);              \
-                term_word2(q0.w, q1.w, t0, t1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7], one);            \
-            } else {                                                                                                      \
-                pair_word2(q0.x, q1.x, l0, l1, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1], one, cnt_lo);        \
-                pair_word2(q0.y, q1.y, l0, l1, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3], one, cnt_lo);        \
-                pair_word2(q0.z, q1.z, l0, l1, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5], one, cnt_lo);      \
-                pair_word2(q0.w, q1.w, l0, l1, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7], one, cnt_lo);    \
-            }                                                                                                             \
-            if ((I) + FK_STAGES < n_stream) cp_async16(my0, tbase + (u64)s_off[(I) + FK_STAGES] * 16);                    \
-            cp_async_commit();                                                                                            \
-            if ((I) + 1 + FK_STAGES < n_stream) cp_async16(my1, tbase + (u64)s_off[(I) + 1 + FK_STAGES] * 16);            \
-            cp_async_commit();                                                                                            \
-        }
-#if FK_UNROLL > 2
-#pragma unroll 1
-        for (; i + FK_UNROLL <= n_two; i += FK_UNROLL) {
+        // Two rows per step: wait for them, pull them into registers, the LUT arithmetic into the packed (x, y) lanes
+        // (pair_word2), then refill their slots with the rows FK_STAGES ahead.  (Four or eight rows per iteration
+        // measured slower at C2: the larger bodies lose more to instruction fetch than they save in address arithmetic.)
+        u32 xacc[8], yacc[8];
 #pragma unroll
-            for (int u = 0; u < FK_UNROLL; u += 2) FK_STEP2(i + u)
-        }
-#endif
+        for (int j = 0; j < 8; j++) { xacc[j] = 0; yacc[j] = 0; }
+        u32 cur = slot_sa;                            // slot of row i; rows i and i + 1 sit one stage apart
 #pragma unroll 1
-        for (; i + 2 <= n_two; i += 2) FK_STEP2(i)
-#undef FK_STEP2
+        for (; i + 2 <= n_two; i += 2) {
+            cp_async_wait<FK_STAGES / 2 - 1>();
+            const u32 sa0 = cur, sa1 = cur + stride_b;
+            const uint4 q0 = lds128(sa0), q1 = lds128(sa1);
+            const uint4 l0 = s_lo[i], l1 = s_lo[i + 1];
+            if (all_terms) {
+                const uint2 h0 = s_lut_hi[i], h1 = s_lut_hi[i + 1];
+                const uint4 t0 = make_uint4(l0.x, l0.y, h0.x, h0.y), t1 = make_uint4(l1.x, l1.y, h1.x, h1.y);
+                term_word2(q0.x, q1.x, t0, t1, xacc[0], yacc[0], xacc[1], yacc[1], cacc[0], cacc[1], one);
+                term_word2(q0.y, q1.y, t0, t1, xacc[2], yacc[2], xacc[3], yacc[3], cacc[2], cacc[3], one);
+                term_word2(q0.z, q1.z, t0, t1, xacc[4], yacc[4], xacc[5], yacc[5], cacc[4], cacc[5], one);
+                term_word2(q0.w, q1.w, t0, t1, xacc[6], yacc[6], xacc[7], yacc[7], cacc[6], cacc[7], one);
+            } else {
+                const uint2 p0 = make_uint2(l0.x, l0.y), p1 = make_uint2(l1.x, l1.y);
+                pair_word2(q0.x, q1.x, p0, p1, xacc[0], yacc[0], xacc[1], yacc[1], cacc[0], cacc[1], one, cnt_lo);
+                pair_word2(q0.y, q1.y, p0, p1, xacc[2], yacc[2], xacc[3], yacc[3], cacc[2], cacc[3], one, cnt_lo);
+                pair_word2(q0.z, q1.z, p0, p1, xacc[4], yacc[4], xacc[5], yacc[5], cacc[4], cacc[5], one, cnt_lo);
+                pair_word2(q0.w, q1.w, p0, p1, xacc[6], yacc[6], xacc[7], yacc[7], cacc[6], cacc[7], one, cnt_lo);
+            }
+            if (i + FK_STAGES < n_stream) cp_async16_sa(sa0, tbase + (u64)l0.z * 16);
+            if (i + 1 + FK_STAGES < n_stream) cp_async16_sa(sa1, tbase + (u64)l1.z * 16);
+            cp_async_commit();
+            cur += 2u * stride_b;
+            if (cur == ring_end) cur = slot_sa;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) unpack_xy(xacc[j], yacc[j], wacc[2 * j], wacc[2 * j + 1]);
+        // single rows (an odd pair row, Term clauses of a mixed read).  Their waits are stricter than needed (the
+        // groups before them hold two rows each), never weaker.
 #pragma unroll 1
         for (; i < n_stream; i++) {
-            cp_async_wait<FK_STAGES - 1>();
+            cp_async_wait<FK_STAGES / 2 - 1>();
             uint4* my = slot + (i % FK_STAGES) * stride;
             const uint4 q = *my;
             const i32 c = i;
             if (c < n_dense) {
-                const uint2 lut = s_lut[c];
+                const uint2 lut = make_uint2(s_lo[c].x, s_lo[c].y);
                 pair_word(q.x, lut, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1]);
                 pair_word(q.y, lut, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3]);
                 pair_word(q.z, lut, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5]);
