@@ -463,6 +463,9 @@ __device__ __forceinline__ u32 cell_code(const Tab4Dev& T, u32 row, u32 doc) {
 #define FK_MAX_CLAUSES 255         // u8 match counters
 #define FK_CAND_CAP 128
 #define FK_STAGES 8                // rows in flight per thread (cp.async ring in shared memory)
+#define FK_EXS_ROW 4                // exception lists of up to this many cells are copied to shared memory by the set-up
+#define FK_EXS_CAP 96              // ... this many cells per CTA in all (the rest is searched in global memory)
+#define FK_EXA_SHARED 0xFFFFFFFFu    // s_exa of a clause whose list sits in shared memory
 #define FK_QMAX 255.0f
 #define FK_ROUND_SLACK 0.51f       // |q - S*tf*value| <= 0.5 (+ float rounding of the product)
 #define FK_REL_SLACK 4e-6f         // float roundings of Lucene's score and of the bound arithmetic
@@ -538,7 +541,11 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     __shared__ u32 s_off[FK_MAX_CLAUSES + 1];           // row offset in the table, in 16-byte units (table < 64 GiB)
     __shared__ float s_val[FK_MAX_CLAUSES + 1];
     __shared__ u32 s_exa[FK_MAX_CLAUSES + 1], s_exn[FK_MAX_CLAUSES + 1];     // exception list of each clause's row
-    __shared__ u8 s_exrows[FK_MAX_CLAUSES + 1];          // the clauses whose row has exceptions
+    __shared__ u8 s_exrows[FK_MAX_CLAUSES + 1];          // the clauses whose row has a long exception list (searched per thread)
+    __shared__ u32 s_sm_doc[FK_EXS_CAP];                 // cells of the short lists: doc, frequency, clause
+    __shared__ float s_sm_f[FK_EXS_CAP];
+    __shared__ u8 s_sm_c[FK_EXS_CAP];
+    __shared__ u32 s_nsmall;
     __shared__ float s_tf[16];
     __shared__ u32 s_sel[16 * TOPN + 1];
     __shared__ u32 s_wmax[16];
@@ -564,7 +571,7 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     const float S = all_terms ? 127.0f / (vr.x * tf16[T4_TF_MAX]) : FK_QMAX / (vr.x * tf16[T4_PAIR_MAX]);
     if (threadIdx.x < 16) s_tf[threadIdx.x] = tf16[threadIdx.x];
     if (threadIdx.x == 0) {
-        s_ncand = 0; s_nexrows = 0; s_over = 0; s_nexc = 0; s_ndense = 0; s_ngap = 0;
+        s_ncand = 0; s_nexrows = 0; s_over = 0; s_nexc = 0; s_ndense = 0; s_ngap = 0; s_nsmall = 0;
         s_qmin = (u32)__float2int_rn(S * vr.y);
         s_cntlo = 0x01010100u * one;
     }
@@ -607,7 +614,27 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
         row_exceptions(T, row, a, ne);
         s_exa[c] = a;
         s_exn[c] = ne;
-        if (ne) s_exrows[atomicAdd(&s_nexrows, 1)] = (u8)c;
+        if (ne) {
+            // Nearly every list is one or two cells long: those are fetched here, next to the other loads of the set-up,
+            // so that the fold after pass 1 reads them from shared memory instead of every thread chasing them through
+            // L2.  Slots a list reserved but could not use (capacity) are marked empty.
+            const u32 at = ne <= FK_EXS_ROW ? atomicAdd(&s_nsmall, ne) : (u32)FK_EXS_CAP;
+            if (at + ne <= FK_EXS_CAP) {
+                s_exa[c] = FK_EXA_SHARED;
+                u32 xd[FK_EXS_ROW]; float xf[FK_EXS_ROW];
+#pragma unroll
+                for (u32 j = 0; j < FK_EXS_ROW; j++) {
+                    xd[j] = j < ne ? __ldg(T.exc_doc + a + j) : 0u;
+                    xf[j] = j < ne ? __ldg(T.exc_freq + a + j) : 0.0f;
+                }
+#pragma unroll
+                for (u32 j = 0; j < FK_EXS_ROW; j++)
+                    if (j < ne) { s_sm_doc[at + j] = xd[j]; s_sm_f[at + j] = xf[j]; s_sm_c[at + j] = (u8)c; }
+            } else {
+                for (u32 j = at; j < FK_EXS_CAP; j++) s_sm_doc[j] = 0xFFFFFFFFu;
+                s_exrows[atomicAdd(&s_nexrows, 1)] = (u8)c;
+            }
+        }
     }
     __syncthreads();
 
@@ -707,9 +734,26 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
             cp_async_commit();
         }
         // ---- exception cells (stored as 0 in the table) of this thread's docs join their lanes with the same
-        //      quantisation: per listed row, binary search to the thread's doc range
-        const int n_exrows = s_nexrows;
+        //      quantisation: the short lists from shared memory, the long ones by binary search to the thread's doc range
         u32 exc_sum = 0, exc_cnt = 0;
+        auto fold_cell = [&](u32 li, u32 c, float freq) {
+            const u32 qe = (u32)min(__float2int_rn(S * s_val[c] * tf_of(freq)), 1 << 20);
+            const u32 qv = qe << (16 * (li & 1u)), cnt1 = 1u << (8 * (li & 3u));
+#pragma unroll
+            for (int k = 0; k < 16; k++) wacc[k] += (u32)k == (li >> 1) ? qv : 0u;     // predicated, statically indexed
+#pragma unroll
+            for (int k = 0; k < 8; k++) cacc[k] += (u32)k == (li >> 2) ? cnt1 : 0u;
+            exc_sum += qe;
+            exc_cnt++;
+            atomicMin(&s_qmin, qe);
+        };
+        const int n_small = (int)min(s_nsmall, (u32)FK_EXS_CAP);
+#pragma unroll 1
+        for (int j = 0; j < n_small; j++) {
+            const u32 li = s_sm_doc[j] - d0;
+            if (li < (u32)FK_DOCS) fold_cell(li, s_sm_c[j], s_sm_f[j]);
+        }
+        const int n_exrows = s_nexrows;
 #pragma unroll 1
         for (int i = 0; i < n_exrows; i++) {
             const u32 c = s_exrows[i], a = s_exa[c], ne = s_exn[c];
@@ -722,15 +766,7 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
             for (; lo < ne; lo++) {
                 const u32 d = __ldg(T.exc_doc + a + lo);
                 if (d >= d0 + FK_DOCS) break;
-                const u32 qe = (u32)min(__float2int_rn(S * s_val[c] * tf_of(__ldg(T.exc_freq + a + lo))), 1 << 20);
-                const u32 li = d - d0, qv = qe << (16 * (li & 1u)), cnt1 = 1u << (8 * (li & 3u));
-#pragma unroll
-                for (int k = 0; k < 16; k++) wacc[k] += (u32)k == (li >> 1) ? qv : 0u;     // predicated, statically indexed
-#pragma unroll
-                for (int k = 0; k < 8; k++) cacc[k] += (u32)k == (li >> 2) ? cnt1 : 0u;
-                exc_sum += qe;
-                exc_cnt++;
-                atomicMin(&s_qmin, qe);
+                fold_cell(d - d0, c, __ldg(T.exc_freq + a + lo));
             }
         }
         // u16 lanes: pair-row weights <= 255 and term-row weights <= 255*tf(14)/tf(7) < 362 (all-term reads: <= 127 each),
@@ -786,21 +822,33 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     const float delta = qmin >= 2.0f ? FK_ROUND_SLACK / qmin + FK_REL_SLACK : 1.0f;
     // a doc can reach the list only if E(d)*(1+delta) >= tau_e*(1-delta)
     const float theta = delta < 1.0f ? tau_e * ((1.0f - delta) / (1.0f + delta)) * (1.0f - FK_REL_SLACK) : 0.0f;
-    // ---- candidates: estimate >= theta
+    // ---- candidates: estimate >= theta.  Few threads get here (1.5 warps per read at C2), so the code is kept small
+    //      instead of unrolled over the register lanes (unrolled it was 19 KB of rarely executed SASS, and the warp that
+    //      ran it spent its time in instruction fetch while the other five waited at the barrier below): the thread parks
+    //      its lanes in its own ring slots (pass 1 is over for this thread, the slots are private) and walks them.
     if (active && !lane_overflow && e_best >= theta && e_best > 0.0f) {
+        uint4* my = ring + threadIdx.x;
+        const u32 stride = blockDim.x;
 #pragma unroll
+        for (int k = 0; k < 4; k++) my[k * stride] = make_uint4(wacc[4 * k], wacc[4 * k + 1], wacc[4 * k + 2], wacc[4 * k + 3]);
+#pragma unroll
+        for (int k = 0; k < 2; k++) my[(4 + k) * stride] = make_uint4(cacc[4 * k], cacc[4 * k + 1], cacc[4 * k + 2], cacc[4 * k + 3]);
+#pragma unroll 1
         for (int i4 = 0; i4 < FK_DOCS; i4 += 4) {
             const float4 nv = *reinterpret_cast<const float4*>(doc_w + d0 + i4);
             const float nr[4] = {nv.x, nv.y, nv.z, nv.w};
+            const u32* wl = reinterpret_cast<const u32*>(my + (i4 >> 3) * stride) + ((i4 >> 1) & 3);   // docs i4..i4+3: two u16x2 words
+            const u32 w01 = wl[0], w23 = wl[1];
+            const u32 cw = reinterpret_cast<const u32*>(my + (4 + (i4 >> 4)) * stride)[(i4 >> 2) & 3];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int i = i4 + k;
-                const u32 Q = prmt(wacc[i >> 1], 0u, (i & 1) ? 0x4432u : 0x4410u);
-                const u32 m = prmt(cacc[i >> 2], 0u, 0x4440u | (u32)(i & 3));
+                const u32 ww = k < 2 ? w01 : w23;
+                const u32 Q = (k & 1) ? ww >> 16 : ww & 0xFFFFu;
+                const u32 m = (cw >> (8 * k)) & 0xFFu;
                 const float e = estimate(Q, m, need, nr[k]);
                 if (e >= theta && e > 0.0f) {
                     int idx = atomicAdd(&s_ncand, 1);
-                    if (idx < FK_CAND_CAP) s_cand[idx] = d0 + i;
+                    if (idx < FK_CAND_CAP) s_cand[idx] = d0 + i4 + k;
                 }
             }
         }
@@ -820,6 +868,7 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     }
     // ---- exact rescoring.  Few candidates: one warp each, lanes over clauses.  Many (full list): the cells are first
     //      fetched in one batch of independent loads (item = candidate j, clause c) into shared memory.
+    const int n_small = (int)min(s_nsmall, (u32)FK_EXS_CAP);
     int pitch_log = 5;                                    // clause pitch of the staging buffer: power of two >= nc
     while ((1 << pitch_log) < nc) pitch_log++;
     const int n_items = n_cand << pitch_log;
@@ -854,11 +903,17 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
         for (i32 c = lane; c < nc; c += 32) {
             const u32 code = staged ? (u32)s_code[(j << pitch_log) + c]
                                     : (s_row[c] >= T.temp_row0 ? 0u : cell_code(T, s_row[c], d));
-            float tf = s_tf[code];
-            if (code == 0u && s_exn[c]) {
-                const float f = exc_lookup(T, s_exa[c], s_exn[c], d);
-                if (f != 0.0f) tf = tf_of(f);
+            // the exception cell of (clause, doc), if any, is looked up without waiting for the code (its cell is
+            // stored as 0): a scan of the short lists in shared memory, or a search that runs beside the cell load
+            float fe = 0.0f;
+            if (s_exn[c]) {
+                if (s_exa[c] == FK_EXA_SHARED) {
+                    for (int x = 0; x < n_small; x++)
+                        if (s_sm_doc[x] == d && s_sm_c[x] == (u8)c) fe = s_sm_f[x];
+                } else fe = exc_lookup(T, s_exa[c], s_exn[c], d);
             }
+            float tf = s_tf[code];
+            if (code == 0u && fe != 0.0f) tf = tf_of(fe);
             if (tf != 0.0f) {
                 sum += (double)__fmul_rn(__fmul_rn(tf, s_val[c]), nrm);          // TFIDFSimScorer#score
                 m++;
