@@ -462,7 +462,9 @@ __device__ __forceinline__ u32 cell_code(const Tab4Dev& T, u32 row, u32 doc) {
 #define FK_DOCS 32                 // docs per thread: one 16-byte vector per row
 #define FK_MAX_CLAUSES 255         // u8 match counters
 #define FK_CAND_CAP 128
-#define FK_STAGES 8                // rows in flight per thread (cp.async ring in shared memory)
+#ifndef FK_STAGES
+#define FK_STAGES 8                // rows in flight per thread (cp.async ring in shared memory); even
+#endif
 #define FK_EXS_ROW 4                // exception lists of up to this many cells are copied to shared memory by the set-up
 #define FK_EXS_CAP 96              // ... this many cells per CTA in all (the rest is searched in global memory)
 #define FK_EXA_SHARED 0xFFFFFFFFu    // s_exa of a clause whose list sits in shared memory
