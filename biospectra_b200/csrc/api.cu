@@ -673,7 +673,8 @@ static void pipeline_phase2a(bsp_classifier* h, Scratch& sc) {
         if ((i64)counts[2] * sc.filter_tiles > 0x7FFFFFFF) throw BspError(BSP_ERR_UNSUPPORTED, "batch too large for the filter path");
         const bool tiled = sc.filter_tiles > 1, naive = qp.alg == ALG_NAIVE;
         const unsigned fgrid = (unsigned)((i64)counts[2] * sc.filter_tiles);
-#define FK_LAUNCH(TI, AT) filter_score_kernel<TI, AT><<<fgrid, threads, ring_bytes, st>>>(T, D, h->tf16.p, sc.list_filter.p, sc.tok_off.p, sc.n_tok.p, \
+        const i32* fk_list = counts[2] == n ? nullptr : sc.list_filter.p;      // all reads: the list is a permutation of 0..n-1
+#define FK_LAUNCH(TI, AT) filter_score_kernel<TI, AT><<<fgrid, threads, ring_bytes, st>>>(T, D, h->tf16.p, fk_list, sc.tok_off.p, sc.n_tok.p, \
             sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.vrange.p, sc.read_ngap.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n, \
             part_doc, part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p, full_topn, 1u, sc.filter_tiles)
         if (tiled) { if (naive) FK_LAUNCH(true, true); else FK_LAUNCH(true, false); }

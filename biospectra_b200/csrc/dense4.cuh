@@ -559,7 +559,9 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     extern __shared__ __align__(16) uint4 ring[];         // FK_STAGES x blockDim.x x 16 B: row ring of pass 1, then the staged cell codes
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
     const int tile = TILED ? blockIdx.x % n_tiles : 0;
-    const i32 r = read_list[TILED ? blockIdx.x / n_tiles : blockIdx.x];
+    // (read_list == nullptr: every read of the batch takes this kernel, in order -- one dependent load less at the start)
+    const i32 rslot = (i32)(TILED ? blockIdx.x / n_tiles : blockIdx.x);
+    const i32 r = read_list ? read_list[rslot] : rslot;
     const i64 base = tok_off[r];
     const i32 n = n_tok[r], nc = n_clauses[r];
     const i32 n_pair = alg == ALG_NAIVE ? 0 : (alg == ALG_CHAIN ? nc : n / 2);
@@ -612,6 +614,37 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
             s_lo[c].y = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
             s_lut_hi[c] = make_uint2(q[8] | (q[9] << 8) | (q[10] << 16) | (q[11] << 24), q[12] | (q[13] << 8) | (q[14] << 16) | (q[15] << 24));
         }
+    }
+    __syncthreads();
+
+    // ---- pass 1: stream the rows.  Thread owns docs [32t, 32t+32): wacc[i] = u16 lanes (doc 2i, 2i+1),
+    //      cacc[j] = u8 lanes (docs 4j..4j+3)
+    const u32 d0 = ((u32)tile * blockDim.x + threadIdx.x) * FK_DOCS;
+    const bool active = (u64)d0 < T.row_bytes * 2;
+    u32 wacc[16], cacc[8];
+#pragma unroll
+    for (int i = 0; i < 16; i++) wacc[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) cacc[i] = 0;
+    const u8* tbase = T.tab + (u64)d0 / 2;
+    asm volatile("" : "+l"(tbase));          // keep the thread's table base in a register pair (one IMAD.WIDE per row address)
+    // Each thread prefetches its own 16-byte slice of the next FK_STAGES rows into its private slots of the
+    // ring (no cross-thread hand-off, so no barriers): FK_STAGES x 16 B in flight per thread.  Slots are
+    // addressed in the shared window directly; one commit group per pair of rows.
+    uint4* slot = ring + threadIdx.x;
+    const u32 stride = blockDim.x;
+    const u32 slot_sa = (u32)__cvta_generic_to_shared(slot), stride_b = stride * 16u, ring_end = slot_sa + FK_STAGES * stride_b;
+    if (active) {
+#pragma unroll
+        for (int st = 0; st < FK_STAGES; st++) {
+            if (st < n_stream) cp_async16_sa(slot_sa + st * stride_b, tbase + (u64)s_off[st] * 16);
+            if (st & 1) cp_async_commit();
+        }
+    }
+    // ---- exception lists of the clauses' rows, looked up while the first rows are on their way (two more dependent
+    //      loads that would otherwise sit in front of them); published by the barrier after pass 1
+    for (i32 c = threadIdx.x; c < nc; c += blockDim.x) {
+        const u32 row = s_row[c];
         u32 a, ne;
         row_exceptions(T, row, a, ne);
         s_exa[c] = a;
@@ -638,31 +671,7 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
             }
         }
     }
-    __syncthreads();
-
-    // ---- pass 1: stream the rows.  Thread owns docs [32t, 32t+32): wacc[i] = u16 lanes (doc 2i, 2i+1),
-    //      cacc[j] = u8 lanes (docs 4j..4j+3)
-    const u32 d0 = ((u32)tile * blockDim.x + threadIdx.x) * FK_DOCS;
-    const bool active = (u64)d0 < T.row_bytes * 2;
-    u32 wacc[16], cacc[8];
-#pragma unroll
-    for (int i = 0; i < 16; i++) wacc[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) cacc[i] = 0;
-    const u8* tbase = T.tab + (u64)d0 / 2;
-    asm volatile("" : "+l"(tbase));          // keep the thread's table base in a register pair (one IMAD.WIDE per row address)
     if (active) {
-        // Each thread prefetches its own 16-byte slice of the next FK_STAGES rows into its private slots of the
-        // ring (no cross-thread hand-off, so no barriers): FK_STAGES x 16 B in flight per thread.  Slots are
-        // addressed in the shared window directly; one commit group per pair of rows.
-        uint4* slot = ring + threadIdx.x;
-        const u32 stride = blockDim.x;
-        const u32 slot_sa = (u32)__cvta_generic_to_shared(slot), stride_b = stride * 16u, ring_end = slot_sa + FK_STAGES * stride_b;
-#pragma unroll
-        for (int st = 0; st < FK_STAGES; st++) {
-            if (st < n_stream) cp_async16_sa(slot_sa + st * stride_b, tbase + (u64)s_off[st] * 16);
-            if (st & 1) cp_async_commit();
-        }
         i32 i = 0;
         const i32 n_two = all_terms ? nc : n_dense;   // rows streamed two at a time through a byte LUT
         // count LUT low word, read from shared memory so that it lives in a vector register: as a literal (or a
@@ -735,6 +744,9 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
             if (i + FK_STAGES < n_stream) cp_async16(my, tbase + (u64)s_off[i + FK_STAGES] * 16);
             cp_async_commit();
         }
+    }
+    __syncthreads();                                  // exception lists (s_exa, s_exn, s_sm_*, s_exrows) are complete
+    if (active) {
         // ---- exception cells (stored as 0 in the table) of this thread's docs join their lanes with the same
         //      quantisation: the short lists from shared memory, the long ones by binary search to the thread's doc range
         u32 exc_sum = 0, exc_cnt = 0;
@@ -824,33 +836,38 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     const float delta = qmin >= 2.0f ? FK_ROUND_SLACK / qmin + FK_REL_SLACK : 1.0f;
     // a doc can reach the list only if E(d)*(1+delta) >= tau_e*(1-delta)
     const float theta = delta < 1.0f ? tau_e * ((1.0f - delta) / (1.0f + delta)) * (1.0f - FK_REL_SLACK) : 0.0f;
-    // ---- candidates: estimate >= theta.  Few threads get here (1.5 warps per read at C2), so the code is kept small
-    //      instead of unrolled over the register lanes (unrolled it was 19 KB of rarely executed SASS, and the warp that
-    //      ran it spent its time in instruction fetch while the other five waited at the barrier below): the thread parks
-    //      its lanes in its own ring slots (pass 1 is over for this thread, the slots are private) and walks them.
-    if (active && !lane_overflow && e_best >= theta && e_best > 0.0f) {
-        uint4* my = ring + threadIdx.x;
-        const u32 stride = blockDim.x;
+    // ---- candidates: estimate >= theta.  Few threads hold one (1.5 warps per read at C2 see any), and a thread walking
+    //      its own 32 docs is a long serial chain that the rest of the CTA waits for at the barrier below (unrolled over
+    //      the register lanes it was also 19 KB of rarely executed SASS).  So the warp does it together: a thread with a
+    //      candidate parks its lanes in its own ring slots (pass 1 is over in this warp's threads, the slots are private
+    //      to them), then the 32 lanes evaluate that thread's 32 docs, one each.
+    {
+        const bool mine = active && !lane_overflow && e_best >= theta && e_best > 0.0f;
+        u32 holders = __ballot_sync(0xFFFFFFFFu, mine);
+        if (holders) {
+            const u32 stride = blockDim.x;
+            if (mine) {
+                uint4* my = ring + threadIdx.x;
 #pragma unroll
-        for (int k = 0; k < 4; k++) my[k * stride] = make_uint4(wacc[4 * k], wacc[4 * k + 1], wacc[4 * k + 2], wacc[4 * k + 3]);
+                for (int k = 0; k < 4; k++) my[k * stride] = make_uint4(wacc[4 * k], wacc[4 * k + 1], wacc[4 * k + 2], wacc[4 * k + 3]);
 #pragma unroll
-        for (int k = 0; k < 2; k++) my[(4 + k) * stride] = make_uint4(cacc[4 * k], cacc[4 * k + 1], cacc[4 * k + 2], cacc[4 * k + 3]);
+                for (int k = 0; k < 2; k++) my[(4 + k) * stride] = make_uint4(cacc[4 * k], cacc[4 * k + 1], cacc[4 * k + 2], cacc[4 * k + 3]);
+            }
+            __syncwarp();
 #pragma unroll 1
-        for (int i4 = 0; i4 < FK_DOCS; i4 += 4) {
-            const float4 nv = *reinterpret_cast<const float4*>(doc_w + d0 + i4);
-            const float nr[4] = {nv.x, nv.y, nv.z, nv.w};
-            const u32* wl = reinterpret_cast<const u32*>(my + (i4 >> 3) * stride) + ((i4 >> 1) & 3);   // docs i4..i4+3: two u16x2 words
-            const u32 w01 = wl[0], w23 = wl[1];
-            const u32 cw = reinterpret_cast<const u32*>(my + (4 + (i4 >> 4)) * stride)[(i4 >> 2) & 3];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const u32 ww = k < 2 ? w01 : w23;
-                const u32 Q = (k & 1) ? ww >> 16 : ww & 0xFFFFu;
-                const u32 m = (cw >> (8 * k)) & 0xFFu;
-                const float e = estimate(Q, m, need, nr[k]);
+            while (holders) {
+                const u32 src = (threadIdx.x & ~31u) + (u32)(__ffs((int)holders) - 1);      // the thread whose docs these are
+                holders &= holders - 1u;
+                const u32* parked = reinterpret_cast<const u32*>(ring + src);              // slot k: + k * stride * 4 words
+                const u32 ww = parked[(u32)(lane >> 3) * stride * 4u + ((u32)(lane >> 1) & 3u)];        // u16 lanes (doc 2i, 2i+1) = word i
+                const u32 cw = parked[(4u + (u32)(lane >> 4)) * stride * 4u + ((u32)(lane >> 2) & 3u)]; // u8 lanes (docs 4j..4j+3) = word j
+                const u32 Q = (lane & 1) ? ww >> 16 : ww & 0xFFFFu;
+                const u32 m = (cw >> (8 * (lane & 3))) & 0xFFu;
+                const u32 d = ((u32)tile * blockDim.x + src) * FK_DOCS + (u32)lane;
+                const float e = estimate(Q, m, need, doc_w[d]);
                 if (e >= theta && e > 0.0f) {
                     int idx = atomicAdd(&s_ncand, 1);
-                    if (idx < FK_CAND_CAP) s_cand[idx] = d0 + i4 + k;
+                    if (idx < FK_CAND_CAP) s_cand[idx] = d;
                 }
             }
         }
@@ -901,24 +918,36 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
         const float nrm = doc_w[d];
         double sum = 0.0;
         i32 m = 0;
+        // four clauses per lane and round: their cell loads (one DRAM access each) are in flight together
 #pragma unroll 1
-        for (i32 c = lane; c < nc; c += 32) {
-            const u32 code = staged ? (u32)s_code[(j << pitch_log) + c]
-                                    : (s_row[c] >= T.temp_row0 ? 0u : cell_code(T, s_row[c], d));
-            // the exception cell of (clause, doc), if any, is looked up without waiting for the code (its cell is
-            // stored as 0): a scan of the short lists in shared memory, or a search that runs beside the cell load
-            float fe = 0.0f;
-            if (s_exn[c]) {
-                if (s_exa[c] == FK_EXA_SHARED) {
-                    for (int x = 0; x < n_small; x++)
-                        if (s_sm_doc[x] == d && s_sm_c[x] == (u8)c) fe = s_sm_f[x];
-                } else fe = exc_lookup(T, s_exa[c], s_exn[c], d);
+        for (i32 cb = lane; cb < nc; cb += 128) {
+            u32 code[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const i32 c = cb + 32 * u;
+                code[u] = 0u;
+                if (c < nc) code[u] = staged ? (u32)s_code[(j << pitch_log) + c]
+                                             : (s_row[c] >= T.temp_row0 ? 0u : cell_code(T, s_row[c], d));
             }
-            float tf = s_tf[code];
-            if (code == 0u && fe != 0.0f) tf = tf_of(fe);
-            if (tf != 0.0f) {
-                sum += (double)__fmul_rn(__fmul_rn(tf, s_val[c]), nrm);          // TFIDFSimScorer#score
-                m++;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const i32 c = cb + 32 * u;
+                if (c >= nc) break;
+                // the exception cell of (clause, doc), if any (its table cell is stored as 0): a scan of the short lists
+                // in shared memory, or a search of the row's list
+                float fe = 0.0f;
+                if (code[u] == 0u && s_exn[c]) {
+                    if (s_exa[c] == FK_EXA_SHARED) {
+                        for (int x = 0; x < n_small; x++)
+                            if (s_sm_doc[x] == d && s_sm_c[x] == (u8)c) fe = s_sm_f[x];
+                    } else fe = exc_lookup(T, s_exa[c], s_exn[c], d);
+                }
+                float tf = s_tf[code[u]];
+                if (fe != 0.0f) tf = tf_of(fe);
+                if (tf != 0.0f) {
+                    sum += (double)__fmul_rn(__fmul_rn(tf, s_val[c]), nrm);          // TFIDFSimScorer#score
+                    m++;
+                }
             }
         }
 #pragma unroll
@@ -926,8 +955,21 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
             sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
             m += __shfl_xor_sync(0xFFFFFFFFu, m, o);
         }
-        if (lane == 0) s_ckey[j] = m >= need ? cand_key(final_score(SIM_TFIDF, sum, m, nc), d) : 0ull;
+        const u64 key = m >= need ? cand_key(final_score(SIM_TFIDF, sum, m, nc), d) : 0ull;
+        if (n_cand == 1) {                                // the usual case: nothing to sort, nobody to wait for
+            if (lane == 0) {
+                if (key) {
+                    part_doc[pbase * TOPN] = global_doc_base + (0xFFFFFFFFu - (u32)(key & 0xFFFFFFFFu));
+                    part_score[pbase * TOPN] = __uint_as_float((u32)(key >> 32));
+                }
+                part_n[pbase] = key ? 1 : 0;
+                if (stats) { atomicAdd(&stats->candidates, 1ull); atomicAdd(&stats->forced, (unsigned long long)s_nexc); }
+            }
+            return;
+        }
+        if (lane == 0) s_ckey[j] = key;
     }
+    if (n_cand == 1) return;                              // (the warps without the candidate)
     __syncthreads();
     // ---- top-10 among the candidates
     if (warp == 0) {
