@@ -82,7 +82,7 @@ def measured_traffic(args, kernel):
     (profiles/r1_ncu_kernel_metrics.json); only valid for the workload the capture was taken on"""
     try:
         with open(os.path.join(ROOT, "profiles", "r1_ncu_kernel_metrics.json")) as f:
-            m = json.load(f)["r1i_filter_final_C2"]
+            m = json.load(f)["r1j_filter_final_C2"]
         if args.workload != "C2" or kernel != "filter_score_kernel" or args.algorithm != "PAIRED_PROXIMITY":
             return None
         def gb(k):
