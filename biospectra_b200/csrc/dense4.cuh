@@ -13,8 +13,12 @@
 //   filter_score_kernel   tf-idf fast path.  Pass 1 streams the read's rows once with packed
 //                         integer SIMD: a per-clause 8-entry byte LUT applied with PRMT turns 8
 //                         nibbles into quantised weights (q = round(S*tf(f)*value_c)), summed in
-//                         u16 lanes, match counts in u8 lanes: ~2 issue slots per (clause, doc) cell,
-//                         so the kernel is bound by the HBM stream, not by fp64.  The sums give
+//                         packed lanes (x += the four weight bytes as one integer, y += the odd
+//                         bytes; u16 lanes are recovered after the loop), match counts in u8 lanes:
+//                         ~2 issue slots per (clause, doc) cell, so the kernel is bound by the HBM
+//                         stream and the issue rate, not by fp64.  The phases around the loop are
+//                         kept short (warp-wide candidate pass, batched cell loads): they are serial
+//                         chains that the other warps of the CTA wait for.  The sums give
 //                         rigorous lower/upper bounds of Lucene's score; docs whose upper bound
 //                         reaches the 10th best lower bound (plus docs with exception cells) are
 //                         rescored exactly (float ops in Lucene's order, double accumulation) and the
