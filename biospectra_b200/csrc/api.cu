@@ -128,9 +128,10 @@ struct bsp_classifier {
     ~bsp_classifier() { delete ref; }
 };
 
-static int fail(std::string* slot, int code, const std::string& msg) {
+// Error text is kept per calling thread only (bsp_last_error reads it back on the same thread): entry points such as
+// bsp_classify_one are called concurrently on one handle, so a per-handle string would be written by several threads.
+static int fail(std::string* /*unused: per-handle slot*/, int code, const std::string& msg) {
     g_last_error = msg;
-    if (slot) *slot = msg;
     return code;
 }
 
@@ -141,7 +142,7 @@ static int fail(std::string* slot, int code, const std::string& msg) {
     catch (const std::exception& e) { return fail((h) ? &(h)->last_error : nullptr, BSP_ERR_STATE, e.what()); }
 
 BSP_API const char* bsp_last_error(const void* handle) {
-    (void)handle;                       // messages are also kept per thread; handle-specific text mirrors it
+    (void)handle;                       // the message of the last failing call made by THIS thread
     return g_last_error.c_str();
 }
 BSP_API const char* bsp_version(void) { return "biospectra-b200 0.1 (sm_100a)"; }
@@ -1053,8 +1054,11 @@ BSP_API int bsp_classify_device(bsp_classifier* h, int32_t n, const void* d_seq_
 BSP_API int bsp_doc_fields(bsp_classifier* h, int32_t doc, const char** filename, const char** header,
                            const char** direction, const char** taxonomy) {
     if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
-    if (doc < 0 || doc >= (i32)h->ix.docs.size()) return fail(&h->last_error, BSP_ERR_ARG, "doc id out of range");
-    const DocMeta& d = h->ix.docs[doc];
+    // ids are the ones classify/merge report: global in doc-partitioned mode (bsp_partition_set_global), local otherwise
+    const i64 ldoc = (i64)doc - h->doc_base_global;
+    if (ldoc < 0 || ldoc >= (i64)h->ix.docs.size())
+        return fail(&h->last_error, BSP_ERR_ARG, "doc id out of range (in doc-partitioned mode: not owned by this partition)");
+    const DocMeta& d = h->ix.docs[ldoc];
     const EntryMeta& m = h->ref->entries[d.entry];
     static const char* DIR[3] = {"forward", "reverse", "min_strand"};       // Indexer.java:211,216,221
     if (filename) *filename = m.filename.c_str();
@@ -1075,9 +1079,11 @@ BSP_API int bsp_index_stats(bsp_classifier* h, int64_t* n_docs, int64_t* n_terms
 
 BSP_API int bsp_doc_info(bsp_classifier* h, int32_t doc, int32_t* num_tokens, int32_t* norm_byte) {
     if (!h) return fail(nullptr, BSP_ERR_ARG, "handle is null");
-    if (doc < 0 || doc >= (i32)h->ix.docs.size()) return fail(&h->last_error, BSP_ERR_ARG, "doc id out of range");
-    if (num_tokens) *num_tokens = (i32)h->ix.doc_ntok[doc];
-    if (norm_byte) *norm_byte = h->ix.doc_norm[doc];
+    const i64 ldoc = (i64)doc - h->doc_base_global;          // same id space as bsp_doc_fields
+    if (ldoc < 0 || ldoc >= (i64)h->ix.docs.size())
+        return fail(&h->last_error, BSP_ERR_ARG, "doc id out of range (in doc-partitioned mode: not owned by this partition)");
+    if (num_tokens) *num_tokens = (i32)h->ix.doc_ntok[ldoc];
+    if (norm_byte) *norm_byte = h->ix.doc_norm[ldoc];
     return BSP_OK;
 }
 

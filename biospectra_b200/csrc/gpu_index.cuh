@@ -530,6 +530,9 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
             ix.arena.release_all();
             positional = false; ix.positional = false; ix.positional_bytes = 0; views.clear();
             ix.notes += "positional index dropped: out of device memory; ";
+            fprintf(stderr, "WARNING biospectra_gpu: out of device memory, the positional index was dropped; reads whose clauses "
+                            "need a slop the dense tables do not hold (reads with N, kmer_skips > 0) will be reported with status "
+                            "error instead of being classified (set positional=1 in bsp_config to fail open() instead)\n");
             si--;
             continue;
         }

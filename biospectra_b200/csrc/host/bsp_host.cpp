@@ -18,6 +18,7 @@
 #include <zlib.h>
 #include <condition_variable>
 #include <deque>
+#include <atomic>
 #include <thread>
 
 namespace bsp {
@@ -186,12 +187,21 @@ bool FASTAReader::readLine(std::string& line) {      // BufferedReader#readLine:
     return true;
 }
 
+// FASTAHeader.<init> (fasta-utils-1.1.jar): a header part must match ^(\S+)\s*$ or ^(\S+)\s+(\S+.*)$, i.e. it is
+// non-empty and starts with a non-blank character (\s = [ \t\n\x0B\f\r]).
+static bool fasta_header_part_ok(const char* p, size_t n) {
+    if (n == 0) return false;
+    const unsigned char c = (unsigned char)p[0];
+    return !(c == ' ' || (c >= 9 && c <= 13));
+}
+
 bool FASTAReader::readNext(FASTAEntry& e) {
-    // org.yeastrc.fasta.FASTAReader#readNext, scanning the file image in place
+    // org.yeastrc.fasta.FASTAReader#readNext, statement for statement (tests/golden/fasta_reader.json holds what the
+    // reference's own class file returns), scanning the file image in place
     static unsigned char UP[256];
     static bool up_init = false;
     if (!up_init) {
-        for (int c = 0; c < 256; c++) UP[c] = c >= 0x80 ? (unsigned char)'?'       // US-ASCII decoding: undecodable byte
+        for (int c = 0; c < 256; c++) UP[c] = c >= 0x80 ? (unsigned char)c       // kept: written as U+FFFD (US-ASCII decoding)
                                               : (unsigned char)toupper(c);          // String#toUpperCase
         up_init = true;
     }
@@ -200,16 +210,39 @@ bool FASTAReader::readNext(FASTAEntry& e) {
         if (!readLine(line)) return false;
     } else { line = pending_; have_pending_ = false; }
     if (line.empty() || line[0] != '>')
-        throw FASTADataError("FASTADataErrorException: expected a header line starting with '>'");
+        throw FASTADataError("FASTADataErrorException: Expected header line, but line did not start with \">\".");
+    {   // the header minus '>' is split on Ctrl-A (String#split: trailing empty parts removed) and every part parsed
+        const char* h = line.data() + 1;
+        size_t hn = line.size() - 1;
+        if (!memchr(h, 1, hn)) {
+            if (!fasta_header_part_ok(h, hn)) throw FASTADataError("FASTADataErrorException: Could not parse FASTA header line");
+        } else {
+            while (hn > 0 && h[hn - 1] == 1) hn--;                    // trailing empties
+            size_t st = 0;
+            while (hn > 0 && st <= hn) {
+                const char* q = (const char*)memchr(h + st, 1, hn - st);
+                size_t en = q ? (size_t)(q - h) : hn;
+                if (!fasta_header_part_ok(h + st, en - st)) throw FASTADataError("FASTADataErrorException: Could not parse FASTA header line");
+                if (!q) break;
+                st = en + 1;
+            }
+        }
+    }
     e.headerLine = line;
     e.sequence.clear();
-    bool any = false;
     const char* d = data_.data();
     const size_t n = data_.size();
-    while (pos_ < n) {
-        const char first = d[pos_];
-        if (first == '>') {                              // next entry: leave it for the next call
-            readLine(pending_);
+    // `while (line.startsWith(";"))` right after the header dereferences null at EOF; then a '>' line is an error
+    bool first = true;
+    while (true) {
+        if (pos_ >= n) {
+            if (first) throw FASTADataError("NullPointerException: header line at end of file");
+            break;
+        }
+        const char c0 = d[pos_];
+        if (c0 == '>') {
+            if (first) throw FASTADataError("FASTADataErrorException: Did not get a sequence line after a header line");
+            readLine(pending_);                                          // next entry: leave it for the next call
             have_pending_ = true;
             break;
         }
@@ -220,14 +253,13 @@ bool FASTAReader::readNext(FASTAEntry& e) {
         size_t stop = cr ? (size_t)(cr - d) : end;
         if (stop < n) pos_ = (d[stop] == '\r' && stop + 1 < n && d[stop + 1] == '\n') ? stop + 2 : stop + 1;
         else pos_ = n;
-        if (first == ';' && stop > st) continue;
-        any = true;
+        if (c0 == ';' && stop > st) continue;            // comment lines do not end the "first line" check
+        first = false;
         const size_t old = e.sequence.size();
         e.sequence.resize(old + (stop - st));
         char* o = &e.sequence[old];
         for (size_t i = st; i < stop; i++) o[i - st] = (char)UP[(unsigned char)d[i]];
     }
-    if (!any) throw FASTADataError("FASTADataErrorException: header without sequence");
     // String#trim: strip chars <= ' ' at both ends
     size_t a = 0, b = e.sequence.size();
     while (a < b && (unsigned char)e.sequence[a] <= ' ') a++;
@@ -343,15 +375,15 @@ void makeClassificationResult(ClassificationResult& r) {
 std::string ClassificationResult::toJson() const {   // beans/ClassificationResult.java:59-117, SearchResultEntry.java:53-121
     std::string o;
     o.reserve(256 + query.size());
-    o += "{\"query_header\":"; jsonm::write_string(o, queryHeader);
-    o += ",\"query\":"; jsonm::write_string(o, query);
+    o += "{\"query_header\":"; jsonm::write_fasta_string(o, queryHeader);
+    o += ",\"query\":"; jsonm::write_fasta_string(o, query);
     o += ",\"result\":[";
     for (size_t i = 0; i < result.size(); i++) {
         const SearchResultEntry& e = result[i];
         if (i) o += ",";
         o += "{\"docid\":" + std::to_string(e.docId) + ",\"rank\":" + std::to_string(e.rank);
         o += ",\"filename\":"; jsonm::write_string(o, e.filename);
-        o += ",\"header\":"; jsonm::write_string(o, e.header);
+        o += ",\"header\":"; jsonm::write_fasta_string(o, e.header);
         o += ",\"sequence_direction\":"; jsonm::write_string(o, e.sequenceDirection);
         o += ",\"taxon_hierarchy\":"; jsonm::write_string(o, e.taxonHierarchy);
         o += ",\"score\":" + jsonm::java_double(e.score) + "}";
@@ -395,7 +427,7 @@ Classifier::Classifier(const Configuration* conf) {
         check_rc(bsp_doc_fields(h_, (int32_t)d, &fn, &hd, &dir, &tax));
         DocInfo& di = docs_[(size_t)d];
         di.json = "\"filename\":"; jsonm::write_string(di.json, fn);
-        di.json += ",\"header\":"; jsonm::write_string(di.json, hd);
+        di.json += ",\"header\":"; jsonm::write_fasta_string(di.json, hd);
         di.json += ",\"sequence_direction\":"; jsonm::write_string(di.json, dir);
         di.json += ",\"taxon_hierarchy\":"; jsonm::write_string(di.json, tax);
         di.hasTaxonomy = tax[0] != 0;
@@ -482,8 +514,8 @@ bool Classifier::appendResultJson(std::string& o, const char* header, size_t hea
         }
     }
     *type = ty;
-    o += "{\"query_header\":"; jsonm::write_string_n(o, header, headerLen);
-    o += ",\"query\":"; jsonm::write_string_n(o, seq, seqLen);
+    o += "{\"query_header\":"; jsonm::write_fasta_string_n(o, header, headerLen);
+    o += ",\"query\":"; jsonm::write_fasta_string_n(o, seq, seqLen);
     o += ",\"result\":[";
     char num[48];
     for (int j = 0; j < nh; j++) {
@@ -633,6 +665,7 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
     typedef std::unique_ptr<ReadBatch> BatchPtr;
     BoundedQueue<BatchPtr> parsed(2), classified(2);
     std::exception_ptr reader_error, writer_error;
+    std::atomic<long long> unscored_reads{0};   // non-empty reads the GPU could not score (e.g. positional index dropped)
 
     std::thread reader_thread([&] {
         try {
@@ -667,7 +700,12 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
                     for (size_t i = i0; i < i1; i++) {
                         // reads the reference's classify() throws on (empty sequence, < 2 k-mers, > 10000 clauses) are
                         // logged and skipped: no line, not counted (LocalClassifier.java:112-114)
-                        if (b->res.status[i] != BSP_READ_OK) continue;
+                        if (b->res.status[i] != BSP_READ_OK) {
+                            // ... but a non-empty read with an error status is one the reference WOULD have classified
+                            // (no scoring path resident for it): never silent — counted, reported on stderr and in gpu_metrics
+                            if (b->res.status[i] == BSP_READ_ERROR && b->soff[i + 1] > b->soff[i]) unscored_reads++;
+                            continue;
+                        }
                         const size_t mark = o.size();
                         int type = 0;
                         if (!cls.appendResultJson(o, b->headers.data() + b->hoff[i], b->hoff[i + 1] - b->hoff[i],
@@ -744,13 +782,18 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
             fprintf(fm, "{\"reads\":%lld,\"gpu_batches\":%lld,\"reads_filter_kernel\":%lld,\"reads_exact_dense_kernel\":%lld,"
                         "\"reads_positional_kernel\":%lld,\"reads_handed_over_by_filter\":%lld,\"docs_rescored_exactly\":%lld,"
                         "\"exception_cells\":%lld,\"kernel_launches\":%lld,\"score_kernel_ms\":%.3f,\"device_pipeline_ms\":%.3f,"
-                        "\"classify_call_wall_ms\":%.3f,\"file_to_file_ms\":%lld}\n",
+                        "\"classify_call_wall_ms\":%.3f,\"file_to_file_ms\":%lld,\"reads_not_scored_gpu_error\":%lld}\n",
                     (long long)gpu_counters[0], gpu_batches, (long long)gpu_counters[3], (long long)gpu_counters[1],
                     (long long)gpu_counters[2], (long long)gpu_counters[7], (long long)gpu_counters[5], (long long)gpu_counters[6],
-                    (long long)gpu_counters[4], gpu_score_ms, gpu_pipe_ms, gpu_wall_ms, summary.endTime - summary.startTime);
+                    (long long)gpu_counters[4], gpu_score_ms, gpu_pipe_ms, gpu_wall_ms, summary.endTime - summary.startTime,
+                    unscored_reads.load());
             fclose(fm);
         }
     }
+    if (unscored_reads.load())
+        fprintf(stderr, "ERROR %lld reads were not scored (status error: no scoring path resident for them, e.g. the positional "
+                        "index was dropped for lack of device memory); they are missing from %s\n",
+                unscored_reads.load(), classifyOutput.c_str());
 }
 
 // The reference's LocalClassifier.classify as written (LocalClassifier.java:88-120): the calling thread reads FASTA
@@ -904,19 +947,24 @@ HOST_API int bsp_host_label_json(const char* const* taxon_hierarchies, int32_t n
     } catch (const std::exception& e) { g_host_error = e.what(); return BSP_ERR_STATE; }
 }
 
-// parse a FASTA file with A.1 semantics; writes "header\tsequence\n" records
+// parse a FASTA file with A.1 semantics; writes "header\x1Fsequence\x1E" records (unit / record separators: headers
+// and sequences may hold tabs and, before the final trim, blanks).  On a data error the records read before
+// it are still written (the reference's callers have processed those entries by the time readNext throws) and the
+// call returns BSP_ERR_IO.
 HOST_API int bsp_host_read_fasta(const char* path, char* out, int64_t cap, int64_t* needed) {
+    std::string o;
+    int rc = BSP_OK;
     try {
         bsp::FASTAReader rd(path);
         bsp::FASTAEntry e;
-        std::string o;
-        while (rd.readNext(e)) { o += e.headerLine; o.push_back('\t'); o += e.sequence; o.push_back('\n'); }
-        if (needed) *needed = (int64_t)o.size() + 1;
-        if ((int64_t)o.size() + 1 > cap) return BSP_ERR_NOMEM;
-        memcpy(out, o.c_str(), o.size() + 1);
-        return BSP_OK;
-    } catch (const bsp::FASTADataError& e) { g_host_error = e.what(); return BSP_ERR_IO; }
-    catch (const std::exception& e) { g_host_error = e.what(); return BSP_ERR_IO; }
+        try {
+            while (rd.readNext(e)) { o += e.headerLine; o.push_back('\x1F'); o += e.sequence; o.push_back('\x1E'); }
+        } catch (const bsp::FASTADataError& ex) { g_host_error = ex.what(); rc = BSP_ERR_IO; }
+    } catch (const std::exception& ex) { g_host_error = ex.what(); return BSP_ERR_IO; }
+    if (needed) *needed = (int64_t)o.size() + 1;
+    if ((int64_t)o.size() + 1 > cap) return BSP_ERR_NOMEM;
+    memcpy(out, o.c_str(), o.size() + 1);
+    return rc;
 }
 
 HOST_API int bsp_host_double_to_string(double d, char* out, int32_t cap) {

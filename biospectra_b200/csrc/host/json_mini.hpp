@@ -147,6 +147,21 @@ inline ValuePtr parse(const std::string& s) { return Parser(s).parse(); }
 // Jackson-style string escaping (JsonStringEncoder): ", \ and control chars
 inline void write_string_n(std::string& o, const char* s, size_t n);
 inline void write_string(std::string& o, const std::string& s) { write_string_n(o, s.data(), s.size()); }
+// Text that came out of a FASTA file: the reference decodes those as US-ASCII (FASTAReaderConstants), so every byte
+// >= 0x80 is the one character U+FFFD, which Jackson writes as the UTF-8 bytes EF BF BD.  The bytes are kept raw in
+// memory (one byte per character keeps offsets and lengths right) and widened here.
+inline void write_fasta_string_n(std::string& o, const char* sp, size_t n) {
+    bool high = false;
+    for (size_t i = 0; i < n; i++) if ((unsigned char)sp[i] >= 0x80) { high = true; break; }
+    if (!high) { write_string_n(o, sp, n); return; }
+    std::string t;
+    t.reserve(n + 16);
+    for (size_t i = 0; i < n; i++) {
+        if ((unsigned char)sp[i] >= 0x80) t += "\xEF\xBF\xBD"; else t.push_back(sp[i]);
+    }
+    write_string_n(o, t.data(), t.size());
+}
+inline void write_fasta_string(std::string& o, const std::string& s) { write_fasta_string_n(o, s.data(), s.size()); }
 inline void write_string_n(std::string& o, const char* sp, size_t n) {
     o.push_back('"');
     // fast path: runs of characters that need no escaping are appended in one go

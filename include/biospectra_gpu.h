@@ -166,7 +166,9 @@ int bsp_classify_device(bsp_classifier* h, int32_t n, const void* d_seq_bytes, c
                         void* d_status, void* d_label, void* d_n_hits, void* d_n_top,
                         void* d_top_doc, void* d_top_score);
 /* stored fields of a document (IndexSearcher.doc(), Classifier.java:361-363);
- * borrowed pointers, valid until close */
+ * borrowed pointers, valid until close.  `doc` is an id as classify / merge report it: after
+ * bsp_partition_set_global that is the GLOBAL id, and the call returns BSP_ERR_ARG for a document another
+ * partition owns (bsp_doc_info follows the same rule). */
 int bsp_doc_fields(bsp_classifier* h, int32_t doc, const char** filename, const char** header,
                    const char** direction, const char** taxonomy);
 int bsp_classifier_close(bsp_classifier* h);

@@ -20,6 +20,7 @@ from __future__ import annotations
 import base64
 import json
 import math
+import re
 import struct
 from fractions import Fraction
 
@@ -40,31 +41,62 @@ def split_lines(text: str):
     return text.replace("\r\n", "\n").replace("\r", "\n").split("\n")
 
 
-def read_fasta(text: str):
-    """Yield (headerLine incl. '>', sequence).  Sequence lines are upper-cased and
-    concatenated without per-line trimming; the whole sequence is trimmed at the
-    end; ';' lines are skipped; a header without sequence is an error."""
+_HDR_NAME = re.compile(r"(\S+)\s*", re.ASCII)               # FASTAHeader.<init>: ^(\S+)\s*$
+_HDR_NAME_DESC = re.compile(r"(\S+)\s+(\S+.*)", re.ASCII)    #                     ^(\S+)\s+(\S+.*)$
+
+
+def _check_header(line: str):
+    """FASTAReader#readNext: the header line minus '>' is split on Ctrl-A and every part must parse as a
+    FASTAHeader (name [description]); e.g. '> x' or a bare '>' raise FASTADataErrorException."""
+    body = line[1:]
+    if "\x01" not in body:
+        parts = [body]                    # String#split: no match -> the input itself (even when empty)
+    else:
+        parts = body.split("\x01")
+        while parts and parts[-1] == "":
+            parts.pop()                   # trailing empty strings are removed
+    for p in parts:
+        if not (_HDR_NAME.fullmatch(p) or _HDR_NAME_DESC.fullmatch(p)):
+            raise ValueError("FASTADataErrorException: Could not parse FASTA header line: \"%s\"" % p)
+
+
+def iter_fasta(text: str):
+    """fasta-utils-1.1.jar!org/yeastrc/fasta/FASTAReader#readNext, statement for statement (pinned by
+    tests/golden/fasta_reader.json, produced by executing that class file).  Yields (headerLine incl. '>', sequence)
+    and raises where the reference throws, after the entries it had already returned."""
     lines = split_lines(text)
     if lines and lines[-1] == "":
         lines.pop()                       # no phantom line after the last newline
-    out = []
-    i = 0
-    n = len(lines)
-    while i < n:
-        line = lines[i]
+    it = iter(lines)
+    last = next(it, None)                 # lineNumber == 0: read the first line
+    while True:
+        line = last
+        if line is None:
+            return
         if not line.startswith(">"):
-            raise ValueError("FASTADataErrorException: expected '>' at line %d" % (i + 1))
+            raise ValueError("FASTADataErrorException: Expected header line, but line did not start with \">\".")
         header = line
-        i += 1
+        _check_header(line)
+        line = next(it, None)
+        while True:                       # while (line.startsWith(";")) — dereferences null at EOF
+            if line is None:
+                raise ValueError("NullPointerException: header line at end of file")
+            if not line.startswith(";"):
+                break
+            line = next(it, None)
+        if line.startswith(">"):
+            raise ValueError("FASTADataErrorException: Did not get a sequence line after a header line")
         seq = []
-        while i < n and not lines[i].startswith(">"):
-            if not lines[i].startswith(";"):
-                seq.append(lines[i].upper())
-            i += 1
-        if not seq:
-            raise ValueError("FASTADataErrorException: header without sequence")
-        out.append((header, java_trim("".join(seq))))
-    return out
+        while line is not None and not line.startswith(">"):
+            if not line.startswith(";"):
+                seq.append(line.upper())  # no per-line trim: interior blanks survive
+            line = next(it, None)
+        last = line
+        yield (header, java_trim("".join(seq)))
+
+
+def read_fasta(text: str):
+    return list(iter_fasta(text))
 
 
 def java_trim(s: str) -> str:
@@ -484,8 +516,66 @@ def clause_freqs(index: Index, clause):
     return out
 
 
+def query_norm(sum_sq):
+    """DefaultSimilarity#queryNorm: (float)(1.0 / Math.sqrt(sumOfSquaredWeights)); IndexSearcher#createNormalizedWeight
+    replaces Inf/NaN by 1.0f."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        qn = f32(1.0 / math.sqrt(float(sum_sq))) if sum_sq > 0 else f32(np.inf)
+    if not np.isfinite(qn):
+        qn = f32(1.0)
+    return qn
+
+
+def raw_query_norm(sum_sq):
+    """DefaultSimilarity#queryNorm alone (no Inf/NaN replacement)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return f32(1.0 / math.sqrt(float(sum_sq))) if sum_sq > 0 else (f32(np.inf) if sum_sq == 0 else f32(np.nan))
+
+
+def tfidf_sum_sq(idfs):
+    """BooleanWeight#getValueForNormalization over IDFStats#getValueForNormalization (queryWeight = idf * 1.0f)."""
+    sum_sq = f32(0.0)
+    for w in idfs:
+        qw = f32(w * f32(1.0))
+        sum_sq = f32(sum_sq + f32(qw * qw))
+    return f32(sum_sq * f32(f32(1.0) * f32(1.0)))
+
+
+def tfidf_values(idfs):
+    """TFIDFSimilarity$IDFStats#normalize: value = (queryWeight * (queryNorm * topLevelBoost)) * idf."""
+    qn = query_norm(tfidf_sum_sq(idfs))
+    return [f32(f32(f32(w * f32(1.0)) * f32(qn * f32(1.0))) * w) for w in idfs]
+
+
+def tfidf_coord(i: int, n_clauses: int):
+    """BooleanWeight#coord / DefaultSimilarity#coord: 0 overlap -> 0; one clause -> 1; else (float)i / (float)n."""
+    if i == 0:
+        return f32(0.0)
+    if n_clauses == 1:
+        return f32(1.0)
+    return f32(i) / f32(n_clauses)
+
+
+def avg_field_length(sum_total_term_freq: int, max_doc: int):
+    """BM25Similarity#avgFieldLength."""
+    return f32(1.0) if sum_total_term_freq <= 0 else f32(float(sum_total_term_freq) / float(max_doc))
+
+
+def bm25_cache(avgdl):
+    """BM25Similarity#computeWeight: cache[x] = k1 * ((1 - b) + b * decodeNormValue(x) / avgdl),
+    decodeNormValue(x) = NORM_TABLE[x] = 1 / (byte315ToFloat(x)^2)."""
+    k1, b = f32(1.2), f32(0.75)
+    cache = []
+    for x in range(256):
+        nv = NORM_TABLE[x]
+        with np.errstate(divide="ignore"):
+            ln = f32(1.0) / f32(nv * nv)
+        cache.append(f32(k1 * f32(f32(f32(1.0) - b) + f32(f32(b * ln) / avgdl))))
+    return cache
+
+
 def search(index: Index, sequence: str, *, skips: int, algorithm: int, scoring: int,
-           msm_ratio: float, top_n: int = 10, check_exact: bool = True):
+           msm_ratio: float, top_n: int = 10, check_exact: bool = True, details: dict | None = None):
     """classify/Classifier.java:341-366 + IndexSearcher/BooleanWeight/BooleanScorer/
     TopScoreDocCollector.  Returns None if the read is dropped (< 2 tokens or more
     than 10000 clauses), else (hits, n_clauses, msm) with hits = [(doc, score f32)]
@@ -502,32 +592,14 @@ def search(index: Index, sequence: str, *, skips: int, algorithm: int, scoring: 
     msm = int(msm_ratio * n_clauses)                  # Classifier.java:257
     idfs = [clause_idf(index, c, scoring) for c in clauses]
     if scoring == TFIDF:
-        sum_sq = f32(0.0)
-        for w in idfs:                                # queryWeight = idf * 1.0f
-            qw = f32(w * f32(1.0))
-            sum_sq = f32(sum_sq + f32(qw * qw))
-        sum_sq = f32(sum_sq * f32(f32(1.0) * f32(1.0)))
-        with np.errstate(divide="ignore", invalid="ignore"):
-            qn = f32(1.0 / math.sqrt(float(sum_sq))) if sum_sq > 0 else f32(np.inf)
-        if not np.isfinite(qn):
-            qn = f32(1.0)
-        values = [f32(f32(f32(w * f32(1.0)) * f32(qn * f32(1.0))) * w) for w in idfs]
-        if n_clauses == 1:
-            coord = [f32(0.0), f32(1.0)]
-        else:
-            coord = [f32(0.0)] + [f32(i) / f32(n_clauses) for i in range(1, n_clauses + 1)]
+        values = tfidf_values(idfs)
+        coord = [tfidf_coord(i, n_clauses) for i in range(n_clauses + 1)]
     else:
-        values = [f32(f32(w * f32(1.0)) * f32(1.0)) for w in idfs]
+        values = [f32(f32(w * f32(1.0)) * f32(1.0)) for w in idfs]     # BM25Stats#normalize: idf * queryBoost * topLevelBoost
         coord = [f32(0.0)] + [f32(1.0)] * n_clauses
-        stt = index.sum_total_term_freq()
-        avgdl = f32(1.0) if stt <= 0 else f32(float(stt) / float(index.max_doc))
-        k1, b = f32(1.2), f32(0.75)
-        cache = []
-        for x in range(256):
-            nv = NORM_TABLE[x]
-            with np.errstate(divide="ignore"):
-                ln = f32(1.0) / f32(nv * nv)
-            cache.append(f32(k1 * f32(f32(f32(1.0) - b) + f32(f32(b * ln) / avgdl))))
+        cache = bm25_cache(avg_field_length(index.sum_total_term_freq(), index.max_doc))
+    if details is not None:
+        details.update(values=values, n_clauses=n_clauses, msm=msm)
 
     acc: dict[int, list] = {}                         # doc -> [exact sum, double sum, count]
     for c, val in zip(clauses, values):
@@ -552,6 +624,8 @@ def search(index: Index, sequence: str, *, skips: int, algorithm: int, scoring: 
             assert Fraction(dsum) == exact, "double accumulation not exact"
         hits.append((d, f32(f32(dsum) * coord[m])))
     hits.sort(key=lambda h: (-float(h[1]), h[0]))     # TopScoreDocCollector order
+    if details is not None:
+        details["total_hits"] = len(hits)
     return hits[:top_n], n_clauses, msm
 
 

@@ -57,6 +57,25 @@ def test_two_partitions_merge_to_single_index(oracle_lib, k, alg, sim, full):
         torch.cuda.synchronize()
         res_g = {key: v.cpu().numpy() for key, v in out.items()}
         common.assert_classify_equal(res_g, res_o, reads, "two partitions k%d" % k, hits_only=not full)
+        # stored fields are addressed with the ids the merge reports (global): every top hit resolves on the partition
+        # that owns it, with the fields of that very document, and is refused by the other one
+        doc_entry = []                                                 # global doc id -> (entry, direction)
+        for i in range(len(ents)):
+            doc_entry.append((i, "forward"))
+            if i != 7:
+                doc_entry.append((i, "reverse"))
+        seen_owner = set()
+        for i in range(len(reads)):
+            for j in range(int(res_g["n_top"][i])):
+                d = int(res_g["top_doc"][i, j])
+                owner = 1 if d >= stats[0][0] else 0
+                seen_owner.add(owner)
+                f = engines[owner].clf.doc_fields(d)
+                assert (f[1], f[2]) == ("h%d" % doc_entry[d][0], doc_entry[d][1]), (d, f)
+                assert engines[owner].clf.doc_info(d) == ox.doc_info(d)
+                with pytest.raises(Exception):
+                    engines[1 - owner].clf.doc_fields(d)
+        assert seen_owner == {0, 1}
     finally:
         for e in engines:
             e.clf.close()
