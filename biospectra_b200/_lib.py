@@ -47,7 +47,7 @@ EXPORTS = [
     "bsp_index_stats", "bsp_doc_info", "bsp_term_postings", "bsp_tokenize", "bsp_last_routes", "bsp_last_counters",
     "bsp_last_timings", "bsp_memory_info", "bsp_partition_df_buffer", "bsp_partition_local_stats",
     "bsp_partition_set_global", "bsp_merge_topk_device", "bsp_read_cost",
-    "bsp_host_index", "bsp_host_classify_local", "bsp_host_classify_local_per_read", "bsp_host_last_error", "bsp_host_label_json", "bsp_host_read_fasta",
+    "bsp_host_index", "bsp_host_classify_local", "bsp_host_classify_local_per_read", "bsp_host_last_error", "bsp_host_label_json", "bsp_host_read_fasta", "bsp_index_add_fasta",
     "bsp_host_double_to_string", "bsp_host_parse_config",
 ]
 
@@ -105,6 +105,7 @@ def lib():
     L.bsp_host_last_error.restype = C.c_char_p
     L.bsp_host_label_json.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.c_char_p, C.c_int32]
     L.bsp_host_read_fasta.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, i64p]
+    L.bsp_index_add_fasta.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.bsp_host_double_to_string.argtypes = [C.c_double, C.c_char_p, C.c_int32]
     L.bsp_host_parse_config.argtypes = [C.c_char_p, cfgp, C.c_char_p, C.c_int32]
     _lib = L

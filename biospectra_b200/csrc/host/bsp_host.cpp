@@ -291,9 +291,8 @@ void Indexer::index(const std::vector<std::string>& fastaDocs) {                
 void Indexer::index(const std::string& fastaDoc) {                                     // :141-148
     index(fastaDoc, FastaFileHelper::findTaxonHierarchyDoc(fastaDoc));
 }
-void Indexer::index(const std::string& fastaDoc, const std::string& taxonDoc) {        // :150-236
-    std::lock_guard<std::mutex> lk(mu_);
-    if (!h_) throw std::runtime_error("indexer is closed");
+// Indexer.index(File fastaDoc, File taxonDoc) (Indexer.java:150-236) on a C-ABI indexer handle
+void index_fasta_into(bsp_indexer* h, const std::string& fastaDoc, const std::string& taxonDoc) {
     std::string taxonTree;
     if (!taxonDoc.empty() && file_exists(taxonDoc)) taxonTree = read_text_file(taxonDoc);   // :157-161
     FASTAReader reader(fastaDoc);
@@ -302,11 +301,16 @@ void Indexer::index(const std::string& fastaDoc, const std::string& taxonDoc) { 
     while (reader.readNext(read)) {
         std::string header = read.headerLine;
         if (!header.empty() && header[0] == '>') header = header.substr(1);            // :167-170
-        int rc = bsp_index_add_entry(h_, filename.c_str(), header.c_str(), taxonTree.c_str(), read.sequence.data(),
+        int rc = bsp_index_add_entry(h, filename.c_str(), header.c_str(), taxonTree.c_str(), read.sequence.data(),
                                      (int64_t)read.sequence.size());
         if (rc != BSP_OK)                                                              // :227-229 log and continue
             fprintf(stderr, "ERROR Exception occurred during index construction: %s\n", last_err().c_str());
     }
+}
+void Indexer::index(const std::string& fastaDoc, const std::string& taxonDoc) {        // :150-236
+    std::lock_guard<std::mutex> lk(mu_);
+    if (!h_) throw std::runtime_error("indexer is closed");
+    index_fasta_into(h_, fastaDoc, taxonDoc);
 }
 void Indexer::close() {                                                                // :239-251
     std::lock_guard<std::mutex> lk(mu_);
@@ -945,6 +949,16 @@ HOST_API int bsp_host_label_json(const char* const* taxon_hierarchies, int32_t n
         memcpy(out, js.c_str(), js.size() + 1);
         return BSP_OK;
     } catch (const std::exception& e) { g_host_error = e.what(); return BSP_ERR_STATE; }
+}
+
+// Indexer.index(File, File) behind the plain C ABI (what the JNI shim's indexAddFasta binds): the library's own
+// FASTAReader + one bsp_index_add_entry per entry.  Entries read before a data error stay indexed, like the reference's.
+HOST_API int bsp_index_add_fasta(bsp_indexer* h, const char* fasta_path, const char* taxd_path_or_null) {
+    if (!h || !fasta_path) { g_host_error = "fastaDoc is null"; return BSP_ERR_ARG; }      // Indexer.java:151-153
+    try {
+        bsp::index_fasta_into(h, fasta_path, taxd_path_or_null ? std::string(taxd_path_or_null) : std::string());
+        return BSP_OK;
+    } catch (const std::exception& ex) { g_host_error = ex.what(); return BSP_ERR_IO; }
 }
 
 // parse a FASTA file with A.1 semantics; writes "header\x1Fsequence\x1E" records (unit / record separators: headers

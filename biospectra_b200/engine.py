@@ -35,6 +35,12 @@ class Indexer:
         seq = _b(sequence)
         _lib.check(self.L.bsp_index_add_entry(self.h, _b(filename), _b(header), _b(taxonomy or ""), seq, len(seq)), self.h)
 
+    def add_fasta(self, fasta_path, taxd_path=None):
+        """Indexer.index(File fastaDoc, File taxonDoc) (Indexer.java:150-236) through bsp_index_add_fasta."""
+        rc = self.L.bsp_index_add_fasta(self.h, _b(str(fasta_path)), _b(str(taxd_path)) if taxd_path else None)
+        if rc:
+            raise IOError(self.L.bsp_host_last_error().decode("utf-8", "replace"))
+
     def add_entry_device(self, filename, header, taxonomy, dev_ptr: int, length: int):
         _lib.check(self.L.bsp_index_add_entry_device(self.h, _b(filename), _b(header), _b(taxonomy or ""),
                                                      C.c_void_p(dev_ptr), length), self.h)

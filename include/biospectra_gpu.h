@@ -99,7 +99,12 @@ int bsp_index_create(const bsp_config* conf, const char* index_path, bsp_indexer
  * logs and skips (Indexer.java:227-229). */
 int bsp_index_add_entry(bsp_indexer* h, const char* filename, const char* header, const char* taxonomy,
                         const char* seq, int64_t seq_len);
-/* same, with the sequence already resident in device memory (uint8 ASCII) */
+/* Indexer.index(File fastaDoc, File taxonDoc) (Indexer.java:150-236) in one call: the library's own FASTA reader
+ * (org.yeastrc.fasta.FASTAReader#readNext semantics, gzip by file name) + one bsp_index_add_entry per entry with
+ * filename = the file's base name; taxd_path may be NULL or missing on disk ("" taxonomy).  A malformed file returns
+ * BSP_ERR_IO after the entries before the error were added (message: bsp_host_last_error()). */
+int bsp_index_add_fasta(bsp_indexer* h, const char* fasta_path, const char* taxd_path_or_null);
+/* same as bsp_index_add_entry, with the sequence already resident in device memory (uint8 ASCII) */
 int bsp_index_add_entry_device(bsp_indexer* h, const char* filename, const char* header, const char* taxonomy,
                                const void* d_seq, int64_t seq_len);
 int bsp_index_close(bsp_indexer* h);

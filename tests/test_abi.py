@@ -86,3 +86,45 @@ def test_no_oracle_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", "Makefile")):
                 txt = open(os.path.join(root, f), errors="replace").read()
                 assert "oracle_lib" not in txt and "spec_oracle" not in txt and "libbsp_oracle" not in txt, f
+
+
+# ------------------------------------------------------------------ the JNI layer (jni/)
+def test_jni_shim_compiles_and_binds_every_native():
+    """jni/biospectra_gpu_jni.c parses and type-checks (against jni/stub/jni.h: no JDK in this image) with warnings as
+    errors, links against the library's exports, and implements exactly the natives BioSpectraGpu.java declares."""
+    import subprocess
+    import tempfile
+    src = os.path.join(ROOT, "jni", "biospectra_gpu_jni.c")
+    with tempfile.TemporaryDirectory() as td:
+        obj = os.path.join(td, "jni.o")
+        subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fPIC", "-c", "-I", os.path.join(ROOT, "jni", "stub"),
+                               "-I", os.path.join(ROOT, "include"), src, "-o", obj])
+        # every bsp_* symbol the shim references is exported by the library
+        und = subprocess.check_output(["nm", "-u", obj], text=True)
+        used = sorted(set(re.findall(r"\b(bsp_[a-z0-9_]+)", und)))
+        assert used and "bsp_classify_one" in used and "bsp_index_add_entry" in used
+        from biospectra_b200 import _lib
+        L = _lib.lib()
+        assert not [s for s in used if not hasattr(L, s)]
+        defined = subprocess.check_output(["nm", "--defined-only", obj], text=True)
+        c_natives = sorted(set(re.findall(r"Java_biospectra_gpu_BioSpectraGpu_(\w+)", defined)))
+    java = open(os.path.join(ROOT, "jni", "java", "biospectra", "gpu", "BioSpectraGpu.java")).read()
+    j_natives = sorted(set(re.findall(r"public static native [\w\[\]]+ (\w+)\(", java)))
+    assert c_natives == j_natives, (c_natives, j_natives)
+    assert len(j_natives) >= 12
+
+
+def test_jni_patches_replace_lucene_in_the_two_seam_classes():
+    """jni/patches/*.patch (made by jni/patches/make_patches.py against /root/reference/src): after patching, Indexer and
+    Classifier call BioSpectraGpu and import nothing from org.apache.lucene."""
+    for name, must in (("Indexer.java.patch", ("BioSpectraGpu.indexCreate", "BioSpectraGpu.indexAddEntry", "BioSpectraGpu.indexClose")),
+                       ("Classifier.java.patch", ("BioSpectraGpu.classifierOpen", "BioSpectraGpu.classifyOne", "BioSpectraGpu.docFields",
+                                                  "BioSpectraGpu.classifierClose"))):
+        txt = open(os.path.join(ROOT, "jni", "patches", name)).read()
+        added = [l[1:] for l in txt.splitlines() if l.startswith("+") and not l.startswith("+++")]
+        removed = [l[1:] for l in txt.splitlines() if l.startswith("-") and not l.startswith("---")]
+        for m in must:
+            assert any(m in l for l in added), (name, m)
+        assert not any("org.apache.lucene" in l for l in added)
+        n_lucene_imports = sum(1 for l in removed if l.startswith("import org.apache.lucene"))
+        assert n_lucene_imports >= 8, (name, n_lucene_imports)
