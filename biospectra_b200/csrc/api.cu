@@ -1269,6 +1269,66 @@ BSP_API int bsp_partition_set_global(bsp_classifier* h, int64_t doc_base, int64_
     API_CATCH(h)
 }
 
+BSP_API int bsp_index_layout(bsp_classifier* h, int64_t out[8]) {
+    if (!h || !out) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    const GpuIndex& ix = h->ix;
+    out[0] = (i64)ix.row_bytes; out[1] = (i64)ix.d_pad; out[2] = (i64)ix.segs.size(); out[3] = (i64)ix.max_seg_docs;
+    out[4] = ix.tables ? 1 : 0; out[5] = ix.positional ? 1 : 0; out[6] = ix.has_pair ? 1 : 0; out[7] = ix.direct ? 0 : 1;
+    return BSP_OK;
+}
+
+BSP_API int bsp_pack_topk_device(bsp_classifier* h, int32_t n, const void* d_n_top, const void* d_top_doc, const void* d_top_score,
+                                 void* d_records) {
+    if (!h || !d_n_top || !d_top_doc || !d_top_score || !d_records) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    API_TRY(h)
+    CUDA_CHECK(cudaSetDevice(h->conf.device));
+    pack_lists_kernel<<<(unsigned)ceil_div(std::max<i64>((i64)n * LIST_REC_WORDS, 1), 256), 256, 0, h->st>>>(
+        n, (const i32*)d_n_top, (const i32*)d_top_doc, (const float*)d_top_score, (i32*)d_records);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaStreamSynchronize(h->st));
+    return BSP_OK;
+    API_CATCH(h)
+}
+
+BSP_API int bsp_merge_topk_records_device(bsp_classifier* h, int32_t n, int32_t parts, const void* d_records, const void* d_part_status,
+                                          void* d_status, void* d_label, void* d_n_hits, void* d_n_top, void* d_top_doc,
+                                          void* d_top_score) {
+    if (!h || !d_records || !d_part_status) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    API_TRY(h)
+    CUDA_CHECK(cudaSetDevice(h->conf.device));
+    merge_records_kernel<<<(unsigned)ceil_div(std::max(n, 1), 128), 128, 0, h->st>>>(n, parts, (const i32*)d_records,
+        (const i32*)d_part_status, (i32*)d_status, (i32*)d_label, (i32*)d_n_hits, (i32*)d_n_top, (i32*)d_top_doc, (float*)d_top_score,
+        (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaStreamSynchronize(h->st));
+    return BSP_OK;
+    API_CATCH(h)
+}
+
+BSP_API int bsp_classifier_set_query(bsp_classifier* h, const bsp_config* query_conf) {
+    if (!h || !query_conf) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    const int rc = check_query_conf(query_conf);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(h->mu);
+    API_TRY(h)
+    if (query_conf->kmer_size != h->conf.kmer_size || (query_conf->min_strand_kmer != 0) != (h->conf.min_strand_kmer != 0))
+        throw BspError(BSP_ERR_ARG, "kmer_size / min_strand_kmer belong to the index: open another classifier for them");
+    if (query_conf->query_algorithm != BSP_NAIVE_KMER && h->ix.tables && !h->ix.has_pair && !h->ix.positional)
+        throw BspError(BSP_ERR_STATE, "the index was opened for NAIVE_KMER without pair tables or positional postings");
+    CUDA_CHECK(cudaSetDevice(h->conf.device));
+    for (int i = 0; i < BSP_SLOTS; i++) CUDA_CHECK(cudaStreamSynchronize(h->sc[i].st));
+    h->conf.kmer_skips = query_conf->kmer_skips;
+    h->conf.query_algorithm = query_conf->query_algorithm;
+    h->conf.scoring_algorithm = query_conf->scoring_algorithm;
+    h->conf.query_term_min_should_match = query_conf->query_term_min_should_match;
+    h->conf.full_topn = query_conf->full_topn;
+    upload_scoring_constants(h);
+    return BSP_OK;
+    API_CATCH(h)
+}
+
 BSP_API int bsp_merge_topk_device(bsp_classifier* h, int32_t n, int32_t parts, const void* d_part_n_top, const void* d_part_doc,
                                   const void* d_part_score, const void* d_part_status, void* d_status, void* d_label,
                                   void* d_n_hits, void* d_n_top, void* d_top_doc, void* d_top_score) {

@@ -855,6 +855,55 @@ __global__ void __launch_bounds__(128) merge_kernel(i32 n_reads, const i32* __re
     }
 }
 
+// Doc-partitioned mode: one record per read and rank, so that the hit lists cross NVLink in ONE all_gather and the merge
+// reads them where the collective left them.  Record = 21 words: n_top | doc[10] (global ids) | score[10] (float bits).
+#define LIST_REC_WORDS (1 + 2 * TOPN)
+__global__ void __launch_bounds__(256) pack_lists_kernel(i32 n_reads, const i32* __restrict__ n_top, const i32* __restrict__ top_doc,
+                                                          const float* __restrict__ top_score, i32* __restrict__ rec) {
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (i64)n_reads * LIST_REC_WORDS) return;
+    const i32 r = (i32)(t / LIST_REC_WORDS), w = (i32)(t % LIST_REC_WORDS);
+    rec[t] = w == 0 ? n_top[r] : (w <= TOPN ? top_doc[(i64)r * TOPN + (w - 1)] : __float_as_int(top_score[(i64)r * TOPN + (w - 1 - TOPN)]));
+}
+// Thread per read over the gathered records, rank-major as all_gather_into_tensor lays them out: rec[(p * n_reads + r) * 21].
+// Same collector order, equal-to-max rule and label as merge_kernel.
+__global__ void __launch_bounds__(128) merge_records_kernel(i32 n_reads, int parts, const i32* __restrict__ rec,
+                                                             const i32* __restrict__ status_in, i32* __restrict__ status,
+                                                             i32* __restrict__ label, i32* __restrict__ n_hits, i32* __restrict__ n_top,
+                                                             i32* __restrict__ top_doc, float* __restrict__ top_score, int full_topn) {
+    const i32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    float bs[TOPN];
+    u32 bd[TOPN];
+    int nt = 0;
+    for (int p = 0; p < parts; p++) {
+        const i32* q = rec + ((i64)p * n_reads + r) * LIST_REC_WORDS;
+        const int np = min(max(q[0], 0), TOPN);
+        for (int j = 0; j < np; j++) {
+            const float s = __int_as_float(q[1 + TOPN + j]);
+            const u32 d = (u32)q[1 + j];
+            int pos = nt;
+            while (pos > 0 && (bs[pos - 1] < s || (bs[pos - 1] == s && bd[pos - 1] > d))) pos--;
+            if (pos >= TOPN) break;
+            const int last = nt < TOPN ? nt : TOPN - 1;
+            for (int x = last; x > pos; x--) { bs[x] = bs[x - 1]; bd[x] = bd[x - 1]; }
+            bs[pos] = s; bd[pos] = d;
+            if (nt < TOPN) nt++;
+        }
+    }
+    int nh = 0;
+    for (int j = 0; j < nt; j++) if ((double)bs[0] - (double)bs[j] == 0.0) nh++;
+    if (!full_topn) nt = nh;
+    if (status) status[r] = status_in[r];
+    if (label) label[r] = nh == 0 ? 0 : (nh == 1 ? 2 : 1);
+    if (n_hits) n_hits[r] = nh;
+    if (n_top) n_top[r] = nt;
+    for (int j = 0; j < TOPN; j++) {
+        if (top_doc) top_doc[(i64)r * TOPN + j] = j < nt ? (i32)bd[j] : -1;
+        if (top_score) top_score[(i64)r * TOPN + j] = j < nt ? bs[j] : 0.0f;
+    }
+}
+
 // Taxonomy-aware label of a read from its hit list (Classifier.java:263-339, after the hits equal to the maximum are
 // known).  lin_off/lin_tax: per document the taxids of TaxonTreeDescription#getClassifiableTaxonomyTree (the entries
 // with a rank, leaf -> root); flags bit0 = the document has a taxonomy string, bit1 = it is malformed (the reference

@@ -169,6 +169,13 @@ class Classifier:
                                               vp(d_n_hits), vp(d_n_top), vp(d_top_doc), vp(d_top_score)), self.h)
 
     # ------------------------------------------------------------- introspection
+    def set_query(self, conf: Configuration):
+        """new query-side settings on the open index (bsp_classifier_set_query): the reference constructs another
+        Classifier(Configuration) on the same index directory for this"""
+        cs = conf.to_struct()
+        _lib.check(self.L.bsp_classifier_set_query(self.h, C.byref(cs)), self.h)
+        self.conf = conf
+
     def doc_fields(self, doc: int):
         p = [C.c_char_p() for _ in range(4)]
         _lib.check(self.L.bsp_doc_fields(self.h, doc, *[C.byref(x) for x in p]), self.h)
@@ -225,6 +232,12 @@ class Classifier:
         _lib.check(self.L.bsp_memory_info(self.h, *[C.byref(x) for x in v]), self.h)
         return dict(zip(("positional_bytes", "table_bytes", "staged_bytes"), [x.value for x in v]))
 
+    def layout(self):
+        out = (C.c_int64 * 8)()
+        _lib.check(self.L.bsp_index_layout(self.h, out), self.h)
+        keys = ("row_bytes", "d_pad", "segments", "max_seg_docs", "tables", "positional", "has_pair", "hash_dictionary")
+        return dict(zip(keys, [int(x) for x in out]))
+
     def read_cost(self, seq_bytes: np.ndarray, offsets: np.ndarray):
         """Cost model of SURVEY.md 8(d) evaluated on the actual index (see bsp_read_cost)."""
         out = np.zeros(8, np.int64)
@@ -253,6 +266,15 @@ class Classifier:
         vp = C.c_void_p
         _lib.check(self.L.bsp_merge_topk_device(self.h, n, parts, vp(p_ntop), vp(p_doc), vp(p_score), vp(p_status), vp(status),
                                                 vp(label), vp(n_hits), vp(n_top), vp(top_doc), vp(top_score)), self.h)
+
+    def pack_topk_device(self, n, n_top, top_doc, top_score, records):
+        vp = C.c_void_p
+        _lib.check(self.L.bsp_pack_topk_device(self.h, n, vp(n_top), vp(top_doc), vp(top_score), vp(records)), self.h)
+
+    def merge_topk_records_device(self, n, parts, records, p_status, status, label, n_hits, n_top, top_doc, top_score):
+        vp = C.c_void_p
+        _lib.check(self.L.bsp_merge_topk_records_device(self.h, n, parts, vp(records), vp(p_status), vp(status), vp(label),
+                                                        vp(n_hits), vp(n_top), vp(top_doc), vp(top_score)), self.h)
 
     def close(self):
         if self.h:

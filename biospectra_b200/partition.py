@@ -7,8 +7,8 @@
   reference entries.  Lucene's docFreq / maxDoc / sumTotalTermFreq are collection-wide
   (lucene!search/IndexSearcher#termStatistics, #collectionStatistics), so after the local build the ranks
   all-reduce the dense per-term df array and exchange (docs, tokens); at query time every rank scores all reads
-  against its own docs, ONE all_gather moves the per-rank hit lists (80 B per read and rank), and the merge applies
-  the collector order (score desc, global doc id asc), the equal-to-max rule (Classifier.java:358-366) and the label.
+  against its own docs, ONE all_gather moves the per-rank hit lists (one 84-byte record per read and rank: n_top |
+  doc[10] | score[10]), and the merge reads the records where the collective left them and applies the collector order (score desc, global doc id asc), the equal-to-max rule (Classifier.java:358-366) and the label.
 
 The engine behind it is anything with the small interface of `GpuPartitionEngine` (the CUDA library); the CPU
 tests drive the same orchestration over gloo with an oracle-backed engine.
@@ -58,14 +58,21 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
+REC_WORDS = 1 + 2 * TOPN        # int32 words per (read, rank) record: n_top | doc[10] | score bits[10]
+
+
 class GpuPartitionEngine:
     """Adapter of biospectra_b200.Classifier (a handle opened with conf.part_rank / part_count, or built from this
-    rank's slice of the entries) to the interface DocPartitionedClassifier drives."""
+    rank's slice of the entries) to the interface DocPartitionedClassifier drives.  The reads go up from page-locked
+    staging buffers on a side stream; outputs and records live in buffers that are reused from step to step."""
 
     def __init__(self, classifier, device):
         import torch
         self.clf = classifier
         self.device = torch.device(device)
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._pin = {}          # name -> pinned host tensor
+        self._dev = {}          # name -> device tensor
 
     def local_stats(self):
         return self.clf.partition_local_stats()
@@ -78,35 +85,73 @@ class GpuPartitionEngine:
     def set_global(self, doc_base, global_docs, global_sum_ttf):
         self.clf.partition_set_global(doc_base, global_docs, global_sum_ttf)
 
-    def classify_lists(self, seq_bytes, offsets):
-        """reads on the host (uint8 array + int64 offsets) -> per-read lists with GLOBAL doc ids, device tensors"""
+    def _buf(self, name, shape, dtype, pinned=False):
         import torch
+        pool = self._pin if pinned else self._dev
+        t = pool.get(name)
+        need = int(np.prod(shape))
+        if t is None or t.dtype != dtype or t.numel() < need:
+            t = (torch.empty(need, dtype=dtype, pin_memory=True) if pinned
+                 else torch.empty(need, dtype=dtype, device=self.device))
+            pool[name] = t
+        return t[:need].view(*shape)
+
+    def upload(self, seq_bytes, offsets):
+        """host reads -> device (page-locked staging, asynchronous copies on a side stream; waited for before use)"""
+        import torch
+        seq_bytes = np.asarray(seq_bytes, np.uint8)
+        offsets = np.asarray(offsets, np.int64)
         n = len(offsets) - 1
-        d_seq = torch.from_numpy(np.ascontiguousarray(seq_bytes, np.uint8)).to(self.device)
-        d_off = torch.from_numpy(np.ascontiguousarray(offsets, np.int64)).to(self.device)
-        o = {k: torch.empty(n, dtype=torch.int32, device=self.device) for k in ("status", "label", "n_hits", "n_top")}
-        o["top_doc"] = torch.empty(n, TOPN, dtype=torch.int32, device=self.device)
-        o["top_score"] = torch.empty(n, TOPN, dtype=torch.float32, device=self.device)
-        torch.cuda.current_stream(self.device).synchronize()
-        self.clf.classify_device(n, d_seq.data_ptr(), d_off.data_ptr(), int(offsets[-1]), o["status"].data_ptr(),
-                                 o["label"].data_ptr(), o["n_hits"].data_ptr(), o["n_top"].data_ptr(), o["top_doc"].data_ptr(),
-                                 o["top_score"].data_ptr())
+        h_seq = self._buf("seq", (len(seq_bytes),), torch.uint8, pinned=True)
+        h_off = self._buf("off", (n + 1,), torch.int64, pinned=True)
+        h_seq.numpy()[:] = seq_bytes
+        h_off.numpy()[:] = offsets
+        d_seq = self._buf("seq", (len(seq_bytes),), torch.uint8)
+        d_off = self._buf("off", (n + 1,), torch.int64)
+        with torch.cuda.stream(self._copy_stream):
+            d_seq.copy_(h_seq, non_blocking=True)
+            d_off.copy_(h_off, non_blocking=True)
+        return d_seq, d_off, int(offsets[-1])
+
+    def _outputs(self, tag, n):
+        import torch
+        o = {k: self._buf(tag + k, (n,), torch.int32) for k in ("status", "label", "n_hits", "n_top")}
+        o["top_doc"] = self._buf(tag + "top_doc", (n, TOPN), torch.int32)
+        o["top_score"] = self._buf(tag + "top_score", (n, TOPN), torch.float32)
         return o
 
-    def merge(self, n, parts, p_status, p_n_top, p_doc, p_score):
+    def classify_records(self, seq_bytes, offsets, device_reads=None):
+        """reads -> (status[n], records[n, 21]) on the device, doc ids GLOBAL.  device_reads = (d_seq, d_off, total_bytes)
+        skips the upload (reads already resident)."""
         import torch
-        o = {k: torch.empty(n, dtype=torch.int32, device=self.device) for k in ("status", "label", "n_hits", "n_top")}
-        o["top_doc"] = torch.empty(n, TOPN, dtype=torch.int32, device=self.device)
-        o["top_score"] = torch.empty(n, TOPN, dtype=torch.float32, device=self.device)
+        n = len(offsets) - 1
+        d_seq, d_off, total = device_reads if device_reads is not None else self.upload(seq_bytes, offsets)
+        o = self._outputs("loc_", n)
+        rec = self._buf("rec", (n, REC_WORDS), torch.int32)
+        self._copy_stream.synchronize()
         torch.cuda.current_stream(self.device).synchronize()
-        self.clf.merge_topk_device(n, parts, p_n_top.data_ptr(), p_doc.data_ptr(), p_score.data_ptr(), p_status.data_ptr(),
-                                   o["status"].data_ptr(), o["label"].data_ptr(), o["n_hits"].data_ptr(), o["n_top"].data_ptr(),
-                                   o["top_doc"].data_ptr(), o["top_score"].data_ptr())
+        self.clf.classify_device(n, d_seq.data_ptr(), d_off.data_ptr(), total, o["status"].data_ptr(), o["label"].data_ptr(),
+                                 o["n_hits"].data_ptr(), o["n_top"].data_ptr(), o["top_doc"].data_ptr(), o["top_score"].data_ptr())
+        self.clf.pack_topk_device(n, o["n_top"].data_ptr(), o["top_doc"].data_ptr(), o["top_score"].data_ptr(), rec.data_ptr())
+        return o["status"], rec
+
+    def gather_buffer(self, world, n):
+        import torch
+        return self._buf("gathered", (world, n, REC_WORDS), torch.int32)
+
+    def merge_records(self, n, parts, status, gathered):
+        import torch
+        o = self._outputs("out_", n)
+        torch.cuda.current_stream(self.device).synchronize()        # the collective wrote `gathered` on torch's stream
+        self.clf.merge_topk_records_device(n, parts, gathered.data_ptr(), status.data_ptr(), o["status"].data_ptr(),
+                                           o["label"].data_ptr(), o["n_hits"].data_ptr(), o["n_top"].data_ptr(),
+                                           o["top_doc"].data_ptr(), o["top_score"].data_ptr())
         return o
 
 
 class DocPartitionedClassifier:
-    """Orchestrates the two collectives of the doc-partitioned mode over `torch.distributed`."""
+    """Orchestrates the collectives of the doc-partitioned mode over `torch.distributed`: at open time the statistics
+    (one all_gather of two scalars + one all_reduce of the df array), per query batch exactly ONE all_gather."""
 
     def __init__(self, engine, group=None):
         import torch.distributed as dist
@@ -117,6 +162,7 @@ class DocPartitionedClassifier:
         self.doc_base = 0
         self.global_docs = 0
         self.global_sum_ttf = 0
+        self.collectives = 0         # data-path collectives issued by classify() so far
 
     def sync_statistics(self):
         """after the local index is built: global df (in place), maxDoc, sumTotalTermFreq, this rank's doc id base"""
@@ -135,18 +181,13 @@ class DocPartitionedClassifier:
         self.engine.set_global(self.doc_base, self.global_docs, self.global_sum_ttf)
         return self
 
-    def classify(self, seq_bytes, offsets):
+    def classify(self, seq_bytes, offsets, device_reads=None):
         """every rank passes the SAME reads; returns the merged per-read results (identical on every rank)"""
-        import torch
         import torch.distributed as dist
         n = len(offsets) - 1
-        loc = self.engine.classify_lists(seq_bytes, offsets)
-        gathered = {}
-        for key in ("n_top", "top_doc", "top_score"):
-            t = loc[key].contiguous()
-            buf = [torch.empty_like(t) for _ in range(self.world)]
-            dist.all_gather(buf, t, group=self.group)
-            g = torch.stack(buf, dim=1).contiguous()          # [n, world, ...]: the layout bsp_merge_topk_device reads
-            gathered[key] = g
+        status, rec = self.engine.classify_records(seq_bytes, offsets, device_reads)
+        gathered = self.engine.gather_buffer(self.world, n)
+        dist.all_gather_into_tensor(gathered.view(self.world * n, REC_WORDS), rec, group=self.group)      # rank-major concatenation
+        self.collectives += 1
         # the per-read status depends on the read only (tokens, clause count): identical on every rank
-        return self.engine.merge(n, self.world, loc["status"], gathered["n_top"], gathered["top_doc"], gathered["top_score"])
+        return self.engine.merge_records(n, self.world, status, gathered)

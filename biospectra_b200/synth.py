@@ -123,11 +123,14 @@ def build_reference_and_reads_cuda(indexer, lengths, n_reads: int, R: int, err: 
     maxlen = R + max(R // 5, 1)
     for g in range(G):
         L = int(lengths[g])
+        wanted = indexer is not None and (rank_slice is None or rank_slice(g))
+        if not wanted and g not in keep_genomes and int(per[g]) == 0:
+            continue                                    # nobody needs this genome (another rank's slice, no reads drawn)
         gen.manual_seed(int(seed) * 1_000_003 + g)
         codes = torch.randint(0, 4, (L,), dtype=torch.uint8, device=device, generator=gen)
         seq = lut[codes.long()]
         del codes
-        if indexer is not None and (rank_slice is None or rank_slice(g)):
+        if wanted:
             # the library packs on its own (non-blocking) stream: the genome must be complete first
             torch.cuda.current_stream(device).synchronize()
             indexer.add_entry_device("%d.fna" % g, header_of(g), "", seq.data_ptr(), L)

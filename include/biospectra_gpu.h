@@ -170,6 +170,11 @@ int bsp_classify_device(bsp_classifier* h, int32_t n, const void* d_seq_bytes, c
                         int64_t total_bytes, int32_t max_len,
                         void* d_status, void* d_label, void* d_n_hits, void* d_n_top,
                         void* d_top_doc, void* d_top_score);
+/* New query-side settings on an open classifier (kmer_skips, query_algorithm, scoring_algorithm,
+ * query_term_min_should_match, full_topn): what constructing a second Classifier(Configuration) on the same index
+ * directory is in the reference (Classifier.java:71-111 -- the IndexReader is reopened, the index is not rebuilt).
+ * kmer_size / min_strand_kmer belong to the index and must match (BSP_ERR_ARG).  Waits for running batches. */
+int bsp_classifier_set_query(bsp_classifier* h, const bsp_config* query_conf);
 /* stored fields of a document (IndexSearcher.doc(), Classifier.java:361-363);
  * borrowed pointers, valid until close.  `doc` is an id as classify / merge report it: after
  * bsp_partition_set_global that is the GLOBAL id, and the call returns BSP_ERR_ARG for a document another
@@ -206,6 +211,10 @@ int bsp_last_timings(bsp_classifier* h, double* score_kernel_ms, double* pipelin
  * query terms (= dictionary probes), [3] sum df, [4] sum ttf over unique terms,
  * [5] A_read bytes (CSR formula), [6] bytes the dense-table layout reads, [7] clauses */
 int bsp_read_cost(bsp_classifier* h, int32_t n, const char* seq_bytes, const int64_t* seq_offsets, int64_t out[8]);
+/* layout of the resident index: [0] bytes per dense-table row, [1] padded doc count of a row, [2] positional segments,
+ * [3] most docs in one segment (<= 256: the warp-per-(segment, read) positional scorer runs, else the CTA one),
+ * [4] dense tables resident, [5] positional postings resident, [6] pair rows built, [7] dictionary: 0 direct table, 1 hash */
+int bsp_index_layout(bsp_classifier* h, int64_t out[8]);
 int bsp_memory_info(bsp_classifier* h, int64_t* positional_bytes, int64_t* table_bytes, int64_t* staged_bytes);
 
 /* --------------------------------------------- doc-partitioned mode plumbing
@@ -224,6 +233,16 @@ int bsp_merge_topk_device(bsp_classifier* h, int32_t n, int32_t parts,
                           const void* d_part_status,
                           void* d_status, void* d_label, void* d_n_hits, void* d_n_top,
                           void* d_top_doc, void* d_top_score);
+
+/* The same exchange with ONE collective: bsp_pack_topk_device turns a rank's lists into one 84-byte record per read
+ * (int32 n_top | int32 doc[10], global ids | float score[10]); the host all-gathers the record arrays rank-major
+ * (records[(rank * n + read) * 21], e.g. ncclAllGather / all_gather_into_tensor) and bsp_merge_topk_records_device merges
+ * them where the collective left them.  All pointers are device pointers. */
+int bsp_pack_topk_device(bsp_classifier* h, int32_t n, const void* d_n_top, const void* d_top_doc, const void* d_top_score,
+                         void* d_records);
+int bsp_merge_topk_records_device(bsp_classifier* h, int32_t n, int32_t parts, const void* d_records, const void* d_part_status,
+                                  void* d_status, void* d_label, void* d_n_hits, void* d_n_top, void* d_top_doc,
+                                  void* d_top_score);
 
 /* ------------------------------------------------ host-side entry points
  * The reference's drivers above the two classes, restated in C++ (no JVM here):

@@ -1,6 +1,6 @@
 """Doc-partitioned mode on one GPU: two handles hold the two halves of the reference (what two ranks would hold);
-the df all-reduce is done by hand on the exposed device buffers, the hit lists are stacked like the all_gather does,
-and bsp_merge_topk_device must reproduce the single-index oracle (which is also what Lucene would return: idf, maxDoc
+the df all-reduce is done by hand on the exposed device buffers, the per-rank records are concatenated like the all_gather does,
+and bsp_merge_topk_records_device must reproduce the single-index oracle (which is also what Lucene would return: idf, maxDoc
 and avgdl are collection-wide)."""
 import random
 
@@ -50,10 +50,32 @@ def test_two_partitions_merge_to_single_index(oracle_lib, k, alg, sim, full):
         data = np.frombuffer(b"".join(r.encode() for r in reads), np.uint8)
         off = np.zeros(len(reads) + 1, np.int64)
         np.cumsum([len(r) for r in reads], out=off[1:])
-        lists = [e.classify_lists(data, off) for e in engines]
+        # what DocPartitionedClassifier.classify does around its one all_gather_into_tensor: per-rank records, concatenated
+        # rank-major, merged in place by bsp_merge_topk_records_device
+        parts = []
+        for e in engines:
+            status, rec = e.classify_records(data, off)
+            torch.cuda.synchronize()
+            parts.append((status.clone(), rec.clone()))
+        gathered = engines[0].gather_buffer(2, len(reads))
+        gathered.copy_(torch.stack([p[1] for p in parts], dim=0))
         torch.cuda.synchronize()
-        g = {key: torch.stack([l[key] for l in lists], dim=1).contiguous() for key in ("n_top", "top_doc", "top_score")}
-        out = engines[0].merge(len(reads), 2, lists[0]["status"], g["n_top"], g["top_doc"], g["top_score"])
+        out = engines[0].merge_records(len(reads), 2, parts[0][0], gathered)
+        # the three-array form of the same exchange (bsp_merge_topk_device) agrees
+        recs = [p[1].cpu().numpy() for p in parts]
+        n_top3 = torch.from_numpy(np.stack([r[:, 0] for r in recs], axis=1).copy()).to(dev)
+        doc3 = torch.from_numpy(np.stack([r[:, 1:11] for r in recs], axis=1).copy()).to(dev)
+        score3 = torch.from_numpy(np.stack([r[:, 11:21] for r in recs], axis=1).copy().view(np.float32)).to(dev)
+        o3 = {k_: torch.empty(len(reads), dtype=torch.int32, device=dev) for k_ in ("status", "label", "n_hits", "n_top")}
+        o3["top_doc"] = torch.empty(len(reads), 10, dtype=torch.int32, device=dev)
+        o3["top_score"] = torch.empty(len(reads), 10, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        engines[0].clf.merge_topk_device(len(reads), 2, n_top3.data_ptr(), doc3.data_ptr(), score3.data_ptr(), parts[0][0].data_ptr(),
+                                         o3["status"].data_ptr(), o3["label"].data_ptr(), o3["n_hits"].data_ptr(), o3["n_top"].data_ptr(),
+                                         o3["top_doc"].data_ptr(), o3["top_score"].data_ptr())
+        torch.cuda.synchronize()
+        for key in o3:
+            assert torch.equal(o3[key], out[key]), key
         torch.cuda.synchronize()
         res_g = {key: v.cpu().numpy() for key, v in out.items()}
         common.assert_classify_equal(res_g, res_o, reads, "two partitions k%d" % k, hits_only=not full)

@@ -48,23 +48,31 @@ class OracleEngine:
         self.doc_base = doc_base
         self.ox.set_global(global_docs, global_sum_ttf, self.df.numpy().astype(np.uint32))
 
-    def classify_lists(self, seq_bytes, offsets):
+    def classify_records(self, seq_bytes, offsets, device_reads=None):
         reads = [bytes(seq_bytes[offsets[i]:offsets[i + 1]]) for i in range(len(offsets) - 1)]
         r = self.ox.classify(reads, **self.qconf)
         doc = r["top_doc"].copy()
         doc[doc >= 0] += self.doc_base
-        return {"status": torch.from_numpy(r["status"]), "n_top": torch.from_numpy(r["n_top"]),
-                "top_doc": torch.from_numpy(doc), "top_score": torch.from_numpy(r["top_score"])}
+        # the record layout of pack_lists_kernel: n_top | doc[10] | score bits[10]
+        rec = np.concatenate([r["n_top"][:, None], doc, r["top_score"].view(np.int32)], axis=1).astype(np.int32)
+        assert rec.shape[1] == partition.REC_WORDS
+        return torch.from_numpy(r["status"]), torch.from_numpy(np.ascontiguousarray(rec))
 
-    def merge(self, n, parts, p_status, p_n_top, p_doc, p_score):
-        """numpy restatement of merge_kernel (collector order: score desc, doc asc; hits equal to the max)"""
-        out = {"status": p_status.numpy().copy(), "n_top": np.zeros(n, np.int32), "n_hits": np.zeros(n, np.int32),
+    def gather_buffer(self, world, n):
+        return torch.empty(world, n, partition.REC_WORDS, dtype=torch.int32)
+
+    def merge_records(self, n, parts, status, gathered):
+        """numpy restatement of merge_records_kernel (collector order: score desc, doc asc; hits equal to the max)"""
+        g = gathered.numpy()
+        out = {"status": status.numpy().copy(), "n_top": np.zeros(n, np.int32), "n_hits": np.zeros(n, np.int32),
                "label": np.zeros(n, np.int32), "top_doc": np.full((n, TOPN), -1, np.int32), "top_score": np.zeros((n, TOPN), np.float32)}
         for i in range(n):
             cand = []
             for p in range(parts):
-                for j in range(int(p_n_top[i, p])):
-                    cand.append((-float(p_score[i, p, j]), int(p_doc[i, p, j])))
+                rec = g[p, i]
+                sc = rec[1 + TOPN:].view(np.float32)
+                for j in range(int(rec[0])):
+                    cand.append((-float(sc[j]), int(rec[1 + j])))
             cand.sort()
             cand = cand[:TOPN]
             out["n_top"][i] = len(cand)
@@ -93,6 +101,7 @@ def _worker(rank, world, port, ents, reads, k, qconf, expected):
         off = np.zeros(len(reads) + 1, np.int64)
         np.cumsum([len(r) for r in reads], out=off[1:])
         res = dp.classify(data, off)
+        assert dp.collectives == 1          # one all_gather per query batch
         exp = expected["res"]
         assert np.array_equal(res["status"], exp["status"])
         assert np.array_equal(res["n_top"], exp["n_top"]), (res["n_top"], exp["n_top"])
