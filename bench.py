@@ -760,7 +760,7 @@ def main():
     expected = None
     if world > 1 and not args.no_secondary and rank == 0:
         m_dp = min(int(os.environ.get("BSP_DOCPART_READS", 200_000)), n)
-        expected = {k: np.array(v[:m_dp]) for k, v in res.items()}
+        expected = {k: np.array(v[:m_dp]) for k, v in res.items() if not k.startswith("_")}
 
     total_reads = n * world
     steps = args.steps
