@@ -108,3 +108,44 @@ def test_c2_batches_split_and_entry_points_agree(c2):
         assert (s[live, j] >= s[live, j + 1]).all()
         tie = live & (s[:, j] == s[:, j + 1])
         assert (d[tie, j] < d[tie, j + 1]).all()
+
+
+# ------------------------------------------------------------------ unequal document lengths against the oracle
+@pytest.mark.parametrize("min_strand", [False, True])
+def test_unequal_length_reference_against_oracle(oracle_lib, min_strand, monkeypatch):
+    """48 genomes of 0.1 - 1.6 Mbp (norm bytes differ between documents, unlike the equal-length C1 reference), 12,000
+    reads at 4 % error + reads with N: the configurations the shipped json does not exercise -- the code default
+    kmer_skips = 5 (Configuration.java:37-44), bm25 (Configuration.java:169-179), min_strand_kmer -- each through the
+    filter kernel and through the kernel the router picks without it, bit for bit against the oracle."""
+    import common
+    from biospectra_b200 import synth
+    rng = np.random.Generator(np.random.PCG64(77))
+    lengths = np.exp(rng.uniform(np.log(1.0e5), np.log(1.6e6), 48)).astype(np.int64)
+    genomes = [synth.genome_numpy(7, g, int(lengths[g])) for g in range(len(lengths))]
+    reads, _src = synth.sample_reads_numpy(genomes, 12_000, 100, 0.04, 17)
+    # every 50th read carries an N in the middle (its window-spanning clauses become gap clauses)
+    reads = [bytes(b"N"[0] if j == len(r) // 2 else c for j, c in enumerate(r)) if i % 50 == 0 else r for i, r in enumerate(reads)]
+    ents = [g.tobytes().decode() for g in genomes]
+    ox = common.build_oracle(oracle_lib, ents, 10, min_strand)
+    norms = {ox.doc_info(d)[1] for d in range(ox.stats()["n_docs"])}
+    assert len(norms) >= 4                                                  # several norm classes
+    g = None
+    try:
+        for kw, okw in ((dict(), dict()), (dict(kmer_skips=5), dict(skips=5)), (dict(scoring_algorithm="bm25"), dict(scoring=1)),
+                        (dict(kmer_skips=5, scoring_algorithm="bm25", query_algorithm="CHAIN_PROXIMITY"), dict(skips=5, scoring=1, algorithm=1))):
+            q = dict(dict(skips=0, algorithm=2, scoring=0, msm=0.5, threads=8), **okw)
+            ro = ox.classify(reads, **q)
+            conf = dict(dict(kmer_skips=0, query_algorithm="PAIRED_PROXIMITY", scoring_algorithm="tfidf"), **kw)
+            if g is None:
+                g = common.build_gpu(ents, 10, min_strand, conf)
+                assert g.stats() == ox.stats()
+            else:
+                from biospectra_b200 import Configuration
+                g.set_query(Configuration(index_path="", kmer_size=10, min_strand_kmer=min_strand, full_topn=1, **conf))
+            for filt in ("1", "0"):
+                monkeypatch.setenv("BSP_FILTER", filt)
+                rg = g.classify_batch(reads)
+                common.assert_classify_equal(rg, ro, reads, "unequal lengths min_strand=%s %s filter=%s" % (min_strand, kw, filt))
+    finally:
+        if g is not None:
+            g.close()
