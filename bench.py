@@ -461,7 +461,7 @@ def secondary_lines(clf, data, o, dev, local, n, peak, peak_src, main_kw, n_docs
     import torch
     out = []
     cases = [("CHAIN_PROXIMITY", dict(query_algorithm="CHAIN_PROXIMITY"), 1.0), ("NAIVE_KMER", dict(query_algorithm="NAIVE_KMER"), 1.0),
-             ("kmer_skips=5 (Configuration.java default)", dict(kmer_skips=5), 0.2), ("bm25", dict(scoring_algorithm="bm25"), 0.2)]
+             ("kmer_skips=5 (Configuration.java default)", dict(kmer_skips=5), 0.2), ("bm25", dict(scoring_algorithm="bm25"), 1.0)]
     sync = torch.cuda.synchronize
     layout = clf.layout()
     for name, kw, frac in cases:

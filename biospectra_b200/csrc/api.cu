@@ -118,6 +118,9 @@ struct bsp_classifier {
     Scratch sc[BSP_SLOTS];              // sub-batches in flight: the next one's scorer is queued before the current one ends
     // scoring constants
     DevBuf<float> idf_by_df, doc_w, tf16;
+    // dense-table side of the per-doc weights: by table column (GpuIndex::docmap), the norm classes present and, per group of
+    // 32 columns, the class with the smallest weight (BM25 filter: Bm25Classes)
+    DevBuf<float> col_w, class_k; DevBuf<u8> group_class; int n_classes = 0; float k_min = 0.0f, k_max = 0.0f;
     // interned ranked lineages (bsp_classifier_set_lineages)
     DevBuf<i64> lin_off; DevBuf<i32> lin_tax; DevBuf<u8> lin_flags; i64 lin_docs = 0;
     i64 global_docs = 0, global_sum_ttf = 0, doc_base_global = 0;
@@ -404,6 +407,29 @@ static void upload_scoring_constants(bsp_classifier* h) {
     for (i64 d = 0; d < D; d++) dw[d] = cache[ix.doc_norm[d]];
     h->doc_w.alloc(dw.size());
     CUDA_CHECK(cudaMemcpyAsync(h->doc_w.p, dw.data(), dw.size() * 4, cudaMemcpyHostToDevice, h->st));
+    // the same weights by table column, the norm classes in column order (columns are sorted by norm byte)
+    std::vector<float> cw(ix.h_docmap.size() + 32 * 32, 1.0f), ck;
+    std::vector<u8> gcls(ix.h_docmap.size() / 32 + 33, 0);
+    int last_byte = -1;
+    for (size_t c = 0; c < ix.h_docmap.size(); c++) {
+        const u32 d = ix.h_docmap[c];
+        if (d == 0xFFFFFFFFu) continue;
+        const int nb = ix.doc_norm[d];
+        cw[c] = cache[nb];
+        if (nb != last_byte) { ck.push_back(cache[nb]); last_byte = nb; }
+        // class of the group = the one with the smallest weight among its columns (BM25: an upper bound for the others)
+        const size_t g = c / 32;
+        const int cls = (int)ck.size() - 1;
+        if (c % 32 == 0 || ck[cls] < ck[gcls[g]]) gcls[g] = (u8)std::min(cls, 255);
+    }
+    if (ck.empty()) ck.push_back(1.0f);
+    h->n_classes = (int)ck.size();
+    h->k_min = *std::min_element(ck.begin(), ck.end());
+    h->k_max = *std::max_element(ck.begin(), ck.end());
+    h->col_w.alloc(cw.size()); h->class_k.alloc(ck.size()); h->group_class.alloc(gcls.size());
+    CUDA_CHECK(cudaMemcpyAsync(h->col_w.p, cw.data(), cw.size() * 4, cudaMemcpyHostToDevice, h->st));
+    CUDA_CHECK(cudaMemcpyAsync(h->class_k.p, ck.data(), ck.size() * 4, cudaMemcpyHostToDevice, h->st));
+    CUDA_CHECK(cudaMemcpyAsync(h->group_class.p, gcls.data(), gcls.size(), cudaMemcpyHostToDevice, h->st));
     // nibble -> per-clause frequency factor: tf-idf tf(freq) = (float)sqrt(freq) (DefaultSimilarity#tf); BM25: freq
     float tl[16];
     for (int c = 0; c < 16; c++) tl[c] = h->conf.scoring_algorithm == BSP_BM25 ? (float)c : (float)std::sqrt((double)c);
@@ -424,8 +450,10 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
         // the filter kernel's cp.async ring needs up to 64 KB of dynamic shared memory (512 threads x 8 stages x 16 B);
         // its residency is bounded by shared memory: ask for the largest carve-out
 #define FK_ATTR(TI, AT)                                                                                                          \
-        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<TI, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * FK_MAXT * 16)); \
-        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<TI, AT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
+        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<TI, AT, SIM_TFIDF>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * FK_MAXT * 16)); \
+        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<TI, AT, SIM_TFIDF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<TI, AT, SIM_BM25>, cudaFuncAttributeMaxDynamicSharedMemorySize, FK_STAGES * FK_MAXT * 16 + FK_BM25_LUT_BYTES)); \
+        CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<TI, AT, SIM_BM25>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
         FK_ATTR(false, false); FK_ATTR(false, true); FK_ATTR(true, false); FK_ATTR(true, true);
 #undef FK_ATTR
         CUDA_CHECK(cudaFuncSetAttribute(score_positional_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(POSW_WARPS * posw_warp_bytes(POSW_DOCS, PW_POS))));
@@ -533,15 +561,18 @@ BSP_API int bsp_classifier_close(bsp_classifier* h) {
 
 // ------------------------------------------------------------------ classification
 // counts: [0] exact-dense reads, [1] positional reads, [2] filter reads, [3] filter overflow (appended to list_dense)
-__global__ void __launch_bounds__(256) route_compact_kernel(const i32* __restrict__ route, i32 n, i32* __restrict__ list_dense,
-                                                             i32* __restrict__ list_pos, i32* __restrict__ list_filter,
-                                                             i32* __restrict__ counts) {
+__global__ void __launch_bounds__(256) route_compact_kernel(const i32* __restrict__ route, const i32* __restrict__ n_clauses, i32 n,
+                                                             i32* __restrict__ list_dense, i32* __restrict__ list_pos,
+                                                             i32* __restrict__ list_filter, i32* __restrict__ counts) {
     i32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     int rt = route[r];
     if (rt == ROUTE_DENSE) list_dense[atomicAdd(&counts[0], 1)] = r;
     else if (rt == ROUTE_POSITIONAL) list_pos[atomicAdd(&counts[1], 1)] = r;
-    else if (rt == ROUTE_FILTER) list_filter[atomicAdd(&counts[2], 1)] = r;
+    else if (rt == ROUTE_FILTER) {
+        list_filter[atomicAdd(&counts[2], 1)] = r;
+        atomicMax(&counts[6], n_clauses[r]);          // most clauses of a filter read: sizes the per-class LUT arrays (BM25)
+    }
 }
 
 __global__ void __launch_bounds__(256) tok_capacity_kernel(const i64* __restrict__ seq_off, i32 n, int k, i64* __restrict__ cap) {
@@ -602,16 +633,22 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     const i64 filter_mode = env_i64("BSP_FILTER", -1);
     // (the filter kernel addresses rows by 32-bit offsets in 16-byte units: table below 64 GiB)
     const bool tab_addressable = ((u64)ix.n_rows + 2) * ix.row_bytes < (64ull << 30);
-    qp.filter_ok = qp.dense_ok && tab_addressable && qp.sim == SIM_TFIDF && filter_mode != 0 && (filter_mode == 1 || D >= 1024);
+    // (BM25: one LUT per norm class of the handle; 16 classes span a 4x range of document lengths)
+    qp.filter_ok = qp.dense_ok && tab_addressable && (qp.sim == SIM_TFIDF || (h->n_classes <= 16 && env_i64("BSP_BM25_FILTER", 1) != 0)) &&
+                   filter_mode != 0 && (filter_mode == 1 || D >= 1024);
+    qp.filter_nc_max = FK_MAX_CLAUSES;
+    if (qp.sim == SIM_BM25)
+        qp.filter_nc_max = (int)std::min<i64>(FK_MAX_CLAUSES, FK_BM25_LUT_BYTES / ((i64)std::max(h->n_classes, 1) * (qp.alg == ALG_NAIVE ? 24 : 16)) - 2);
     weights_kernel<<<(unsigned)ceil_div((i64)n * 32, 256), 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p,
                                                                sc.tok_df.p, h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p,
                                                                sc.n_clauses.p, sc.msm.p, sc.route.p, sc.status_in.p, sc.vrange.p,
                                                                sc.gaps.p, sc.gap_cnt.p + GC, sc.read_ngap.p);
     CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));
-    route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, n, sc.list_dense.p, sc.list_pos.p, sc.list_filter.p,
-                                                                     sc.counts.p);
+    route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, sc.n_clauses.p, n, sc.list_dense.p, sc.list_pos.p,
+                                                                     sc.list_filter.p, sc.counts.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(sc.h_counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 6, sc.counts.p + 6, 4, cudaMemcpyDeviceToHost, st));      // most clauses of a filter read
     CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 5, sc.gap_cnt.p + GC, 4, cudaMemcpyDeviceToHost, st));   // # gap clauses
     // partial top-10 buffers
     sc.dense_threads = (int)std::min<i64>(512, round_up(std::max<i64>(ceil_div(ix.d_pad, EX_DPT), 1), 32));
@@ -645,15 +682,16 @@ static void pipeline_phase2a(bsp_classifier* h, Scratch& sc) {
         const u32 tmp_base = (u32)ix.n_exc + (u32)sc.slot_index * GC * GAP_LIST;
         const int gf_dcap = ix.max_seg_docs <= POSW_DOCS ? (int)round_up(std::max<i64>(ix.max_seg_docs, 1), 32) : 0;
         gap_fill_kernel<<<(unsigned)ceil_div(ng * n_segs * 32, 256), 256, gf_dcap ? 8 * phrase_stage_bytes(gf_dcap, PW_POS) : 0, st>>>(
-            ix.d_segs.p, n_segs, sc.gaps.p, sc.gap_cnt.p + GC, GC, sc.gap_cnt.p, ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base,
+            ix.d_segs.p, n_segs, ix.colmap.p, sc.gaps.p, sc.gap_cnt.p + GC, GC, sc.gap_cnt.p, ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base,
             gf_dcap, PW_POS);
         gap_sort_kernel<<<(unsigned)ceil_div(ng * 32, 256), 256, 0, st>>>(sc.gaps.p, sc.gap_cnt.p + GC, GC, sc.gap_cnt.p,
             ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base, sc.route.p, sc.status_in.p, qp.positional_ok);
         CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));
-        route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, n, sc.list_dense.p, sc.list_pos.p, sc.list_filter.p,
-                                                                         sc.counts.p);
+        route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, sc.n_clauses.p, n, sc.list_dense.p, sc.list_pos.p,
+                                                                         sc.list_filter.p, sc.counts.p);
         KERNEL_CHECK();
         CUDA_CHECK(cudaMemcpyAsync(sc.h_counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 6, sc.counts.p + 6, 4, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
     }
     i32* counts = sc.cnt;
@@ -675,11 +713,19 @@ static void pipeline_phase2a(bsp_classifier* h, Scratch& sc) {
         const bool tiled = sc.filter_tiles > 1, naive = qp.alg == ALG_NAIVE;
         const unsigned fgrid = (unsigned)((i64)counts[2] * sc.filter_tiles);
         const i32* fk_list = counts[2] == n ? nullptr : sc.list_filter.p;      // all reads: the list is a permutation of 0..n-1
-#define FK_LAUNCH(TI, AT) filter_score_kernel<TI, AT><<<fgrid, threads, ring_bytes, st>>>(T, D, h->tf16.p, fk_list, sc.tok_off.p, sc.n_tok.p, \
-            sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.vrange.p, sc.read_ngap.p, h->doc_w.p, qp.alg, gbase, parts_stride, part_n, \
+        Bm25Classes bm;
+        bm.class_k = h->class_k.p; bm.group_class = h->group_class.p; bm.n_classes = h->n_classes;
+        bm.nc_cap = (int)round_up((i64)std::min<i64>(std::max(sc.h_counts[6], 1), qp.filter_nc_max) + 1, 2);
+        bm.k_min = h->k_min; bm.k_max = h->k_max; bm.k1p1 = 1.2f + 1.0f;
+        const bool bm25 = qp.sim == SIM_BM25;
+        const size_t lut_bytes = bm25 ? (size_t)bm.n_classes * bm.nc_cap * (naive ? 24 : 16) : 0;
+#define FK_LAUNCH(TI, AT, SIM) filter_score_kernel<TI, AT, SIM><<<fgrid, threads, ring_bytes + lut_bytes, st>>>(T, D, h->tf16.p, bm, fk_list, sc.tok_off.p, sc.n_tok.p, \
+            sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.vrange.p, sc.read_ngap.p, h->col_w.p, qp.alg, gbase, parts_stride, part_n, \
             part_doc, part_score, sc.route.p, sc.list_dense.p + counts[0], sc.counts.p + 3, sc.fstats.p, full_topn, 1u, sc.filter_tiles)
-        if (tiled) { if (naive) FK_LAUNCH(true, true); else FK_LAUNCH(true, false); }
-        else { if (naive) FK_LAUNCH(false, true); else FK_LAUNCH(false, false); }
+#define FK_LAUNCH2(TI, AT) do { if (bm25) FK_LAUNCH(TI, AT, SIM_BM25); else FK_LAUNCH(TI, AT, SIM_TFIDF); } while (0)
+        if (tiled) { if (naive) FK_LAUNCH2(true, true); else FK_LAUNCH2(true, false); }
+        else { if (naive) FK_LAUNCH2(false, true); else FK_LAUNCH2(false, false); }
+#undef FK_LAUNCH2
 #undef FK_LAUNCH
         KERNEL_CHECK();
         sc.launches++;
@@ -715,11 +761,11 @@ static void pipeline_phase2b(bsp_classifier* h, Scratch& sc, const BatchOut& out
         unsigned grid = (unsigned)((i64)n_exact * n_tiles);
         if (qp.sim == SIM_TFIDF)
             exact_score_kernel<SIM_TFIDF><<<grid, sc.dense_threads, 0, st>>>(T, D, h->tf16.p, sc.list_dense.p, sc.tok_off.p, sc.n_tok.p,
-                sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, sp.k1p1, gbase, n_tiles, parts_stride,
+                sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, h->col_w.p, sp.k1p1, gbase, n_tiles, parts_stride,
                 part_n, part_doc, part_score);
         else
             exact_score_kernel<SIM_BM25><<<grid, sc.dense_threads, 0, st>>>(T, D, h->tf16.p, sc.list_dense.p, sc.tok_off.p, sc.n_tok.p,
-                sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, sp.k1p1, gbase, n_tiles, parts_stride,
+                sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, h->col_w.p, sp.k1p1, gbase, n_tiles, parts_stride,
                 part_n, part_doc, part_score);
         launches++;
     }

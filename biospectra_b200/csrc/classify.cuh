@@ -25,7 +25,7 @@
 #define ROUTE_NONE 0             // dropped / error: no scoring
 #define ROUTE_DENSE 1            // exact_score_kernel over the 4-bit tables
 #define ROUTE_POSITIONAL 2
-#define ROUTE_FILTER 3           // filter_score_kernel (tf-idf, <= 255 clauses)
+#define ROUTE_FILTER 3           // filter_score_kernel (<= 255 clauses; BM25: <= 16 norm classes in the handle)
 
 #define ST_OK 0
 #define ST_DROPPED 1
@@ -157,7 +157,8 @@ struct QueryParams {
     i64 max_doc;            // global maxDoc (all partitions)
     int dense_ok;           // dense tables resident
     int positional_ok;      // positional segments resident
-    int filter_ok;          // fast filter path usable (tf-idf, doc count within one CTA)
+    int filter_ok;          // fast filter path usable
+    int filter_nc_max;      // most clauses of a read the filter takes (255 count lanes; BM25: the per-class LUT arrays must fit)
     u64 pair_row0;          // first pair row of the dense table (= 4^k)
     int gap_ok;             // gap clauses can be evaluated sparsely (dense tables AND positional postings resident)
     u32 temp_row0;          // row id of gap clause 0 of the sub-batch
@@ -362,7 +363,16 @@ __global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq
             vmin = fminf(vmin, __shfl_xor_sync(0xFFFFFFFFu, vmin, o));
         }
         if (lane == 0) vrange[r] = make_float2(vmax, vmin);
-    }   // BM25Stats#normalize: weight = idf * 1 * 1
+    } else {   // BM25Stats#normalize: weight = idf * 1 * 1
+        float vmax = 0.0f, vmin = 3.0e38f;
+        for (i32 c = lane; c < nc; c += 32) { const float v = clause_val[base + c]; vmax = fmaxf(vmax, v); vmin = fminf(vmin, v); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xFFFFFFFFu, vmax, o));
+            vmin = fminf(vmin, __shfl_xor_sync(0xFFFFFFFFu, vmin, o));
+        }
+        if (lane == 0) vrange[r] = make_float2(vmax, vmin);
+    }
     if (dense) {
         const u8* s = seq + seq_off[r];
         for (i32 c = lane; c < nc; c += 32) {
@@ -385,7 +395,7 @@ __global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq
         read_ngap[r] = n_gap;
         msm_out[r] = (i32)(qp.msm_ratio * (double)nc);   // Classifier.java:257
         // u8 count lanes of the filter kernel: <= 255 clauses (the u16 weight lanes then hold 255 * 255 at most)
-        const bool fast = dense && qp.filter_ok && nc <= 255;
+        const bool fast = dense && qp.filter_ok && nc <= qp.filter_nc_max;
         if (fast) { route[r] = ROUTE_FILTER; status[r] = ST_OK; }
         else if (dense) { route[r] = ROUTE_DENSE; status[r] = ST_OK; }
         else if (qp.positional_ok) { route[r] = ROUTE_POSITIONAL; status[r] = ST_OK; }

@@ -36,12 +36,18 @@ struct Tab4Dev {
     u64 row_bytes;
     u64 pair_row0;          // 4^k
     const u32* exc_off;     // [n_rows + 2]
-    const u32* exc_doc;     // handle-global doc ids, ascending within a row
+    const u32* exc_doc;     // table columns (see docmap), ascending within a row
     const float* exc_freq;
     u32 zero_row;           // = n_rows: an all-zero row without exceptions
     u32 temp_row0;          // = n_rows + 1: temporary rows of the current sub-batch's gap clauses
     u32 tmp_base;           // their match lists live at exc_doc/exc_freq[tmp_base + g * GAP_LIST ...]
     const u32* gap_cnt;     // [gap_cap] matches per gap clause
+    // Table columns are the handle's documents sorted by (norm byte, doc id): docs that share a length norm sit next to
+    // each other, so a thread's 32 columns belong to one norm class except at the few class boundaries (the BM25 bound
+    // needs a per-class LUT; tf-idf is indifferent to the order).  docmap[column] = doc id (0xFFFFFFFF for padding
+    // columns); the build kernels take the inverse (colmap[doc]).  Everything inside the table kernels is in columns;
+    // doc ids appear only in the order keys and the outputs.
+    const u32* docmap;
 };
 
 // exception list (first entry, count) and table row of a clause row id
@@ -74,7 +80,7 @@ __device__ __forceinline__ void nibble_or(u32* __restrict__ row32, u32 doc, u32 
 }
 
 // warp per term of the segment
-__global__ void __launch_bounds__(256) tf_table4_kernel(SegDev s, u32* __restrict__ tab32, u64 row_words, ExcBuild ex) {
+__global__ void __launch_bounds__(256) tf_table4_kernel(SegDev s, const u32* __restrict__ colmap, u32* __restrict__ tab32, u64 row_words, ExcBuild ex) {
     const int lane = threadIdx.x & 31;
     const u32 t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= s.n_terms) return;
@@ -86,7 +92,7 @@ __global__ void __launch_bounds__(256) tf_table4_kernel(SegDev s, u32* __restric
         bool has = i < b;
         u32 doc = 0, code = 0;
         if (has) {
-            doc = s.doc_base + s.post_doc[i];
+            doc = colmap[s.doc_base + s.post_doc[i]];
             u32 tf = s.post_pos[i + 1] - s.post_pos[i];
             if (tf <= T4_TF_MAX) code = tf;
             else { exc_append(ex, (u32)key, doc, (float)tf); has = false; }
@@ -96,7 +102,7 @@ __global__ void __launch_bounds__(256) tf_table4_kernel(SegDev s, u32* __restric
 }
 
 // warp per (k+1)-mer row u
-__global__ void __launch_bounds__(256) pair_table4_kernel(SegDev s, int k, int min_strand, u32* __restrict__ tab32, u64 row_words,
+__global__ void __launch_bounds__(256) pair_table4_kernel(SegDev s, const u32* __restrict__ colmap, int k, int min_strand, u32* __restrict__ tab32, u64 row_words,
                                                            u64 pair_row0, ExcBuild ex, u64 n_rows) {
     const int lane = threadIdx.x & 31;
     const u64 u = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -118,7 +124,7 @@ __global__ void __launch_bounds__(256) pair_table4_kernel(SegDev s, int k, int m
         if (i < b0) {
             const float f = phrase_freq_at(s, i, a1, b1, a1 + (i - a0), 2, same);
             if (f != 0.0f) {
-                doc = s.doc_base + s.post_doc[i];
+                doc = colmap[s.doc_base + s.post_doc[i]];
                 const u32 c = (u32)f;
                 if ((float)c == f && c >= 1u && c <= T4_PAIR_MAX) { code = c; has = true; }
                 else exc_append(ex, (u32)(pair_row0 + u), doc, f);
@@ -142,7 +148,7 @@ __device__ __forceinline__ void stage_term_async(const SegDev& s, u32 a, u32 n, 
     for (u32 i = lane; i <= n; i += 32) { if (i < n) cp_async4(w_doc + i, s.post_doc + a + i); cp_async4(w_pp + i, s.post_pos + a + i); }
     for (u32 i = lane; i < m; i += 32) cp_async4(w_pos + i, s.positions + p + i);
 }
-__global__ void __launch_bounds__(PT_WARPS * 32) pair_table4_staged_kernel(SegDev s, int k, int min_strand, u32* __restrict__ tab32,
+__global__ void __launch_bounds__(PT_WARPS * 32) pair_table4_staged_kernel(SegDev s, const u32* __restrict__ colmap, int k, int min_strand, u32* __restrict__ tab32,
                                                                             u64 row_words, u64 pair_row0, ExcBuild ex, u64 n_kmers,
                                                                             int dcap, int pcap) {
     extern __shared__ __align__(16) u8 pt_raw[];
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(PT_WARPS * 32) pair_table4_staged_kernel(SegDe
                     f = phrase_freq_at(s, a0 + i, a1, a1 + n1, a1 + i, 2, same);
                 }
                 if (f != 0.0f) {
-                    doc = s.doc_base + (staged ? w_doc0[i] : s.post_doc[a0 + i]);
+                    doc = colmap[s.doc_base + (staged ? w_doc0[i] : s.post_doc[a0 + i])];
                     const u32 cc = (u32)f;
                     if ((float)cc == f && cc >= 1u && cc <= T4_PAIR_MAX) { code = cc; has = true; }
                     else exc_append(ex, (u32)(pair_row0 + u), doc, f);
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(256) exc_offsets_kernel(const u64* __restrict_
 
 // ---- gap clauses: evaluate against the positional postings, keep the (few) matching docs as a sorted list
 // warp per (gap clause, segment); idle warps (no such clause in this sub-batch) leave at once
-__global__ void __launch_bounds__(256) gap_fill_kernel(const SegDev* __restrict__ segs, int n_segs, const GapClause* __restrict__ gaps,
+__global__ void __launch_bounds__(256) gap_fill_kernel(const SegDev* __restrict__ segs, int n_segs, const u32* __restrict__ colmap, const GapClause* __restrict__ gaps,
                                                         const u32* __restrict__ gap_count, u32 gap_cap, u32* __restrict__ gap_cnt,
                                                         u32* __restrict__ tmp_doc, float* __restrict__ tmp_freq,
                                                         int dcap /* 0: no staging (segments of more than 256 docs) */, int pcap) {
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(256) gap_fill_kernel(const SegDev* __restrict_
     auto keep = [&](u32 local_doc, float f) {
         const u32 pos = atomicAdd(&gap_cnt[g], 1u);
         if (pos < GAP_LIST) {
-            tmp_doc[(u64)g * GAP_LIST + pos] = s.doc_base + local_doc;
+            tmp_doc[(u64)g * GAP_LIST + pos] = colmap[s.doc_base + local_doc];
             tmp_freq[(u64)g * GAP_LIST + pos] = f;
         }
     };
@@ -473,6 +479,7 @@ __device__ __forceinline__ u32 cell_code(const Tab4Dev& T, u32 row, u32 doc) {
 #define FK_EXS_CAP 96              // ... this many cells per CTA in all (the rest is searched in global memory)
 #define FK_EXA_SHARED 0xFFFFFFFFu    // s_exa of a clause whose list sits in shared memory
 #define FK_QMAX 255.0f
+#define FK_BM25_LUT_BYTES (40 * 1024)   // BM25: per-class clause LUTs behind the ring (classes x (clauses + 1) x 16 B, NAIVE_KMER 24 B)
 #define FK_ROUND_SLACK 0.51f       // |q - S*tf*value| <= 0.5 (+ float rounding of the product)
 #define FK_REL_SLACK 4e-6f         // float roundings of Lucene's score and of the bound arithmetic
 
@@ -529,10 +536,23 @@ __device__ __forceinline__ float exc_lookup(const Tab4Dev& T, u32 a, u32 n, u32 
     return (lo < n && __ldg(T.exc_doc + a + lo) == d) ? __ldg(T.exc_freq + a + lo) : 0.0f;
 }
 
+// BM25 (Configuration.java:169-179): score(d) = sum_c w_c (k1+1) f / (f + K_d), K_d = cache[norm byte of d]; no coord.  The
+// cell weight depends on the document through K_d, so the byte LUT of a clause exists once per norm class; table columns
+// are sorted by norm byte (Tab4Dev::docmap), a thread's 32 columns share a class except at the class boundaries.  A thread
+// takes the LUT of the smallest K among its columns: exact for the columns of that class, an over-estimate for the others
+// (larger K, smaller true weights) -- those may become candidates (rescoring is exact) but never set the threshold.
+struct Bm25Classes {
+    const float* class_k;       // [n_classes] K of each norm class present in the handle, in column order
+    const u8* group_class;      // [d_pad / 32] class with the smallest K among the group's columns
+    int n_classes;
+    int nc_cap;                 // clause capacity of one class's LUT array (>= clauses of every read of the launch + 1)
+    float k_min, k_max, k1p1;
+};
+
 // TILED: several doc tiles per read (more than 16,384 docs, or a capped CTA size); ALLTERMS: NAIVE_KMER (term rows only)
-template <bool TILED, bool ALLTERMS>
+template <bool TILED, bool ALLTERMS, int SIM>
 __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
-        Tab4Dev T, u32 n_docs, const float* __restrict__ tf16, const i32* __restrict__ read_list,
+        Tab4Dev T, u32 n_docs, const float* __restrict__ tf16, Bm25Classes bm, const i32* __restrict__ read_list,
         const i64* __restrict__ tok_off, const i32* __restrict__ n_tok, const float* __restrict__ clause_val,
         const u32* __restrict__ clause_row, const i32* __restrict__ n_clauses, const i32* __restrict__ msm,
         const float2* __restrict__ read_vrange, const i32* __restrict__ read_ngap, const float* __restrict__ doc_w, int alg, u32 global_doc_base, int parts_stride,
@@ -560,7 +580,12 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     __shared__ int s_ncand, s_nexrows, s_over, s_ndense, s_ngap;
     __shared__ u32 s_qmin, s_nexc, s_cntlo;
 
+    __shared__ float s_ratio[SIM == SIM_BM25 ? 16 * 16 : 1];      // BM25: f / (f + K_class) per (class slot, code), 16 classes per launch
     extern __shared__ __align__(16) uint4 ring[];         // FK_STAGES x blockDim.x x 16 B: row ring of pass 1, then the staged cell codes
+    // BM25: behind the ring, per class the clause LUTs (uint4: q codes 0..3 | 4..7 | prefetch offset), then for NAIVE_KMER the
+    // high halves (uint2: codes 8..11 | 12..15)
+    uint4* const lut_cls = ring + (size_t)FK_STAGES * blockDim.x;
+    uint2* const lut_cls_hi = reinterpret_cast<uint2*>(lut_cls + (size_t)bm.n_classes * bm.nc_cap);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
     const int tile = TILED ? blockIdx.x % n_tiles : 0;
     // (read_list == nullptr: every read of the batch takes this kernel, in order -- one dependent load less at the start)
@@ -576,11 +601,20 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     const float2 vr = read_vrange[r];
     // (NAIVE_KMER has term rows only: all 15 codes go through the byte LUT, weights <= 127)
     const bool all_terms = ALLTERMS;
-    const float S = all_terms ? 127.0f / (vr.x * tf16[T4_TF_MAX]) : FK_QMAX / (vr.x * tf16[T4_PAIR_MAX]);
+    // BM25: the largest cell weight is w_max (k1+1) f_max / (f_max + K_min), the smallest w_min (k1+1) / (1 + K_max)
+    const float cmax = all_terms ? (float)T4_TF_MAX : (float)T4_PAIR_MAX;
+    const float S = SIM == SIM_BM25 ? (all_terms ? 127.0f : FK_QMAX) / (vr.x * bm.k1p1 * (cmax / (cmax + bm.k_min)))
+                                    : (all_terms ? 127.0f / (vr.x * tf16[T4_TF_MAX]) : FK_QMAX / (vr.x * tf16[T4_PAIR_MAX]));
     if (threadIdx.x < 16) s_tf[threadIdx.x] = tf16[threadIdx.x];
+    if (SIM == SIM_BM25) {
+        for (int i = threadIdx.x; i < bm.n_classes * 16; i += blockDim.x) {
+            const float f = (float)(i & 15);
+            s_ratio[i] = f / (f + bm.class_k[i >> 4]);
+        }
+    }
     if (threadIdx.x == 0) {
         s_ncand = 0; s_nexrows = 0; s_over = 0; s_nexc = 0; s_ndense = 0; s_ngap = 0; s_nsmall = 0;
-        s_qmin = (u32)__float2int_rn(S * vr.y);
+        s_qmin = SIM == SIM_BM25 ? (u32)(S * vr.y * bm.k1p1 * (1.0f / (1.0f + bm.k_max)) * 0.9999f) : (u32)__float2int_rn(S * vr.y);
         s_cntlo = 0x01010100u * one;
     }
     __syncthreads();
@@ -600,9 +634,28 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
         s_row[c] = row;
         const u32 off16 = row < T.temp_row0 ? row * (u32)(T.row_bytes >> 4) : 0u;
         s_off[c] = off16;
-        if (c >= FK_STAGES) s_lo[c - FK_STAGES].z = off16;
-        const float sv = S * v;
-        if (c0 < n_pair) {
+        if (c >= FK_STAGES) {
+            s_lo[c - FK_STAGES].z = off16;
+            if (SIM == SIM_BM25) for (int cl = 0; cl < bm.n_classes; cl++) lut_cls[(size_t)cl * bm.nc_cap + c - FK_STAGES].z = off16;
+        }
+        const float sv = SIM == SIM_BM25 ? S * v * bm.k1p1 : S * v;
+        if (SIM == SIM_BM25) {
+            if (c0 < n_pair || all_terms) {
+                for (int cl = 0; cl < bm.n_classes; cl++) {
+                    const float* rt = s_ratio + cl * 16;
+                    u32 q[16];
+                    q[0] = 0; q[15] = 0;
+                    const u32 cap = all_terms ? 127u : 255u;
+#pragma unroll
+                    for (int j = 1; j < 15; j++) q[j] = min((u32)__float2int_rn(sv * rt[j]), cap);
+                    uint4* e = lut_cls + (size_t)cl * bm.nc_cap + c;
+                    e->x = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+                    e->y = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
+                    if (all_terms)
+                        lut_cls_hi[(size_t)cl * bm.nc_cap + c] = make_uint2(q[8] | (q[9] << 8) | (q[10] << 16) | (q[11] << 24), q[12] | (q[13] << 8) | (q[14] << 16) | (q[15] << 24));
+                }
+            }
+        } else if (c0 < n_pair) {
             u32 q[8];
             q[0] = 0;
 #pragma unroll
@@ -632,6 +685,17 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     for (int i = 0; i < 8; i++) cacc[i] = 0;
     const u8* tbase = T.tab + (u64)d0 / 2;
     asm volatile("" : "+l"(tbase));          // keep the thread's table base in a register pair (one IMAD.WIDE per row address)
+    // clause LUTs this thread reads: the read's (tf-idf), or those of the thread's norm class (BM25)
+    const uint4* lo_tab = s_lo;
+    const uint2* hi_tab = s_lut_hi;
+    int cls = 0;
+    float k_thr = 0.0f;
+    if (SIM == SIM_BM25) {
+        cls = active ? (int)bm.group_class[d0 / FK_DOCS] : 0;
+        k_thr = bm.class_k[cls];
+        lo_tab = lut_cls + (size_t)cls * bm.nc_cap;
+        hi_tab = lut_cls_hi + (size_t)cls * bm.nc_cap;
+    }
     // Each thread prefetches its own 16-byte slice of the next FK_STAGES rows into its private slots of the
     // ring (no cross-thread hand-off, so no barriers): FK_STAGES x 16 B in flight per thread.  Slots are
     // addressed in the shared window directly; one commit group per pair of rows.
@@ -693,9 +757,9 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
             cp_async_wait<FK_STAGES / 2 - 1>();
             const u32 sa0 = cur, sa1 = cur + stride_b;
             const uint4 q0 = lds128(sa0), q1 = lds128(sa1);
-            const uint4 l0 = s_lo[i], l1 = s_lo[i + 1];
+            const uint4 l0 = lo_tab[i], l1 = lo_tab[i + 1];
             if (all_terms) {
-                const uint2 h0 = s_lut_hi[i], h1 = s_lut_hi[i + 1];
+                const uint2 h0 = hi_tab[i], h1 = hi_tab[i + 1];
                 const uint4 t0 = make_uint4(l0.x, l0.y, h0.x, h0.y), t1 = make_uint4(l1.x, l1.y, h1.x, h1.y);
                 term_word2(q0.x, q1.x, t0, t1, xacc[0], yacc[0], xacc[1], yacc[1], cacc[0], cacc[1], one);
                 term_word2(q0.y, q1.y, t0, t1, xacc[2], yacc[2], xacc[3], yacc[3], cacc[2], cacc[3], one);
@@ -725,20 +789,21 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
             const uint4 q = *my;
             const i32 c = i;
             if (c < n_dense) {
-                const uint2 lut = make_uint2(s_lo[c].x, s_lo[c].y);
+                const uint2 lut = make_uint2(lo_tab[c].x, lo_tab[c].y);
                 pair_word(q.x, lut, wacc[0], wacc[1], wacc[2], wacc[3], cacc[0], cacc[1]);
                 pair_word(q.y, lut, wacc[4], wacc[5], wacc[6], wacc[7], cacc[2], cacc[3]);
                 pair_word(q.z, lut, wacc[8], wacc[9], wacc[10], wacc[11], cacc[4], cacc[5]);
                 pair_word(q.w, lut, wacc[12], wacc[13], wacc[14], wacc[15], cacc[6], cacc[7]);
             } else {                                  // Term clause (tf 1..14): nibble at a time
-                const float sv = S * s_val[c];
+                const float sv = SIM == SIM_BM25 ? S * s_val[c] * bm.k1p1 : S * s_val[c];
+                const float* wt = SIM == SIM_BM25 ? s_ratio + cls * 16 : s_tf;
                 const u32 w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                 for (int x = 0; x < 4; x++) {
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const u32 code = (w[x] >> (4 * j)) & 15u;
-                        const u32 qv = (u32)__float2int_rn(sv * s_tf[code]);
+                        const u32 qv = (u32)__float2int_rn(sv * wt[code]);
                         wacc[4 * x + (j >> 1)] += qv << (16 * (j & 1));
                         cacc[2 * x + (j >> 2)] += (code ? 1u : 0u) << (8 * (j & 3));
                     }
@@ -755,7 +820,8 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
         //      quantisation: the short lists from shared memory, the long ones by binary search to the thread's doc range
         u32 exc_sum = 0, exc_cnt = 0;
         auto fold_cell = [&](u32 li, u32 c, float freq) {
-            const u32 qe = (u32)min(__float2int_rn(S * s_val[c] * tf_of(freq)), 1 << 20);
+            const u32 qe = SIM == SIM_BM25 ? (u32)min(__float2int_rn(S * s_val[c] * bm.k1p1 * (freq / (freq + k_thr))), 1 << 20)
+                                           : (u32)min(__float2int_rn(S * s_val[c] * tf_of(freq)), 1 << 20);
             const u32 qv = qe << (16 * (li & 1u)), cnt1 = 1u << (8 * (li & 3u));
 #pragma unroll
             for (int k = 0; k < 16; k++) wacc[k] += (u32)k == (li >> 1) ? qv : 0u;     // predicated, statically indexed
@@ -789,13 +855,15 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
         }
         // u16 lanes: pair-row weights <= 255 and term-row weights <= 255*tf(14)/tf(7) < 362 (all-term reads: <= 127 each),
         // plus this thread's exception cells
-        const u32 lane_max = all_terms ? 127u * (u32)nc : 255u * (u32)n_pair + 362u * (u32)(nc - n_pair);
+        // (BM25 term rows: 14 / (14 + K) against 7 / (7 + K) of the pair rows the scale is set for: < 2 x 255)
+        const u32 lane_max = all_terms ? 127u * (u32)nc : 255u * (u32)n_pair + (SIM == SIM_BM25 ? 510u : 362u) * (u32)(nc - n_pair);
         if (lane_max + exc_sum > 65535u) s_over = 1;
         if (exc_cnt) atomicAdd(&s_nexc, exc_cnt);
     }
     // ---- pass 2: per-thread best estimate, then the block's 10th best (full list) or best (result set only).
     //      Padded docs have no cells (m = 0).
-    float e_best = 0.0f;
+    float e_best = 0.0f;          // best estimate among the thread's docs that may set the threshold
+    float e_any = 0.0f;           // best estimate among all of them (BM25: incl. the over-estimated docs of another class)
     // Only docs with m >= need have an estimate, and a read matches few of them that often: test the 32 count bytes of
     // the thread at once.  byte >= need  <=>  bit 7 of ((byte | 0x80) - need) | byte, for need <= 128 (no borrow
     // crosses a byte: byte | 0x80 >= need).
@@ -817,10 +885,15 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
                 const int i = i4 + k;
                 const u32 Q = prmt(wacc[i >> 1], 0u, (i & 1) ? 0x4432u : 0x4410u);
                 const u32 m = prmt(cacc[i >> 2], 0u, 0x4440u | (u32)(i & 3));
-                e_best = fmaxf(e_best, estimate(Q, m, need, nr[k]));
+                if (SIM == SIM_BM25) {
+                    const float e = (i32)m >= need ? (float)Q : 0.0f;          // no coord, K_d is in the weights
+                    e_any = fmaxf(e_any, e);
+                    if (nr[k] == k_thr) e_best = fmaxf(e_best, e);
+                } else e_best = fmaxf(e_best, estimate(Q, m, need, nr[k]));
             }
         }
     }
+    if (SIM != SIM_BM25) e_any = e_best;
     // full_topn: 10 docs are known to score >= tau_e*(1-delta); otherwise only the docs that can tie at the maximum
     // matter (Classifier.java:358-366 keeps the hits equal to the top score), so tau_e is the best estimate
     u32 sel;
@@ -846,7 +919,7 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     //      candidate parks its lanes in its own ring slots (pass 1 is over in this warp's threads, the slots are private
     //      to them), then the 32 lanes evaluate that thread's 32 docs, one each.
     {
-        const bool mine = active && !lane_overflow && e_best >= theta && e_best > 0.0f;
+        const bool mine = active && !lane_overflow && e_any >= theta && e_any > 0.0f;
         u32 holders = __ballot_sync(0xFFFFFFFFu, mine);
         if (holders) {
             const u32 stride = blockDim.x;
@@ -868,7 +941,7 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
                 const u32 Q = (lane & 1) ? ww >> 16 : ww & 0xFFFFu;
                 const u32 m = (cw >> (8 * (lane & 3))) & 0xFFu;
                 const u32 d = ((u32)tile * blockDim.x + src) * FK_DOCS + (u32)lane;
-                const float e = estimate(Q, m, need, doc_w[d]);
+                const float e = SIM == SIM_BM25 ? ((i32)m >= need ? (float)Q : 0.0f) : estimate(Q, m, need, doc_w[d]);
                 if (e >= theta && e > 0.0f) {
                     int idx = atomicAdd(&s_ncand, 1);
                     if (idx < FK_CAND_CAP) s_cand[idx] = d;
@@ -946,10 +1019,10 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
                             if (s_sm_doc[x] == d && s_sm_c[x] == (u8)c) fe = s_sm_f[x];
                     } else fe = exc_lookup(T, s_exa[c], s_exn[c], d);
                 }
-                float tf = s_tf[code[u]];
-                if (fe != 0.0f) tf = tf_of(fe);
+                float tf = s_tf[code[u]];                                              // BM25: the frequency itself
+                if (fe != 0.0f) tf = SIM == SIM_BM25 ? fe : tf_of(fe);
                 if (tf != 0.0f) {
-                    sum += (double)__fmul_rn(__fmul_rn(tf, s_val[c]), nrm);          // TFIDFSimScorer#score
+                    sum += (double)clause_doc_score(SIM, tf, s_val[c], nrm, bm.k1p1);     // TFIDFSimScorer#score / BM25DocScorer#score
                     m++;
                 }
             }
@@ -959,7 +1032,7 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
             sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
             m += __shfl_xor_sync(0xFFFFFFFFu, m, o);
         }
-        const u64 key = m >= need ? cand_key(final_score(SIM_TFIDF, sum, m, nc), d) : 0ull;
+        const u64 key = m >= need ? cand_key(final_score(SIM, sum, m, nc), T.docmap[d]) : 0ull;
         if (n_cand == 1) {                                // the usual case: nothing to sort, nobody to wait for
             if (lane == 0) {
                 if (key) {
@@ -1115,7 +1188,7 @@ __global__ void __launch_bounds__(512) exact_score_kernel(
 #pragma unroll
     for (int i = 0; i < EX_DPT; i++) {
         i32 m = (i32)((cnt[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
-        sc[i] = (active && d0 + i < n_docs && m >= need) ? final_score(SIM, acc[i], m, nc) : -1.0f;
+        sc[i] = (active && m >= need) ? final_score(SIM, acc[i], m, nc) : -1.0f;      // padding columns have no cells: m = 0
     }
     const i64 pbase = (i64)r * parts_stride + tile;
     i32 found = 0;
@@ -1126,7 +1199,7 @@ __global__ void __launch_bounds__(512) exact_score_kernel(
             mine = 0;
 #pragma unroll
             for (int i = 0; i < EX_DPT; i++)
-                if (sc[i] >= 0.0f) { u64 kk = cand_key(sc[i], d0 + i); if (kk > mine) mine = kk; }
+                if (sc[i] >= 0.0f) { u64 kk = cand_key(sc[i], T.docmap[d0 + i]); if (kk > mine) mine = kk; }
             dirty = false;
         }
         u64 best = block_max_u64(mine, red);
@@ -1136,7 +1209,7 @@ __global__ void __launch_bounds__(512) exact_score_kernel(
             part_doc[pbase * TOPN + round] = global_doc_base + d;
             part_score[pbase * TOPN + round] = __uint_as_float((u32)(best >> 32));
 #pragma unroll
-            for (int i = 0; i < EX_DPT; i++) if (d0 + i == d) sc[i] = -1.0f;
+            for (int i = 0; i < EX_DPT; i++) if (sc[i] >= 0.0f && T.docmap[d0 + i] == d) sc[i] = -1.0f;
             dirty = true;
         }
         found++;

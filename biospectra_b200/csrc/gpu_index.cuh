@@ -188,6 +188,8 @@ struct GpuIndex {
     // dense 4-bit table
     DevBuf<u8> tab4; u64 d_pad = 0, row_bytes = 0, n_rows = 0, pair_row0 = 0;
     DevBuf<u32> exc_off, exc_doc; DevBuf<float> exc_freq; i64 n_exc = 0; u32 gap_cap = GAP_CAP_DEFAULT;
+    // table column order: docs sorted by (norm byte, doc id) -- see Tab4Dev::docmap
+    DevBuf<u32> colmap, docmap; std::vector<u32> h_docmap;
     // slot: pipeline slot whose gap-clause lists (tail of the exception arrays) and counters the view refers to
     Tab4Dev tab4_view(int slot, const u32* gap_cnt) const {
         Tab4Dev t;
@@ -196,6 +198,7 @@ struct GpuIndex {
         t.zero_row = (u32)n_rows; t.temp_row0 = (u32)n_rows + 1;
         t.tmp_base = (u32)n_exc + (u32)slot * gap_cap * GAP_LIST;
         t.gap_cnt = gap_cnt;
+        t.docmap = docmap.p;
         return t;
     }
     u32 max_seg_docs = 0;
@@ -404,6 +407,19 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
     CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
     ix.d_pad = (u64)round_up(std::max<i64>(D, 1), 32);
     ix.row_bytes = ix.d_pad / 2;
+    {
+        // column order of the dense tables: stable counting sort of the docs by norm byte
+        std::vector<u32> h_colmap((size_t)std::max<i64>(D, 1));
+        ix.h_docmap.assign((size_t)ix.d_pad + 64, 0xFFFFFFFFu);          // (+ slack: vector loads of the last thread)
+        u32 start[257] = {0};
+        for (i64 d = 0; d < D; d++) start[ix.doc_norm[d] + 1]++;
+        for (int b = 0; b < 256; b++) start[b + 1] += start[b];
+        for (i64 d = 0; d < D; d++) { const u32 c = start[ix.doc_norm[d]]++; h_colmap[d] = c; ix.h_docmap[c] = (u32)d; }
+        ix.colmap.alloc(h_colmap.size()); ix.docmap.alloc(ix.h_docmap.size());
+        CUDA_CHECK(cudaMemcpyAsync(ix.colmap.p, h_colmap.data(), h_colmap.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(ix.docmap.p, ix.h_docmap.data(), ix.h_docmap.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));                           // h_colmap leaves scope
+    }
     const bool can_tables = ix.direct;          // 2k <= 24: at most 5 * 4^12 rows
     ix.pair_row0 = 1ull << (2 * k);
     ix.n_rows = can_tables ? (ix.pair_row0 + (opt.need_pair_table ? (1ull << (2 * (k + 1))) : 0ull)) : 0ull;
@@ -550,7 +566,7 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
                 count_new_terms_kernel<<<(unsigned)ceil_div(seg.n_terms, 256), 256, 0, st>>>(v, d_prev.p, (int)views.size(), d_counter.p);
         }
         if (tables && seg.n_terms) {
-            tf_table4_kernel<<<(unsigned)ceil_div((u64)seg.n_terms * 32, 256), 256, 0, st>>>(v, (u32*)ix.tab4.p, ix.row_bytes / 4, exb);
+            tf_table4_kernel<<<(unsigned)ceil_div((u64)seg.n_terms * 32, 256), 256, 0, st>>>(v, ix.colmap.p, (u32*)ix.tab4.p, ix.row_bytes / 4, exb);
             if (ix.has_pair) {
                 u64 rows = 1ull << (2 * (k + 1));
                 if (seg.n_docs <= POSW_DOCS && !getenv("BSP_PAIR_TABLE_DIRECT")) {
@@ -560,9 +576,9 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
                     CUDA_CHECK(cudaFuncSetAttribute(pair_table4_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)(PT_WARPS * pair_stage_warp_bytes(POSW_DOCS, PW_POS))));
                     pair_table4_staged_kernel<<<(unsigned)ceil_div(rows / 4, PT_WARPS), PT_WARPS * 32, smem, st>>>(
-                        v, k, ix.min_strand, (u32*)ix.tab4.p, ix.row_bytes / 4, ix.pair_row0, exb, rows / 4, dcap, PW_POS);
+                        v, ix.colmap.p, k, ix.min_strand, (u32*)ix.tab4.p, ix.row_bytes / 4, ix.pair_row0, exb, rows / 4, dcap, PW_POS);
                 } else {
-                    pair_table4_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(v, k, ix.min_strand, (u32*)ix.tab4.p,
+                    pair_table4_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(v, ix.colmap.p, k, ix.min_strand, (u32*)ix.tab4.p,
                                                                                           ix.row_bytes / 4, ix.pair_row0, exb, rows);
                 }
             }

@@ -42,7 +42,7 @@ def test_index_and_classify_bit_exact(case, oracle_lib, monkeypatch):
     finally:
         g.close()
     # dense 4-bit tables on (small k): reads whose clauses all have slop 2 take a dense route --
-    # every doc scored exactly (BSP_FILTER=0), or bound-and-rescore (BSP_FILTER=1, tf-idf only)
+    # every doc scored exactly (BSP_FILTER=0), or bound-and-rescore (BSP_FILTER=1; bm25 through per-norm-class LUTs)
     if k <= 8:
         for filt in ("0", "1"):
             monkeypatch.setenv("BSP_FILTER", filt)
@@ -51,7 +51,7 @@ def test_index_and_classify_bit_exact(case, oracle_lib, monkeypatch):
                 res_g = g.classify_batch(reads)
                 common.assert_classify_equal(res_g, res_o, reads, "dense+positional filter=" + filt)
                 routes = set(g.last_routes(len(reads))[res_o["status"] == 0])
-                assert routes <= ({1, 2} if (filt == "0" or case["sim"]) else {1, 2, 3}), routes
+                assert routes <= ({1, 2} if filt == "0" else {1, 2, 3}), routes
             finally:
                 g.close()
 
