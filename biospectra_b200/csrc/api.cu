@@ -52,6 +52,7 @@ struct Scratch {
     DevBuf<FilterStats> fstats; DevBuf<float2> vrange;
     DevBuf<GapClause> gaps; DevBuf<u32> gap_cnt;       // gap clauses of the sub-batch; gap_cnt[cap] matches, [cap] = #clauses
     int slot_index = 0;
+    bool front_fused = false;
     DevBuf<i32> part_n; DevBuf<u32> part_doc; DevBuf<float> part_score;
     DevBuf<i32> o_status, o_label, o_nhits, o_ntop, o_doc; DevBuf<float> o_score;
     DevBuf<i32> o_taxlabel, o_taxidx;
@@ -608,11 +609,6 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     sc.tok_cap.ensure((size_t)n + 1);
     tok_capacity_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(d_seq_off, n, k, sc.tok_cap.p);
     exclusive_scan<i64, i64>(sc.tok_cap.p, sc.tok_off.p, (u64)n, sc.tok_off.p + n, sc.scan_tmp, st);
-    tokenize_kernel<<<(unsigned)ceil_div((i64)n * 32, 256), 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, k, h->conf.kmer_skips,
-                                                                          ix.min_strand, sc.tok_key.p, sc.tok_pos.p, sc.n_tok.p);
-    token_df_kernel<<<(unsigned)ceil_div((i64)n * 32, 256), 256, 0, st>>>(sc.tok_key.p, sc.tok_off.p, sc.n_tok.p, n,
-                                                                          ix.direct ? ix.df_dense.p : nullptr, ix.d_segs.p,
-                                                                          ix.positional ? (int)ix.segs.size() : 0, sc.tok_df.p);
     QueryParams& qp = sc.qp;
     qp.k = k; qp.skips = h->conf.kmer_skips; qp.min_strand = ix.min_strand; qp.alg = h->conf.query_algorithm;
     qp.sim = h->conf.scoring_algorithm == BSP_BM25 ? SIM_BM25 : SIM_TFIDF;
@@ -639,10 +635,21 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     qp.filter_nc_max = FK_MAX_CLAUSES;
     if (qp.sim == SIM_BM25)
         qp.filter_nc_max = (int)std::min<i64>(FK_MAX_CLAUSES, FK_BM25_LUT_BYTES / ((i64)std::max(h->n_classes, 1) * (qp.alg == ALG_NAIVE ? 24 : 16)) - 2);
-    weights_kernel<<<(unsigned)ceil_div((i64)n * 32, 256), 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p,
-                                                               sc.tok_df.p, h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p,
-                                                               sc.n_clauses.p, sc.msm.p, sc.route.p, sc.status_in.p, sc.vrange.p,
-                                                               sc.gaps.p, sc.gap_cnt.p + GC, sc.read_ngap.p);
+    const unsigned wgrid = (unsigned)ceil_div((i64)n * 32, 256);
+    sc.front_fused = h->conf.kmer_skips == 0 && ix.direct && env_i64("BSP_FRONT_FUSED", 1) != 0;
+    if (sc.front_fused) {
+        front_kernel<<<wgrid, 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, ix.min_strand, ix.df_dense.p, sc.tok_key.p, sc.tok_pos.p,
+                                            sc.tok_df.p, sc.n_tok.p, h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p,
+                                            sc.msm.p, sc.route.p, sc.status_in.p, sc.vrange.p, sc.gaps.p, sc.gap_cnt.p + GC, sc.read_ngap.p);
+    } else {
+        tokenize_kernel<<<wgrid, 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, k, h->conf.kmer_skips, ix.min_strand, sc.tok_key.p,
+                                               sc.tok_pos.p, sc.n_tok.p);
+        token_df_kernel<<<wgrid, 256, 0, st>>>(sc.tok_key.p, sc.tok_off.p, sc.n_tok.p, n, ix.direct ? ix.df_dense.p : nullptr, ix.d_segs.p,
+                                               ix.positional ? (int)ix.segs.size() : 0, sc.tok_df.p);
+        weights_kernel<<<wgrid, 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p, sc.tok_df.p,
+                                              h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.route.p,
+                                              sc.status_in.p, sc.vrange.p, sc.gaps.p, sc.gap_cnt.p + GC, sc.read_ngap.p);
+    }
     CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));
     route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, sc.n_clauses.p, n, sc.list_dense.p, sc.list_pos.p,
                                                                      sc.list_filter.p, sc.counts.p);
@@ -703,7 +710,7 @@ static void pipeline_phase2a(bsp_classifier* h, Scratch& sc) {
     const Tab4Dev T = ix.tab4_view(sc.slot_index, sc.gap_cnt.p);
     const int full_topn = (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0;
     CUDA_CHECK(cudaEventRecord(sc.ev[1], st));
-    sc.launches = 9;      // tok_capacity, 4 scan kernels, tokenize, token_df, weights, route_compact
+    sc.launches = sc.front_fused ? 7 : 9;      // tok_capacity, 4 scan kernels, front (or tokenize, token_df, weights), route_compact
     sc.filter_launched = false;
     if (counts[2] > 0) {
         CUDA_CHECK(cudaMemsetAsync(sc.fstats.p, 0, sizeof(FilterStats), st));

@@ -179,13 +179,14 @@ __device__ __forceinline__ int base_code_dev(u8 c) {
 
 // Warp per read: lucene/KmerSequenceTokenizer.java:115-154 + SequenceCompressFilter.
 // tok_off[r] = capacity offset of read r's token slots (max(len-k+1,0) each).
-__global__ void __launch_bounds__(256) tokenize_kernel(const u8* __restrict__ seq, const i64* __restrict__ seq_off, i32 n_reads,
-                                                        const i64* __restrict__ tok_off, int k, int skips, int min_strand,
-                                                        u64* __restrict__ tok_key, u32* __restrict__ tok_pos,
-                                                        i32* __restrict__ n_tok) {
-    const int lane = threadIdx.x & 31;
-    const i32 r = (i32)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
-    if (r >= n_reads) return;
+// `codes` (optional): 64 bytes of shared memory private to the warp.  With it the kmer_skips = 0 path stages the 2-bit codes
+// of the 32 + k - 1 bases a round of 32 windows covers (two coalesced byte loads per lane) and builds the windows from
+// shared memory instead of k byte loads from global memory per window; `df_dense` (optional) looks each token's document
+// frequency up where the token is emitted (tok_df), which saves token_df_kernel's pass over the keys.
+__device__ __forceinline__ void tokenize_read(const u8* __restrict__ seq, const i64* __restrict__ seq_off, i32 r, int lane,
+                                              const i64* __restrict__ tok_off, int k, int skips, int min_strand,
+                                              u64* __restrict__ tok_key, u32* __restrict__ tok_pos, i32* __restrict__ n_tok,
+                                              u8* codes, const u32* __restrict__ df_dense, u32* __restrict__ tok_df) {
     const u8* s = seq + seq_off[r];
     const i64 len = seq_off[r + 1] - seq_off[r];
     const i64 nwin = len - k + 1;
@@ -193,7 +194,29 @@ __global__ void __launch_bounds__(256) tokenize_kernel(const u8* __restrict__ se
     u32* offs = tok_pos + tok_off[r];
     i32 cnt = 0;
     if (nwin > 0) {
-        if (skips == 0) {
+        if (skips == 0 && codes != nullptr) {
+            u32* dfs = tok_df + tok_off[r];
+            for (i64 w0 = 0; w0 < nwin; w0 += 32) {
+                __syncwarp();
+                codes[lane] = w0 + lane < len ? (u8)(base_code_dev(s[w0 + lane]) & 7) : (u8)4;           // invalid base: bit 2 set
+                if (lane < k - 1) codes[32 + lane] = w0 + 32 + lane < len ? (u8)(base_code_dev(s[w0 + 32 + lane]) & 7) : (u8)4;
+                __syncwarp();
+                const i64 w = w0 + lane;
+                u64 v = 0;
+                u32 bad = 0;
+                for (int i = 0; i < k; i++) { const u32 b = codes[lane + i]; bad |= b; v = (v << 2) | (u64)(b & 3u); }
+                const bool ok = w < nwin && !(bad & 4u);
+                const u32 bal = __ballot_sync(0xFFFFFFFFu, ok);
+                if (ok) {
+                    const i32 o = cnt + __popc(bal & ((1u << lane) - 1u));
+                    const u64 key = canon_kmer(v, k, min_strand);
+                    keys[o] = key;
+                    offs[o] = (u32)w;
+                    if (df_dense) dfs[o] = df_dense[key];
+                }
+                cnt += __popc(bal);
+            }
+        } else if (skips == 0) {
             // every valid window is a token: ordered compaction by ballot
             for (i64 w0 = 0; w0 < nwin; w0 += 32) {
                 i64 w = w0 + lane;
@@ -242,6 +265,15 @@ __global__ void __launch_bounds__(256) tokenize_kernel(const u8* __restrict__ se
     }
     if (lane == 0) n_tok[r] = cnt;
 }
+__global__ void __launch_bounds__(256) tokenize_kernel(const u8* __restrict__ seq, const i64* __restrict__ seq_off, i32 n_reads,
+                                                        const i64* __restrict__ tok_off, int k, int skips, int min_strand,
+                                                        u64* __restrict__ tok_key, u32* __restrict__ tok_pos,
+                                                        i32* __restrict__ n_tok) {
+    const int lane = threadIdx.x & 31;
+    const i32 r = (i32)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
+    if (r >= n_reads) return;
+    tokenize_read(seq, seq_off, r, lane, tok_off, k, skips, min_strand, tok_key, tok_pos, n_tok, nullptr, nullptr, nullptr);
+}
 
 // number of clauses for n tokens (Classifier.java:113-200; offsetDiff > 0 always holds)
 __host__ __device__ __forceinline__ i32 clause_count(int alg, i32 n) {
@@ -285,22 +317,19 @@ __global__ void __launch_bounds__(256) token_df_kernel(const u64* __restrict__ t
 // Warp per read: msm, clause weights (A.5) and routing.  Lanes work on clauses in parallel; the only order-dependent
 // step -- BooleanWeight#getValueForNormalization's float sum over the clauses -- is replayed in clause order.
 //   clause_val[tok_off[r] + c] = value_c ; clause_row[...] = dense-table row (dense route)
-__global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq, const i64* __restrict__ seq_off, i32 n_reads,
-                                                       const i64* __restrict__ tok_off, const i32* __restrict__ n_tok,
-                                                       const u64* __restrict__ tok_key, const u32* __restrict__ tok_pos,
-                                                       const u32* __restrict__ tok_df, const float* __restrict__ idf_by_df,
-                                                       QueryParams qp,
-                                                       float* __restrict__ clause_val, u32* __restrict__ clause_row,
-                                                       i32* __restrict__ n_clauses, i32* __restrict__ msm_out,
-                                                       i32* __restrict__ route, i32* __restrict__ status,
-                                                       float2* __restrict__ vrange /* per read: (max, min) clause value */,
-                                                       GapClause* __restrict__ gaps, u32* __restrict__ gap_count,
-                                                       i32* __restrict__ read_ngap /* per read: # gap clauses registered */) {
-    const int lane = threadIdx.x & 31;
-    const i32 r = (i32)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
-    if (r >= n_reads) return;
+__device__ __forceinline__ void weights_read(const u8* __restrict__ seq, const i64* __restrict__ seq_off, i32 r, int lane,
+                                             const i64* __restrict__ tok_off, i32 n,
+                                             // (no __restrict__: front_kernel wrote these arrays a moment ago -- they must not
+                                             //  be read through the non-coherent path)
+                                             const u64* tok_key, const u32* tok_pos, const u32* tok_df,
+                                             const float* __restrict__ idf_by_df, const QueryParams& qp,
+                                             float* __restrict__ clause_val, u32* __restrict__ clause_row,
+                                             i32* __restrict__ n_clauses, i32* __restrict__ msm_out,
+                                             i32* __restrict__ route, i32* __restrict__ status,
+                                             float2* __restrict__ vrange /* per read: (max, min) clause value */,
+                                             GapClause* __restrict__ gaps, u32* __restrict__ gap_count,
+                                             i32* __restrict__ read_ngap /* per read: # gap clauses registered */) {
     const i64 base = tok_off[r];
-    const i32 n = n_tok[r];
     const i32 nc = clause_count(qp.alg, n);
     if (n <= 1 || nc > MAX_CLAUSES) {               // Classifier.java:223-227 / TooManyClauses
         if (lane == 0) { n_clauses[r] = nc; msm_out[r] = 0; route[r] = ROUTE_NONE; status[r] = ST_DROPPED; }
@@ -401,6 +430,47 @@ __global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq
         else if (qp.positional_ok) { route[r] = ROUTE_POSITIONAL; status[r] = ST_OK; }
         else { route[r] = ROUTE_NONE; status[r] = ST_ERROR; }
     }
+}
+__global__ void __launch_bounds__(256) weights_kernel(const u8* __restrict__ seq, const i64* __restrict__ seq_off, i32 n_reads,
+                                                       const i64* __restrict__ tok_off, const i32* __restrict__ n_tok,
+                                                       const u64* __restrict__ tok_key, const u32* __restrict__ tok_pos,
+                                                       const u32* __restrict__ tok_df, const float* __restrict__ idf_by_df,
+                                                       QueryParams qp,
+                                                       float* __restrict__ clause_val, u32* __restrict__ clause_row,
+                                                       i32* __restrict__ n_clauses, i32* __restrict__ msm_out,
+                                                       i32* __restrict__ route, i32* __restrict__ status, float2* __restrict__ vrange,
+                                                       GapClause* __restrict__ gaps, u32* __restrict__ gap_count,
+                                                       i32* __restrict__ read_ngap) {
+    const int lane = threadIdx.x & 31;
+    const i32 r = (i32)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
+    if (r >= n_reads) return;
+    weights_read(seq, seq_off, r, lane, tok_off, n_tok[r], tok_key, tok_pos, tok_df, idf_by_df, qp, clause_val, clause_row, n_clauses,
+                 msm_out, route, status, vrange, gaps, gap_count, read_ngap);
+}
+
+// The three kernels in front of the scorer as one (kmer_skips = 0, direct term table): a warp tokenises its read out of
+// shared-memory staged codes, looks each token's df up as it emits it and goes on to the clause weights and the route
+// while its tokens are still in L1 -- one launch and one pass over the keys instead of three.
+__global__ void __launch_bounds__(256) front_kernel(const u8* __restrict__ seq, const i64* __restrict__ seq_off, i32 n_reads,
+                                                     const i64* __restrict__ tok_off, int min_strand, const u32* __restrict__ df_dense,
+                                                     u64* __restrict__ tok_key, u32* __restrict__ tok_pos, u32* __restrict__ tok_df,
+                                                     i32* __restrict__ n_tok, const float* __restrict__ idf_by_df, QueryParams qp,
+                                                     float* __restrict__ clause_val, u32* __restrict__ clause_row,
+                                                     i32* __restrict__ n_clauses, i32* __restrict__ msm_out,
+                                                     i32* __restrict__ route, i32* __restrict__ status, float2* __restrict__ vrange,
+                                                     GapClause* __restrict__ gaps, u32* __restrict__ gap_count,
+                                                     i32* __restrict__ read_ngap) {
+    __shared__ u8 s_codes[8][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i32 r = (i32)((blockIdx.x * (u64)blockDim.x + threadIdx.x) >> 5);
+    if (r >= n_reads) return;
+    tokenize_read(seq, seq_off, r, lane, tok_off, qp.k, 0, min_strand, tok_key, tok_pos, n_tok, s_codes[warp], df_dense, tok_df);
+    __syncwarp();                                    // the warp's own token arrays (global memory, same SM) are complete
+    i32 n = 0;
+    if (lane == 0) n = n_tok[r];
+    n = __shfl_sync(0xFFFFFFFFu, n, 0);
+    weights_read(seq, seq_off, r, lane, tok_off, n, tok_key, tok_pos, tok_df, idf_by_df, qp, clause_val, clause_row, n_clauses,
+                 msm_out, route, status, vrange, gaps, gap_count, read_ngap);
 }
 
 // ------------------------------------------------------------------ scoring math
