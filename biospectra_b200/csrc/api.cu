@@ -420,8 +420,15 @@ static void upload_scoring_constants(bsp_classifier* h) {
         if (nb != last_byte) { ck.push_back(cache[nb]); last_byte = nb; }
         // class of the group = the one with the smallest weight among its columns (BM25: an upper bound for the others)
         const size_t g = c / 32;
-        const int cls = (int)ck.size() - 1;
-        if (c % 32 == 0 || ck[cls] < ck[gcls[g]]) gcls[g] = (u8)std::min(cls, 255);
+        const int cls = std::min((int)ck.size() - 1, 127);
+        if (c % 32 == 0) gcls[g] = (u8)cls;
+        else if ((gcls[g] & 0x7F) != cls) gcls[g] = (u8)(0x80 | (ck[cls] < ck[gcls[g] & 0x7F] ? cls : (gcls[g] & 0x7F)));
+    }
+    // groups with padding columns (the last one) and classes beyond the 7-bit index are "mixed": per-doc weights are loaded
+    for (size_t g = 0; g < gcls.size(); g++) {
+        bool pad = false;
+        for (size_t c = g * 32; c < g * 32 + 32; c++) pad |= c >= ix.h_docmap.size() || ix.h_docmap[c] == 0xFFFFFFFFu;
+        if (pad || (int)ck.size() > 128 || env_i64("BSP_NO_UNIFORM", 0) != 0) gcls[g] |= 0x80;
     }
     if (ck.empty()) ck.push_back(1.0f);
     h->n_classes = (int)ck.size();

@@ -543,7 +543,8 @@ __device__ __forceinline__ float exc_lookup(const Tab4Dev& T, u32 a, u32 n, u32 
 // (larger K, smaller true weights) -- those may become candidates (rescoring is exact) but never set the threshold.
 struct Bm25Classes {
     const float* class_k;       // [n_classes] K of each norm class present in the handle, in column order
-    const u8* group_class;      // [d_pad / 32] class with the smallest K among the group's columns
+    const u8* group_class;      // [d_pad / 32] bits 0-6: class with the smallest K among the group's columns; bit 7: the group
+                                //              holds columns of more than one class (or padding columns)
     int n_classes;
     int nc_cap;                 // clause capacity of one class's LUT array (>= clauses of every read of the launch + 1)
     float k_min, k_max, k1p1;
@@ -690,8 +691,10 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     const uint2* hi_tab = s_lut_hi;
     int cls = 0;
     float k_thr = 0.0f;
+    const u32 gcls = active ? (u32)bm.group_class[d0 / FK_DOCS] : 0x80u;
+    const bool uniform = !(gcls & 0x80u);       // all 32 columns share one norm class: one per-doc weight for the thread
     if (SIM == SIM_BM25) {
-        cls = active ? (int)bm.group_class[d0 / FK_DOCS] : 0;
+        cls = (int)(gcls & 0x7Fu);
         k_thr = bm.class_k[cls];
         lo_tab = lut_cls + (size_t)cls * bm.nc_cap;
         hi_tab = lut_cls_hi + (size_t)cls * bm.nc_cap;
@@ -875,7 +878,20 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
         for (int j = 0; j < 8; j++) f |= ((cacc[j] | 0x80808080u) - need4) | cacc[j];
         any_m = (f & 0x80808080u) != 0u;
     }
-    if (any_m) {
+    if (any_m && uniform) {
+        // one norm class (all but the few groups at class boundaries): the best estimate is the largest integer Q*m (tf-idf)
+        // or Q (BM25) times the class weight -- no per-doc weights to load, no per-doc float arithmetic
+        u32 tmax = 0;
+#pragma unroll
+        for (int i = 0; i < FK_DOCS; i++) {
+            const u32 Q = prmt(wacc[i >> 1], 0u, (i & 1) ? 0x4432u : 0x4410u);
+            const u32 m = prmt(cacc[i >> 2], 0u, 0x4440u | (u32)(i & 3));
+            const u32 t = (i32)m >= need ? (SIM == SIM_BM25 ? Q : Q * m) : 0u;
+            tmax = max(tmax, t);
+        }
+        e_best = SIM == SIM_BM25 ? (float)tmax : (float)tmax * bm.class_k[gcls & 0x7Fu];
+        e_any = e_best;
+    } else if (any_m) {
 #pragma unroll
         for (int i4 = 0; i4 < FK_DOCS; i4 += 4) {
             const float4 nv = *reinterpret_cast<const float4*>(doc_w + d0 + i4);
