@@ -488,6 +488,47 @@ def secondary_lines(clf, data, o, dev, local, n, peak, peak_src, main_kw, n_docs
     return out
 
 
+def lclassify_line(clf, data, n, labels):
+    """File to file on the resident index: LocalClassifier.classify(inputFasta, classifyOutput, summaryOutput)
+    (LocalClassifier.java:60-131) through bsp_host_classify_file -- FASTA reader thread, GPU batches, formatter threads, in-order
+    writer of the reference's per-read JSON lines.  Files live in /dev/shm (tmpfs) when it exists."""
+    import shutil
+    import tempfile
+    from biospectra_b200 import synth
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    d = tempfile.mkdtemp(prefix="bsp_lc_", dir=base)
+    try:
+        off = data["offsets"]
+        seq = data["seq_bytes"]
+        src = data["src"]
+        path = os.path.join(d, "reads.fa")
+        with open(path, "wb") as f:
+            chunk = []
+            for i in range(n):
+                chunk.append(b">" + synth.header_of(int(src[i])).encode() + b"\n" + seq[off[i]:off[i + 1]].tobytes() + b"\n")
+                if len(chunk) == 65536:
+                    f.write(b"".join(chunk)); chunk = []
+            f.write(b"".join(chunk))
+        in_bytes = os.path.getsize(path)
+        threads = min(os.cpu_count() or 4, 16)
+        res_path, sum_path = os.path.join(d, "reads.fa.result"), os.path.join(d, "reads.fa.result.sum")
+        clf.classify_file(path, res_path, sum_path, worker_threads=threads)          # warm-up (page cache, pinned buffers)
+        t0 = time.perf_counter()
+        clf.classify_file(path, res_path, sum_path, worker_threads=threads)
+        el = time.perf_counter() - t0
+        with open(sum_path) as f:
+            summ = json.load(f)
+        out_bytes = os.path.getsize(res_path)
+        ok = (summ.get("total") == n and summ.get("classified") == labels["classified"] and summ.get("vague") == labels["vague"]
+              and summ.get("unknown") == labels["unknown"])
+        return {"name": "lclassify file to file (FASTA in, .result / .result.sum out) on the resident index", "reads": n,
+                "value": n / el, "unit": "reads/s", "seconds": el, "worker_threads": threads, "input_bytes": in_bytes,
+                "output_bytes": out_bytes, "summary": {k_: summ.get(k_) for k_ in ("total", "unknown", "vague", "classified")},
+                "summary_matches_device_labels": bool(ok), "files_in": d.split("/")[1]}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def large_k_line(k, dev, local, peak, peak_src):
     """One k > 12 index (the authors' sweep goes to k = 24, benchmark/scripts/run.py:11): hash dictionary + CSR postings, no dense
     tables.  10 Gbp of 16-mers need 240 GB of postings, so this line uses the 1 Gbp `mid` reference (300 genomes)."""
@@ -799,6 +840,8 @@ def main():
                                       "labels": labels, "dropped": int((res["status"] == 1).sum()), "errors": int((res["status"] == 2).sum())}}
         if world == 1 and not args.no_secondary and args.k == 10:
             line["secondary"] = secondary_lines(clf, data, o, dev, local, n, peak, peak_src, main_kw, stats["n_docs"])
+            if (res["status"] == 0).all():
+                line["secondary"].append(lclassify_line(clf, data, n, labels))
     clf.close()
     del o
     torch.cuda.empty_cache()

@@ -46,8 +46,8 @@ EXPORTS = [
     "bsp_classifier_set_microbatch", "bsp_microbatch_stats", "bsp_classifier_set_lineages", "bsp_classify_packed_tax", "bsp_doc_fields", "bsp_classifier_close",
     "bsp_index_stats", "bsp_doc_info", "bsp_term_postings", "bsp_tokenize", "bsp_last_routes", "bsp_last_counters",
     "bsp_last_timings", "bsp_memory_info", "bsp_partition_df_buffer", "bsp_partition_local_stats",
-    "bsp_partition_set_global", "bsp_merge_topk_device", "bsp_read_cost", "bsp_classifier_set_query", "bsp_index_layout", "bsp_pack_topk_device", "bsp_merge_topk_records_device",
-    "bsp_host_index", "bsp_host_classify_local", "bsp_host_classify_local_per_read", "bsp_host_last_error", "bsp_host_label_json", "bsp_host_read_fasta", "bsp_index_add_fasta",
+    "bsp_partition_set_global", "bsp_merge_topk_device", "bsp_read_cost", "bsp_classifier_set_query", "bsp_host_classify_file", "bsp_index_layout", "bsp_pack_topk_device", "bsp_merge_topk_records_device",
+    "bsp_host_index", "bsp_host_classify_local", "bsp_host_classify_local_per_read", "bsp_host_last_error", "bsp_host_label_json", "bsp_host_read_fasta", "bsp_host_read_fasta_striped", "bsp_index_add_fasta",
     "bsp_host_double_to_string", "bsp_host_parse_config",
 ]
 
@@ -73,6 +73,7 @@ def lib():
     L.bsp_pack_topk_device.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
     L.bsp_merge_topk_records_device.argtypes = [vp, C.c_int32, C.c_int32] + [vp] * 8
     L.bsp_index_layout.argtypes = [vp, i64p]
+    L.bsp_host_classify_file.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32]
     L.bsp_index_create.argtypes = [cfgp, C.c_char_p, C.POINTER(vp)]
     L.bsp_index_add_entry.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64]
     L.bsp_index_add_entry_device.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, vp, C.c_int64]

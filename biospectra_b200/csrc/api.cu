@@ -1,6 +1,7 @@
 // api.cu -- C ABI of libbiospectra_gpu.so (see include/biospectra_gpu.h).
 #include "../../include/biospectra_gpu.h"
 #include "gpu_index.cuh"
+#include "filter3.cuh"
 
 #include <dirent.h>
 #include <errno.h>
@@ -53,6 +54,10 @@ struct Scratch {
     DevBuf<GapClause> gaps; DevBuf<u32> gap_cnt;       // gap clauses of the sub-batch; gap_cnt[cap] matches, [cap] = #clauses
     int slot_index = 0;
     bool front_fused = false;
+    // filter3.cuh: per-read headers / clause records / exception cells, candidate lists, read-wide thresholds
+    DevBuf<F3Hdr> f3_hdr; DevBuf<uint4> f3_rec; DevBuf<uint2> f3_rec_hi, f3_cand; DevBuf<F3Cell> f3_cells; DevBuf<F3Long> f3_longs;
+    DevBuf<i32> f3_cand_n, f3_long_over; DevBuf<u32> f3_tau, f3_prolog;
+    bool filter_v3 = false;
     DevBuf<i32> part_n; DevBuf<u32> part_doc; DevBuf<float> part_score;
     DevBuf<i32> o_status, o_label, o_nhits, o_ntop, o_doc; DevBuf<float> o_score;
     DevBuf<i32> o_taxlabel, o_taxidx;
@@ -122,6 +127,8 @@ struct bsp_classifier {
     // dense-table side of the per-doc weights: by table column (GpuIndex::docmap), the norm classes present and, per group of
     // 32 columns, the class with the smallest weight (BM25 filter: Bm25Classes)
     DevBuf<float> col_w, class_k; DevBuf<u8> group_class; int n_classes = 0; float k_min = 0.0f, k_max = 0.0f;
+    DevBuf<float2> group_w;             // per group of 32 columns: (smallest, largest) per-doc weight
+    int sm_count = 148;
     // interned ranked lineages (bsp_classifier_set_lineages)
     DevBuf<i64> lin_off; DevBuf<i32> lin_tax; DevBuf<u8> lin_flags; i64 lin_docs = 0;
     i64 global_docs = 0, global_sum_ttf = 0, doc_base_global = 0;
@@ -434,6 +441,15 @@ static void upload_scoring_constants(bsp_classifier* h) {
     h->n_classes = (int)ck.size();
     h->k_min = *std::min_element(ck.begin(), ck.end());
     h->k_max = *std::max_element(ck.begin(), ck.end());
+    std::vector<float2> gw(gcls.size() + 512, make_float2(1.0f, 1.0f));
+    for (size_t g = 0; g * 32 < ix.h_docmap.size(); g++) {
+        float lo = 3.0e38f, hi = 0.0f;
+        for (size_t c = g * 32; c < g * 32 + 32 && c < ix.h_docmap.size(); c++)
+            if (ix.h_docmap[c] != 0xFFFFFFFFu) { lo = std::min(lo, cw[c]); hi = std::max(hi, cw[c]); }
+        if (hi > 0.0f || lo < 3.0e38f) gw[g] = make_float2(lo, hi);
+    }
+    h->group_w.alloc(gw.size());
+    CUDA_CHECK(cudaMemcpyAsync(h->group_w.p, gw.data(), gw.size() * sizeof(float2), cudaMemcpyHostToDevice, h->st));
     h->col_w.alloc(cw.size()); h->class_k.alloc(ck.size()); h->group_class.alloc(gcls.size());
     CUDA_CHECK(cudaMemcpyAsync(h->col_w.p, cw.data(), cw.size() * 4, cudaMemcpyHostToDevice, h->st));
     CUDA_CHECK(cudaMemcpyAsync(h->class_k.p, ck.data(), ck.size() * 4, cudaMemcpyHostToDevice, h->st));
@@ -464,6 +480,11 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
         CUDA_CHECK(cudaFuncSetAttribute(filter_score_kernel<TI, AT, SIM_BM25>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared))
         FK_ATTR(false, false); FK_ATTR(false, true); FK_ATTR(true, false); FK_ATTR(true, true);
 #undef FK_ATTR
+        CUDA_CHECK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, conf->device));
+        CUDA_CHECK(cudaFuncSetAttribute(filter3_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f3_smem_bytes(FK3_MAXW, false)));
+        CUDA_CHECK(cudaFuncSetAttribute(filter3_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f3_smem_bytes(FK3_MAXW, true)));
+        CUDA_CHECK(cudaFuncSetAttribute(filter3_stream_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_CHECK(cudaFuncSetAttribute(filter3_stream_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_CHECK(cudaFuncSetAttribute(score_positional_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(POSW_WARPS * posw_warp_bytes(POSW_DOCS, PW_POS))));
         CUDA_CHECK(cudaFuncSetAttribute(score_positional_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_CHECK(cudaFuncSetAttribute(gap_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * phrase_stage_bytes(POSW_DOCS, PW_POS))));
@@ -727,11 +748,49 @@ static void pipeline_phase2a(bsp_classifier* h, Scratch& sc) {
         const bool tiled = sc.filter_tiles > 1, naive = qp.alg == ALG_NAIVE;
         const unsigned fgrid = (unsigned)((i64)counts[2] * sc.filter_tiles);
         const i32* fk_list = counts[2] == n ? nullptr : sc.list_filter.p;      // all reads: the list is a permutation of 0..n-1
+        const bool bm25 = qp.sim == SIM_BM25;
+        // third-generation filter (filter3.cuh): prep -> link -> persistent bulk-copy stream -> rescore.  tf-idf, one doc tile.
+        sc.filter_v3 = !bm25 && sc.filter_tiles == 1 && ix.d_pad <= (u64)FK3_MAXW * 1024 && env_i64("BSP_FILTER_V3", 0) != 0;
+        if (sc.filter_v3) {
+            const i32 nf = counts[2];
+            const int cand_cap = full_topn ? FK_CAND_CAP : 32;
+            const int W = (int)std::max<i64>(1, ceil_div((i64)ix.d_pad, 1024));
+            const size_t smem = f3_smem_bytes(W, naive);
+            int per_sm = 1;
+            if (naive) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter3_stream_kernel<true>, W * 32, smem));
+            else CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, filter3_stream_kernel<false>, W * 32, smem));
+            per_sm = (int)std::max<i64>(1, std::min<i64>(per_sm, env_i64("BSP_F3_CTAS", 32)));
+            const i32 G = (i32)std::max<i64>(1, std::min<i64>(nf, (i64)h->sm_count * per_sm));
+            const size_t n_rec = (size_t)sc.tok_key.n + 2 * (size_t)n + 64;
+            sc.f3_hdr.ensure(n); sc.f3_rec.ensure(n_rec);
+            if (naive) sc.f3_rec_hi.ensure(n_rec);
+            sc.f3_cells.ensure((size_t)n * FK3_CELLS); sc.f3_longs.ensure((size_t)n * FK3_LONG);
+            sc.f3_cand.ensure((size_t)n * cand_cap); sc.f3_cand_n.ensure(n); sc.f3_tau.ensure(n); sc.f3_long_over.ensure(n);
+            sc.f3_prolog.ensure((size_t)G * FK3_STAGES);
+            const u32 zero_off = T.zero_row * (u32)(T.row_bytes >> 4);
+            const unsigned pgrid = (unsigned)ceil_div((i64)nf * 32, 256);
+#define F3_PREP(AT) filter3_prep_kernel<AT><<<pgrid, 256, 0, st>>>(T, h->tf16.p, fk_list, nf, sc.tok_off.p, sc.n_tok.p, sc.clause_val.p, \
+                sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.vrange.p, sc.read_ngap.p, sc.gaps.p, qp.alg, sc.f3_hdr.p, sc.f3_rec.p, sc.f3_rec_hi.p, \
+                sc.f3_cells.p, sc.f3_longs.p, sc.f3_cand_n.p, sc.f3_tau.p, sc.f3_long_over.p, sc.route.p, sc.list_dense.p + counts[0], \
+                sc.counts.p + 3, sc.fstats.p)
+            if (naive) F3_PREP(true); else F3_PREP(false);
+#undef F3_PREP
+            filter3_link_kernel<<<pgrid, 256, 0, st>>>(sc.f3_hdr.p, sc.f3_rec.p, fk_list, nf, sc.tok_off.p, G, zero_off, sc.f3_prolog.p);
+#define F3_STREAM(AT) filter3_stream_kernel<AT><<<(unsigned)G, W * 32, smem, st>>>(T, sc.f3_hdr.p, sc.f3_rec.p, sc.f3_rec_hi.p, sc.f3_cells.p, \
+                sc.f3_longs.p, sc.f3_prolog.p, fk_list, nf, sc.tok_off.p, h->tf16.p, h->col_w.p, h->group_w.p, cand_cap, sc.f3_cand_n.p, \
+                sc.f3_cand.p, sc.f3_tau.p, sc.f3_long_over.p, full_topn, 1u)
+            if (naive) F3_STREAM(true); else F3_STREAM(false);
+#undef F3_STREAM
+            filter3_rescore_kernel<<<pgrid, 256, 0, st>>>(T, sc.f3_hdr.p, sc.f3_cells.p, sc.f3_longs.p, fk_list, nf, sc.tok_off.p,
+                sc.clause_val.p, sc.clause_row.p, h->tf16.p, h->col_w.p, cand_cap, sc.f3_cand_n.p, sc.f3_cand.p, sc.f3_tau.p,
+                sc.f3_long_over.p, gbase, parts_stride, part_n, part_doc, part_score, sc.route.p, sc.list_dense.p + counts[0],
+                sc.counts.p + 3, sc.fstats.p);
+            sc.launches += 3;
+        } else {
         Bm25Classes bm;
         bm.class_k = h->class_k.p; bm.group_class = h->group_class.p; bm.n_classes = h->n_classes;
         bm.nc_cap = (int)round_up((i64)std::min<i64>(std::max(sc.h_counts[6], 1), qp.filter_nc_max) + 1, 2);
         bm.k_min = h->k_min; bm.k_max = h->k_max; bm.k1p1 = 1.2f + 1.0f;
-        const bool bm25 = qp.sim == SIM_BM25;
         const size_t lut_bytes = bm25 ? (size_t)bm.n_classes * bm.nc_cap * (naive ? 24 : 16) : 0;
 #define FK_LAUNCH(TI, AT, SIM) filter_score_kernel<TI, AT, SIM><<<fgrid, threads, ring_bytes + lut_bytes, st>>>(T, D, h->tf16.p, bm, fk_list, sc.tok_off.p, sc.n_tok.p, \
             sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.vrange.p, sc.read_ngap.p, h->col_w.p, qp.alg, gbase, parts_stride, part_n, \
@@ -741,6 +800,7 @@ static void pipeline_phase2a(bsp_classifier* h, Scratch& sc) {
         else { if (naive) FK_LAUNCH2(false, true); else FK_LAUNCH2(false, false); }
 #undef FK_LAUNCH2
 #undef FK_LAUNCH
+        }
         KERNEL_CHECK();
         sc.launches++;
         sc.filter_launched = true;
@@ -804,7 +864,7 @@ static void pipeline_phase2b(bsp_classifier* h, Scratch& sc, const BatchOut& out
     }
     KERNEL_CHECK();
     CUDA_CHECK(cudaEventRecord(sc.ev[2], st));
-    merge_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(n, sc.route.p, sc.status_in.p, n_tiles, parts_pos, sc.filter_tiles, parts_stride, part_n,
+    merge_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(n, sc.route.p, sc.status_in.p, n_tiles, parts_pos, sc.filter_v3 ? 1 : sc.filter_tiles, parts_stride, part_n,
                                                              part_doc, part_score, out.status, out.label, out.n_hits, out.n_top,
                                                              out.top_doc, out.top_score, full_topn);
     KERNEL_CHECK();

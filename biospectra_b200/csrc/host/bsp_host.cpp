@@ -49,6 +49,10 @@ static void make_dirs(const std::string& path) {
         if (i < path.size()) cur.push_back(path[i]);
     }
 }
+static long long env_ll(const char* name, long long dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoll(v) : dflt;
+}
 static long long now_ms() {
     return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
 }
@@ -157,7 +161,29 @@ std::vector<std::string> FastaFileHelper::findFastaDocs(const std::string& path)
 }
 std::string FastaFileHelper::findTaxonHierarchyDoc(const std::string& fasta) { return fasta + ".taxd"; }   // :66-68
 
+FASTAReader::FASTAReader(const FASTAReader& whole, size_t begin, size_t end)
+    : data_(whole.data_), pos_(std::min(begin, whole.data_->size())), end_(std::min(end, whole.data_->size())) {}
+
+std::vector<size_t> FASTAReader::stripeCuts(size_t target) const {
+    const std::string& d = *data_;
+    std::vector<size_t> cuts{0};
+    if (target == 0) target = 1;
+    size_t at = target;
+    while (at < d.size()) {
+        // the next '>' that starts a line (after \n or \r: BufferedReader#readLine ends a line at either)
+        const char* q = (const char*)memchr(d.data() + at, '>', d.size() - at);
+        if (!q) break;
+        const size_t p = (size_t)(q - d.data());
+        if (p > 0 && (d[p - 1] == '\n' || d[p - 1] == '\r')) { cuts.push_back(p); at = p + target; }
+        else at = p + 1;
+    }
+    cuts.push_back(d.size());
+    return cuts;
+}
+
 FASTAReader::FASTAReader(const std::string& path) {
+    std::string data_local;
+    std::string& data_ = data_local;
     // utils/FastaFileReader.java:29-39: gzip iff the lower-cased name ends .gz/.zip
     if (CompressedFileFilter::accept(base_name(path))) {
         gzFile g = gzopen(path.c_str(), "rb");
@@ -173,15 +199,18 @@ FASTAReader::FASTAReader(const std::string& path) {
     } else {
         data_ = read_text_file(path);
     }
+    this->end_ = data_local.size();
+    this->data_ = std::make_shared<const std::string>(std::move(data_local));
 }
 
 bool FASTAReader::readLine(std::string& line) {      // BufferedReader#readLine: \n, \r\n, \r
-    if (pos_ >= data_.size()) return false;
+    const std::string& d = *data_;
+    if (pos_ >= end_) return false;
     size_t st = pos_;
-    while (pos_ < data_.size() && data_[pos_] != '\n' && data_[pos_] != '\r') pos_++;
-    line.assign(data_, st, pos_ - st);
-    if (pos_ < data_.size()) {
-        if (data_[pos_] == '\r' && pos_ + 1 < data_.size() && data_[pos_ + 1] == '\n') pos_ += 2;
+    while (pos_ < end_ && d[pos_] != '\n' && d[pos_] != '\r') pos_++;
+    line.assign(d, st, pos_ - st);
+    if (pos_ < end_) {
+        if (d[pos_] == '\r' && pos_ + 1 < d.size() && d[pos_ + 1] == '\n') pos_ += 2;
         else pos_++;
     }
     return true;
@@ -230,12 +259,14 @@ bool FASTAReader::readNext(FASTAEntry& e) {
     }
     e.headerLine = line;
     e.sequence.clear();
-    const char* d = data_.data();
-    const size_t n = data_.size();
+    const char* d = data_->data();
+    const size_t n = end_;
     // `while (line.startsWith(";"))` right after the header dereferences null at EOF; then a '>' line is an error
     bool first = true;
     while (true) {
         if (pos_ >= n) {
+            // (a stripe that ends behind a header line: the next stripe starts with '>', the reference's reader sees that line)
+            if (first && n < data_->size()) throw FASTADataError("FASTADataErrorException: Did not get a sequence line after a header line");
             if (first) throw FASTADataError("NullPointerException: header line at end of file");
             break;
         }
@@ -422,6 +453,17 @@ Classifier::Classifier(const Configuration* conf) {
     bsp_config c = conf->toStruct();
     check_rc(bsp_classifier_open(&c, conf->indexPath.c_str(), &h_));                   // validates k, skips, dir
     workerThreads_ = conf->workerThreads > 0 ? conf->workerThreads : 1;
+    initDocs();
+}
+
+// an already open handle (not closed by this object): the batch driver over an index that is resident
+Classifier::Classifier(bsp_classifier* adopted, int workerThreads) : h_(adopted), owned_(false) {
+    if (!adopted) throw IllegalArgument("handle is null");
+    workerThreads_ = workerThreads > 0 ? workerThreads : 1;
+    initDocs();
+}
+
+void Classifier::initDocs() {
     // stored fields of every document (IndexSearcher.doc, Classifier.java:361-363), rendered and parsed once
     int64_t nDocs = 0;
     check_rc(bsp_index_stats(h_, &nDocs, nullptr, nullptr, nullptr));
@@ -542,7 +584,8 @@ bool Classifier::appendResultJson(std::string& o, const char* header, size_t hea
 }
 Classifier::~Classifier() { close(); }
 void Classifier::close() {
-    if (h_) { bsp_classifier_close(h_); h_ = nullptr; }
+    if (h_ && owned_) bsp_classifier_close(h_);
+    h_ = nullptr;
 }
 
 void Classifier::classifyBatch(const std::vector<std::string>& headers, const std::vector<std::string>& sequences,
@@ -671,19 +714,87 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
     std::exception_ptr reader_error, writer_error;
     std::atomic<long long> unscored_reads{0};   // non-empty reads the GPU could not score (e.g. positional index dropped)
 
+    // Reader stage, striped: the file image is cut at entry starts into stripes of ~8 MB, `parsers` threads parse stripes
+    // side by side (each with its own FASTAReader over its byte range), and the reader thread hands their entries on in file
+    // order, packed into batches.  A malformed entry ends the stream where the reference's reader would have thrown: the
+    // entries before it are delivered, everything behind it is dropped, the error is rethrown at the end.
+    struct Stripe { BatchPtr batch; std::exception_ptr error; bool done = false; };
+    const std::vector<size_t> cuts = reader.stripeCuts((size_t)std::max<long long>(1 << 16, env_ll("BSP_FASTA_STRIPE_BYTES", 8 << 20)));
+    const size_t n_stripes = cuts.size() - 1;
+    std::vector<Stripe> stripes(n_stripes);
+    std::mutex smu;
+    std::condition_variable scv;
+    size_t next_stripe = 0, delivered = 0;
+    bool stop_parsing = false;
+    const int parsers = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(n_stripes, env_ll("BSP_FASTA_PARSERS", 6)),
+                                                                           (long long)std::max(1u, std::thread::hardware_concurrency())));
+    auto parse_stripes = [&] {
+        while (true) {
+            size_t i;
+            {
+                std::unique_lock<std::mutex> lk(smu);
+                // at most 2 x parsers stripes ahead of the hand-off (bounded memory)
+                scv.wait(lk, [&] { return stop_parsing || next_stripe >= n_stripes || next_stripe < delivered + 2 * (size_t)parsers; });
+                if (stop_parsing || next_stripe >= n_stripes) return;
+                i = next_stripe++;
+            }
+            Stripe st;
+            st.batch.reset(new ReadBatch());
+            try {
+                FASTAReader part(reader, cuts[i], cuts[i + 1]);
+                FASTAEntry read;
+                ReadBatch& b = *st.batch;
+                b.headers.reserve((cuts[i + 1] - cuts[i]) / 2);
+                b.seqs.reserve(cuts[i + 1] - cuts[i]);
+                while (part.readNext(read)) {
+                    b.headers += read.headerLine;                                      // header INCLUDING '>' (:94)
+                    b.hoff.push_back(b.headers.size());
+                    b.seqs += read.sequence;
+                    b.soff.push_back((int64_t)b.seqs.size());
+                }
+            } catch (...) { st.error = std::current_exception(); }
+            {
+                std::lock_guard<std::mutex> lk(smu);
+                stripes[i].batch = std::move(st.batch);
+                stripes[i].error = st.error;
+                stripes[i].done = true;
+            }
+            scv.notify_all();
+        }
+    };
     std::thread reader_thread([&] {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < parsers; t++) pool.emplace_back(parse_stripes);
         try {
-            FASTAEntry read;
             BatchPtr b(new ReadBatch());
-            while (reader.readNext(read)) {
-                b->headers += read.headerLine;                                         // header INCLUDING '>' (:94)
-                b->hoff.push_back(b->headers.size());
-                b->seqs += read.sequence;
-                b->soff.push_back((int64_t)b->seqs.size());
-                if (b->size() >= BATCH_READS || b->seqs.size() >= BATCH_BYTES) { parsed.push(std::move(b)); b.reset(new ReadBatch()); }
+            for (size_t i = 0; i < n_stripes; i++) {
+                Stripe st;
+                {
+                    std::unique_lock<std::mutex> lk(smu);
+                    scv.wait(lk, [&] { return stripes[i].done; });
+                    st = std::move(stripes[i]);
+                    delivered = i + 1;
+                }
+                scv.notify_all();
+                ReadBatch& p = *st.batch;
+                if (b->size() == 0 && !st.error && p.size() >= BATCH_READS / 2) {
+                    parsed.push(std::move(st.batch));                                  // large enough on its own: no copy
+                } else {
+                    const size_t h0 = b->headers.size();
+                    const int64_t s0 = (int64_t)b->seqs.size();
+                    b->headers += p.headers;
+                    b->seqs += p.seqs;
+                    for (size_t k = 1; k < p.hoff.size(); k++) b->hoff.push_back(h0 + p.hoff[k]);
+                    for (size_t k = 1; k < p.soff.size(); k++) b->soff.push_back(s0 + p.soff[k]);
+                    if (b->size() >= BATCH_READS || b->seqs.size() >= BATCH_BYTES) { parsed.push(std::move(b)); b.reset(new ReadBatch()); }
+                }
+                if (st.error) { reader_error = st.error; break; }
             }
             if (b->size()) parsed.push(std::move(b));
         } catch (...) { reader_error = std::current_exception(); }
+        { std::lock_guard<std::mutex> lk(smu); stop_parsing = true; }
+        scv.notify_all();
+        for (auto& th : pool) th.join();
         parsed.close();
     });
 
@@ -862,6 +973,8 @@ void LocalClassifier::classifyPerRead(const std::string& inputFasta, const std::
 }
 
 // ------------------------------------------------------------------ drivers (BioSpectra.java:110-161)
+LocalClassifier::LocalClassifier(bsp_classifier* adopted, int workerThreads) : classifier_(adopted, workerThreads) {}
+
 void runIndex(const std::string& jsonConfiguration, const std::string& indexDir, const std::string& referenceDir, int device) {
     Configuration conf;
     if (!jsonConfiguration.empty()) conf = Configuration::createInstanceFromFile(jsonConfiguration);
@@ -939,6 +1052,18 @@ HOST_API int bsp_host_classify_local_per_read(const char* json_conf, const char*
 }
 
 // Pure host helpers exported for CPU-side tests (no GPU needed)
+HOST_API int bsp_host_classify_file(bsp_classifier* h, const char* input_fasta, const char* result_path, const char* summary_path,
+                                    int32_t worker_threads) {
+    try {
+        if (!h || !input_fasta || !result_path) throw bsp::IllegalArgument("null argument");
+        bsp::LocalClassifier lc(h, worker_threads);
+        lc.classify(input_fasta, result_path, summary_path ? summary_path : "");
+        return BSP_OK;
+    } catch (const bsp::IllegalArgument& e) { g_host_error = e.what(); return BSP_ERR_ARG; }
+    catch (const bsp::IOError& e) { g_host_error = e.what(); return BSP_ERR_IO; }
+    catch (const std::exception& e) { g_host_error = e.what(); return BSP_ERR_STATE; }
+}
+
 HOST_API int bsp_host_label_json(const char* const* taxon_hierarchies, int32_t n, char* out, int32_t cap) {
     try {
         bsp::ClassificationResult r;
@@ -974,6 +1099,28 @@ HOST_API int bsp_host_read_fasta(const char* path, char* out, int64_t cap, int64
         try {
             while (rd.readNext(e)) { o += e.headerLine; o.push_back('\x1F'); o += e.sequence; o.push_back('\x1E'); }
         } catch (const bsp::FASTADataError& ex) { g_host_error = ex.what(); rc = BSP_ERR_IO; }
+    } catch (const std::exception& ex) { g_host_error = ex.what(); return BSP_ERR_IO; }
+    if (needed) *needed = (int64_t)o.size() + 1;
+    if ((int64_t)o.size() + 1 > cap) return BSP_ERR_NOMEM;
+    memcpy(out, o.c_str(), o.size() + 1);
+    return rc;
+}
+
+// the same through stripes of `stripe_bytes` (what LocalClassifier's reader stage does on several threads): must equal
+// bsp_host_read_fasta byte for byte, error code included (the entries before a malformed one are kept)
+HOST_API int bsp_host_read_fasta_striped(const char* path, int64_t stripe_bytes, char* out, int64_t cap, int64_t* needed) {
+    std::string o;
+    int rc = BSP_OK;
+    try {
+        bsp::FASTAReader whole(path);
+        const std::vector<size_t> cuts = whole.stripeCuts((size_t)std::max<int64_t>(stripe_bytes, 1));
+        for (size_t i = 0; i + 1 < cuts.size() && rc == BSP_OK; i++) {
+            bsp::FASTAReader rd(whole, cuts[i], cuts[i + 1]);
+            bsp::FASTAEntry e;
+            try {
+                while (rd.readNext(e)) { o += e.headerLine; o.push_back('\x1F'); o += e.sequence; o.push_back('\x1E'); }
+            } catch (const bsp::FASTADataError& ex) { g_host_error = ex.what(); rc = BSP_ERR_IO; }
+        }
     } catch (const std::exception& ex) { g_host_error = ex.what(); return BSP_ERR_IO; }
     if (needed) *needed = (int64_t)o.size() + 1;
     if ((int64_t)o.size() + 1 > cap) return BSP_ERR_NOMEM;

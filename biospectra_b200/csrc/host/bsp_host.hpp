@@ -6,6 +6,7 @@
 
 #include <mutex>
 #include <stdexcept>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -46,11 +47,18 @@ struct FASTAEntry { std::string headerLine, sequence; };
 class FASTAReader {
 public:
     explicit FASTAReader(const std::string& path);
+    // a reader over bytes [begin, end) of another reader's file image (begin at the start of a line); the image is shared
+    FASTAReader(const FASTAReader& whole, size_t begin, size_t end);
     bool readNext(FASTAEntry& e);      // false at EOF; throws FASTADataError
+    // Offsets at which the file image can be cut into independently parsable stripes of about `target` bytes: every
+    // cut is the start of a line that begins with '>' (such a line starts an entry wherever it stands).  First element 0,
+    // last element = size of the image.
+    std::vector<size_t> stripeCuts(size_t target) const;
+    size_t imageSize() const { return data_->size(); }
 private:
     bool readLine(std::string& line);
-    std::string data_;
-    size_t pos_ = 0;
+    std::shared_ptr<const std::string> data_;
+    size_t pos_ = 0, end_ = 0;
     std::string pending_;
     bool have_pending_ = false;
 };
@@ -98,6 +106,7 @@ struct ClassificationResultSummary {
 class Classifier {
 public:
     explicit Classifier(const Configuration* conf);
+    Classifier(bsp_classifier* adopted, int workerThreads);     // an open handle, left open by close()
     ~Classifier();
     // false when the reference would have thrown inside classify (read dropped by its callers)
     bool classify(const std::string& header, const std::string& sequence, ClassificationResult& out);
@@ -125,7 +134,9 @@ public:
                           const PackedResults& r, int32_t i, int* type) const;
     int workerThreads() const { return workerThreads_; }
 private:
+    void initDocs();
     bsp_classifier* h_ = nullptr;
+    bool owned_ = true;
     std::vector<DocInfo> docs_;
     int workerThreads_ = 4;
     bool deviceLca_ = true;               // labels with taxonomy computed on the device (BSP_HOST_LCA=1: on the host)
@@ -134,6 +145,7 @@ private:
 class LocalClassifier {
 public:
     explicit LocalClassifier(const Configuration* conf);
+    LocalClassifier(bsp_classifier* adopted, int workerThreads);
     bool classify(const std::string& header, const std::string& sequence, ClassificationResult& out) {
         return classifier_.classify(header, sequence, out);
     }

@@ -176,6 +176,13 @@ class Classifier:
         _lib.check(self.L.bsp_classifier_set_query(self.h, C.byref(cs)), self.h)
         self.conf = conf
 
+    def classify_file(self, input_fasta, result_path, summary_path=None, worker_threads=4):
+        """LocalClassifier.classify(inputFasta, classifyOutput, summaryOutput) on this open index (bsp_host_classify_file)"""
+        rc = self.L.bsp_host_classify_file(self.h, _b(str(input_fasta)), _b(str(result_path)),
+                                           _b(str(summary_path)) if summary_path else None, worker_threads)
+        if rc:
+            raise IOError(self.L.bsp_host_last_error().decode("utf-8", "replace"))
+
     def doc_fields(self, doc: int):
         p = [C.c_char_p() for _ in range(4)]
         _lib.check(self.L.bsp_doc_fields(self.h, doc, *[C.byref(x) for x in p]), self.h)

@@ -262,10 +262,18 @@ int bsp_host_classify_local(const char* json_conf, const char* index_dir, const 
  * the concurrent calls meet in bsp_classify_one's micro-batches. */
 int bsp_host_classify_local_per_read(const char* json_conf, const char* index_dir, const char* input_dir,
                                      const char* output_dir, int32_t device, int32_t threads);
+/* LocalClassifier.classify(File inputFasta, File classifyOutput, File summaryOutput) (LocalClassifier.java:60-131) over an
+ * index that is already open: reader thread -> GPU batches -> `worker_threads` formatter threads -> in-order writer.  The
+ * handle stays open.  summary_path may be NULL. */
+int bsp_host_classify_file(bsp_classifier* h, const char* input_fasta, const char* result_path, const char* summary_path,
+                           int32_t worker_threads);
 const char* bsp_host_last_error(void);
 /* pure host helpers (no GPU): used by the CPU-side tests */
 int bsp_host_label_json(const char* const* taxon_hierarchies, int32_t n, char* out, int32_t cap);
 int bsp_host_read_fasta(const char* path, char* out, int64_t cap, int64_t* needed);
+/* the same file read in stripes of ~stripe_bytes cut at entry starts, the way the batch driver's parser threads read it:
+ * byte-identical output and return code */
+int bsp_host_read_fasta_striped(const char* path, int64_t stripe_bytes, char* out, int64_t cap, int64_t* needed);
 int bsp_host_double_to_string(double d, char* out, int32_t cap);
 int bsp_host_parse_config(const char* json, bsp_config* out, char* index_path, int32_t cap);
 

@@ -163,3 +163,51 @@ def test_java_double_formatting(L, x, s):
     assert L.bsp_host_double_to_string(x, buf, 64) == 0
     assert buf.value.decode() == s
     assert float(buf.value) == x
+
+
+def _read_both(L, path, stripe):
+    out = []
+    for fn, args in ((L.bsp_host_read_fasta, ()), (L.bsp_host_read_fasta_striped, (C.c_int64(stripe),))):
+        cap = 1 << 22
+        buf = C.create_string_buffer(cap)
+        need = C.c_int64()
+        rc = fn(str(path).encode(), *args, buf, cap, C.byref(need))
+        out.append((rc, buf.value, L.bsp_host_last_error() if rc else b""))
+    return out
+
+
+@pytest.mark.parametrize("c", FASTA_GOLDEN, ids=[c["name"] for c in FASTA_GOLDEN])
+@pytest.mark.parametrize("stripe", [1, 7, 64])
+def test_striped_fasta_reader_on_the_reference_cases(L, tmp_path, c, stripe):
+    """The batch driver parses a read file in stripes cut at entry starts (several parser threads): whatever the stripe
+    size, the entries, their order, the return code and the error text are those of the one-pass reader -- on the
+    executed-reference cases (CR / CRLF line ends, ';' lines, headers without a sequence, malformed headers)."""
+    p = tmp_path / (c["name"] + ".fa")
+    p.write_bytes(c["text"].encode("latin-1"))
+    whole, striped = _read_both(L, p, stripe)
+    assert whole == striped
+
+
+def test_striped_fasta_reader_random_files(L, tmp_path):
+    rng = random.Random(12)
+    eols = ["\n", "\r\n", "\r"]
+    for case in range(60):
+        parts = []
+        for e in range(rng.randint(1, 40)):
+            eol = rng.choice(eols)
+            parts.append(">" + "".join(rng.choice("abc|> \t;1") for _ in range(rng.randint(1, 12))).lstrip(" \t") + "x" + eol)
+            for _line in range(rng.randint(0 if rng.random() < 0.05 else 1, 4)):
+                if rng.random() < 0.1:
+                    parts.append(";" + "c" * rng.randint(0, 5) + eol)
+                body = "".join(rng.choice("ACGTNacgt >;") for _ in range(rng.randint(0, 30)))
+                if body.startswith(">"):
+                    body = "A" + body
+                parts.append(body + eol)
+        text = "".join(parts)
+        if rng.random() < 0.3:
+            text = text.rstrip("\r\n")
+        p = tmp_path / ("r%d.fa" % case)
+        p.write_bytes(text.encode("latin-1"))
+        for stripe in (1, 13, 100, 1 << 20):
+            whole, striped = _read_both(L, p, stripe)
+            assert whole == striped, (case, stripe, text)
