@@ -518,13 +518,19 @@ def lclassify_line(clf, data, n, labels):
         el = time.perf_counter() - t0
         with open(sum_path) as f:
             summ = json.load(f)
+        try:
+            with open(res_path + ".gpu_metrics.json") as f:
+                gm = json.load(f)
+        except Exception:
+            gm = {}
         out_bytes = os.path.getsize(res_path)
         ok = (summ.get("total") == n and summ.get("classified") == labels["classified"] and summ.get("vague") == labels["vague"]
               and summ.get("unknown") == labels["unknown"])
         return {"name": "lclassify file to file (FASTA in, .result / .result.sum out) on the resident index", "reads": n,
                 "value": n / el, "unit": "reads/s", "seconds": el, "worker_threads": threads, "input_bytes": in_bytes,
                 "output_bytes": out_bytes, "summary": {k_: summ.get(k_) for k_ in ("total", "unknown", "vague", "classified")},
-                "summary_matches_device_labels": bool(ok), "files_in": d.split("/")[1]}
+                "summary_matches_device_labels": bool(ok), "files_in": d.split("/")[1],
+                "stage_ms": dict(gm.get("stage_ms", {}), gpu_calls_wall=gm.get("classify_call_wall_ms"), gpu_batches=gm.get("gpu_batches"))}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <dirent.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 #include <condition_variable>
 #include <deque>
@@ -60,7 +61,34 @@ static std::string read_text_file(const std::string& path) {
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) throw IOError("cannot open " + path);
     std::string s;
-    char buf[1 << 16];
+    struct stat sb;
+    if (fstat(fileno(f), &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+        // a regular file: one allocation, large unbuffered reads straight into it
+        s.resize((size_t)sb.st_size);
+        const int fd = fileno(f);
+        const size_t total = s.size();
+        auto read_range = [&](size_t a, size_t b) {           // pread until [a, b) is filled or the file ends
+            while (a < b) {
+                const ssize_t n = pread(fd, &s[a], std::min<size_t>(b - a, (size_t)32 << 20), (off_t)a);
+                if (n <= 0) return a;
+                a += (size_t)n;
+            }
+            return a;
+        };
+        size_t got = total;
+        if (total >= ((size_t)32 << 20)) {                    // a large file: four ranges side by side (page-cache copies overlap)
+            const int R = 4;
+            size_t ends[R];
+            std::vector<std::thread> th;
+            for (int i = 0; i < R; i++) th.emplace_back([&, i] { ends[i] = read_range(total * i / R, total * (i + 1) / R); });
+            for (auto& t : th) t.join();
+            for (int i = R - 1; i >= 0; i--) if (ends[i] < total * (i + 1) / R) got = ends[i];      // first short range ends the data
+        } else got = read_range(0, total);
+        s.resize(got);
+        if (got == total) lseek(fd, (off_t)total, SEEK_SET);  // the buffered reads below continue behind it
+        else { fclose(f); return s; }
+    }
+    char buf[1 << 16];                                   // whatever follows (the file grew, or it is not a regular file)
     size_t n;
     while ((n = fread(buf, 1, sizeof buf, f)) > 0) s.append(buf, n);
     fclose(f);
@@ -702,15 +730,21 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
     std::string pd = parent_dir(classifyOutput);
     if (!pd.empty() && !file_exists(pd)) make_dirs(pd);                                // :69-71
     if (!summaryOutput.empty()) { std::string sd = parent_dir(summaryOutput); if (!sd.empty() && !file_exists(sd)) make_dirs(sd); }
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
     FASTAReader reader(inputFasta);
+    const double file_load_ms = ms_since(t_begin);
+    double reader_done_ms = 0, format_ms = 0, write_ms = 0;          // stage clocks (gpu_metrics.json)
     FILE* fw = fopen(classifyOutput.c_str(), "wb");
     if (!fw) throw IOError("cannot create " + classifyOutput);
     ClassificationResultSummary summary;
     summary.queryFilename = base_name(inputFasta);
     summary.startTime = now_ms();
-    const size_t BATCH_READS = 262144, BATCH_BYTES = (size_t)64 << 20;
+    const size_t BATCH_READS = (size_t)std::max<long long>(1024, env_ll("BSP_HOST_BATCH_READS", 131072)), BATCH_BYTES = (size_t)64 << 20;
     typedef std::unique_ptr<ReadBatch> BatchPtr;
-    BoundedQueue<BatchPtr> parsed(2), classified(2);
+    BoundedQueue<BatchPtr> parsed(3), classified(3);
     std::exception_ptr reader_error, writer_error;
     std::atomic<long long> unscored_reads{0};   // non-empty reads the GPU could not score (e.g. positional index dropped)
 
@@ -726,8 +760,9 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
     std::condition_variable scv;
     size_t next_stripe = 0, delivered = 0;
     bool stop_parsing = false;
-    const int parsers = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(n_stripes, env_ll("BSP_FASTA_PARSERS", 6)),
-                                                                           (long long)std::max(1u, std::thread::hardware_concurrency())));
+    const long long hw = (long long)std::max(1u, std::thread::hardware_concurrency());
+    const int parsers = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(n_stripes, env_ll("BSP_FASTA_PARSERS", 12)),
+                                                                           std::max<long long>(1, hw / 2)));
     auto parse_stripes = [&] {
         while (true) {
             size_t i;
@@ -795,18 +830,63 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
         { std::lock_guard<std::mutex> lk(smu); stop_parsing = true; }
         scv.notify_all();
         for (auto& th : pool) th.join();
+        reader_done_ms = ms_since(t_begin);
         parsed.close();
     });
 
     const Classifier& cls = classifier_;
     const int T = std::max(1, cls.workerThreads());
+    // formatted JSON of one batch (one string per formatter thread, in read order) on its way to the file
+    typedef std::unique_ptr<std::vector<std::string>> ChunkPtr;
+    BoundedQueue<ChunkPtr> formatted(2);
+    std::exception_ptr file_error;
+    std::thread file_thread([&] {
+        try {
+            // striped writer: the chunks of a batch land at their file offsets from several threads at once
+            const int fdw = fileno(fw);
+            off_t file_off = 0;
+            ChunkPtr c;
+            while (formatted.pop(c)) {
+                const auto t_wr = std::chrono::steady_clock::now();
+                const size_t nc = c->size();
+                std::vector<off_t> at(nc + 1, file_off);
+                for (size_t i = 0; i < nc; i++) at[i + 1] = at[i] + (off_t)(*c)[i].size();
+                std::atomic<size_t> next{0};
+                std::atomic<bool> failed{false};
+                auto put = [&] {
+                    for (size_t i = next++; i < nc; i = next++) {
+                        const std::string& o = (*c)[i];
+                        size_t done = 0;
+                        while (done < o.size()) {
+                            const ssize_t n = pwrite(fdw, o.data() + done, o.size() - done, at[i] + (off_t)done);
+                            if (n <= 0) { failed = true; return; }
+                            done += (size_t)n;
+                        }
+                    }
+                };
+                const int W = (int)std::min<size_t>(nc, (size_t)std::max<long long>(1, std::min<long long>(env_ll("BSP_HOST_WRITERS", 4), hw / 4)));
+                std::vector<std::thread> th;
+                for (int t = 1; t < W; t++) th.emplace_back(put);
+                put();
+                for (auto& t : th) t.join();
+                if (failed) throw IOError("write failed: " + classifyOutput);
+                file_off = at[nc];
+                write_ms += ms_since(t_wr);
+            }
+        } catch (...) {
+            file_error = std::current_exception();
+            ChunkPtr drop;
+            while (formatted.pop(drop)) {}
+        }
+    });
     std::thread writer_thread([&] {
         try {
             BatchPtr b;
             while (classified.pop(b)) {
                 const size_t n = b->size();
                 const int nt = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, n / 4096));
-                std::vector<std::string> chunk((size_t)nt);
+                ChunkPtr chunk_holder(new std::vector<std::string>((size_t)nt));
+                std::vector<std::string>& chunk = *chunk_holder;
                 std::vector<long long> counts((size_t)nt * 3, 0);
                 auto work = [&](int t) {
                     const size_t i0 = n * (size_t)t / (size_t)nt, i1 = n * (size_t)(t + 1) / (size_t)nt;
@@ -834,22 +914,24 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
                         counts[(size_t)t * 3 + (size_t)type]++;
                     }
                 };
+                const auto t_fmt = std::chrono::steady_clock::now();
                 std::vector<std::thread> pool;
                 for (int t = 1; t < nt; t++) pool.emplace_back(work, t);
                 work(0);
                 for (auto& th : pool) th.join();
+                format_ms += ms_since(t_fmt);
                 for (int t = 0; t < nt; t++) {
-                    if (!chunk[(size_t)t].empty() && fwrite(chunk[(size_t)t].data(), 1, chunk[(size_t)t].size(), fw) != chunk[(size_t)t].size())
-                        throw IOError("write failed: " + classifyOutput);
                     summary.unknown += counts[(size_t)t * 3]; summary.vague += counts[(size_t)t * 3 + 1];
                     summary.classified += counts[(size_t)t * 3 + 2];
                 }
+                formatted.push(std::move(chunk_holder));       // the file thread writes it while the next batch is formatted
             }
         } catch (...) {
             writer_error = std::current_exception();
             BatchPtr drop;
             while (classified.pop(drop)) {}
         }
+        formatted.close();
     });
 
     std::exception_ptr gpu_error;
@@ -876,9 +958,11 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
     classified.close();
     reader_thread.join();
     writer_thread.join();
+    file_thread.join();
     fclose(fw);
     if (gpu_error) std::rethrow_exception(gpu_error);
     if (writer_error) std::rethrow_exception(writer_error);
+    if (file_error) std::rethrow_exception(file_error);
     if (reader_error) std::rethrow_exception(reader_error);
     summary.total = summary.unknown + summary.vague + summary.classified;
     summary.endTime = now_ms();
@@ -897,11 +981,12 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
             fprintf(fm, "{\"reads\":%lld,\"gpu_batches\":%lld,\"reads_filter_kernel\":%lld,\"reads_exact_dense_kernel\":%lld,"
                         "\"reads_positional_kernel\":%lld,\"reads_handed_over_by_filter\":%lld,\"docs_rescored_exactly\":%lld,"
                         "\"exception_cells\":%lld,\"kernel_launches\":%lld,\"score_kernel_ms\":%.3f,\"device_pipeline_ms\":%.3f,"
-                        "\"classify_call_wall_ms\":%.3f,\"file_to_file_ms\":%lld,\"reads_not_scored_gpu_error\":%lld}\n",
+                        "\"classify_call_wall_ms\":%.3f,\"file_to_file_ms\":%lld,\"reads_not_scored_gpu_error\":%lld,"
+                        "\"stage_ms\":{\"file_load\":%.1f,\"reader_done_at\":%.1f,\"format\":%.1f,\"write\":%.1f,\"parser_threads\":%d}}\n",
                     (long long)gpu_counters[0], gpu_batches, (long long)gpu_counters[3], (long long)gpu_counters[1],
                     (long long)gpu_counters[2], (long long)gpu_counters[7], (long long)gpu_counters[5], (long long)gpu_counters[6],
                     (long long)gpu_counters[4], gpu_score_ms, gpu_pipe_ms, gpu_wall_ms, summary.endTime - summary.startTime,
-                    unscored_reads.load());
+                    unscored_reads.load(), file_load_ms, reader_done_ms, format_ms, write_ms, parsers);
             fclose(fm);
         }
     }
