@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbiospectra_gpu.so")
+# BSP_LIB: another build of the same library (A/B runs of build-time variants)
+LIB_PATH = os.environ.get("BSP_LIB") or os.path.join(_HERE, "libbiospectra_gpu.so")
 
 BSP_TOPN = 10
 NAIVE_KMER, CHAIN_PROXIMITY, PAIRED_PROXIMITY = 0, 1, 2
@@ -45,7 +46,7 @@ EXPORTS = [
     "bsp_classify_batch", "bsp_classify_packed", "bsp_classify_device", "bsp_classify_one",
     "bsp_classifier_set_microbatch", "bsp_microbatch_stats", "bsp_classifier_set_lineages", "bsp_classify_packed_tax", "bsp_doc_fields", "bsp_classifier_close",
     "bsp_index_stats", "bsp_doc_info", "bsp_term_postings", "bsp_tokenize", "bsp_last_routes", "bsp_last_counters",
-    "bsp_last_timings", "bsp_memory_info", "bsp_partition_df_buffer", "bsp_partition_local_stats",
+    "bsp_last_timings", "bsp_last_gap_join", "bsp_memory_info", "bsp_partition_df_buffer", "bsp_partition_local_stats",
     "bsp_partition_set_global", "bsp_merge_topk_device", "bsp_read_cost", "bsp_classifier_set_query", "bsp_host_classify_file", "bsp_index_layout", "bsp_pack_topk_device", "bsp_merge_topk_records_device",
     "bsp_host_index", "bsp_host_classify_local", "bsp_host_classify_local_per_read", "bsp_host_last_error", "bsp_host_label_json", "bsp_host_read_fasta", "bsp_host_read_fasta_striped", "bsp_index_add_fasta",
     "bsp_host_double_to_string", "bsp_host_parse_config",
@@ -98,6 +99,7 @@ def lib():
     L.bsp_last_routes.argtypes = [vp, C.c_int32, vp]
     L.bsp_last_counters.argtypes = [vp, vp]
     L.bsp_last_timings.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.bsp_last_gap_join.argtypes = [vp, vp, C.POINTER(C.c_double)]
     L.bsp_memory_info.argtypes = [vp, i64p, i64p, i64p]
     L.bsp_partition_df_buffer.argtypes = [vp, C.POINTER(vp), i64p]
     L.bsp_partition_local_stats.argtypes = [vp, i64p, i64p]

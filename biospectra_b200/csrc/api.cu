@@ -51,7 +51,16 @@ struct Scratch {
     DevBuf<u64> tok_key; DevBuf<u32> tok_pos, tok_df, clause_row; DevBuf<float> clause_val;
     DevBuf<i32> n_tok, n_clauses, msm, route, status_in, list_dense, list_pos, list_filter, counts, read_ngap;
     DevBuf<FilterStats> fstats; DevBuf<float2> vrange;
-    DevBuf<GapClause> gaps; DevBuf<u32> gap_cnt;       // gap clauses of the sub-batch; gap_cnt[cap] matches, [cap] = #clauses
+    // gap clauses of the sub-batch (gapjoin.cuh): the clauses, counters ([0] clauses registered, [1] matches appended,
+    // [2] chunks), per-clause offsets of the sorted match lists, and the join's working arrays
+    DevBuf<GapClause> gaps; DevBuf<u32> gap_ctr, gap_off;
+    i64 gc = 0, gc_min = 0;             // capacity of `gaps`; what the last overflow asked for
+    DevBuf<u32> gj_keys, gj_keys_alt, gj_vals, gj_vals_alt, gj_mg, gj_mcol, gj_v, gj_v_alt; DevBuf<uint2> gj_chunks;
+    DevBuf<float> gj_mfreq; DevBuf<u64> gj_k64, gj_k64_alt; DevBuf<unsigned long long> gj_bytes;
+    RadixSortTemp gj_rst;
+    const u8* in_seq = nullptr; const i64* in_off = nullptr; i64 in_bytes = 0;   // phase 1 inputs (re-run when `gaps` was too short)
+    DevBuf<i32> pos_slot;               // read -> index in list_pos (the positional scorer's partial lists are per list entry)
+    DevBuf<i32> ppart_n; DevBuf<u32> ppart_doc; DevBuf<float> ppart_score;
     int slot_index = 0;
     bool front_fused = false;
     // filter3.cuh: per-read headers / clause records / exception cells, candidate lists, read-wide thresholds
@@ -66,18 +75,18 @@ struct Scratch {
     u8* pin_in = nullptr; size_t pin_in_bytes = 0;
     PinBuf pin_routes;                  // routes of the sub-batch on their way to bsp_last_routes
     bool routes_pending = false;
-    i32* h_counts = nullptr;            // pinned: [0..3] route counts, [4] filter overflow
+    i32* h_counts = nullptr;            // pinned: [0..3] route counts, [4] filter overflow, [5] gap clauses, [6] most clauses, [7..9] gap join
     FilterStats* h_fstats = nullptr;    // pinned
     // state between the two phases of a sub-batch
     i32 n = 0; int n_tiles = 1, parts_pos = 0, parts_stride = 1, dense_threads = 32, filter_threads = 32, filter_tiles = 1;
     QueryParams qp; bool busy = false;
     i32 r0 = 0;                         // first read of the sub-batch in the caller's arrays
     i32 cnt[4] = {0, 0, 0, 0};          // route counts between the two halves of phase 2: dense, positional, filter, overflow
-    i64 launches = 0; bool filter_launched = false;
+    i64 launches = 0, launches_gap = 0; bool filter_launched = false;
     void init() {
         CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
-        CUDA_CHECK(cudaMallocHost((void**)&h_counts, 8 * sizeof(i32)));
+        CUDA_CHECK(cudaMallocHost((void**)&h_counts, 16 * sizeof(i32)));
         CUDA_CHECK(cudaMallocHost((void**)&h_fstats, sizeof(FilterStats)));
     }
     ~Scratch() {
@@ -136,6 +145,8 @@ struct bsp_classifier {
     std::vector<i32> last_routes;
     i64 counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double score_ms = 0, pipe_ms = 0;
+    // gap join of the last batch: clauses, chunks, matches, position bytes fetched, kernel time; tail entries wanted next time
+    i64 gj_clauses = 0, gj_chunks = 0, gj_matches = 0, gj_bytes = 0; double gj_ms = 0; size_t gap_tail_want = 0;
     ~bsp_classifier() { delete ref; }
 };
 
@@ -487,7 +498,6 @@ static bsp_classifier* make_classifier(const bsp_config* conf, RefStore* ref) {
         CUDA_CHECK(cudaFuncSetAttribute(filter3_stream_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CUDA_CHECK(cudaFuncSetAttribute(score_positional_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(POSW_WARPS * posw_warp_bytes(POSW_DOCS, PW_POS))));
         CUDA_CHECK(cudaFuncSetAttribute(score_positional_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CUDA_CHECK(cudaFuncSetAttribute(gap_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * phrase_stage_bytes(POSW_DOCS, PW_POS))));
         BuildOptions opt;
         opt.want_tables = conf->dense_tables;
         opt.want_positional = conf->positional;
@@ -592,12 +602,13 @@ BSP_API int bsp_classifier_close(bsp_classifier* h) {
 // counts: [0] exact-dense reads, [1] positional reads, [2] filter reads, [3] filter overflow (appended to list_dense)
 __global__ void __launch_bounds__(256) route_compact_kernel(const i32* __restrict__ route, const i32* __restrict__ n_clauses, i32 n,
                                                              i32* __restrict__ list_dense, i32* __restrict__ list_pos,
-                                                             i32* __restrict__ list_filter, i32* __restrict__ counts) {
+                                                             i32* __restrict__ list_filter, i32* __restrict__ counts,
+                                                             i32* __restrict__ pos_slot) {
     i32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     int rt = route[r];
     if (rt == ROUTE_DENSE) list_dense[atomicAdd(&counts[0], 1)] = r;
-    else if (rt == ROUTE_POSITIONAL) list_pos[atomicAdd(&counts[1], 1)] = r;
+    else if (rt == ROUTE_POSITIONAL) { const i32 at = atomicAdd(&counts[1], 1); list_pos[at] = r; pos_slot[r] = at; }
     else if (rt == ROUTE_FILTER) {
         list_filter[atomicAdd(&counts[2], 1)] = r;
         atomicMax(&counts[6], n_clauses[r]);          // most clauses of a filter read: sizes the per-class LUT arrays (BM25)
@@ -623,6 +634,7 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     GpuIndex& ix = h->ix;
     cudaStream_t st = sc.st;
     const int k = ix.k;
+    sc.in_seq = d_seq; sc.in_off = d_seq_off; sc.in_bytes = total_bytes;
     i64 tok_cap_total = total_bytes;        // sum(max(len-k+1,0)) <= total bytes
     sc.tok_off.ensure((size_t)n + 1);
     sc.tok_key.ensure((size_t)tok_cap_total + 1); sc.tok_pos.ensure((size_t)tok_cap_total + 1);
@@ -630,6 +642,7 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     sc.clause_row.ensure((size_t)tok_cap_total + 1);
     sc.n_tok.ensure(n); sc.n_clauses.ensure(n); sc.msm.ensure(n); sc.route.ensure(n); sc.status_in.ensure(n);
     sc.list_dense.ensure(n); sc.list_pos.ensure(n); sc.list_filter.ensure(n); sc.counts.ensure(8); sc.vrange.ensure(n); sc.read_ngap.ensure(n);
+    sc.pos_slot.ensure(n);
     if (!sc.fstats.p) sc.fstats.alloc(1);
     sc.n = n; sc.busy = true;
     CUDA_CHECK(cudaEventRecord(sc.ev[0], st));
@@ -647,10 +660,20 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     qp.pair_row0 = ix.pair_row0;
     qp.gap_ok = qp.dense_ok && ix.has_pair && ix.positional && env_i64("BSP_DISABLE_GAP", 0) == 0;
     qp.temp_row0 = (u32)ix.n_rows + 1;
-    const u32 GC = ix.gap_cap;
+    // Gap clauses of the sub-batch.  With kmer_skips > 0 every phrase clause is one (about len / (skips + 1) tokens per read);
+    // otherwise only the clauses next to an N are.  A list that turns out too short is grown and phase 1 runs again
+    // (pipeline_phase2a).
+    i64 gc_want = std::max<i64>(ix.gap_cap, sc.gc_min);
+    if (h->conf.kmer_skips > 0) {
+        const i64 toks = total_bytes / (h->conf.kmer_skips + 1) + n;
+        gc_want = std::max<i64>(gc_want, (qp.alg == ALG_CHAIN ? toks : toks / 2 + n) + 1024);
+    }
+    gc_want = std::min<i64>(gc_want, (i64)1 << 28);
+    if (sc.gc < gc_want) { sc.gc = gc_want; sc.gaps.alloc((size_t)sc.gc); sc.gap_off.alloc((size_t)sc.gc + 2); }
+    if (!sc.gap_ctr.p) { sc.gap_ctr.alloc(4); sc.gj_bytes.alloc(1); }
+    const u32 GC = (u32)sc.gc;
     qp.gap_cap = GC;
-    if (!sc.gaps.p) { sc.gaps.alloc(GC); sc.gap_cnt.alloc((size_t)GC + 1); }
-    if (qp.gap_ok) CUDA_CHECK(cudaMemsetAsync(sc.gap_cnt.p, 0, ((size_t)GC + 1) * sizeof(u32), st));
+    CUDA_CHECK(cudaMemsetAsync(sc.gap_ctr.p, 0, 16, st));
     // fast filter path: tf-idf; CTA per (doc tile, read), 32 docs per thread, <= 512 threads per tile.
     // BSP_FILTER: 0 off, 1 whenever usable, unset = only where it pays (enough docs to fill a CTA)
     const u32 D = (u32)ix.docs.size();
@@ -668,7 +691,7 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     if (sc.front_fused) {
         front_kernel<<<wgrid, 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, ix.min_strand, ix.df_dense.p, sc.tok_key.p, sc.tok_pos.p,
                                             sc.tok_df.p, sc.n_tok.p, h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p,
-                                            sc.msm.p, sc.route.p, sc.status_in.p, sc.vrange.p, sc.gaps.p, sc.gap_cnt.p + GC, sc.read_ngap.p);
+                                            sc.msm.p, sc.route.p, sc.status_in.p, sc.vrange.p, sc.gaps.p, sc.gap_ctr.p, sc.read_ngap.p);
     } else {
         tokenize_kernel<<<wgrid, 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, k, h->conf.kmer_skips, ix.min_strand, sc.tok_key.p,
                                                sc.tok_pos.p, sc.n_tok.p);
@@ -676,15 +699,15 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
                                                ix.positional ? (int)ix.segs.size() : 0, sc.tok_df.p);
         weights_kernel<<<wgrid, 256, 0, st>>>(d_seq, d_seq_off, n, sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p, sc.tok_df.p,
                                               h->idf_by_df.p, qp, sc.clause_val.p, sc.clause_row.p, sc.n_clauses.p, sc.msm.p, sc.route.p,
-                                              sc.status_in.p, sc.vrange.p, sc.gaps.p, sc.gap_cnt.p + GC, sc.read_ngap.p);
+                                              sc.status_in.p, sc.vrange.p, sc.gaps.p, sc.gap_ctr.p, sc.read_ngap.p);
     }
     CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));
     route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, sc.n_clauses.p, n, sc.list_dense.p, sc.list_pos.p,
-                                                                     sc.list_filter.p, sc.counts.p);
+                                                                     sc.list_filter.p, sc.counts.p, sc.pos_slot.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(sc.h_counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 6, sc.counts.p + 6, 4, cudaMemcpyDeviceToHost, st));      // most clauses of a filter read
-    CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 5, sc.gap_cnt.p + GC, 4, cudaMemcpyDeviceToHost, st));   // # gap clauses
+    CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 5, sc.gap_ctr.p, 4, cudaMemcpyDeviceToHost, st));        // # gap clauses
     // partial top-10 buffers
     sc.dense_threads = (int)std::min<i64>(512, round_up(std::max<i64>(ceil_div(ix.d_pad, EX_DPT), 1), 32));
     sc.n_tiles = (int)std::max<i64>(1, ceil_div(ix.d_pad, (i64)sc.dense_threads * EX_DPT));
@@ -693,10 +716,129 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     const i64 ft_cap = std::min<i64>(FK_MAXT, std::max<i64>(32, round_up(env_i64("BSP_FILTER_THREADS", 512), 32)));
     sc.filter_threads = (int)std::min<i64>(ft_cap, round_up(std::max<i64>(ceil_div(ix.d_pad, FK_DOCS), 1), 32));
     sc.filter_tiles = (int)std::max<i64>(1, ceil_div(ix.d_pad, (i64)sc.filter_threads * FK_DOCS));
-    sc.parts_stride = std::max(std::max(std::max(sc.n_tiles, sc.parts_pos), sc.filter_tiles), 1);
+    sc.parts_stride = std::max(std::max(sc.n_tiles, sc.filter_tiles), 1);       // (the positional scorer has its own lists: ppart_*)
     sc.part_n.ensure((size_t)n * sc.parts_stride);
     sc.part_doc.ensure((size_t)n * sc.parts_stride * TOPN);
     sc.part_score.ensure((size_t)n * sc.parts_stride * TOPN);
+}
+
+// (start, length) directory of the positional index for the gap join; built once per handle, on first use
+static void ensure_gap_directory(bsp_classifier* h, cudaStream_t st) {
+    GpuIndex& ix = h->ix;
+    if (ix.pse.p) return;
+    const u64 nt = 1ull << (2 * ix.k);
+    const size_t S = ix.segs.size();
+    ix.pse.alloc((size_t)nt * std::max<size_t>(S, 1));
+    CUDA_CHECK(cudaMemsetAsync(ix.pse.p, 0, ix.pse.bytes(), st));
+    std::vector<GjSeg> gs(S);
+    size_t lut_total = 0;
+    for (size_t i = 0; i < S; i++) lut_total += ((size_t)ix.segs[i].n_tok >> GJ_LUT_SHIFT) + 2;
+    ix.gj_lut.alloc(lut_total);
+    size_t lut_at = 0;
+    for (size_t i = 0; i < S; i++) {
+        const Segment& sg = ix.segs[i];
+        const u32 nb = (u32)(((size_t)sg.n_tok >> GJ_LUT_SHIFT) + 2);
+        gs[i].positions = sg.positions.p; gs[i].doc_tok = sg.doc_tok.p; gs[i].doc_lut = ix.gj_lut.p + lut_at;
+        gs[i].n_docs = sg.n_docs; gs[i].doc_base = sg.doc_base;
+        if (sg.n_terms) pse_build_kernel<<<(unsigned)ceil_div(sg.n_terms, 256), 256, 0, st>>>(sg.view(), ix.pse.p + (size_t)i * nt);
+        gj_doc_lut_kernel<<<(unsigned)ceil_div(nb, 256), 256, 0, st>>>(sg.doc_tok.p, sg.n_docs, nb, ix.gj_lut.p + lut_at);
+        lut_at += nb;
+    }
+    KERNEL_CHECK();
+    ix.d_gjsegs.alloc(S + 1);
+    if (S) CUDA_CHECK(cudaMemcpyAsync(ix.d_gjsegs.p, gs.data(), S * sizeof(GjSeg), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    ix.positional_bytes += ix.pse.bytes();
+    CUDA_CHECK(cudaFuncSetAttribute(gap_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GJ_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(gap_join_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+}
+
+// Room for the gap-clause match lists behind the exception arrays (`entries` per pipeline slot).  Called with every slot idle.
+static void ensure_gap_tail(bsp_classifier* h, size_t entries) {
+    GpuIndex& ix = h->ix;
+    if (!ix.tables || entries <= ix.gap_tail) return;
+    if ((u64)ix.n_exc + (u64)BSP_SLOTS * entries >= ((u64)1 << 32)) entries = (size_t)((((u64)1 << 32) - 1 - (u64)ix.n_exc) / BSP_SLOTS);
+    if (entries <= ix.gap_tail) return;
+    for (auto& sc : h->sc) CUDA_CHECK(cudaStreamSynchronize(sc.st));
+    DevBuf<u32> nd; DevBuf<float> nf;
+    nd.alloc((size_t)ix.n_exc + BSP_SLOTS * entries); nf.alloc((size_t)ix.n_exc + BSP_SLOTS * entries);
+    if (ix.n_exc) {
+        CUDA_CHECK(cudaMemcpy(nd.p, ix.exc_doc.p, (size_t)ix.n_exc * 4, cudaMemcpyDeviceToDevice));
+        CUDA_CHECK(cudaMemcpy(nf.p, ix.exc_freq.p, (size_t)ix.n_exc * 4, cudaMemcpyDeviceToDevice));
+    }
+    ix.table_bytes += nd.bytes() + nf.bytes() - ix.exc_doc.bytes() - ix.exc_freq.bytes();
+    ix.exc_doc = std::move(nd); ix.exc_freq = std::move(nf);
+    ix.gap_tail = entries;
+}
+// before a batch: with kmer_skips > 0 every phrase clause is a gap clause -- about `clauses` of them per sub-batch
+static void prepare_gap_tail(bsp_classifier* h, i64 clauses) {
+    size_t want = h->gap_tail_want;
+    if (h->conf.kmer_skips > 0 && h->conf.query_algorithm != BSP_NAIVE_KMER) want = std::max<size_t>(want, (size_t)clauses * 4);
+    ensure_gap_tail(h, want);
+}
+
+// The sub-batch's gap clauses against the positional index (gapjoin.cuh): sort by first k-mer, chunks, the join, then the
+// matches sorted by (clause, column) into the slot's tail of the exception arrays + per-clause offsets.
+static void gap_join(bsp_classifier* h, Scratch& sc, u32 n_g) {
+    GpuIndex& ix = h->ix;
+    cudaStream_t st = sc.st;
+    ensure_gap_directory(h, st);
+    sc.gj_keys.ensure(n_g); sc.gj_keys_alt.ensure(n_g); sc.gj_vals.ensure(n_g); sc.gj_vals_alt.ensure(n_g); sc.gj_chunks.ensure(n_g);
+    u32 *keys = sc.gj_keys.p, *keys_alt = sc.gj_keys_alt.p, *vals = sc.gj_vals.p, *vals_alt = sc.gj_vals_alt.p;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    gj_keys_kernel<<<(unsigned)ceil_div(n_g, 256), 256, 0, st>>>(sc.gaps.p, n_g, keys, vals);
+    radix_sort_pairs<u32>(&keys, &vals, &keys_alt, &vals_alt, n_g, 2 * ix.k, sc.gj_rst, st);
+    gj_chunk_kernel<<<(unsigned)ceil_div(n_g, 256), 256, 0, st>>>(keys, n_g, sc.gj_chunks.p, sc.gap_ctr.p + 2);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 7, sc.gap_ctr.p + 2, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    const u32 n_chunks = (u32)sc.h_counts[7];
+    const u32 cap = (u32)std::min<size_t>(ix.gap_tail, 0xFFFFFFF0u);
+    sc.gj_mg.ensure(cap); sc.gj_mcol.ensure(cap); sc.gj_mfreq.ensure(cap);
+    CUDA_CHECK(cudaMemsetAsync(sc.gj_bytes.p, 0, 8, st));
+    GjOut out;
+    out.g = sc.gj_mg.p; out.col = sc.gj_mcol.p; out.freq = sc.gj_mfreq.p; out.cap = cap;
+    out.n_match = sc.gap_ctr.p + 1; out.pos_bytes = sc.gj_bytes.p;
+    CUDA_CHECK(cudaEventRecord(e0, st));
+    if (n_chunks)
+        gap_join_kernel<<<(unsigned)ceil_div(n_chunks, GJ_WARPS), GJ_WARPS * 32, GJ_SMEM_BYTES, st>>>(
+            ix.d_gjsegs.p, (int)ix.segs.size(), ix.pse.p, 1ull << (2 * ix.k), sc.gaps.p, vals, sc.gj_chunks.p, sc.gap_ctr.p + 2, ix.colmap.p, out);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaEventRecord(e1, st));
+    unsigned long long pos_bytes = 0;
+    CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 8, sc.gap_ctr.p + 1, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(&pos_bytes, sc.gj_bytes.p, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    u32 n_m = (u32)sc.h_counts[8];
+    const int overflow = n_m > cap ? 1 : 0;
+    if (overflow) { h->gap_tail_want = std::max<size_t>(h->gap_tail_want, (size_t)n_m * 2); n_m = 0; }   // more room next batch
+    h->gj_clauses += n_g; h->gj_chunks += n_chunks; h->gj_matches += n_m; h->gj_bytes += (i64)pos_bytes; h->gj_ms += ms;
+    const u32 tmp_base = (u32)ix.n_exc + (u32)((size_t)sc.slot_index * ix.gap_tail);
+    sc.gj_k64.ensure(std::max<u32>(n_m, 1)); sc.gj_k64_alt.ensure(std::max<u32>(n_m, 1));
+    sc.gj_v.ensure(std::max<u32>(n_m, 1)); sc.gj_v_alt.ensure(std::max<u32>(n_m, 1));
+    u64 *k64 = sc.gj_k64.p, *k64_alt = sc.gj_k64_alt.p; u32 *v = sc.gj_v.p, *v_alt = sc.gj_v_alt.p;
+    if (n_m) {
+        exc_keys_kernel<<<(unsigned)ceil_div(n_m, 256), 256, 0, st>>>(sc.gj_mg.p, sc.gj_mcol.p, n_m, k64, v);
+        int g_bits = 1;
+        while ((1ull << g_bits) < (u64)n_g) g_bits++;
+        radix_sort_pairs<u64>(&k64, &v, &k64_alt, &v_alt, n_m, 32 + g_bits, sc.gj_rst, st);
+        exc_gather_kernel<<<(unsigned)ceil_div(n_m, 256), 256, 0, st>>>(k64, v, sc.gj_mfreq.p, n_m, ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base);
+    }
+    exc_offsets_kernel<<<(unsigned)ceil_div((u64)n_g + 1, 256), 256, 0, st>>>(k64, n_m, n_g, sc.gap_off.p);
+    gj_overflow_kernel<<<(unsigned)ceil_div(n_g, 256), 256, 0, st>>>(sc.gaps.p, n_g, sc.gap_off.p, overflow, sc.route.p, sc.status_in.p,
+                                                                     sc.qp.positional_ok);
+    CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));
+    route_compact_kernel<<<(unsigned)ceil_div(sc.n, 256), 256, 0, st>>>(sc.route.p, sc.n_clauses.p, sc.n, sc.list_dense.p, sc.list_pos.p,
+                                                                        sc.list_filter.p, sc.counts.p, sc.pos_slot.p);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(sc.h_counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 6, sc.counts.p + 6, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    sc.launches_gap = 6 + (n_m ? 2 + 2 * ((32 + 24 + 7) / 8) : 0) + 2 * ((2 * ix.k + 7) / 8);      // (sort passes: histogram + scatter each)
 }
 
 // phase 2a: wait for the route counts, (gap pre-pass), launch the filter scorer and queue the read-back of what it hands
@@ -707,38 +849,24 @@ static void pipeline_phase2a(bsp_classifier* h, Scratch& sc) {
     const i32 n = sc.n;
     const QueryParams& qp = sc.qp;
     CUDA_CHECK(cudaStreamSynchronize(st));                  // route counts have arrived
-    if (qp.gap_ok && sc.h_counts[5] > 0) {
-        // gap clauses (reads with an N, kmer_skips > 0): matches from the positional postings -> sorted lists in the tail
-        // of the exception arrays; a clause with too many matches sends its read to the positional scorer, so the route
-        // lists are rebuilt afterwards
-        const int n_segs = (int)ix.segs.size();
-        const u32 GC = ix.gap_cap;
-        const i64 ng = std::min<i64>((u32)sc.h_counts[5], GC);
-        const u32 tmp_base = (u32)ix.n_exc + (u32)sc.slot_index * GC * GAP_LIST;
-        const int gf_dcap = ix.max_seg_docs <= POSW_DOCS ? (int)round_up(std::max<i64>(ix.max_seg_docs, 1), 32) : 0;
-        gap_fill_kernel<<<(unsigned)ceil_div(ng * n_segs * 32, 256), 256, gf_dcap ? 8 * phrase_stage_bytes(gf_dcap, PW_POS) : 0, st>>>(
-            ix.d_segs.p, n_segs, ix.colmap.p, sc.gaps.p, sc.gap_cnt.p + GC, GC, sc.gap_cnt.p, ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base,
-            gf_dcap, PW_POS);
-        gap_sort_kernel<<<(unsigned)ceil_div(ng * 32, 256), 256, 0, st>>>(sc.gaps.p, sc.gap_cnt.p + GC, GC, sc.gap_cnt.p,
-            ix.exc_doc.p + tmp_base, ix.exc_freq.p + tmp_base, sc.route.p, sc.status_in.p, qp.positional_ok);
-        CUDA_CHECK(cudaMemsetAsync(sc.counts.p, 0, 32, st));
-        route_compact_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(sc.route.p, sc.n_clauses.p, n, sc.list_dense.p, sc.list_pos.p,
-                                                                         sc.list_filter.p, sc.counts.p);
-        KERNEL_CHECK();
-        CUDA_CHECK(cudaMemcpyAsync(sc.h_counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 6, sc.counts.p + 6, 4, cudaMemcpyDeviceToHost, st));
+    sc.launches_gap = 0;
+    if (qp.gap_ok && (i64)(u32)sc.h_counts[5] > sc.gc) {
+        // more gap clauses than the list holds: grow it and redo phase 1 (the clauses past the end were not kept)
+        sc.gc_min = (i64)(u32)sc.h_counts[5] + (i64)(u32)sc.h_counts[5] / 8 + 1024;
+        pipeline_phase1(h, sc, n, sc.in_seq, sc.in_off, sc.in_bytes);
         CUDA_CHECK(cudaStreamSynchronize(st));
     }
+    if (qp.gap_ok && sc.h_counts[5] > 0) gap_join(h, sc, (u32)std::min<i64>((u32)sc.h_counts[5], sc.gc));
     i32* counts = sc.cnt;
     counts[0] = sc.h_counts[0]; counts[1] = sc.h_counts[1]; counts[2] = sc.h_counts[2]; counts[3] = 0;
     const u32 D = (u32)ix.docs.size();
     const int parts_stride = sc.parts_stride;
     i32* part_n = sc.part_n.p; u32* part_doc = sc.part_doc.p; float* part_score = sc.part_score.p;
     const u32 gbase = (u32)h->doc_base_global;
-    const Tab4Dev T = ix.tab4_view(sc.slot_index, sc.gap_cnt.p);
+    const Tab4Dev T = ix.tab4_view(sc.slot_index, sc.gap_off.p);
     const int full_topn = (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0;
     CUDA_CHECK(cudaEventRecord(sc.ev[1], st));
-    sc.launches = sc.front_fused ? 7 : 9;      // tok_capacity, 4 scan kernels, front (or tokenize, token_df, weights), route_compact
+    sc.launches = (sc.front_fused ? 7 : 9) + sc.launches_gap;      // tok_capacity, 4 scan kernels, front (or tokenize, token_df, weights), route_compact
     sc.filter_launched = false;
     if (counts[2] > 0) {
         CUDA_CHECK(cudaMemsetAsync(sc.fstats.p, 0, sizeof(FilterStats), st));
@@ -821,7 +949,7 @@ static void pipeline_phase2b(bsp_classifier* h, Scratch& sc, const BatchOut& out
     i32* part_n = sc.part_n.p; u32* part_doc = sc.part_doc.p; float* part_score = sc.part_score.p;
     SimParams sp; sp.sim = qp.sim; sp.k1p1 = 1.2f + 1.0f;
     const u32 gbase = (u32)h->doc_base_global;
-    const Tab4Dev T = ix.tab4_view(sc.slot_index, sc.gap_cnt.p);
+    const Tab4Dev T = ix.tab4_view(sc.slot_index, sc.gap_off.p);
     const int full_topn = (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0;
     i64 launches = sc.launches;
     FilterStats fs = {0, 0, 0};
@@ -846,6 +974,8 @@ static void pipeline_phase2b(bsp_classifier* h, Scratch& sc, const BatchOut& out
     if (counts[1] > 0) {
         size_t smem = (size_t)ix.max_seg_docs * 10 + 16;
         i64 blocks = (i64)counts[1] * parts_pos;
+        // partial top-10 lists of the positional scorer: one per (list entry, segment)
+        sc.ppart_n.ensure((size_t)blocks); sc.ppart_doc.ensure((size_t)blocks * TOPN); sc.ppart_score.ensure((size_t)blocks * TOPN);
         const i64 MAXG = 0x7FFFFFFF;
         if (blocks > MAXG) throw BspError(BSP_ERR_UNSUPPORTED, "batch too large for the positional path");
         if (ix.max_seg_docs <= POSW_DOCS && env_i64("BSP_POS_BLOCK_KERNEL", 0) == 0) {
@@ -854,19 +984,19 @@ static void pipeline_phase2b(bsp_classifier* h, Scratch& sc, const BatchOut& out
             const int dcap = (int)round_up(std::max<i64>(ix.max_seg_docs, 1), 32);
             score_positional_warp_kernel<<<(unsigned)wblocks, POSW_WARPS * 32, POSW_WARPS * posw_warp_bytes(dcap, PW_POS), st>>>(ix.d_segs.p, parts_pos, sc.list_pos.p, counts[1],
                 sc.tok_off.p, sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p, sc.clause_val.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, qp, sp, gbase,
-                parts_stride, part_n, part_doc, part_score, (int)env_i64("BSP_POS_STAGE", 1), dcap, PW_POS);
+                sc.ppart_n.p, sc.ppart_doc.p, sc.ppart_score.p, (int)env_i64("BSP_POS_STAGE", 1), dcap, PW_POS);
         } else {
             score_positional_kernel<<<(unsigned)blocks, POS_THREADS, smem, st>>>(ix.d_segs.p, parts_pos, sc.list_pos.p, counts[1], sc.tok_off.p,
                 sc.n_tok.p, sc.tok_key.p, sc.tok_pos.p, sc.clause_val.p, sc.n_clauses.p, sc.msm.p, h->doc_w.p, qp, sp, gbase,
-                parts_stride, part_n, part_doc, part_score);
+                sc.ppart_n.p, sc.ppart_doc.p, sc.ppart_score.p);
         }
         launches++;
     }
     KERNEL_CHECK();
     CUDA_CHECK(cudaEventRecord(sc.ev[2], st));
     merge_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(n, sc.route.p, sc.status_in.p, n_tiles, parts_pos, sc.filter_v3 ? 1 : sc.filter_tiles, parts_stride, part_n,
-                                                             part_doc, part_score, out.status, out.label, out.n_hits, out.n_top,
-                                                             out.top_doc, out.top_score, full_topn);
+                                                             part_doc, part_score, sc.pos_slot.p, sc.ppart_n.p, sc.ppart_doc.p, sc.ppart_score.p,
+                                                             out.status, out.label, out.n_hits, out.n_top, out.top_doc, out.top_score, full_topn);
     KERNEL_CHECK();
     CUDA_CHECK(cudaEventRecord(sc.ev[3], st));
     h->counters[0] += n; h->counters[1] += n_exact; h->counters[2] += counts[1]; h->counters[3] += counts[2] - counts[3];
@@ -891,6 +1021,8 @@ static void pipeline_collect(bsp_classifier* h, Scratch& sc) {
 static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const i64* d_seq_off, i64 total_bytes,
                                const BatchOut& out) {
     Scratch& sc = h->sc[0];
+    prepare_gap_tail(h, total_bytes / (h->conf.kmer_skips + 1) + 2 * (i64)n);
+    h->gj_clauses = h->gj_chunks = h->gj_matches = h->gj_bytes = 0; h->gj_ms = 0;
     pipeline_phase1(h, sc, n, d_seq, d_seq_off, total_bytes);
     pipeline_phase2a(h, sc);
     pipeline_phase2b(h, sc, out);
@@ -938,7 +1070,16 @@ static int classify_packed_impl(bsp_classifier* h, i32 n, const char* seq_bytes,
     for (auto& c : h->counters) c = 0;
     h->score_ms = 0; h->pipe_ms = 0;
     h->last_routes.assign(n, 0);
-    const i32 SUB = (i32)std::max<i64>(1, env_i64("BSP_SUB_BATCH", 131072));
+    // (kmer_skips > 0: the gap join shares a first k-mer's positions among the clauses of the sub-batch that start with it --
+    //  4^k terms want a sub-batch of a million reads)
+    const bool all_gap = h->conf.kmer_skips > 0 && h->conf.query_algorithm != BSP_NAIVE_KMER;
+    const i32 SUB = (i32)std::max<i64>(1, all_gap ? env_i64("BSP_SUB_BATCH_GAP", 1048576) : env_i64("BSP_SUB_BATCH", 131072));
+    {
+        const i32 m0 = std::min(SUB, n);
+        const i64 bytes0 = n > 0 ? (seq_offsets[n] - seq_offsets[0]) / std::max(1, n) * m0 : 0;
+        prepare_gap_tail(h, bytes0 / (h->conf.kmer_skips + 1) + 2 * (i64)m0);
+    }
+    h->gj_clauses = h->gj_chunks = h->gj_matches = h->gj_bytes = 0; h->gj_ms = 0;
     // Software pipeline over sub-batches, BSP_SLOTS slots.  Iteration i copies sub-batch i in and queues its tokenizer /
     // weights (phase 1), launches the scorer of sub-batch i-1 (phase 2a: its route counts arrived while sub-batch i-2
     // was being scored) and only then waits for the scorer of sub-batch i-2 to finish, merges and copies it out (phase
@@ -1307,6 +1448,14 @@ BSP_API int bsp_last_timings(bsp_classifier* h, double* score_kernel_ms, double*
     return BSP_OK;
 }
 
+BSP_API int bsp_last_gap_join(bsp_classifier* h, int64_t out[4], double* join_kernel_ms) {
+    if (!h || !out) return fail(nullptr, BSP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    out[0] = h->gj_clauses; out[1] = h->gj_chunks; out[2] = h->gj_matches; out[3] = h->gj_bytes;
+    if (join_kernel_ms) *join_kernel_ms = h->gj_ms;
+    return BSP_OK;
+}
+
 BSP_API int bsp_memory_info(bsp_classifier* h, int64_t* positional_bytes, int64_t* table_bytes, int64_t* staged_bytes) {
     if (!h) return fail(nullptr, BSP_ERR_ARG, "null argument");
     if (positional_bytes) *positional_bytes = h->ix.positional ? (i64)h->ix.positional_bytes : 0;
@@ -1458,7 +1607,8 @@ BSP_API int bsp_merge_topk_device(bsp_classifier* h, int32_t n, int32_t parts, c
     CUDA_CHECK(cudaSetDevice(h->conf.device));
     // layout: [n][parts] lists; status is taken from part 0 (identical on every rank: it depends on the read only)
     merge_kernel<<<(unsigned)ceil_div(std::max(n, 1), 128), 128, 0, h->st>>>(n, nullptr, (const i32*)d_part_status, parts, parts, parts, parts,
-        (const i32*)d_part_n_top, (const u32*)d_part_doc, (const float*)d_part_score, (i32*)d_status, (i32*)d_label, (i32*)d_n_hits,
+        (const i32*)d_part_n_top, (const u32*)d_part_doc, (const float*)d_part_score, nullptr, (const i32*)d_part_n_top,
+        (const u32*)d_part_doc, (const float*)d_part_score, (i32*)d_status, (i32*)d_label, (i32*)d_n_hits,
         (i32*)d_n_top, (i32*)d_top_doc, (float*)d_top_score, (h->conf.full_topn || env_i64("BSP_FULL_TOPN", 0)) ? 1 : 0);
     KERNEL_CHECK();
     CUDA_CHECK(cudaStreamSynchronize(h->st));

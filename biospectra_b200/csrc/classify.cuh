@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
         const i64* __restrict__ tok_off, const i32* __restrict__ n_tok, const u64* __restrict__ tok_key,
         const u32* __restrict__ tok_pos, const float* __restrict__ clause_val, const i32* __restrict__ n_clauses,
         const i32* __restrict__ msm, const float* __restrict__ doc_w, QueryParams qp, SimParams sp, u32 global_doc_base,
-        int parts_stride, i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score) {
+        i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score) {
     extern __shared__ __align__(16) u8 smem_raw[];
     __shared__ ClauseStage stage[POS_CHUNK];
     __shared__ u64 red[33];
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(POS_THREADS) score_positional_kernel(
     }
     __syncthreads();
     // fused top-10: rounds of block arg-max
-    const i64 pbase = (i64)r * parts_stride + sidx;
+    const i64 pbase = (i64)(blockIdx.x % n_list) * n_segs + sidx;        // (entry of the read list, segment)
     i32 found = 0;
     for (int round = 0; round < TOPN; round++) {
         u64 best = 0;
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_w
         const i64* __restrict__ tok_off, const i32* __restrict__ n_tok, const u64* __restrict__ tok_key,
         const u32* __restrict__ tok_pos, const float* __restrict__ clause_val, const i32* __restrict__ n_clauses,
         const i32* __restrict__ msm, const float* __restrict__ doc_w, QueryParams qp, SimParams sp, u32 global_doc_base,
-        int parts_stride, i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score, int stage_ok,
+        i32* __restrict__ part_n, u32* __restrict__ part_doc, float* __restrict__ part_score, int stage_ok,
         int dcap /* >= docs of any segment, multiple of 32 */, int pcap) {
     extern __shared__ __align__(16) u8 pw_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -865,7 +865,7 @@ __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_w
             if (m >= need) keys[j] = cand_key(final_score(sp.sim, acc[d], m, nc), d);
         }
     }
-    const i64 pbase = (i64)r * parts_stride + sidx;
+    const i64 pbase = (pair % n_list) * n_segs + sidx;                   // (entry of the read list, segment)
     i32 found = 0;
     for (int round = 0; round < TOPN; round++) {
         u64 lm = 0;
@@ -895,8 +895,10 @@ __global__ void __launch_bounds__(POSW_WARPS * 32, POSW_MINB) score_positional_w
 // label by score tier (Classifier.java:263-339 without taxonomy).
 __global__ void __launch_bounds__(128) merge_kernel(i32 n_reads, const i32* __restrict__ route, const i32* __restrict__ status_in,
                                                      int parts_dense, int parts_pos, int parts_filter, int parts_stride,
-                                                     const i32* __restrict__ part_n, const u32* __restrict__ part_doc,
-                                                     const float* __restrict__ part_score,
+                                                     const i32* __restrict__ part_n_d, const u32* __restrict__ part_doc_d,
+                                                     const float* __restrict__ part_score_d,
+                                                     const i32* __restrict__ pos_slot, const i32* __restrict__ part_n_p,
+                                                     const u32* __restrict__ part_doc_p, const float* __restrict__ part_score_p,
                                                      i32* __restrict__ status, i32* __restrict__ label, i32* __restrict__ n_hits,
                                                      i32* __restrict__ n_top, i32* __restrict__ top_doc,
                                                      float* __restrict__ top_score, int full_topn) {
@@ -907,8 +909,14 @@ __global__ void __launch_bounds__(128) merge_kernel(i32 n_reads, const i32* __re
     int nt = 0;
     const int rt = route ? route[r] : ROUTE_POSITIONAL;
     const int parts = rt == ROUTE_DENSE ? parts_dense : (rt == ROUTE_POSITIONAL ? parts_pos : (rt == ROUTE_FILTER ? parts_filter : 0));
+    // the positional scorer keeps its partial lists per (entry of its read list, segment), the table scorers per (read, tile)
+    const bool pos = rt == ROUTE_POSITIONAL;
+    const i32* part_n = pos ? part_n_p : part_n_d;
+    const u32* part_doc = pos ? part_doc_p : part_doc_d;
+    const float* part_score = pos ? part_score_p : part_score_d;
+    const i64 pb0 = pos ? (i64)(pos_slot ? pos_slot[r] : r) * parts_pos : (i64)r * parts_stride;
     for (int p = 0; p < parts; p++) {
-        const i64 pb = (i64)r * parts_stride + p;
+        const i64 pb = pb0 + p;
         const int np = part_n[pb];
         for (int j = 0; j < np; j++) {
             const float s = part_score[pb * TOPN + j];

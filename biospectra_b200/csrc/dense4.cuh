@@ -40,8 +40,8 @@ struct Tab4Dev {
     const float* exc_freq;
     u32 zero_row;           // = n_rows: an all-zero row without exceptions
     u32 temp_row0;          // = n_rows + 1: temporary rows of the current sub-batch's gap clauses
-    u32 tmp_base;           // their match lists live at exc_doc/exc_freq[tmp_base + g * GAP_LIST ...]
-    const u32* gap_cnt;     // [gap_cap] matches per gap clause
+    u32 tmp_base;           // their match lists (sorted by column) live at exc_doc/exc_freq[tmp_base + gap_off[g] ...]
+    const u32* gap_off;     // [gap clauses + 1] first match of every gap clause (gapjoin.cuh)
     // Table columns are the handle's documents sorted by (norm byte, doc id): docs that share a length norm sit next to
     // each other, so a thread's 32 columns belong to one norm class except at the few class boundaries (the BM25 bound
     // needs a per-class LUT; tf-idf is indifferent to the order).  docmap[column] = doc id (0xFFFFFFFF for padding
@@ -52,7 +52,7 @@ struct Tab4Dev {
 
 // exception list (first entry, count) and table row of a clause row id
 __device__ __forceinline__ void row_exceptions(const Tab4Dev& T, u32 row, u32& a, u32& n) {
-    if (row >= T.temp_row0) { const u32 g = row - T.temp_row0; a = T.tmp_base + g * GAP_LIST; n = min(T.gap_cnt[g], (u32)GAP_LIST); }
+    if (row >= T.temp_row0) { const u32 g = row - T.temp_row0, o = T.gap_off[g]; a = T.tmp_base + o; n = min(T.gap_off[g + 1] - o, (u32)GAP_LIST); }
     else { a = T.exc_off[row]; n = T.exc_off[row + 1] - a; }
 }
 __device__ __forceinline__ u32 row_data(const Tab4Dev& T, u32 row) { return row >= T.temp_row0 ? T.zero_row : row; }
@@ -253,87 +253,6 @@ __global__ void __launch_bounds__(256) exc_offsets_kernel(const u64* __restrict_
         if ((keys[mid] >> 32) < r) lo = mid + 1; else hi = mid;
     }
     exc_off[r] = lo;
-}
-
-// ---- gap clauses: evaluate against the positional postings, keep the (few) matching docs as a sorted list
-// warp per (gap clause, segment); idle warps (no such clause in this sub-batch) leave at once
-__global__ void __launch_bounds__(256) gap_fill_kernel(const SegDev* __restrict__ segs, int n_segs, const u32* __restrict__ colmap, const GapClause* __restrict__ gaps,
-                                                        const u32* __restrict__ gap_count, u32 gap_cap, u32* __restrict__ gap_cnt,
-                                                        u32* __restrict__ tmp_doc, float* __restrict__ tmp_freq,
-                                                        int dcap /* 0: no staging (segments of more than 256 docs) */, int pcap) {
-    extern __shared__ __align__(16) u8 gf_raw[];          // PhraseStage per warp (classify.cuh)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u64 w = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const u32 ng = min(*gap_count, gap_cap);
-    const u32 g = (u32)(w / (u64)n_segs);
-    if (g >= ng) return;
-    const SegDev s = segs[w % (u64)n_segs];
-    const GapClause gc = gaps[g];
-    const bool same = gc.k0 == gc.k1;
-    const u32 t0 = seg_find_term(s, gc.k0);
-    if (t0 == NO_TERM) return;
-    u32 a1 = 0, b1 = 0;
-    if (same) { a1 = s.term_off[t0]; b1 = s.term_off[t0 + 1]; }
-    else {
-        const u32 t1 = seg_find_term(s, gc.k1);
-        if (t1 == NO_TERM) return;
-        a1 = s.term_off[t1]; b1 = s.term_off[t1 + 1];
-    }
-    const u32 a0 = s.term_off[t0], b0 = s.term_off[t0 + 1];
-    auto keep = [&](u32 local_doc, float f) {
-        const u32 pos = atomicAdd(&gap_cnt[g], 1u);
-        if (pos < GAP_LIST) {
-            tmp_doc[(u64)g * GAP_LIST + pos] = colmap[s.doc_base + local_doc];
-            tmp_freq[(u64)g * GAP_LIST + pos] = f;
-        }
-    };
-    // staged like the warp scorer: both slices in shared memory, one scan for the docs that can match at all
-    const u32 n0 = b0 - a0, n1 = b1 - a1;
-    if (!same && n0 && n1 && dcap > 0 && s.n_docs <= (u32)dcap) {
-        const u32 p0 = s.post_pos[a0], m0 = s.post_pos[b0] - p0, p1 = s.post_pos[a1], m1 = s.post_pos[b1] - p1;
-        if (m0 + 3 <= (u32)pcap && m1 + 3 <= (u32)pcap) {
-            const PhraseStage W = phrase_stage_at(gf_raw + (size_t)warp * phrase_stage_bytes(dcap, pcap), dcap, pcap);
-            for (u32 d = lane; d < (u32)dcap; d += 32) { W.inv[d] = 0; W.hit[d] = 0; }
-            __syncwarp();
-            phrase_matches_staged(s, W, a0, n0, p0, m0, a1, n1, p1, m1, gc.slop, lane, keep);
-            return;
-        }
-    }
-    for (u32 i = a0 + lane; i < b0; i += 32) {
-        const float f = phrase_freq_at(s, i, a1, b1, a1 + (i - a0), gc.slop, same);
-        if (f != 0.0f) keep(s.post_doc[i], f);
-    }
-}
-
-// warp per gap clause: sort its matches by doc id (the filter and the exact scorer binary-search them); a clause with
-// more than GAP_LIST matches sends its read to the positional scorer instead
-__global__ void __launch_bounds__(256) gap_sort_kernel(const GapClause* __restrict__ gaps, const u32* __restrict__ gap_count,
-                                                        u32 gap_cap, const u32* __restrict__ gap_cnt, u32* __restrict__ tmp_doc,
-                                                        float* __restrict__ tmp_freq, i32* __restrict__ route, i32* __restrict__ status,
-                                                        int positional_ok) {
-    __shared__ u32 sd[8][GAP_LIST];
-    __shared__ float sf[8][GAP_LIST];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= min(*gap_count, gap_cap)) return;
-    const u32 n = gap_cnt[g];
-    if (n > GAP_LIST) {
-        if (lane == 0) {
-            const i32 r = gaps[g].read;
-            route[r] = positional_ok ? ROUTE_POSITIONAL : ROUTE_NONE;
-            if (!positional_ok) status[r] = ST_ERROR;
-        }
-        return;
-    }
-    for (u32 i = lane; i < n; i += 32) { sd[warp][i] = tmp_doc[(u64)g * GAP_LIST + i]; sf[warp][i] = tmp_freq[(u64)g * GAP_LIST + i]; }
-    __syncwarp();
-    for (u32 i = lane; i < n; i += 32) {          // rank sort: a doc appears at most once per clause
-        const u32 d = sd[warp][i];
-        u32 rank = 0;
-        for (u32 j = 0; j < n; j++) rank += sd[warp][j] < d;
-        tmp_doc[(u64)g * GAP_LIST + rank] = d;
-        tmp_freq[(u64)g * GAP_LIST + rank] = sf[warp][i];
-    }
 }
 
 // ------------------------------------------------------------------ shared helpers

@@ -11,6 +11,7 @@
 //              d_pad/2 bytes, plus the sorted exception list (see dense4.cuh).
 #pragma once
 #include "dense4.cuh"
+#include "gapjoin.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -187,17 +188,21 @@ struct GpuIndex {
     DevBuf<u32> df_dense; DevBuf<u32> ttf_dense;
     // dense 4-bit table
     DevBuf<u8> tab4; u64 d_pad = 0, row_bytes = 0, n_rows = 0, pair_row0 = 0;
-    DevBuf<u32> exc_off, exc_doc; DevBuf<float> exc_freq; i64 n_exc = 0; u32 gap_cap = GAP_CAP_DEFAULT;
+    DevBuf<u32> exc_off, exc_doc; DevBuf<float> exc_freq; i64 n_exc = 0;
+    // the tail of the exception arrays holds the gap-clause match lists of the pipeline slots: gap_tail entries each
+    u32 gap_cap = GAP_CAP_DEFAULT; size_t gap_tail = 0;
+    // gap join (gapjoin.cuh): per segment the (start, length) of every term's positions, built when the first gap clause shows up
+    DevBuf<uint2> pse; DevBuf<GjSeg> d_gjsegs; DevBuf<u16> gj_lut;
     // table column order: docs sorted by (norm byte, doc id) -- see Tab4Dev::docmap
     DevBuf<u32> colmap, docmap; std::vector<u32> h_docmap;
-    // slot: pipeline slot whose gap-clause lists (tail of the exception arrays) and counters the view refers to
-    Tab4Dev tab4_view(int slot, const u32* gap_cnt) const {
+    // slot: pipeline slot whose gap-clause lists (tail of the exception arrays) the view refers to
+    Tab4Dev tab4_view(int slot, const u32* gap_off) const {
         Tab4Dev t;
         t.tab = tab4.p; t.row_bytes = row_bytes; t.pair_row0 = pair_row0;
         t.exc_off = exc_off.p; t.exc_doc = exc_doc.p; t.exc_freq = exc_freq.p;
         t.zero_row = (u32)n_rows; t.temp_row0 = (u32)n_rows + 1;
-        t.tmp_base = (u32)n_exc + (u32)slot * gap_cap * GAP_LIST;
-        t.gap_cnt = gap_cnt;
+        t.tmp_base = (u32)n_exc + (u32)((size_t)slot * gap_tail);
+        t.gap_off = gap_off;
         t.docmap = docmap.p;
         return t;
     }
@@ -426,7 +431,7 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
     u64 tf_bytes = can_tables ? ix.pair_row0 * ix.row_bytes : 0;
     u64 pair_bytes = (can_tables && opt.need_pair_table) ? ((1ull << (2 * (k + 1))) * ix.row_bytes) : 0;
     ix.gap_cap = (u32)std::max<i64>(opt.gap_cap, 1);
-    if (ix.n_rows + ix.gap_cap + 2 >= ((u64)1 << 32)) throw BspError(-5, "dense table row count exceeds 2^32");
+    if (ix.n_rows + ((u64)1 << 28) >= ((u64)1 << 32)) throw BspError(-5, "dense table row count exceeds 2^32");   // (+ 2^28 gap clause rows)
     bool tables = false;
     if (can_tables && opt.want_tables != 2) {
         if (opt.want_tables == 1) tables = true;
@@ -620,7 +625,8 @@ static void build_gpu_index(GpuIndex& ix, RefStore& ref, const BuildOptions& opt
         const u32 n = (u32)ne;
         ix.exc_off.alloc(ix.n_rows + 2);
         // the tail of the exception arrays holds the gap-clause match lists of the two pipeline slots
-        const size_t tail = (size_t)BSP_SLOTS * ix.gap_cap * GAP_LIST;      // one gap-list region per pipeline slot
+        ix.gap_tail = (size_t)ix.gap_cap * GAP_LIST;
+        const size_t tail = (size_t)BSP_SLOTS * ix.gap_tail;                 // one gap-list region per pipeline slot
         if ((u64)n + tail >= ((u64)1 << 32)) throw BspError(-5, "exception + gap lists exceed 2^32 entries");
         ix.exc_doc.alloc((size_t)n + tail); ix.exc_freq.alloc((size_t)n + tail);
         DevBuf<u64> ka, kb; DevBuf<u32> va, vb;

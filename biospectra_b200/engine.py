@@ -234,6 +234,12 @@ class Classifier:
         _lib.check(self.L.bsp_last_timings(self.h, C.byref(a), C.byref(b)), self.h)
         return {"score_kernel_ms": a.value, "pipeline_ms": b.value}
 
+    def last_gap_join(self):
+        c = np.zeros(4, np.int64)
+        ms = C.c_double()
+        _lib.check(self.L.bsp_last_gap_join(self.h, c.ctypes.data, C.byref(ms)), self.h)
+        return dict(zip(("clauses", "chunks", "matches", "position_bytes"), [int(x) for x in c]), join_kernel_ms=ms.value)
+
     def memory_info(self):
         v = [C.c_int64() for _ in range(3)]
         _lib.check(self.L.bsp_memory_info(self.h, *[C.byref(x) for x in v]), self.h)

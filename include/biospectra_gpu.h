@@ -206,6 +206,11 @@ int bsp_last_counters(bsp_classifier* h, int64_t counters[8]);
 /* kernel time (ms, CUDA events on the handle's stream) of the dominant scoring kernel
  * and of the whole device pipeline in the last batch */
 int bsp_last_timings(bsp_classifier* h, double* score_kernel_ms, double* pipeline_ms);
+/* gap join of the last batch (phrase clauses whose k-mers are not adjacent in the read -- every phrase clause with
+ * kmer_skips > 0, Configuration.java:37-44 / Classifier.java:160-200 -- evaluated against the positional index, sorted by
+ * first k-mer): out[0] gap clauses, [1] chunks (clauses sharing a first k-mer, one warp each), [2] (clause, document)
+ * matches, [3] position bytes the join kernel fetched; its time in ms (CUDA events on the handle's streams) */
+int bsp_last_gap_join(bsp_classifier* h, int64_t out[4], double* join_kernel_ms);
 /* Cost model of SURVEY.md 8(d) evaluated on the actual index for a read set (host
  * buffers as in bsp_classify_packed): out[0] reads that are scored, [1] tokens, [2] unique
  * query terms (= dictionary probes), [3] sum df, [4] sum ttf over unique terms,
