@@ -57,7 +57,7 @@ struct Scratch {
     i64 gc = 0, gc_min = 0;             // capacity of `gaps`; what the last overflow asked for
     DevBuf<u32> gj_keys, gj_keys_alt, gj_vals, gj_vals_alt, gj_mg, gj_mcol, gj_v, gj_v_alt; DevBuf<uint2> gj_chunks;
     DevBuf<float> gj_mfreq; DevBuf<u64> gj_k64, gj_k64_alt; DevBuf<unsigned long long> gj_bytes;
-    RadixSortTemp gj_rst;
+    RadixSortTemp gj_rst; DevBuf<GjOut> gj_out; DevBuf<u32> gj_sizes;
     const u8* in_seq = nullptr; const i64* in_off = nullptr; i64 in_bytes = 0;   // phase 1 inputs (re-run when `gaps` was too short)
     DevBuf<i32> pos_slot;               // read -> index in list_pos (the positional scorer's partial lists are per list entry)
     DevBuf<i32> ppart_n; DevBuf<u32> ppart_doc; DevBuf<float> ppart_score;
@@ -789,7 +789,11 @@ static void gap_join(bsp_classifier* h, Scratch& sc, u32 n_g) {
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     gj_keys_kernel<<<(unsigned)ceil_div(n_g, 256), 256, 0, st>>>(sc.gaps.p, n_g, keys, vals);
     radix_sort_pairs<u32>(&keys, &vals, &keys_alt, &vals_alt, n_g, 2 * ix.k, sc.gj_rst, st);
-    gj_chunk_kernel<<<(unsigned)ceil_div(n_g, 256), 256, 0, st>>>(keys, n_g, sc.gj_chunks.p, sc.gap_ctr.p + 2);
+    sc.gj_sizes.ensure(32);
+    CUDA_CHECK(cudaMemsetAsync(sc.gj_sizes.p, 0, 32 * 4, st));
+    gj_chunk_kernel<<<(unsigned)ceil_div(n_g, 256), 256, 0, st>>>(keys, n_g, sc.gj_chunks.p, sc.gj_sizes.p, 0);
+    gj_chunk_offsets_kernel<<<1, 1, 0, st>>>(sc.gj_sizes.p, sc.gap_ctr.p + 2);
+    gj_chunk_kernel<<<(unsigned)ceil_div(n_g, 256), 256, 0, st>>>(keys, n_g, sc.gj_chunks.p, sc.gj_sizes.p, 1);
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 7, sc.gap_ctr.p + 2, 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
@@ -800,10 +804,12 @@ static void gap_join(bsp_classifier* h, Scratch& sc, u32 n_g) {
     GjOut out;
     out.g = sc.gj_mg.p; out.col = sc.gj_mcol.p; out.freq = sc.gj_mfreq.p; out.cap = cap;
     out.n_match = sc.gap_ctr.p + 1; out.pos_bytes = sc.gj_bytes.p;
+    sc.gj_out.ensure(1);
+    CUDA_CHECK(cudaMemcpyAsync(sc.gj_out.p, &out, sizeof out, cudaMemcpyHostToDevice, st));     // (pageable source: staged before the call returns)
     CUDA_CHECK(cudaEventRecord(e0, st));
     if (n_chunks)
         gap_join_kernel<<<(unsigned)ceil_div(n_chunks, GJ_WARPS), GJ_WARPS * 32, GJ_SMEM_BYTES, st>>>(
-            ix.d_gjsegs.p, (int)ix.segs.size(), ix.pse.p, 1ull << (2 * ix.k), sc.gaps.p, vals, sc.gj_chunks.p, sc.gap_ctr.p + 2, ix.colmap.p, out);
+            ix.d_gjsegs.p, (int)ix.segs.size(), ix.pse.p, 1ull << (2 * ix.k), sc.gaps.p, vals, sc.gj_chunks.p, sc.gap_ctr.p + 2, ix.colmap.p, sc.gj_out.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaEventRecord(e1, st));
     unsigned long long pos_bytes = 0;
@@ -838,7 +844,7 @@ static void gap_join(bsp_classifier* h, Scratch& sc, u32 n_g) {
     CUDA_CHECK(cudaMemcpyAsync(sc.h_counts, sc.counts.p, 16, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 6, sc.counts.p + 6, 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    sc.launches_gap = 6 + (n_m ? 2 + 2 * ((32 + 24 + 7) / 8) : 0) + 2 * ((2 * ix.k + 7) / 8);      // (sort passes: histogram + scatter each)
+    sc.launches_gap = 8 + (n_m ? 2 + 2 * ((32 + 24 + 7) / 8) : 0) + 2 * ((2 * ix.k + 7) / 8);      // (sort passes: histogram + scatter each)
 }
 
 // phase 2a: wait for the route counts, (gap pre-pass), launch the filter scorer and queue the read-back of what it hands

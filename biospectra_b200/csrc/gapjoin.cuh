@@ -28,11 +28,16 @@
 #ifndef GJ_ACAP
 #define GJ_ACAP 512              // positions of the first term staged at a time (longer slices: block by block)
 #endif
+#ifndef GJ_WARPS
 #define GJ_WARPS 8
+#endif
 #ifndef GJ_MINB
 #define GJ_MINB 2
 #endif
-#define GJ_VEC 3                 // 16-byte vectors per lane and round of the second term (vector q = positions [128 q, 128 q + 128))
+#ifndef GJ_VEC
+#define GJ_VEC 3
+#endif
+//                 // 16-byte vectors per lane and round of the second term (vector q = positions [128 q, 128 q + 128))
 #define GJ_ROUND (GJ_VEC * 128)  // 384 positions per round
 #ifndef GJ_BM_WORDS
 #define GJ_BM_WORDS 2048         // words of a warp's bucket bit table (power of two, multiple of 128): 65,536 bits
@@ -79,8 +84,12 @@ __global__ void __launch_bounds__(256) gj_keys_kernel(const GapClause* __restric
     vals[i] = i;
 }
 
-// runs of equal first k-mers in the sorted key array -> chunks (first sorted index, clause count <= GJ_C)
-__global__ void __launch_bounds__(256) gj_chunk_kernel(const u32* __restrict__ keys, u32 n, uint2* __restrict__ chunks, u32* __restrict__ n_chunks) {
+// runs of equal first k-mers in the sorted key array -> chunks (first sorted index, clause count <= GJ_C), grouped by
+// clause count, largest first: the warps of a CTA then carry similar loads (a CTA's shared memory is held until its
+// slowest warp is done) and the long chunks start first.  sizes[0..8]: chunks per clause count, sizes[9..17]: first
+// chunk of every count, sizes[18..26]: cursors.  mode 0 counts, gj_chunk_offsets_kernel lays the groups out, mode 1 writes.
+__global__ void __launch_bounds__(256) gj_chunk_kernel(const u32* __restrict__ keys, u32 n, uint2* __restrict__ chunks, u32* __restrict__ sizes,
+                                                        int mode) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u32 key = keys[i];
@@ -90,9 +99,22 @@ __global__ void __launch_bounds__(256) gj_chunk_kernel(const u32* __restrict__ k
         const u32 mid = (lo + hi) >> 1;
         if (keys[mid] == key) lo = mid + 1; else hi = mid;
     }
-    const u32 len = lo - i, nch = (len + GJ_C - 1) / GJ_C;
-    const u32 base = atomicAdd(n_chunks, nch);
-    for (u32 j = 0; j < nch; j++) chunks[base + j] = make_uint2(i + j * GJ_C, min((u32)GJ_C, len - j * GJ_C));
+    const u32 len = lo - i, full = len / GJ_C, rest = len % GJ_C;
+    if (mode == 0) {
+        if (full) atomicAdd(&sizes[GJ_C], full);
+        if (rest) atomicAdd(&sizes[rest], 1u);
+        return;
+    }
+    if (full) {
+        const u32 base = sizes[9 + GJ_C] + atomicAdd(&sizes[18 + GJ_C], full);
+        for (u32 j = 0; j < full; j++) chunks[base + j] = make_uint2(i + j * GJ_C, (u32)GJ_C);
+    }
+    if (rest) chunks[sizes[9 + rest] + atomicAdd(&sizes[18 + rest], 1u)] = make_uint2(i + full * GJ_C, rest);
+}
+__global__ void gj_chunk_offsets_kernel(u32* __restrict__ sizes, u32* __restrict__ n_chunks) {
+    u32 at = 0;
+    for (int c = GJ_C; c >= 1; c--) { sizes[9 + c] = at; at += sizes[c]; }
+    *n_chunks = at;
 }
 
 __device__ __forceinline__ uint4 ldg_stream16(const u32* p) {
@@ -124,8 +146,10 @@ __device__ __forceinline__ u32 gj_lower_bound(const u32* __restrict__ P, u32 n, 
 // the staged block.  Exact evaluation on the global slices; the document is reported by the first of its occurrences
 // of t1 that has a close partner inside the document, and (slices staged block by block) by the block that holds that
 // partner.
-__device__ __noinline__ void gj_verify(const GjSeg sg, u32 pA, u32 mA, u32 blk0, u32 blk_n, u32 pB, u32 mB, u32 b, int slop,
-                                       bool same, u32 g, const u32* __restrict__ colmap, const GjOut out) {
+__device__ __noinline__ void gj_verify(const GjSeg* __restrict__ sgp, u32 pA, u32 mA, u32 blk0, u32 blk_n, u32 pB, u32 mB, u32 b, int slop,
+                                       bool same, u32 g, const u32* __restrict__ colmap, const GjOut* __restrict__ outp) {
+    const GjSeg sg = *sgp;
+    const GjOut out = *outp;
     u32 lo = 0, hi = sg.n_docs;                            // last doc whose first ordinal is <= b
     while (hi - lo > 1) {
         const u32 mid = (lo + hi) >> 1;
@@ -165,8 +189,9 @@ __device__ __noinline__ void gj_verify(const GjSeg sg, u32 pA, u32 mA, u32 blk0,
 // The common case of a hit, on the staged block: the document from the segment's bucket LUT, the first term's positions
 // inside it by a short scan around the hit in shared memory, the second term's by a short scan in global memory (just
 // fetched: L2).  Returns false when the scan reaches the edge of a partially staged slice (the caller takes gj_verify).
-__device__ __noinline__ bool gj_verify_staged(const GjSeg& sg, const u32* A, u32 nA, bool whole, u32 i, u32 pB, u32 mB, u32 jb,
-                                                 int slop, bool same, u32 g, const u32* __restrict__ colmap, const GjOut& out) {
+__device__ __noinline__ bool gj_verify_staged(const GjSeg* __restrict__ sgp, const u32* A, u32 nA, bool whole, u32 i, u32 pB, u32 mB, u32 jb,
+                                                 int slop, bool same, u32 g, const u32* __restrict__ colmap, const GjOut* __restrict__ outp) {
+    const GjSeg sg = *sgp;
     const u32* B = sg.positions + pB;
     const u32 b = B[jb];
     u32 d = sg.doc_lut[b >> GJ_LUT_SHIFT];
@@ -197,6 +222,7 @@ __device__ __noinline__ bool gj_verify_staged(const GjSeg& sg, const u32* A, u32
     const float f = same ? sloppy_freq_same(A + ia0, (int)(ia1 - ia0), slop)
                          : sloppy_freq_distinct(A + ia0, (int)(ia1 - ia0), B + jb0, (int)(jb1 - jb0), slop);
     if (f != 0.0f) {
+        const GjOut out = *outp;
         const u32 at = atomicAdd(out.n_match, 1u);
         if (at < out.cap) { out.g[at] = g; out.col[at] = colmap[sg.doc_base + d]; out.freq[at] = f; }
     }
@@ -214,7 +240,7 @@ __device__ __forceinline__ u32 gj_hash2(u32 word_index) { return ((word_index * 
 __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
         const GjSeg* __restrict__ segs, int n_segs, const uint2* __restrict__ pse, u64 n_terms,
         const GapClause* __restrict__ gaps, const u32* __restrict__ order, const uint2* __restrict__ chunks,
-        const u32* __restrict__ n_chunks, const u32* __restrict__ colmap, const GjOut out) {
+        const u32* __restrict__ n_chunks, const u32* __restrict__ colmap, const GjOut* __restrict__ outp) {
     extern __shared__ __align__(16) u8 gj_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 w = blockIdx.x * GJ_WARPS + warp;
@@ -248,7 +274,7 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
     const int bs = 32 - __clz(2 * max_slop);                 // 2^bs >= 2 slop + 1
     const u32 bias = 1u << bs;
     if (lane < cnt && my_term == t0) my_slop = -my_slop;     // same-term clause: marked by the sign
-    unsigned long long fetched = 0;
+    u32 fetched = 0;                                         // positions fetched (warp-uniform)
 
     auto stage_first = [&](int sidx, uint2 d, u32* buf) {       // first block of the first term's slice of segment sidx
         const u32 pA = __shfl_sync(0xFFFFFFFFu, d.x, GJ_C), mA = __shfl_sync(0xFFFFFFFFu, d.y, GJ_C);
@@ -278,6 +304,23 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
     }
     stage_first(0, d_cur, abuf);
     cp_async_commit();
+    // the segment's live clauses (non-empty slices on both sides) and the first round of the first one: requested a whole
+    // loop turn before it is needed
+    u32 live = 0, pB = 0, mB = 0, r0 = 0;
+    int c = -1;
+    uint4 v[GJ_VEC], vn[GJ_VEC];
+    const u32* positions = nullptr;
+    auto open_segment = [&](int sidx, uint2 d) {
+        live = __ballot_sync(0xFFFFFFFFu, lane < cnt && d.y != 0u);
+        if (__shfl_sync(0xFFFFFFFFu, d.y, GJ_C) == 0u) live = 0u;
+        positions = segs[sidx].positions;
+        c = __ffs(live) - 1; r0 = 0;
+        if (c >= 0) {
+            pB = __shfl_sync(0xFFFFFFFFu, d.x, c); mB = __shfl_sync(0xFFFFFFFFu, d.y, c);
+            load_round(v, positions, pB, mB, 0);
+        }
+    };
+    open_segment(0, d_cur);
     for (int s = 0; s < n_segs; s++) {
         __syncwarp();                                        // the buffer the next copies land in is no longer read
         uint2 d_nn = make_uint2(0, 0);
@@ -286,30 +329,18 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
         if (s + 1 < n_segs) stage_first(s + 1, d_nxt, abuf + ((s + 1) & 1) * (GJ_ACAP + 8));
         cp_async_commit();
         const u32 pA = __shfl_sync(0xFFFFFFFFu, d_cur.x, GJ_C), mA = __shfl_sync(0xFFFFFFFFu, d_cur.y, GJ_C);
-        // clauses with a non-empty second slice in this segment
-        u32 live = __ballot_sync(0xFFFFFFFFu, lane < cnt && d_cur.y != 0u);
-        if (mA == 0u) live = 0u;
-        const GjSeg sg = segs[s];
-        // the first round of the first live clause is requested before the wait for the staged block
-        int c = __ffs(live) - 1;
-        u32 pB = 0, mB = 0, r0 = 0;
-        uint4 v[GJ_VEC], vn[GJ_VEC];
-        if (c >= 0) {
-            pB = __shfl_sync(0xFFFFFFFFu, d_cur.x, c); mB = __shfl_sync(0xFFFFFFFFu, d_cur.y, c);
-            load_round(v, sg.positions, pB, mB, 0);
-            clear_table();                                   // while the copies land
-        }
+        if (c >= 0) clear_table();                           // while the copies land
         cp_async_wait1();
         __syncwarp();
         if (live != 0u) {
             const u32 mine_b = (live >> lane) & 1u ? d_cur.y : 0u;
-            fetched += 4ull * ((unsigned long long)mA + (unsigned long long)__reduce_add_sync(0xFFFFFFFFu, mine_b) * ((mA + GJ_ACAP - 1) / GJ_ACAP));
+            fetched += mA + __reduce_add_sync(0xFFFFFFFFu, mine_b) * ((mA + GJ_ACAP - 1) / GJ_ACAP);
             for (u32 blk0 = 0; blk0 < mA; blk0 += GJ_ACAP) {
                 const u32 nA = min((u32)GJ_ACAP, mA - blk0);
                 const u32 offA = (pA + blk0) & 3u;
                 if (blk0) {                                  // later blocks of a long slice: staged on the spot, every clause again
                     __syncwarp();
-                    const u32* src = sg.positions + (pA + blk0 - offA);
+                    const u32* src = positions + (pA + blk0 - offA);
                     for (u32 i = 4u * (u32)lane; i < nA + offA; i += 128) cp_async16(buf + i, src + i);
                     cp_async_commit();
                     clear_table();
@@ -317,7 +348,7 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
                     __syncwarp();
                     c = __ffs(live) - 1; r0 = 0;
                     pB = __shfl_sync(0xFFFFFFFFu, d_cur.x, c); mB = __shfl_sync(0xFFFFFFFFu, d_cur.y, c);
-                    load_round(v, sg.positions, pB, mB, 0);
+                    load_round(v, positions, pB, mB, 0);
                 }
                 u32* const A = buf + offA;
                 if (lane == 0) { A[nA] = 0xFFFFFFFFu; A[nA + 1] = 0xFFFFFFFFu; }
@@ -347,39 +378,37 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
                         r2 = 0;
                         if (c2 >= 0) { pB2 = __shfl_sync(0xFFFFFFFFu, d_cur.x, c2); mB2 = __shfl_sync(0xFFFFFFFFu, d_cur.y, c2); }
                     }
-                    if (c2 >= 0) load_round(vn, sg.positions, pB2, mB2, r2);
+                    if (c2 >= 0) load_round(vn, positions, pB2, mB2, r2);
                     // ---- probe this round: x = b - 1 - slop + bias is the biased low end of the window
                     const int sslop = __shfl_sync(0xFFFFFFFFu, my_slop, c);
                     const bool same = sslop < 0;
                     const u32 slop = (u32)(same ? -sslop : sslop);
                     const u32 xoff = bias - 1u - slop;
                     const u32 offB = pB & 3u, endB = offB + mB;
-                    u32 hits = 0;
+                    // (elements outside the slice -- zeros behind its end in the last vector, the previous term's last positions in
+                    //  front of an unaligned start -- are probed like the others and dropped where a flag is looked at)
+                    u32 hits = 0;                                        // two bits per element
 #pragma unroll
                     for (int q = 0; q < GJ_VEC; q++) {
                         if (r0 + (u32)(128 * q) < endB) {                              // (warp-uniform)
                             const u32 bv[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-                            u32 h4 = 0;
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
                                 const u32 x = bv[j] + xoff;
                                 const u32 word = lds32(bm_sa | ((x >> (bs + 3)) & (u32)((GJ_BM_WORDS - 1) << 2)));
                                 const u32 t = __funnelshift_r(word, 0u, x >> bs) & 3u;          // (shift count taken mod 32)
-                                h4 |= ((t + 3u) >> 2) << j;
+                                hits = t * (1u << (2 * (4 * q + j))) + hits;                      // (the multiply-add pipe is idle)
                             }
-                            // elements of the vector that belong to the slice: [offB, endB) in the aligned stream
-                            const int e0 = (int)(r0 + (u32)(128 * q + 4 * lane));
-                            const int lo_j = max((int)offB - e0, 0), hi_j = min((int)endB - e0, 4);
-                            const u32 vm = hi_j > lo_j ? ((1u << hi_j) - 1u) & ~((1u << lo_j) - 1u) : 0u;
-                            hits |= (h4 & vm) << (4 * q);
                         }
                     }
                     if (__any_sync(0xFFFFFFFFu, hits != 0u)) {
                         // flagged elements: the second hash, then the exact check on the staged block (binary search), then the document
                         const u32 g = __shfl_sync(0xFFFFFFFFu, my_g, c);
                         while (hits) {
-                            const int bit = __ffs(hits) - 1;
-                            hits &= hits - 1u;
+                            const int bit = (__ffs(hits) - 1) >> 1;
+                            hits &= ~(3u << (2 * bit));
+                            const u32 e = r0 + (u32)(128 * (bit >> 2) + 4 * lane + (bit & 3));
+                            if (e < offB || e >= endB) continue;                       // not an element of the slice
                             const u32 b = gj_sel(v, bit);
                             const u32 k0 = (b + xoff) >> bs;
                             if (((bm[gj_hash2(k0 >> 5)] >> (k0 & 31u)) & 3u) == 0u) continue;
@@ -391,9 +420,9 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
                             }
                             if (same && A[i] == b) i++;
                             if (A[i] - lo > b - 1u + slop - lo) continue;        // the bits were other buckets'
-                            const u32 jb = r0 + (u32)(128 * (bit >> 2) + 4 * lane + (bit & 3)) - offB;
-                            if (!gj_verify_staged(sg, A, nA, whole, i, pB, mB, jb, (int)slop, same, g, colmap, out))
-                                gj_verify(sg, pA, mA, blk0, nA, pB, mB, b, (int)slop, same, g, colmap, out);
+                            const u32 jb = e - offB;
+                            if (!gj_verify_staged(segs + s, A, nA, whole, i, pB, mB, jb, (int)slop, same, g, colmap, outp))
+                                gj_verify(segs + s, pA, mA, blk0, nA, pB, mB, b, (int)slop, same, g, colmap, outp);
                         }
                         __syncwarp();
                     }
@@ -404,9 +433,10 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
             }
         }
         d_cur = d_nxt; d_nxt = d_nn;
+        if (s + 1 < n_segs) open_segment(s + 1, d_cur);
     }
     cp_async_wait0();
-    if (lane == 0) atomicAdd(out.pos_bytes, fetched);        // (warp-uniform)
+    if (lane == 0) atomicAdd(outp->pos_bytes, 4ull * (unsigned long long)fetched);
 }
 
 // after the matches were sorted by (clause, column): a clause with more than GAP_LIST matches sends its read to the

@@ -1,0 +1,15 @@
+set -x
+mkdir -p gpurun_out/r2k
+timeout 600 python -m pytest tests/test_gpu_gapjoin.py -x -q > gpurun_out/r2k/pytest_gapjoin.log 2>&1; echo "rc=$?" >> gpurun_out/r2k/pytest_gapjoin.log
+tail -5 gpurun_out/r2k/pytest_gapjoin.log
+B="python bench.py --skips 5 --no-secondary --no-cpu-baseline --steps 2 --warmup 1"
+timeout 600 $B > gpurun_out/r2k/bench_default.json 2> gpurun_out/r2k/bench_default.err
+for f in gpurun_out/r2k/bench_*.json; do python - "$f" <<'PY'
+import json,sys
+try:
+    d=json.load(open(sys.argv[1])); r=d["roofline"]
+    print(sys.argv[1], "reads/s %.0f step %.1f ms join %.1f ms frac %.3f matches %d chunks %d segs %d build %.1fs" % (d["value"], d["ms_per_step"], r.get("kernel_ms_per_launch",0), r["frac"], r.get("matches",0), r.get("chunks",0), d["index"]["segments"], d["index"]["build_seconds"]))
+except Exception as e:
+    print(sys.argv[1], "failed", e)
+PY
+done
