@@ -84,19 +84,22 @@ class ClockSampler(threading.Thread):
 
 
 def measured_traffic(args, kernel):
-    """dram__bytes_read+write per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r1_ncu_kernel_metrics.json); only valid for the workload the capture was taken on"""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_kernel_metrics.json")) as f:
-            m = json.load(f)["r1j_filter_final_C2"]
-        if args.workload != "C2" or kernel != "filter_score_kernel" or args.algorithm != "PAIRED_PROXIMITY":
-            return None
-        def gb(k):
-            v, u = float(m[k]["value"]), m[k]["unit"]
-            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
-        return gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
-    except Exception:
+    """dram__bytes_read+write per launch of the dominant kernel from the committed `ncu --set full` capture of the same kernel
+    on the same workload (profiles/r2_ncu_kernel_metrics.json, else round 1's); only valid for that workload"""
+    if args.workload != "C2" or kernel != "filter_score_kernel" or args.algorithm != "PAIRED_PROXIMITY":
         return None
+    for fn, key in (("r2_ncu_kernel_metrics.json", "r2_filter_final_C2"), ("r1_ncu_kernel_metrics.json", "r1j_filter_final_C2")):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                m = json.load(f)[key]
+
+            def gb(k):
+                v, u = float(m[k]["value"]), m[k]["unit"]
+                return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+            return gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
+        except Exception:
+            continue
+    return None
 
 
 def shipped_config(**kw):
@@ -585,13 +588,23 @@ def large_k_line(k, dev, local, peak, peak_src):
         layout = clf.layout()
         st = clf.stats()
         roof = route_roofline(cnt, cost, layout, st["n_docs"], total, kernel_ms / 1e3 / 2, peak, peak_src)
+        # k > 12: every (token, segment) costs a probe of the segment's open-addressing dictionary -- at least the 32-byte sector of
+        # the key slot -- before any posting is read, and a 16-mer is present in about one segment only: the probes, not the
+        # postings of SURVEY 8(d)'s A_read, are what this path fetches
+        probes = cost["tokens"] * layout["segments"]
+        alg = cost["bytes_csr"] + 32 * probes
+        ks = kernel_ms / 1e3 / 2
+        roof.update(algorithmic_bytes_per_launch=alg, achieved=alg / ks / 1e9 if ks > 0 else 0.0, frac=(alg / ks / 1e9 / peak) if ks > 0 else 0.0,
+                    byte_model="A_read (SURVEY.md 8d) + one 32-byte sector per (token, segment) dictionary probe; latency-bound random access",
+                    dictionary_probes_per_s=probes / ks if ks > 0 else 0.0)
         src_doc = 2 * data["src"].astype(np.int64)
         top = o["top_doc"][:, 0].cpu().numpy()
         return {"name": "k=%d (hash dictionary + CSR postings), mid reference: %d genomes / %.1f Gbp" % (k, wl["genomes"], wl["total_bp"] / 1e9),
                 "reads": n, "value": n * 2 / el, "unit": "reads/s", "ms_per_step": el / 2 * 1e3, "build_seconds": t_build,
                 "index": dict(st, **layout), "source_doc_is_top_hit": float((top == src_doc).mean()),
                 "routes": {"filter": cnt["filter_reads"], "exact_dense": cnt["dense_reads"], "positional": cnt["positional_reads"]},
-                "roofline": {k_: roof[k_] for k_ in ("kernel", "achieved", "frac", "algorithmic_bytes_per_launch", "byte_model", "kernel_ms_per_launch")}}
+                "roofline": {k_: roof[k_] for k_ in ("kernel", "achieved", "frac", "algorithmic_bytes_per_launch", "byte_model", "kernel_ms_per_launch",
+                                                     "dictionary_probes_per_s")}}
     finally:
         clf.close()
 
@@ -879,7 +892,9 @@ def main():
         if world == 1 and not args.no_secondary and args.k == 10:
             del data["d_seq"], data["d_off"]
             torch.cuda.empty_cache()
-            line["secondary"].append(large_k_line(16, dev, local, *peaks()))
+            for k_big in (16, 20):            # benchmark/scripts/run.py:137-171 sweeps k = 5..24
+                line["secondary"].append(large_k_line(k_big, dev, local, *peaks()))
+                torch.cuda.empty_cache()
         if want_cpu:
             n_cpu = int(os.environ.get("BSP_CPU_SAMPLE_READS", 200000))
             points, arm, (dt, res_o) = cpu_arm_points(wl, lengths, data["kept"], S, n_cpu, ALG_ID[args.algorithm], skips=args.skips,
