@@ -6,10 +6,12 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library; the product (biospectra_b200/) never does.
  *
- * PARITY UNPINNED: the reference ships no tests or golden outputs and cannot run
- * here (no JVM).  This file is pinned by (1) the hand-traced known answers of
- * SURVEY.md Appendix B and (2) bit-for-bit agreement with the literal Python spec
- * oracle (oracle/spec_oracle.py) on randomized corpora (tests/test_oracle_*.py).
+ * PARITY PINNED BY EXECUTION: the reference ships no tests or golden outputs and no JVM
+ * exists here; oracle/minijvm.py executes the reference's own lucene-core-5.3.1.jar /
+ * fasta-utils-1.1.jar and tests/golden/lucene_*.json holds what they returned.  This file
+ * must reproduce those vectors bit for bit (tests/test_lucene_golden.py), agree bit for bit
+ * with the literal Python spec oracle (oracle/spec_oracle.py) on randomized corpora
+ * (tests/test_oracle_cross.py) and with SURVEY.md Appendix B (tests/test_oracle_kat.py).
  *
  * Citations: paths are relative to /root/reference; "lucene!X#m" means class X,
  * method m of libs/lucene-core-5.3.1.jar (restated from the class files,

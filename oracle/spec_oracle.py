@@ -6,10 +6,15 @@ path and of the Lucene 5.3.1 arithmetic it delegates to.  Written to be
 only.  The fast C oracle (oracle/bsp_oracle.c) and the CUDA path are both
 checked against it.
 
-PARITY UNPINNED: the reference ships no tests / golden outputs and cannot be
-executed here (no JVM); the Lucene rules below were restated from the 5.3.1
-class files and are pinned only by the hand-traced
-known-answer values of SURVEY.md Appendix B (tests/test_oracle_kat.py).
+PARITY PINNED BY EXECUTION: the reference ships no tests / golden outputs and no
+JVM exists here, so oracle/minijvm.py executes the reference's own class files
+(libs/lucene-core-5.3.1.jar, fasta-utils-1.1.jar) and tests/golden/lucene_*.json
+holds what they returned (SmallFloat, DefaultSimilarity / BM25Similarity,
+SloppyPhraseScorer#phraseFreq, whole IndexSearcher.search runs, FASTAReader);
+tests/test_lucene_golden.py requires this oracle to reproduce every vector bit for
+bit.  The two Java *source* files on the path (KmerSequenceTokenizer.java,
+Classifier.java) are restated below line by line (no compiler here); SURVEY.md
+Appendix B's tokenizer / clause-count rows check them (tests/test_oracle_kat.py).
 
 Every function cites the reference file:line (relative to /root/reference) or
 the Lucene class#method it follows.  All float32 arithmetic goes through

@@ -8,7 +8,7 @@
 #   tools/ref_lucene_run.sh <reference checkout> <workdir> [make_parity_corpus.py options]
 set -euo pipefail
 if ! command -v java >/dev/null || ! command -v javac >/dev/null; then
-    echo "java/javac not found: the reference cannot run here, parity stays unpinned" >&2
+    echo "java/javac not found: the reference cannot run here (side-by-side parity stays unpinned; the oracle is pinned by tests/golden/lucene_*.json)" >&2
     exit 3
 fi
 REF=${1:?reference checkout}; WORK=${2:?work directory}; shift 2
