@@ -436,7 +436,8 @@ def gap_join_roofline(gj, peak, peak_src):
             "peak_source": peak_src, "algorithmic_bytes_per_launch": gj["position_bytes"], "kernel_ms_per_launch": gj["join_kernel_ms"],
             "byte_model": "4 B x positions: per (chunk of <= 8 clauses sharing the first k-mer, segment) that k-mer's slice once + every "
                           "clause's second k-mer slice; directory lookups (8 B per term and segment) not counted",
-            "clauses": gj["clauses"], "chunks": gj["chunks"], "matches": gj["matches"]}
+            "clauses": gj["clauses"], "chunks": gj["chunks"], "matches": gj["matches"], "candidates": gj.get("candidates"),
+            "verify_kernel_ms_per_launch": gj.get("verify_kernel_ms")}
 
 
 def route_roofline(cnt, cost, layout, n_docs, total_read_bytes, kernel_s, peak, peak_src, traffic=None, gap_join=None):
@@ -505,7 +506,7 @@ def secondary_lines(clf, data, o, dev, local, n, peak, peak_src, main_kw, n_docs
                     "routes": {"filter": cnt["filter_reads"], "exact_dense": cnt["dense_reads"], "positional": cnt["positional_reads"]},
                     "classified_fraction": float(((o["label"][:m] == 2) & ok).sum() / max(int(ok.sum()), 1)),
                     "roofline": {k_: roof[k_] for k_ in ("kernel", "achieved", "frac", "algorithmic_bytes_per_launch", "byte_model",
-                                                         "kernel_ms_per_launch", "clauses", "chunks", "matches") if k_ in roof}})
+                                                         "kernel_ms_per_launch", "clauses", "chunks", "matches", "candidates", "verify_kernel_ms_per_launch") if k_ in roof}})
     clf.set_query(shipped_config(device=local, **main_kw))
     return out
 

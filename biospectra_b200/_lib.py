@@ -99,7 +99,7 @@ def lib():
     L.bsp_last_routes.argtypes = [vp, C.c_int32, vp]
     L.bsp_last_counters.argtypes = [vp, vp]
     L.bsp_last_timings.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
-    L.bsp_last_gap_join.argtypes = [vp, vp, C.POINTER(C.c_double)]
+    L.bsp_last_gap_join.argtypes = [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.bsp_memory_info.argtypes = [vp, i64p, i64p, i64p]
     L.bsp_partition_df_buffer.argtypes = [vp, C.POINTER(vp), i64p]
     L.bsp_partition_local_stats.argtypes = [vp, i64p, i64p]

@@ -57,7 +57,7 @@ struct Scratch {
     i64 gc = 0, gc_min = 0;             // capacity of `gaps`; what the last overflow asked for
     DevBuf<u32> gj_keys, gj_keys_alt, gj_vals, gj_vals_alt, gj_mg, gj_mcol, gj_v, gj_v_alt; DevBuf<uint2> gj_chunks;
     DevBuf<float> gj_mfreq; DevBuf<u64> gj_k64, gj_k64_alt; DevBuf<unsigned long long> gj_bytes;
-    RadixSortTemp gj_rst; DevBuf<GjOut> gj_out; DevBuf<u32> gj_sizes;
+    RadixSortTemp gj_rst; DevBuf<u32> gj_sizes; DevBuf<GjCand> gj_cand;
     const u8* in_seq = nullptr; const i64* in_off = nullptr; i64 in_bytes = 0;   // phase 1 inputs (re-run when `gaps` was too short)
     DevBuf<i32> pos_slot;               // read -> index in list_pos (the positional scorer's partial lists are per list entry)
     DevBuf<i32> ppart_n; DevBuf<u32> ppart_doc; DevBuf<float> ppart_score;
@@ -146,7 +146,7 @@ struct bsp_classifier {
     i64 counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double score_ms = 0, pipe_ms = 0;
     // gap join of the last batch: clauses, chunks, matches, position bytes fetched, kernel time; tail entries wanted next time
-    i64 gj_clauses = 0, gj_chunks = 0, gj_matches = 0, gj_bytes = 0; double gj_ms = 0; size_t gap_tail_want = 0;
+    i64 gj_clauses = 0, gj_chunks = 0, gj_matches = 0, gj_bytes = 0, gj_cands = 0; double gj_ms = 0, gj_verify_ms = 0; size_t gap_tail_want = 0;
     ~bsp_classifier() { delete ref; }
 };
 
@@ -285,6 +285,22 @@ static std::string rd_str(FILE* f) {
     std::string s(n, '\0'); rd(f, &s[0], n); return s;
 }
 
+// Two page-locked bounce buffers for the index file: the copy of one chunk to / from the device overlaps the file I/O of
+// the other (truly asynchronous copies need page-locked memory; the round-1 code went through one pageable buffer with a
+// stream synchronize per 64 MB).
+struct IoRing {
+    static constexpr size_t CH = (size_t)16 << 20;      // words per chunk
+    u32* buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    IoRing() {
+        for (int i = 0; i < 2; i++) {
+            CUDA_CHECK(cudaMallocHost((void**)&buf[i], CH * 4));
+            CUDA_CHECK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+    }
+    ~IoRing() { for (int i = 0; i < 2; i++) { if (buf[i]) cudaFreeHost(buf[i]); if (ev[i]) cudaEventDestroy(ev[i]); } }
+};
+
 static void write_index_file(const std::string& dir, RefStore& ref, cudaStream_t st) {
     std::string tmp = dir + "/" + IDX_FILE + ".tmp", fin = dir + "/" + IDX_FILE;
     FILE* f = fopen(tmp.c_str(), "wb");
@@ -297,16 +313,24 @@ static void write_index_file(const std::string& dir, RefStore& ref, cudaStream_t
             wr(f, v, sizeof v);
             wr_str(f, m.filename); wr_str(f, m.header); wr_str(f, m.taxonomy);
         }
-        const size_t CH = (size_t)16 << 20;     // words per copy
-        std::vector<u32> buf(CH);
+        IoRing ring;
+        const size_t CH = IoRing::CH;
         for (int which = 0; which < 2; which++) {
             const u32* src = which == 0 ? ref.packed.p : ref.mask.p;
             size_t words = (size_t)(which == 0 ? ref.used_bases / 16 : ref.used_bases / 32);
-            for (size_t o = 0; o < words; o += CH) {
-                size_t n = std::min(CH, words - o);
-                CUDA_CHECK(cudaMemcpyAsync(buf.data(), src + o, n * 4, cudaMemcpyDeviceToHost, st));
-                CUDA_CHECK(cudaStreamSynchronize(st));
-                wr(f, buf.data(), n * 4);
+            const size_t chunks = (words + CH - 1) / CH;
+            // chunk c travels to the host while chunk c - 1 is written to the file
+            for (size_t c = 0; c <= chunks; c++) {
+                if (c < chunks) {
+                    const size_t o = c * CH, n = std::min(CH, words - o);
+                    CUDA_CHECK(cudaMemcpyAsync(ring.buf[c & 1], src + o, n * 4, cudaMemcpyDeviceToHost, st));
+                    CUDA_CHECK(cudaEventRecord(ring.ev[c & 1], st));
+                }
+                if (c > 0) {
+                    const size_t o = (c - 1) * CH, n = std::min(CH, words - o);
+                    CUDA_CHECK(cudaEventSynchronize(ring.ev[(c - 1) & 1]));
+                    wr(f, ring.buf[(c - 1) & 1], n * 4);
+                }
             }
         }
         if (fflush(f) != 0) throw BspError(BSP_ERR_IO, "flush failed");
@@ -360,20 +384,24 @@ static RefStore* read_index_file(const std::string& dir, int part_rank, int part
         i64 b1 = e1 < nE ? all[e1].base_off : used;
         i64 span = b1 - b0;
         ref->reserve_bases(span + 128, st);
-        const size_t CH = (size_t)16 << 20;
-        std::vector<u32> buf(CH);
+        IoRing ring;
+        const size_t CH = IoRing::CH;
         for (int which = 0; which < 2; which++) {
             u32* dst = which == 0 ? ref->packed.p : ref->mask.p;
             i64 per = which == 0 ? 16 : 32;
             i64 file_base = data_pos + (which == 0 ? 0 : (used / 16) * 4);
             size_t words = (size_t)(span / per);
             if (fseek(f, file_base + (b0 / per) * 4, SEEK_SET) != 0) throw BspError(BSP_ERR_IO, "seek failed");
-            for (size_t o = 0; o < words; o += CH) {
+            // chunk c is read from the file while chunk c - 1 travels to the device
+            size_t c = 0;
+            for (size_t o = 0; o < words; o += CH, c++) {
                 size_t n = std::min(CH, words - o);
-                rd(f, buf.data(), n * 4);
-                CUDA_CHECK(cudaMemcpyAsync(dst + o, buf.data(), n * 4, cudaMemcpyHostToDevice, st));
-                CUDA_CHECK(cudaStreamSynchronize(st));
+                if (c >= 2) CUDA_CHECK(cudaEventSynchronize(ring.ev[c & 1]));       // the buffer's previous copy has left it
+                rd(f, ring.buf[c & 1], n * 4);
+                CUDA_CHECK(cudaMemcpyAsync(dst + o, ring.buf[c & 1], n * 4, cudaMemcpyHostToDevice, st));
+                CUDA_CHECK(cudaEventRecord(ring.ev[c & 1], st));
             }
+            CUDA_CHECK(cudaStreamSynchronize(st));
         }
         for (u64 e = e0; e < e1; e++) {
             EntryMeta m = std::move(all[e]);
@@ -627,6 +655,8 @@ struct BatchOut {     // device pointers (any may be null except status)
     i32 *status, *label, *n_hits, *n_top, *top_doc; float* top_score;
 };
 
+static bool ensure_gap_directory(bsp_classifier* h, cudaStream_t st);
+
 // ---- the device pipeline of one sub-batch, in two phases so that two sub-batches can be in flight:
 //   phase 1 (enqueue only): tokenize -> df -> weights/routing -> route lists; the route counts travel to a pinned mailbox
 //   phase 2: wait for the counts, launch the scorers (grid sizes depend on the counts), merge; everything on sc.st
@@ -659,6 +689,8 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     qp.positional_ok = ix.positional ? 1 : 0;
     qp.pair_row0 = ix.pair_row0;
     qp.gap_ok = qp.dense_ok && ix.has_pair && ix.positional && env_i64("BSP_DISABLE_GAP", 0) == 0;
+    // (the join's position directory is built the first time a batch may carry gap clauses; without it they take the positional scorer)
+    if (qp.gap_ok && qp.alg != ALG_NAIVE && !ensure_gap_directory(h, st)) qp.gap_ok = 0;
     qp.temp_row0 = (u32)ix.n_rows + 1;
     // Gap clauses of the sub-batch.  With kmer_skips > 0 every phrase clause is one (about len / (skips + 1) tokens per read);
     // otherwise only the clauses next to an N are.  A list that turns out too short is grown and phase 1 runs again
@@ -723,11 +755,22 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
 }
 
 // (start, length) directory of the positional index for the gap join; built once per handle, on first use
-static void ensure_gap_directory(bsp_classifier* h, cudaStream_t st) {
+static bool ensure_gap_directory(bsp_classifier* h, cudaStream_t st) {
     GpuIndex& ix = h->ix;
-    if (ix.pse.p) return;
+    if (ix.pse.p) return true;
+    if (ix.gap_join_off) return false;
     const u64 nt = 1ull << (2 * ix.k);
     const size_t S = ix.segs.size();
+    {
+        // 8 B x 4^k x segments: 0.64 GB at C2 (k = 10, 76 segments), 10 GB at k = 12 -- only where it fits comfortably
+        size_t free_b = 0, total_b = 0;
+        CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        if ((double)nt * (double)std::max<size_t>(S, 1) * 8.0 > 0.4 * (double)free_b) {
+            ix.gap_join_off = true;
+            ix.notes += "gap join off: its position directory does not fit; ";
+            return false;
+        }
+    }
     ix.pse.alloc((size_t)nt * std::max<size_t>(S, 1));
     CUDA_CHECK(cudaMemsetAsync(ix.pse.p, 0, ix.pse.bytes(), st));
     std::vector<GjSeg> gs(S);
@@ -751,6 +794,7 @@ static void ensure_gap_directory(bsp_classifier* h, cudaStream_t st) {
     ix.positional_bytes += ix.pse.bytes();
     CUDA_CHECK(cudaFuncSetAttribute(gap_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GJ_SMEM_BYTES));
     CUDA_CHECK(cudaFuncSetAttribute(gap_join_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return true;
 }
 
 // Room for the gap-clause match lists behind the exception arrays (`entries` per pipeline slot).  Called with every slot idle.
@@ -773,7 +817,7 @@ static void ensure_gap_tail(bsp_classifier* h, size_t entries) {
 // before a batch: with kmer_skips > 0 every phrase clause is a gap clause -- about `clauses` of them per sub-batch
 static void prepare_gap_tail(bsp_classifier* h, i64 clauses) {
     size_t want = h->gap_tail_want;
-    if (h->conf.kmer_skips > 0 && h->conf.query_algorithm != BSP_NAIVE_KMER) want = std::max<size_t>(want, (size_t)clauses * 4);
+    if (h->conf.kmer_skips > 0 && h->conf.query_algorithm != BSP_NAIVE_KMER) want = std::max<size_t>(want, (size_t)clauses * 6);
     ensure_gap_tail(h, want);
 }
 
@@ -782,11 +826,10 @@ static void prepare_gap_tail(bsp_classifier* h, i64 clauses) {
 static void gap_join(bsp_classifier* h, Scratch& sc, u32 n_g) {
     GpuIndex& ix = h->ix;
     cudaStream_t st = sc.st;
-    ensure_gap_directory(h, st);
     sc.gj_keys.ensure(n_g); sc.gj_keys_alt.ensure(n_g); sc.gj_vals.ensure(n_g); sc.gj_vals_alt.ensure(n_g); sc.gj_chunks.ensure(n_g);
     u32 *keys = sc.gj_keys.p, *keys_alt = sc.gj_keys_alt.p, *vals = sc.gj_vals.p, *vals_alt = sc.gj_vals_alt.p;
-    cudaEvent_t e0, e1;
-    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    cudaEvent_t e0, e1, e2;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreate(&e2));
     gj_keys_kernel<<<(unsigned)ceil_div(n_g, 256), 256, 0, st>>>(sc.gaps.p, n_g, keys, vals);
     radix_sort_pairs<u32>(&keys, &vals, &keys_alt, &vals_alt, n_g, 2 * ix.k, sc.gj_rst, st);
     sc.gj_sizes.ensure(32);
@@ -799,29 +842,39 @@ static void gap_join(bsp_classifier* h, Scratch& sc, u32 n_g) {
     CUDA_CHECK(cudaStreamSynchronize(st));
     const u32 n_chunks = (u32)sc.h_counts[7];
     const u32 cap = (u32)std::min<size_t>(ix.gap_tail, 0xFFFFFFF0u);
-    sc.gj_mg.ensure(cap); sc.gj_mcol.ensure(cap); sc.gj_mfreq.ensure(cap);
+    sc.gj_mg.ensure(cap); sc.gj_mcol.ensure(cap); sc.gj_mfreq.ensure(cap); sc.gj_cand.ensure(cap);
     CUDA_CHECK(cudaMemsetAsync(sc.gj_bytes.p, 0, 8, st));
     GjOut out;
     out.g = sc.gj_mg.p; out.col = sc.gj_mcol.p; out.freq = sc.gj_mfreq.p; out.cap = cap;
     out.n_match = sc.gap_ctr.p + 1; out.pos_bytes = sc.gj_bytes.p;
-    sc.gj_out.ensure(1);
-    CUDA_CHECK(cudaMemcpyAsync(sc.gj_out.p, &out, sizeof out, cudaMemcpyHostToDevice, st));     // (pageable source: staged before the call returns)
     CUDA_CHECK(cudaEventRecord(e0, st));
-    if (n_chunks)
+    if (n_chunks) {
+        // the join appends candidates (clause, segment, occurrence); a thread per candidate then does the per-document work
         gap_join_kernel<<<(unsigned)ceil_div(n_chunks, GJ_WARPS), GJ_WARPS * 32, GJ_SMEM_BYTES, st>>>(
-            ix.d_gjsegs.p, (int)ix.segs.size(), ix.pse.p, 1ull << (2 * ix.k), sc.gaps.p, vals, sc.gj_chunks.p, sc.gap_ctr.p + 2, ix.colmap.p, sc.gj_out.p);
+            ix.d_gjsegs.p, (int)ix.segs.size(), ix.pse.p, 1ull << (2 * ix.k), sc.gaps.p, vals, sc.gj_chunks.p, sc.gap_ctr.p + 2,
+            sc.gj_cand.p, sc.gap_ctr.p + 3, cap, sc.gj_bytes.p, sc.route.p, sc.status_in.p, sc.qp.positional_ok);
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        gj_verify_kernel<<<(unsigned)ceil_div(cap, 256), 256, 0, st>>>(sc.gj_cand.p, sc.gap_ctr.p + 3, cap, ix.d_gjsegs.p, ix.pse.p,
+                                                                       1ull << (2 * ix.k), sc.gaps.p, ix.colmap.p, out);
+    } else {
+        CUDA_CHECK(cudaEventRecord(e1, st));
+    }
     KERNEL_CHECK();
-    CUDA_CHECK(cudaEventRecord(e1, st));
+    CUDA_CHECK(cudaEventRecord(e2, st));
     unsigned long long pos_bytes = 0;
     CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 8, sc.gap_ctr.p + 1, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(sc.h_counts + 9, sc.gap_ctr.p + 3, 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(&pos_bytes, sc.gj_bytes.p, 8, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    float ms = 0;
+    float ms = 0, ms_v = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaEventElapsedTime(&ms_v, e1, e2);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     u32 n_m = (u32)sc.h_counts[8];
-    const int overflow = n_m > cap ? 1 : 0;
-    if (overflow) { h->gap_tail_want = std::max<size_t>(h->gap_tail_want, (size_t)n_m * 2); n_m = 0; }   // more room next batch
+    const u32 n_cand = (u32)sc.h_counts[9];
+    const int overflow = (n_m > cap || n_cand > cap) ? 1 : 0;
+    if (overflow) { h->gap_tail_want = std::max<size_t>(h->gap_tail_want, (size_t)std::max(n_m, n_cand) * 2); n_m = 0; }   // more room next batch
+    h->gj_cands += n_cand; h->gj_verify_ms += ms_v;
     h->gj_clauses += n_g; h->gj_chunks += n_chunks; h->gj_matches += n_m; h->gj_bytes += (i64)pos_bytes; h->gj_ms += ms;
     const u32 tmp_base = (u32)ix.n_exc + (u32)((size_t)sc.slot_index * ix.gap_tail);
     sc.gj_k64.ensure(std::max<u32>(n_m, 1)); sc.gj_k64_alt.ensure(std::max<u32>(n_m, 1));
@@ -1028,7 +1081,7 @@ static void classify_on_device(bsp_classifier* h, i32 n, const u8* d_seq, const 
                                const BatchOut& out) {
     Scratch& sc = h->sc[0];
     prepare_gap_tail(h, total_bytes / (h->conf.kmer_skips + 1) + 2 * (i64)n);
-    h->gj_clauses = h->gj_chunks = h->gj_matches = h->gj_bytes = 0; h->gj_ms = 0;
+    h->gj_clauses = h->gj_chunks = h->gj_matches = h->gj_bytes = h->gj_cands = 0; h->gj_ms = h->gj_verify_ms = 0;
     pipeline_phase1(h, sc, n, d_seq, d_seq_off, total_bytes);
     pipeline_phase2a(h, sc);
     pipeline_phase2b(h, sc, out);
@@ -1085,7 +1138,7 @@ static int classify_packed_impl(bsp_classifier* h, i32 n, const char* seq_bytes,
         const i64 bytes0 = n > 0 ? (seq_offsets[n] - seq_offsets[0]) / std::max(1, n) * m0 : 0;
         prepare_gap_tail(h, bytes0 / (h->conf.kmer_skips + 1) + 2 * (i64)m0);
     }
-    h->gj_clauses = h->gj_chunks = h->gj_matches = h->gj_bytes = 0; h->gj_ms = 0;
+    h->gj_clauses = h->gj_chunks = h->gj_matches = h->gj_bytes = h->gj_cands = 0; h->gj_ms = h->gj_verify_ms = 0;
     // Software pipeline over sub-batches, BSP_SLOTS slots.  Iteration i copies sub-batch i in and queues its tokenizer /
     // weights (phase 1), launches the scorer of sub-batch i-1 (phase 2a: its route counts arrived while sub-batch i-2
     // was being scored) and only then waits for the scorer of sub-batch i-2 to finish, merges and copies it out (phase
@@ -1454,11 +1507,13 @@ BSP_API int bsp_last_timings(bsp_classifier* h, double* score_kernel_ms, double*
     return BSP_OK;
 }
 
-BSP_API int bsp_last_gap_join(bsp_classifier* h, int64_t out[4], double* join_kernel_ms) {
+BSP_API int bsp_last_gap_join(bsp_classifier* h, int64_t out[4], double* join_kernel_ms, double* verify_kernel_ms, int64_t* candidates) {
     if (!h || !out) return fail(nullptr, BSP_ERR_ARG, "null argument");
     std::lock_guard<std::mutex> lk(h->mu);
     out[0] = h->gj_clauses; out[1] = h->gj_chunks; out[2] = h->gj_matches; out[3] = h->gj_bytes;
     if (join_kernel_ms) *join_kernel_ms = h->gj_ms;
+    if (verify_kernel_ms) *verify_kernel_ms = h->gj_verify_ms;
+    if (candidates) *candidates = h->gj_cands;
     return BSP_OK;
 }
 

@@ -142,67 +142,40 @@ __device__ __forceinline__ u32 gj_lower_bound(const u32* __restrict__ P, u32 n, 
     return lo;
 }
 
-// One lane, one hit: occurrence b of the second term has an occurrence of the first one within the slop somewhere in
-// the staged block.  Exact evaluation on the global slices; the document is reported by the first of its occurrences
-// of t1 that has a close partner inside the document, and (slices staged block by block) by the block that holds that
-// partner.
-__device__ __noinline__ void gj_verify(const GjSeg* __restrict__ sgp, u32 pA, u32 mA, u32 blk0, u32 blk_n, u32 pB, u32 mB, u32 b, int slop,
-                                       bool same, u32 g, const u32* __restrict__ colmap, const GjOut* __restrict__ outp) {
-    const GjSeg sg = *sgp;
-    const GjOut out = *outp;
-    u32 lo = 0, hi = sg.n_docs;                            // last doc whose first ordinal is <= b
-    while (hi - lo > 1) {
-        const u32 mid = (lo + hi) >> 1;
-        if (sg.doc_tok[mid] <= b) lo = mid; else hi = mid;
-    }
-    const u32 d = lo, ds = sg.doc_tok[d], de = sg.doc_tok[d + 1];
-    const u32* A = sg.positions + pA;
-    const u32* B = sg.positions + pB;
-    const u32 ia0 = gj_lower_bound(A, mA, ds), ia1 = gj_lower_bound(A, mA, de);
-    if (ia0 == ia1) return;
-    const u32 jb0 = gj_lower_bound(B, mB, ds), jb1 = gj_lower_bound(B, mB, de);
-    bool mine = false;
-    for (u32 j = jb0; j < jb1; j++) {
-        const u32 bb = B[j];
-        u32 partner = 0xFFFFFFFFu;
-        for (u32 i = ia0; i < ia1; i++) {
-            const u32 a = A[i];
-            if (same && a == bb) continue;
-            const int dist = (int)bb - 1 - (int)a;
-            if (dist >= -slop && dist <= slop) { partner = i; break; }
-        }
-        if (partner != 0xFFFFFFFFu) {
-            mine = bb == b && partner >= blk0 && partner < blk0 + blk_n;
-            break;
-        }
-        if (bb >= b) break;                                // b has no partner inside its own document
-    }
-    if (!mine) return;
-    const float f = same ? sloppy_freq_same(A + ia0, (int)(ia1 - ia0), slop)
-                         : sloppy_freq_distinct(A + ia0, (int)(ia1 - ia0), B + jb0, (int)(jb1 - jb0), slop);
-    if (f != 0.0f) {
-        const u32 at = atomicAdd(out.n_match, 1u);
-        if (at < out.cap) { out.g[at] = g; out.col[at] = colmap[sg.doc_base + d]; out.freq[at] = f; }
-    }
-}
+// Candidates: (clause, segment, index of an occurrence b of the second k-mer) for which the join found an occurrence of the
+// first k-mer inside the window [b - 1 - slop, b - 1 + slop] -- each (clause, segment, b) at most once.  The join only
+// appends them; gj_verify_kernel (thread per candidate) does everything that needs the document: which document b lies in
+// (bucket LUT), both k-mers' positions inside it (binary search / short scans on the global slices), whether b is the
+// first of the document's occurrences with a partner INSIDE the document (that one reports the document; a partner in the
+// neighbouring document is no match), the literal sweep (sloppy_freq_distinct / _same), and the append of
+// (clause, table column, frequency).
+struct GjCand { u32 g, seg, jb; };
 
-// The common case of a hit, on the staged block: the document from the segment's bucket LUT, the first term's positions
-// inside it by a short scan around the hit in shared memory, the second term's by a short scan in global memory (just
-// fetched: L2).  Returns false when the scan reaches the edge of a partially staged slice (the caller takes gj_verify).
-__device__ __noinline__ bool gj_verify_staged(const GjSeg* __restrict__ sgp, const u32* A, u32 nA, bool whole, u32 i, u32 pB, u32 mB, u32 jb,
-                                                 int slop, bool same, u32 g, const u32* __restrict__ colmap, const GjOut* __restrict__ outp) {
-    const GjSeg sg = *sgp;
-    const u32* B = sg.positions + pB;
+__global__ void __launch_bounds__(256) gj_verify_kernel(const GjCand* __restrict__ cand, const u32* __restrict__ n_cand, u32 cand_cap,
+                                                         const GjSeg* __restrict__ segs, const uint2* __restrict__ pse, u64 n_terms,
+                                                         const GapClause* __restrict__ gaps, const u32* __restrict__ colmap, const GjOut out) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= min(*n_cand, cand_cap)) return;
+    const GjCand c = cand[t];
+    const GapClause gc = gaps[c.g];
+    const GjSeg sg = segs[c.seg];
+    const uint2 dA = __ldg(pse + (u64)c.seg * n_terms + gc.k0), dB = __ldg(pse + (u64)c.seg * n_terms + gc.k1);
+    const bool same = gc.k0 == gc.k1;
+    const int slop = gc.slop;
+    const u32* A = sg.positions + dA.x;
+    const u32* B = sg.positions + dB.x;
+    const u32 mA = dA.y, mB = dB.y, jb = c.jb;
     const u32 b = B[jb];
     u32 d = sg.doc_lut[b >> GJ_LUT_SHIFT];
     while (sg.doc_tok[d + 1] <= b) d++;
     const u32 ds = sg.doc_tok[d], de = sg.doc_tok[d + 1];
-    u32 ia0 = i;                                                 // [ia0, ia1): the first term's positions inside the document
-    if (A[i] >= ds) { while (ia0 > 0 && A[ia0 - 1] >= ds) ia0--; }
-    else { while (A[ia0] < ds) ia0++; }                          // (sentinels behind the block)
+    // the first k-mer's positions inside the document: from the lower bound of the window's low end, outwards
+    const u32 lo = b > (u32)slop + 1u ? b - 1u - (u32)slop : 0u;
+    u32 ia0 = gj_lower_bound(A, mA, max(lo, ds));
+    while (ia0 > 0 && A[ia0 - 1] >= ds) ia0--;
     u32 ia1 = ia0;
-    while (A[ia1] < de) ia1++;
-    if (!whole && (ia0 == 0 || ia1 >= nA)) return false;
+    while (ia1 < mA && A[ia1] < de) ia1++;
+    if (ia0 == ia1) return;
     u32 jb0 = jb, jb1 = jb + 1;
     while (jb0 > 0 && B[jb0 - 1] >= ds) jb0--;
     while (jb1 < mB && B[jb1] < de) jb1++;
@@ -218,15 +191,13 @@ __device__ __noinline__ bool gj_verify_staged(const GjSeg* __restrict__ sgp, con
         }
         if (partner) { mine = j == jb; break; }
     }
-    if (!mine) return true;
+    if (!mine) return;
     const float f = same ? sloppy_freq_same(A + ia0, (int)(ia1 - ia0), slop)
                          : sloppy_freq_distinct(A + ia0, (int)(ia1 - ia0), B + jb0, (int)(jb1 - jb0), slop);
     if (f != 0.0f) {
-        const GjOut out = *outp;
         const u32 at = atomicAdd(out.n_match, 1u);
-        if (at < out.cap) { out.g[at] = g; out.col[at] = colmap[sg.doc_base + d]; out.freq[at] = f; }
+        if (at < out.cap) { out.g[at] = c.g; out.col[at] = colmap[sg.doc_base + d]; out.freq[at] = f; }
     }
-    return true;
 }
 
 __device__ __forceinline__ u32 gj_sel(const uint4 (&v)[GJ_VEC], int bit) {      // element `bit` of the round's registers
@@ -240,7 +211,8 @@ __device__ __forceinline__ u32 gj_hash2(u32 word_index) { return ((word_index * 
 __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
         const GjSeg* __restrict__ segs, int n_segs, const uint2* __restrict__ pse, u64 n_terms,
         const GapClause* __restrict__ gaps, const u32* __restrict__ order, const uint2* __restrict__ chunks,
-        const u32* __restrict__ n_chunks, const u32* __restrict__ colmap, const GjOut* __restrict__ outp) {
+        const u32* __restrict__ n_chunks, GjCand* __restrict__ cand, u32* __restrict__ n_cand, u32 cand_cap,
+        unsigned long long* __restrict__ pos_bytes, i32* __restrict__ route, i32* __restrict__ status, int positional_ok) {
     extern __shared__ __align__(16) u8 gj_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 w = blockIdx.x * GJ_WARPS + warp;
@@ -351,6 +323,7 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
                     load_round(v, positions, pB, mB, 0);
                 }
                 u32* const A = buf + offA;
+                const u32 prev_last = blk0 ? positions[pA + blk0 - 1u] : 0u;             // last position of the block before this one
                 if (lane == 0) { A[nA] = 0xFFFFFFFFu; A[nA + 1] = 0xFFFFFFFFu; }
                 // ---- bit table (a Bloom filter with two hashes of the word index): bucket k = (a + bias) >> bs sets bit k & 31 of
                 // words h1(k >> 5) and h2(k >> 5); bit 31 of a word also stands for bucket 0 of the next one, so that the two
@@ -366,7 +339,6 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
                     }
                 }
                 __syncwarp();
-                const bool whole = mA <= (u32)GJ_ACAP;
                 const int steps = 32 - __clz(nA);            // binary search steps: 2^steps > nA
                 u32 todo = live;
                 while (c >= 0) {
@@ -418,11 +390,20 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
                                 const u32 t = i + (1u << st);
                                 if (t <= nA && A[t - 1] < lo) i = t;
                             }
+                            // a slice staged block by block: the block that holds the FIRST position >= lo reports the candidate
+                            const bool edge = blk0 != 0u && i == 0u && prev_last >= lo;
                             if (same && A[i] == b) i++;
                             if (A[i] - lo > b - 1u + slop - lo) continue;        // the bits were other buckets'
-                            const u32 jb = e - offB;
-                            if (!gj_verify_staged(segs + s, A, nA, whole, i, pB, mB, jb, (int)slop, same, g, colmap, outp))
-                                gj_verify(segs + s, pA, mA, blk0, nA, pB, mB, b, (int)slop, same, g, colmap, outp);
+                            if (edge) {
+                                if (same) {          // (the skipped a == b may sit at a block edge: leave this read to the positional scorer)
+                                    const i32 r = gaps[g].read;
+                                    route[r] = positional_ok ? ROUTE_POSITIONAL : ROUTE_NONE;
+                                    if (!positional_ok) status[r] = ST_ERROR;
+                                }
+                                continue;
+                            }
+                            const u32 at = atomicAdd(n_cand, 1u);
+                            if (at < cand_cap) { GjCand cd; cd.g = g; cd.seg = (u32)s; cd.jb = e - offB; cand[at] = cd; }
                         }
                         __syncwarp();
                     }
@@ -436,7 +417,7 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
         if (s + 1 < n_segs) open_segment(s + 1, d_cur);
     }
     cp_async_wait0();
-    if (lane == 0) atomicAdd(outp->pos_bytes, 4ull * (unsigned long long)fetched);
+    if (lane == 0) atomicAdd(pos_bytes, 4ull * (unsigned long long)fetched);
 }
 
 // after the matches were sorted by (clause, column): a clause with more than GAP_LIST matches sends its read to the

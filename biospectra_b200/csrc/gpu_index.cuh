@@ -192,7 +192,7 @@ struct GpuIndex {
     // the tail of the exception arrays holds the gap-clause match lists of the pipeline slots: gap_tail entries each
     u32 gap_cap = GAP_CAP_DEFAULT; size_t gap_tail = 0;
     // gap join (gapjoin.cuh): per segment the (start, length) of every term's positions, built when the first gap clause shows up
-    DevBuf<uint2> pse; DevBuf<GjSeg> d_gjsegs; DevBuf<u16> gj_lut;
+    DevBuf<uint2> pse; DevBuf<GjSeg> d_gjsegs; DevBuf<u16> gj_lut; bool gap_join_off = false;
     // table column order: docs sorted by (norm byte, doc id) -- see Tab4Dev::docmap
     DevBuf<u32> colmap, docmap; std::vector<u32> h_docmap;
     // slot: pipeline slot whose gap-clause lists (tail of the exception arrays) the view refers to

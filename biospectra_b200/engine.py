@@ -236,9 +236,10 @@ class Classifier:
 
     def last_gap_join(self):
         c = np.zeros(4, np.int64)
-        ms = C.c_double()
-        _lib.check(self.L.bsp_last_gap_join(self.h, c.ctypes.data, C.byref(ms)), self.h)
-        return dict(zip(("clauses", "chunks", "matches", "position_bytes"), [int(x) for x in c]), join_kernel_ms=ms.value)
+        ms, ms_v, cand = C.c_double(), C.c_double(), C.c_int64()
+        _lib.check(self.L.bsp_last_gap_join(self.h, c.ctypes.data, C.byref(ms), C.byref(ms_v), C.byref(cand)), self.h)
+        return dict(zip(("clauses", "chunks", "matches", "position_bytes"), [int(x) for x in c]), join_kernel_ms=ms.value,
+                    verify_kernel_ms=ms_v.value, candidates=cand.value)
 
     def memory_info(self):
         v = [C.c_int64() for _ in range(3)]

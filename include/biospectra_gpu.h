@@ -209,8 +209,10 @@ int bsp_last_timings(bsp_classifier* h, double* score_kernel_ms, double* pipelin
 /* gap join of the last batch (phrase clauses whose k-mers are not adjacent in the read -- every phrase clause with
  * kmer_skips > 0, Configuration.java:37-44 / Classifier.java:160-200 -- evaluated against the positional index, sorted by
  * first k-mer): out[0] gap clauses, [1] chunks (clauses sharing a first k-mer, one warp each), [2] (clause, document)
- * matches, [3] position bytes the join kernel fetched; its time in ms (CUDA events on the handle's streams) */
-int bsp_last_gap_join(bsp_classifier* h, int64_t out[4], double* join_kernel_ms);
+ * matches, [3] position bytes the join kernel fetched; the join kernel's and the per-candidate verification kernel's time
+ * in ms (CUDA events on the handle's streams); candidates = occurrences of the second k-mer with an occurrence of the
+ * first one inside the window (before the per-document check).  The last three pointers may be null. */
+int bsp_last_gap_join(bsp_classifier* h, int64_t out[4], double* join_kernel_ms, double* verify_kernel_ms, int64_t* candidates);
 /* Cost model of SURVEY.md 8(d) evaluated on the actual index for a read set (host
  * buffers as in bsp_classify_packed): out[0] reads that are scored, [1] tokens, [2] unique
  * query terms (= dictionary probes), [3] sum df, [4] sum ttf over unique terms,
