@@ -26,25 +26,27 @@
 
 #define GJ_C 8                   // clauses per chunk (they share the first k-mer)
 #ifndef GJ_ACAP
-#define GJ_ACAP 512              // positions of the first term staged at a time (longer slices: block by block)
+#define GJ_ACAP 384              // positions of the first term staged at a time (longer slices: block by block)
 #endif
 #ifndef GJ_WARPS
-#define GJ_WARPS 8
+#define GJ_WARPS 10               // 2 CTAs of 10 warps per SM: 111 KB of shared memory each (measured: 8 x 2 aligned 283 ms, 10 x 2 248 ms, 8 x 3 with 32 Kbit tables 256 ms)
 #endif
 #ifndef GJ_MINB
 #define GJ_MINB 2
 #endif
 #ifndef GJ_VEC
-#define GJ_VEC 3
+#define GJ_VEC 3                 // 16-byte vectors per lane and round of the second term (vector q = positions [128 q, 128 q + 128))
 #endif
-//                 // 16-byte vectors per lane and round of the second term (vector q = positions [128 q, 128 q + 128))
 #define GJ_ROUND (GJ_VEC * 128)  // 384 positions per round
 #ifndef GJ_BM_WORDS
 #define GJ_BM_WORDS 2048         // words of a warp's bucket bit table (power of two, multiple of 128): 65,536 bits
 #endif
 #define GJ_BM_BYTES (GJ_BM_WORDS * 4)
 // dynamic shared memory of a CTA: the bit tables (+ one table of slack: they are aligned to their size) and the staging buffers
-#define GJ_SMEM_BYTES (GJ_WARPS * GJ_BM_BYTES + GJ_BM_BYTES + GJ_WARPS * 2 * (GJ_ACAP + 8) * 4)
+#ifndef GJ_ALIGNED
+#define GJ_ALIGNED 0             // tables aligned to their size (address = base | offset) at the cost of one table of slack per CTA
+#endif
+#define GJ_SMEM_BYTES (GJ_WARPS * GJ_BM_BYTES + GJ_ALIGNED * GJ_BM_BYTES + GJ_WARPS * 2 * (GJ_ACAP + 8) * 4)
 #define GJ_LUT_SHIFT 16          // doc_lut[ordinal >> 16] = document of the bucket's first ordinal
 
 struct __align__(16) GjSeg { const u32* positions; const u32* doc_tok; const u16* doc_lut; u32 n_docs, doc_base; };
@@ -220,7 +222,11 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
     // shared memory: the warps' bit tables first, each aligned to its own size (a table address is base | offset), then
     // their staging buffers
     const u32 raw_sa = (u32)__cvta_generic_to_shared(gj_raw);
+#if GJ_ALIGNED
     const u32 bm0_sa = (raw_sa + (u32)(GJ_BM_BYTES - 1)) & ~(u32)(GJ_BM_BYTES - 1);
+#else
+    const u32 bm0_sa = raw_sa;
+#endif
     const u32 bm_sa = bm0_sa + (u32)warp * GJ_BM_BYTES;
     u32* const bm = reinterpret_cast<u32*>(gj_raw + (bm_sa - raw_sa));
     u32* const abuf = reinterpret_cast<u32*>(gj_raw + (bm0_sa - raw_sa) + GJ_WARPS * GJ_BM_BYTES) + (size_t)warp * 2 * (GJ_ACAP + 8);
@@ -367,7 +373,11 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
                                 const u32 x = bv[j] + xoff;
+#if GJ_ALIGNED
                                 const u32 word = lds32(bm_sa | ((x >> (bs + 3)) & (u32)((GJ_BM_WORDS - 1) << 2)));
+#else
+                                const u32 word = lds32(bm_sa + ((x >> (bs + 3)) & (u32)((GJ_BM_WORDS - 1) << 2)));
+#endif
                                 const u32 t = __funnelshift_r(word, 0u, x >> bs) & 3u;          // (shift count taken mod 32)
                                 hits = t * (1u << (2 * (4 * q + j))) + hits;                      // (the multiply-add pipe is idle)
                             }
