@@ -151,7 +151,7 @@ __device__ __forceinline__ u32 gj_lower_bound(const u32* __restrict__ P, u32 n, 
 // first of the document's occurrences with a partner INSIDE the document (that one reports the document; a partner in the
 // neighbouring document is no match), the literal sweep (sloppy_freq_distinct / _same), and the append of
 // (clause, table column, frequency).
-struct GjCand { u32 g, seg, jb; };
+struct __align__(16) GjCand { u32 g, seg, jb, ia; };     // ia: index of the partner the join found in the first k-mer's slice
 
 __global__ void __launch_bounds__(256) gj_verify_kernel(const GjCand* __restrict__ cand, const u32* __restrict__ n_cand, u32 cand_cap,
                                                          const GjSeg* __restrict__ segs, const uint2* __restrict__ pse, u64 n_terms,
@@ -172,9 +172,9 @@ __global__ void __launch_bounds__(256) gj_verify_kernel(const GjCand* __restrict
     while (sg.doc_tok[d + 1] <= b) d++;
     const u32 ds = sg.doc_tok[d], de = sg.doc_tok[d + 1];
     // the first k-mer's positions inside the document: from the lower bound of the window's low end, outwards
-    const u32 lo = b > (u32)slop + 1u ? b - 1u - (u32)slop : 0u;
-    u32 ia0 = gj_lower_bound(A, mA, max(lo, ds));
-    while (ia0 > 0 && A[ia0 - 1] >= ds) ia0--;
+    u32 ia0 = min(c.ia, mA);                                     // the partner the join found; outwards from there
+    if (ia0 < mA && A[ia0] >= ds) { while (ia0 > 0 && A[ia0 - 1] >= ds) ia0--; }
+    else { while (ia0 < mA && A[ia0] < ds) ia0++; }
     u32 ia1 = ia0;
     while (ia1 < mA && A[ia1] < de) ia1++;
     if (ia0 == ia1) return;
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
                                 continue;
                             }
                             const u32 at = atomicAdd(n_cand, 1u);
-                            if (at < cand_cap) { GjCand cd; cd.g = g; cd.seg = (u32)s; cd.jb = e - offB; cand[at] = cd; }
+                            if (at < cand_cap) { GjCand cd; cd.g = g; cd.seg = (u32)s; cd.jb = e - offB; cd.ia = blk0 + i; cand[at] = cd; }
                         }
                         __syncwarp();
                     }

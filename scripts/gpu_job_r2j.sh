@@ -1,10 +1,10 @@
 set -x
-mkdir -p gpurun_out/r2p
-timeout 600 python -m pytest tests/test_gpu_gapjoin.py -x -q > gpurun_out/r2p/pytest_gapjoin.log 2>&1; echo "rc=$?" >> gpurun_out/r2p/pytest_gapjoin.log
-tail -5 gpurun_out/r2p/pytest_gapjoin.log
+mkdir -p gpurun_out/r2u
+timeout 600 python -m pytest tests/test_gpu_gapjoin.py -x -q > gpurun_out/r2u/pytest_gapjoin.log 2>&1; echo "rc=$?" >> gpurun_out/r2u/pytest_gapjoin.log
+tail -5 gpurun_out/r2u/pytest_gapjoin.log
 B="python bench.py --skips 5 --no-secondary --no-cpu-baseline --steps 2 --warmup 1"
-timeout 600 $B > gpurun_out/r2p/bench_default.json 2> gpurun_out/r2p/bench_default.err
-for f in gpurun_out/r2p/bench_*.json; do python - "$f" <<'PY'
+timeout 600 $B > gpurun_out/r2u/bench_default.json 2> gpurun_out/r2u/bench_default.err
+for f in gpurun_out/r2u/bench_*.json; do python - "$f" <<'PY'
 import json,sys
 try:
     d=json.load(open(sys.argv[1])); r=d["roofline"]

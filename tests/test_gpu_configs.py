@@ -89,6 +89,32 @@ def test_c1_result_set_mode_and_bm25(c1, monkeypatch):
         g.close()
 
 
+@pytest.mark.parametrize("alg,scoring", [("PAIRED_PROXIMITY", "tfidf"), ("CHAIN_PROXIMITY", "tfidf"), ("PAIRED_PROXIMITY", "bm25")])
+def test_c1_full_size_code_default_kmer_skips(c1, alg, scoring, monkeypatch):
+    """C1 at full size with the CODE default kmer_skips = 5 (Configuration.java:37-44; the shipped json says 0): every phrase
+    clause is a gap clause, evaluated by the gap join (gapjoin.cuh) and scored by the filter kernel / the exact kernel; all
+    10,000 reads bit for bit against the oracle, and 2,000 of them through the positional scorer"""
+    genomes, reads, src, ox = c1
+    a = {"CHAIN_PROXIMITY": 1, "PAIRED_PROXIMITY": 2}[alg]
+    res_o = ox.classify(reads, skips=5, algorithm=a, scoring=1 if scoring == "bm25" else 0, msm=0.5, threads=8)
+    g = _gpu(genomes, kmer_skips=5, query_algorithm=alg, scoring_algorithm=scoring, full_topn=1, dense_tables=1, positional=1)
+    try:
+        for filt in ("1", "0"):
+            monkeypatch.setenv("BSP_FILTER", filt)
+            res_g = g.classify_batch(reads)
+            common.assert_classify_equal(res_g, res_o, reads, "C1 skips=5 %s %s filter=%s" % (alg, scoring, filt))
+            gj = g.last_gap_join()
+            nc = int(res_o["n_clauses"][res_o["status"] == 0].sum())       # (PAIRED: a trailing Term clause is not a gap clause)
+            assert nc - len(reads) <= gj["clauses"] <= nc and gj["matches"] > 0
+            assert g.last_counters()["positional_reads"] == 0
+        monkeypatch.setenv("BSP_DISABLE_GAP", "1")
+        res_g = g.classify_batch(reads[:2000])
+        common.assert_classify_equal(res_g, {k: v[:2000] for k, v in res_o.items()}, reads, "C1 skips=5 positional")
+        assert (g.last_routes(2000)[res_o["status"][:2000] == 0] == 2).all()
+    finally:
+        g.close()
+
+
 def test_error_rate_and_read_length_sweep(oracle_lib, monkeypatch):
     """configs[4]: 0-8 % error x 100-250 bp reads exercising the vague / unknown thresholds (smaller reference: 12 genomes
     of 300 kbp with two related pairs so that VAGUE ties occur), default code path (kmer_skips from the shipped json = 0)

@@ -117,7 +117,7 @@ def test_clause_list_grows(oracle_lib, monkeypatch):
         g.set_query(Configuration(index_path="", kmer_size=6, kmer_skips=5, query_algorithm="CHAIN_PROXIMITY", full_topn=1))
         rg = g.classify_batch(reads)
         common.assert_classify_equal(rg, ro, reads, "clause list")
-        assert g.last_gap_join()["clauses"] == int(ro["n_clauses"][ro["status"] == 0].sum())
+        assert g.last_gap_join()["clauses"] == int(ro["n_clauses"][ro["status"] == 0].sum())       # (CHAIN: every clause is a phrase)
     finally:
         g.close()
 
