@@ -742,7 +742,7 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
     ClassificationResultSummary summary;
     summary.queryFilename = base_name(inputFasta);
     summary.startTime = now_ms();
-    const size_t BATCH_READS = (size_t)std::max<long long>(1024, env_ll("BSP_HOST_BATCH_READS", 131072)), BATCH_BYTES = (size_t)64 << 20;
+    const size_t BATCH_READS = (size_t)std::max<long long>(1024, env_ll("BSP_HOST_BATCH_READS", 65536)), BATCH_BYTES = (size_t)64 << 20;
     typedef std::unique_ptr<ReadBatch> BatchPtr;
     BoundedQueue<BatchPtr> parsed(3), classified(3);
     std::exception_ptr reader_error, writer_error;
