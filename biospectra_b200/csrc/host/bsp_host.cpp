@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <chrono>
 #include <dirent.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -193,7 +195,7 @@ FASTAReader::FASTAReader(const FASTAReader& whole, size_t begin, size_t end)
     : data_(whole.data_), pos_(std::min(begin, whole.data_->size())), end_(std::min(end, whole.data_->size())) {}
 
 std::vector<size_t> FASTAReader::stripeCuts(size_t target) const {
-    const std::string& d = *data_;
+    const FileImage& d = *data_;
     std::vector<size_t> cuts{0};
     if (target == 0) target = 1;
     size_t at = target;
@@ -225,18 +227,36 @@ FASTAReader::FASTAReader(const std::string& path) {
         gzclose(g);
         if (n < 0 || (err != Z_OK && err != Z_STREAM_END)) throw IOError("gzip error reading " + path);
     } else {
+        // a regular file is mapped, not copied (BSP_FASTA_MMAP=0: read into a buffer like everything else)
+        const int fd = env_ll("BSP_FASTA_MMAP", 1) != 0 ? open(path.c_str(), O_RDONLY) : -1;
+        if (fd >= 0) {
+            struct stat sb;
+            if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+                void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (m != MAP_FAILED) {
+                    madvise(m, (size_t)sb.st_size, MADV_WILLNEED);
+                    close(fd);
+                    this->end_ = (size_t)sb.st_size;
+                    this->data_ = std::make_shared<const FileImage>((const char*)m, (size_t)sb.st_size);
+                    return;
+                }
+            }
+            close(fd);
+        }
         data_ = read_text_file(path);
     }
     this->end_ = data_local.size();
-    this->data_ = std::make_shared<const std::string>(std::move(data_local));
+    this->data_ = std::make_shared<const FileImage>(std::move(data_local));
 }
 
+FileImage::~FileImage() { if (mapped_ && p_) munmap(const_cast<char*>(p_), n_); }
+
 bool FASTAReader::readLine(std::string& line) {      // BufferedReader#readLine: \n, \r\n, \r
-    const std::string& d = *data_;
+    const FileImage& d = *data_;
     if (pos_ >= end_) return false;
     size_t st = pos_;
     while (pos_ < end_ && d[pos_] != '\n' && d[pos_] != '\r') pos_++;
-    line.assign(d, st, pos_ - st);
+    line.assign(d.data() + st, pos_ - st);
     if (pos_ < end_) {
         if (d[pos_] == '\r' && pos_ + 1 < d.size() && d[pos_ + 1] == '\n') pos_ += 2;
         else pos_++;

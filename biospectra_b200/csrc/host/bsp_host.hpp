@@ -43,6 +43,26 @@ struct FastaFileHelper {
     static std::string findTaxonHierarchyDoc(const std::string& fastaPath);
 };
 
+// The bytes of an input file: a read-only mapping of a regular file (no copy: the parser threads fault the page-cache pages
+// in side by side), or an owned buffer (gzip input, pipes).
+class FileImage {
+public:
+    FileImage() {}
+    explicit FileImage(std::string&& owned) : owned_(std::move(owned)), p_(owned_.data()), n_(owned_.size()) {}
+    FileImage(const char* mapped, size_t n) : p_(mapped), n_(n), mapped_(true) {}
+    FileImage(const FileImage&) = delete;
+    FileImage& operator=(const FileImage&) = delete;
+    ~FileImage();
+    const char* data() const { return p_; }
+    size_t size() const { return n_; }
+    char operator[](size_t i) const { return p_[i]; }
+private:
+    std::string owned_;
+    const char* p_ = nullptr;
+    size_t n_ = 0;
+    bool mapped_ = false;
+};
+
 struct FASTAEntry { std::string headerLine, sequence; };
 class FASTAReader {
 public:
@@ -57,7 +77,7 @@ public:
     size_t imageSize() const { return data_->size(); }
 private:
     bool readLine(std::string& line);
-    std::shared_ptr<const std::string> data_;
+    std::shared_ptr<const FileImage> data_;
     size_t pos_ = 0, end_ = 0;
     std::string pending_;
     bool have_pending_ = false;
