@@ -31,6 +31,16 @@ struct BspError : public std::runtime_error {
     } while (0)
 
 #define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
+// Debug build (make EXTRA=-DBSP_DEBUG_BOUNDS): device-side bounds assertions around the shared-memory rings, tables and
+// lists of the scoring kernels -- compute-sanitizer is not available on every pool, this is what the GPU tests can be run
+// under instead (a failing assertion traps the kernel: the call returns BSP_ERR_CUDA and the test fails).  Nothing in a
+// release build.
+#ifdef BSP_DEBUG_BOUNDS
+#include <cassert>
+#define BSP_ASSERT(cond) assert(cond)
+#else
+#define BSP_ASSERT(cond) ((void)0)
+#endif
 
 static inline i64 ceil_div(i64 a, i64 b) { return (a + b - 1) / b; }
 static inline i64 round_up(i64 a, i64 b) { return ceil_div(a, b) * b; }

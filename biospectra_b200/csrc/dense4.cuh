@@ -654,10 +654,12 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
                 }
 #pragma unroll
                 for (u32 j = 0; j < FK_EXS_ROW; j++)
-                    if (j < ne) { s_sm_doc[at + j] = xd[j]; s_sm_f[at + j] = xf[j]; s_sm_c[at + j] = (u8)c; }
+                    if (j < ne) { BSP_ASSERT(at + j < (u32)FK_EXS_CAP); s_sm_doc[at + j] = xd[j]; s_sm_f[at + j] = xf[j]; s_sm_c[at + j] = (u8)c; }
             } else {
                 for (u32 j = at; j < FK_EXS_CAP; j++) s_sm_doc[j] = 0xFFFFFFFFu;
-                s_exrows[atomicAdd(&s_nexrows, 1)] = (u8)c;
+                const int xr = atomicAdd(&s_nexrows, 1);
+                BSP_ASSERT(xr >= 0 && xr <= FK_MAX_CLAUSES && c <= FK_MAX_CLAUSES);
+                s_exrows[xr] = (u8)c;
             }
         }
     }
@@ -678,6 +680,7 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
         for (; i + 2 <= n_two; i += 2) {
             cp_async_wait<FK_STAGES / 2 - 1>();
             const u32 sa0 = cur, sa1 = cur + stride_b;
+            BSP_ASSERT(sa0 >= slot_sa && sa1 < ring_end && i + 1 < nc && nc <= FK_MAX_CLAUSES);       // both slots inside this thread's ring
             const uint4 q0 = lds128(sa0), q1 = lds128(sa1);
             const uint4 l0 = lo_tab[i], l1 = lo_tab[i + 1];
             if (all_terms) {
@@ -879,6 +882,7 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
                 const float e = SIM == SIM_BM25 ? ((i32)m >= need ? (float)Q : 0.0f) : estimate(Q, m, need, doc_w[d]);
                 if (e >= theta && e > 0.0f) {
                     int idx = atomicAdd(&s_ncand, 1);
+                    BSP_ASSERT(idx >= 0);
                     if (idx < FK_CAND_CAP) s_cand[idx] = d;
                 }
             }

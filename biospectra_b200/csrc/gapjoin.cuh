@@ -167,10 +167,13 @@ __global__ void __launch_bounds__(256) gj_verify_kernel(const GjCand* __restrict
     const u32* A = sg.positions + dA.x;
     const u32* B = sg.positions + dB.x;
     const u32 mA = dA.y, mB = dB.y, jb = c.jb;
+    BSP_ASSERT(jb < mB && c.ia <= mA && mA > 0u);
     const u32 b = B[jb];
     u32 d = sg.doc_lut[b >> GJ_LUT_SHIFT];
+    BSP_ASSERT(d < sg.n_docs && sg.doc_tok[d] <= b);
     while (sg.doc_tok[d + 1] <= b) d++;
     const u32 ds = sg.doc_tok[d], de = sg.doc_tok[d + 1];
+    BSP_ASSERT(d < sg.n_docs && ds <= b && b < de);
     // the first k-mer's positions inside the document: from the lower bound of the window's low end, outwards
     u32 ia0 = min(c.ia, mA);                                     // the partner the join found; outwards from there
     if (ia0 < mA && A[ia0] >= ds) { while (ia0 > 0 && A[ia0 - 1] >= ds) ia0--; }
@@ -334,7 +337,9 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
                 // ---- bit table (a Bloom filter with two hashes of the word index): bucket k = (a + bias) >> bs sets bit k & 31 of
                 // words h1(k >> 5) and h2(k >> 5); bit 31 of a word also stands for bucket 0 of the next one, so that the two
                 // buckets of a window are always found in one word
+                BSP_ASSERT(offA + nA + 1u < (u32)(GJ_ACAP + 8) && nA >= 1u);                  // block + sentinels inside the staging buffer
                 for (u32 i = lane; i < nA; i += 32) {
+                    BSP_ASSERT(i == 0u || A[i - 1] < A[i]);                                     // a slice ascends strictly
                     const u32 k = (A[i] + bias) >> bs;
                     const u32 wi = k >> 5, bit = 1u << (k & 31u);
                     atomicOr(&bm[wi & (GJ_BM_WORDS - 1)], bit);
@@ -403,6 +408,7 @@ __global__ void __launch_bounds__(GJ_WARPS * 32, GJ_MINB) gap_join_kernel(
                             // a slice staged block by block: the block that holds the FIRST position >= lo reports the candidate
                             const bool edge = blk0 != 0u && i == 0u && prev_last >= lo;
                             if (same && A[i] == b) i++;
+                            BSP_ASSERT(i <= nA + 1u && e - offB < mB);
                             if (A[i] - lo > b - 1u + slop - lo) continue;        // the bits were other buckets'
                             if (edge) {
                                 if (same) {          // (the skipped a == b may sit at a block edge: leave this read to the positional scorer)
