@@ -16,4 +16,4 @@ NCU="ncu --clock-control none --profile-from-start off"
 timeout 900 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $OUT/launches_C2_step.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_launch.log 2>&1
 timeout 900 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $OUT/launches_C2_skips5_step.csv python bench.py --skips 5 --steps 1 --warmup 1 --no-cpu-baseline --no-secondary > $OUT/ncu_launch5.log 2>&1
 timeout 1200 $NCU --set full --import-source on -k regex:filter_score_kernel -c 1 -o $OUT/filter_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-secondary > $OUT/ncu_full.log 2>&1
-tail -3 $OUT/pytest_gpu.log $OUT/smoke.log
+tail -n 3 $OUT/pytest_gpu.log; tail -n 3 $OUT/smoke.log
