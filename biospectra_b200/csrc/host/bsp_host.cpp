@@ -611,14 +611,14 @@ bool Classifier::appendResultJson(std::string& o, const char* header, size_t hea
     o += "{\"query_header\":"; jsonm::write_fasta_string_n(o, header, headerLen);
     o += ",\"query\":"; jsonm::write_fasta_string_n(o, seq, seqLen);
     o += ",\"result\":[";
-    char num[48];
     for (int j = 0; j < nh; j++) {
         if (j) o.push_back(',');
-        int len = snprintf(num, sizeof num, "{\"docid\":%d,\"rank\":%d,", docs[j], j);
-        o.append(num, (size_t)len);
+        o += "{\"docid\":"; jsonm::append_int(o, docs[j]);
+        o += ",\"rank\":"; jsonm::append_int(o, j);
+        o.push_back(',');
         o += docs_[(size_t)docs[j]].json;
         o += ",\"score\":";
-        o += jsonm::java_double((double)scores[j]);
+        jsonm::append_java_double(o, (double)scores[j]);
         o.push_back('}');
     }
     static const char* TYPE[3] = {"UNKNOWN", "VAGUE", "CLASSIFIED"};
@@ -859,6 +859,8 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
     // formatted JSON of one batch (one string per formatter thread, in read order) on its way to the file
     typedef std::unique_ptr<std::vector<std::string>> ChunkPtr;
     BoundedQueue<ChunkPtr> formatted(2);
+    std::mutex spare_mu;
+    std::vector<ChunkPtr> spare_chunks;             // written chunks on their way back to the formatter
     std::exception_ptr file_error;
     std::thread file_thread([&] {
         try {
@@ -892,6 +894,8 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
                 if (failed) throw IOError("write failed: " + classifyOutput);
                 file_off = at[nc];
                 write_ms += ms_since(t_wr);
+                // the buffers go back to the formatter (their pages stay mapped: no page faults for the next batch's text)
+                { std::lock_guard<std::mutex> lk(spare_mu); if (spare_chunks.size() < 4) spare_chunks.push_back(std::move(c)); }
             }
         } catch (...) {
             file_error = std::current_exception();
@@ -905,7 +909,14 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
             while (classified.pop(b)) {
                 const size_t n = b->size();
                 const int nt = (int)std::min<size_t>((size_t)T, std::max<size_t>(1, n / 4096));
-                ChunkPtr chunk_holder(new std::vector<std::string>((size_t)nt));
+                ChunkPtr chunk_holder;
+                { std::lock_guard<std::mutex> lk(spare_mu); if (!spare_chunks.empty()) { chunk_holder = std::move(spare_chunks.back()); spare_chunks.pop_back(); } }
+                if (!chunk_holder) chunk_holder.reset(new std::vector<std::string>());
+                if (chunk_holder->size() > (size_t)nt) {           // keep the strings with the largest capacities
+                    std::sort(chunk_holder->begin(), chunk_holder->end(), [](const std::string& a, const std::string& b) { return a.capacity() > b.capacity(); });
+                }
+                chunk_holder->resize((size_t)nt);
+                for (std::string& o : *chunk_holder) o.clear();
                 std::vector<std::string>& chunk = *chunk_holder;
                 std::vector<long long> counts((size_t)nt * 3, 0);
                 auto work = [&](int t) {

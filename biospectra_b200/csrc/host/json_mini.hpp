@@ -188,38 +188,61 @@ inline void write_string_n(std::string& o, const char* sp, size_t n) {
 
 // java.lang.Double#toString layout: shortest digits that round-trip; plain decimal for
 // 1e-3 <= |d| < 1e7, otherwise d.dddE[-]n
-inline std::string java_double(double d) {
-    if (std::isnan(d)) return "NaN";
-    if (std::isinf(d)) return d > 0 ? "Infinity" : "-Infinity";
-    if (d == 0) return std::signbit(d) ? "-0.0" : "0.0";
+// appends the text to `o` without intermediate strings (the result formatter calls this for every hit)
+inline void append_java_double(std::string& o, double d) {
+    if (std::isnan(d)) { o += "NaN"; return; }
+    if (std::isinf(d)) { o += d > 0 ? "Infinity" : "-Infinity"; return; }
+    if (d == 0) { o += std::signbit(d) ? "-0.0" : "0.0"; return; }
     char buf[64];
-    // shortest digits that round-trip (std::to_chars), scientific layout: [-]d.ddddde[+-]xx
+    // shortest digits that round-trip (std::to_chars), scientific layout: [-]d[.ddddd]e[+-]xx
     auto tc = std::to_chars(buf, buf + sizeof buf - 1, d, std::chars_format::scientific);
-    *tc.ptr = 0;
-    // buf = [-]d.ddddde[+-]xx
-    std::string s(buf);
-    bool neg = s[0] == '-';
-    if (neg) s = s.substr(1);
-    size_t epos = s.find('e');
-    int exp10 = atoi(s.c_str() + epos + 1);
-    std::string digits;
-    for (size_t i = 0; i < epos; i++) if (s[i] != '.') digits.push_back(s[i]);
-    std::string out;
-    double ad = std::fabs(d);
+    const char* p = buf;
+    const char* end = tc.ptr;
+    if (*p == '-') { o.push_back('-'); p++; }
+    const char* e = p;
+    while (e < end && *e != 'e') e++;
+    int exp10 = 0;
+    {
+        const char* q = e + 1;
+        bool eneg = false;
+        if (q < end && (*q == '+' || *q == '-')) { eneg = *q == '-'; q++; }
+        for (; q < end; q++) exp10 = exp10 * 10 + (*q - '0');
+        if (eneg) exp10 = -exp10;
+    }
+    char digits[32];
+    int nd = 0;
+    for (const char* q = p; q < e; q++) if (*q != '.') digits[nd++] = *q;
+    const double ad = std::fabs(d);
     if (ad >= 1e-3 && ad < 1e7) {
         if (exp10 >= 0) {
-            std::string ip = digits.substr(0, std::min<size_t>(digits.size(), (size_t)exp10 + 1));
-            while ((int)ip.size() < exp10 + 1) ip.push_back('0');
-            std::string fp = digits.size() > (size_t)exp10 + 1 ? digits.substr(exp10 + 1) : "0";
-            out = ip + "." + fp;
+            const int ni = exp10 + 1;                       // digits before the point
+            for (int i = 0; i < ni; i++) o.push_back(i < nd ? digits[i] : '0');
+            o.push_back('.');
+            if (nd > ni) o.append(digits + ni, (size_t)(nd - ni)); else o.push_back('0');
         } else {
-            out = "0." + std::string((size_t)(-exp10 - 1), '0') + digits;
+            o += "0.";
+            o.append((size_t)(-exp10 - 1), '0');
+            o.append(digits, (size_t)nd);
         }
     } else {
-        std::string fp = digits.size() > 1 ? digits.substr(1) : "0";
-        out = digits.substr(0, 1) + "." + fp + "E" + std::to_string(exp10);
+        o.push_back(digits[0]);
+        o.push_back('.');
+        if (nd > 1) o.append(digits + 1, (size_t)(nd - 1)); else o.push_back('0');
+        o.push_back('E');
+        char eb[16];
+        auto te = std::to_chars(eb, eb + sizeof eb, exp10);
+        o.append(eb, (size_t)(te.ptr - eb));
     }
-    return neg ? "-" + out : out;
+}
+inline std::string java_double(double d) {
+    std::string o;
+    append_java_double(o, d);
+    return o;
+}
+inline void append_int(std::string& o, long long v) {
+    char b[24];
+    auto t = std::to_chars(b, b + sizeof b, v);
+    o.append(b, (size_t)(t.ptr - b));
 }
 
 }  // namespace jsonm
