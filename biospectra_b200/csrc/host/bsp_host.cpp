@@ -855,7 +855,7 @@ void LocalClassifier::classify(const std::string& inputFasta, const std::string&
     });
 
     const Classifier& cls = classifier_;
-    const int T = std::max(1, cls.workerThreads());
+    const int T = (int)std::max<long long>(1, std::min<long long>(cls.workerThreads(), env_ll("BSP_HOST_FORMATTERS", 1 << 20)));
     // formatted JSON of one batch (one string per formatter thread, in read order) on its way to the file
     typedef std::unique_ptr<std::vector<std::string>> ChunkPtr;
     BoundedQueue<ChunkPtr> formatted(2);
