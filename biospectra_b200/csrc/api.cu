@@ -707,14 +707,15 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     qp.gap_cap = GC;
     CUDA_CHECK(cudaMemsetAsync(sc.gap_ctr.p, 0, 16, st));
     // fast filter path: tf-idf; CTA per (doc tile, read), 32 docs per thread, <= 512 threads per tile.
-    // BSP_FILTER: 0 off, 1 whenever usable, unset = only where it pays (enough docs to fill a CTA)
+    // BSP_FILTER: 0 off, 1 whenever usable, unset = from 256 documents up (at 600 documents the filter kernel takes 2.1 ms per
+    // 200 k reads against 6.5 ms for the all-exact kernel; below a few hundred both are noise)
     const u32 D = (u32)ix.docs.size();
     const i64 filter_mode = env_i64("BSP_FILTER", -1);
     // (the filter kernel addresses rows by 32-bit offsets in 16-byte units: table below 64 GiB)
     const bool tab_addressable = ((u64)ix.n_rows + 2) * ix.row_bytes < (64ull << 30);
     // (BM25: one LUT per norm class of the handle; 16 classes span a 4x range of document lengths)
     qp.filter_ok = qp.dense_ok && tab_addressable && (qp.sim == SIM_TFIDF || (h->n_classes <= 16 && env_i64("BSP_BM25_FILTER", 1) != 0)) &&
-                   filter_mode != 0 && (filter_mode == 1 || D >= 1024);
+                   filter_mode != 0 && (filter_mode == 1 || D >= 256);
     qp.filter_nc_max = FK_MAX_CLAUSES;
     if (qp.sim == SIM_BM25)
         qp.filter_nc_max = (int)std::min<i64>(FK_MAX_CLAUSES, FK_BM25_LUT_BYTES / ((i64)std::max(h->n_classes, 1) * (qp.alg == ALG_NAIVE ? 24 : 16)) - 2);
