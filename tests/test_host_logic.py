@@ -49,6 +49,25 @@ def test_fasta_reader_matches_the_reference_class_file(L, tmp_path, c):
     assert (err is None) == (c["error"] is None), (err, c["error"])
 
 
+@pytest.mark.parametrize("mmap", ["0", "1"])
+def test_fasta_reader_mapped_and_buffered_images_agree(L, tmp_path, monkeypatch, mmap):
+    """FASTAReader takes a regular file as a read-only mapping (FileImage, BSP_FASTA_MMAP=1, the default) or reads it into a
+    buffer (BSP_FASTA_MMAP=0, also what gzip input and pipes get): every executed-reference case gives the same entries and
+    the same error either way; an empty file (nothing to map) yields no entries."""
+    monkeypatch.setenv("BSP_FASTA_MMAP", mmap)
+    for c in FASTA_GOLDEN:
+        p = tmp_path / (c["name"] + ".fa")
+        p.write_bytes(c["text"].encode("latin-1"))
+        recs, err = read_fasta_c(L, p, partial=True)
+        want = [tuple("".join(chr(0xFFFD) if ord(ch) >= 0x80 else ch for ch in x) for x in e) for e in recs]
+        assert want == [tuple(e) for e in c["entries"]], c["name"]
+        assert (err is None) == (c["error"] is None), (c["name"], err, c["error"])
+    empty = tmp_path / "empty.fa"
+    empty.write_bytes(b"")
+    recs, err = read_fasta_c(L, empty, partial=True)
+    assert recs == [] and err is None
+
+
 FASTA_CASES = [
     ">h1 desc\nACGT\nacgtnn\n>h2\nTTTT\n",
     ">h1\r\nAC GT\r\n;comment line\r\nGG\r\n>h2\rTT\r",
