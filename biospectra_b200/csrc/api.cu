@@ -713,8 +713,9 @@ static void pipeline_phase1(bsp_classifier* h, Scratch& sc, i32 n, const u8* d_s
     const i64 filter_mode = env_i64("BSP_FILTER", -1);
     // (the filter kernel addresses rows by 32-bit offsets in 16-byte units: table below 64 GiB)
     const bool tab_addressable = ((u64)ix.n_rows + 2) * ix.row_bytes < (64ull << 30);
-    // (BM25: one LUT per norm class of the handle; 16 classes span a 4x range of document lengths)
-    qp.filter_ok = qp.dense_ok && tab_addressable && (qp.sim == SIM_TFIDF || (h->n_classes <= 16 && env_i64("BSP_BM25_FILTER", 1) != 0)) &&
+    // (BM25: one LUT per norm class of the handle; 32 classes span a 256x range of document lengths.  The per-class LUTs share
+    //  FK_BM25_LUT_BYTES of shared memory: more classes leave room for fewer clauses, see filter_nc_max)
+    qp.filter_ok = qp.dense_ok && tab_addressable && (qp.sim == SIM_TFIDF || (h->n_classes <= FK_BM25_CLASSES && env_i64("BSP_BM25_FILTER", 1) != 0)) &&
                    filter_mode != 0 && (filter_mode == 1 || D >= 256);
     qp.filter_nc_max = FK_MAX_CLAUSES;
     if (qp.sim == SIM_BM25)

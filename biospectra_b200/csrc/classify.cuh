@@ -25,7 +25,7 @@
 #define ROUTE_NONE 0             // dropped / error: no scoring
 #define ROUTE_DENSE 1            // exact_score_kernel over the 4-bit tables
 #define ROUTE_POSITIONAL 2
-#define ROUTE_FILTER 3           // filter_score_kernel (<= 255 clauses; BM25: <= 16 norm classes in the handle)
+#define ROUTE_FILTER 3           // filter_score_kernel (<= 255 clauses; BM25: <= 32 norm classes in the handle)
 
 #define ST_OK 0
 #define ST_DROPPED 1

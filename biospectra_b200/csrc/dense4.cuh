@@ -398,6 +398,7 @@ __device__ __forceinline__ u32 cell_code(const Tab4Dev& T, u32 row, u32 doc) {
 #define FK_EXS_CAP 96              // ... this many cells per CTA in all (the rest is searched in global memory)
 #define FK_EXA_SHARED 0xFFFFFFFFu    // s_exa of a clause whose list sits in shared memory
 #define FK_QMAX 255.0f
+#define FK_BM25_CLASSES 32             // norm classes of a handle the BM25 filter takes (8 classes per factor 4 of document length: a 256 x range)
 #define FK_BM25_LUT_BYTES (40 * 1024)   // BM25: per-class clause LUTs behind the ring (classes x (clauses + 1) x 16 B, NAIVE_KMER 24 B)
 #define FK_ROUND_SLACK 0.51f       // |q - S*tf*value| <= 0.5 (+ float rounding of the product)
 #define FK_REL_SLACK 4e-6f         // float roundings of Lucene's score and of the bound arithmetic
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(FK_MAXT, FK_MINB) filter_score_kernel(
     __shared__ int s_ncand, s_nexrows, s_over, s_ndense, s_ngap;
     __shared__ u32 s_qmin, s_nexc, s_cntlo;
 
-    __shared__ float s_ratio[SIM == SIM_BM25 ? 16 * 16 : 1];      // BM25: f / (f + K_class) per (class slot, code), 16 classes per launch
+    __shared__ float s_ratio[SIM == SIM_BM25 ? FK_BM25_CLASSES * 16 : 1];      // BM25: f / (f + K_class) per (class, code)
     extern __shared__ __align__(16) uint4 ring[];         // FK_STAGES x blockDim.x x 16 B: row ring of pass 1, then the staged cell codes
     // BM25: behind the ring, per class the clause LUTs (uint4: q codes 0..3 | 4..7 | prefetch offset), then for NAIVE_KMER the
     // high halves (uint2: codes 8..11 | 12..15)

@@ -149,3 +149,32 @@ def test_unequal_length_reference_against_oracle(oracle_lib, min_strand, monkeyp
     finally:
         if g is not None:
             g.close()
+
+
+def test_bm25_filter_with_more_than_16_norm_classes(oracle_lib, monkeypatch):
+    """60 genomes of 3 kbp - 800 kbp (a 260 x range of document lengths: 8 norm bytes per factor 4, 25+ classes): BM25 stays on
+    the filter kernel (per-class byte LUTs for up to 32 classes; 16 in round 1) and agrees with the oracle bit for bit, also
+    for NAIVE_KMER and with the all-exact kernel beside it"""
+    import common
+    from biospectra_b200 import synth, Configuration
+    rng = np.random.Generator(np.random.PCG64(5))
+    lengths = np.exp(rng.uniform(np.log(3.0e3), np.log(8.0e5), 60)).astype(np.int64)
+    genomes = [synth.genome_numpy(9, g, int(lengths[g])) for g in range(len(lengths))]
+    reads, _src = synth.sample_reads_numpy(genomes, 4_000, 100, 0.03, 23)
+    ents = [g.tobytes().decode() for g in genomes]
+    ox = common.build_oracle(oracle_lib, ents, 8, False)
+    norms = {ox.doc_info(d)[1] for d in range(ox.stats()["n_docs"])}
+    assert 16 < len(norms) <= 32, len(norms)
+    g = common.build_gpu(ents, 8, False, dict(kmer_skips=0, query_algorithm="PAIRED_PROXIMITY", scoring_algorithm="bm25"))
+    try:
+        for alg, a in (("PAIRED_PROXIMITY", 2), ("NAIVE_KMER", 0)):
+            ro = ox.classify(reads, skips=0, algorithm=a, scoring=1, msm=0.5, threads=8)
+            g.set_query(Configuration(index_path="", kmer_size=8, full_topn=1, kmer_skips=0, query_algorithm=alg, scoring_algorithm="bm25"))
+            for filt in ("1", "0"):
+                monkeypatch.setenv("BSP_FILTER", filt)
+                rg = g.classify_batch(reads)
+                common.assert_classify_equal(rg, ro, reads, "bm25, %d norm classes, %s, filter=%s" % (len(norms), alg, filt))
+                if filt == "1":
+                    assert (g.last_routes(len(reads))[ro["status"] == 0] == 3).mean() > (0.9 if a == 2 else 0.5)   # (NAIVE_KMER: 24 B per clause and class)
+    finally:
+        g.close()
