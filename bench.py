@@ -427,12 +427,31 @@ def timed_steps(fn, steps, sync, clf=None):
     return time.perf_counter() - t, kernel_ms, pipe_ms, launches
 
 
+def gap_join_traffic(gj):
+    """dram read + write bytes of the committed `--set full` capture of gap_join_kernel (profiles/r2_ncu_gap_join.json), valid when
+    the launch did the same work as the captured one (same position bytes within 2 %: C2, kmer_skips = 5, 1 M reads)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_gap_join.json")) as f:
+            m = json.load(f)["r2gj_gap_join_final_full_1m_reads"]
+
+        def gb(k):
+            v, u = float(m[k]["value"]), m[k]["unit"]
+            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+        if abs(gj["position_bytes"] - 675542134176) > 0.02 * 675542134176:
+            return None
+        return gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
+    except Exception:
+        return None
+
+
 def gap_join_roofline(gj, peak, peak_src):
     """gap_join_kernel (gapjoin.cuh): achieved = position bytes the launch fetched (counted by the kernel: the first term's
     slice once per chunk and segment, every clause's second-term slice once per segment) / its CUDA-event time"""
     s = gj["join_kernel_ms"] / 1e3
     ach = gj["position_bytes"] / s / 1e9 if s > 0 else 0.0
-    return {"bound": "hbm", "kernel": "gap_join_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    traffic = gap_join_traffic(gj)
+    return {"bound": "hbm", "kernel": "gap_join_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+            "traffic_frac": (traffic / s / 1e9 / peak) if (traffic and s > 0) else None,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": gj["position_bytes"], "kernel_ms_per_launch": gj["join_kernel_ms"],
             "byte_model": "4 B x positions: per (chunk of <= 8 clauses sharing the first k-mer, segment) that k-mer's slice once + every "
                           "clause's second k-mer slice; directory lookups (8 B per term and segment) not counted",
