@@ -872,9 +872,10 @@ def main():
         peak, peak_src = peaks()
         per_launch_s = (kernel_ms / 1e3) / steps
         roof = route_roofline(cnt, cost, layout, stats["n_docs"], total_bytes, per_launch_s, peak, peak_src, gap_join=gj)
-        roof["traffic"] = measured_traffic(args, roof["kernel"]) if default_cfg else None
-        if roof["traffic"]:
-            roof["traffic_frac"] = roof["traffic"] / per_launch_s / 1e9 / peak
+        if roof["kernel"] != "gap_join_kernel":          # (the gap join's record carries its own committed capture)
+            roof["traffic"] = measured_traffic(args, roof["kernel"]) if default_cfg else None
+            if roof["traffic"]:
+                roof["traffic_frac"] = roof["traffic"] / per_launch_s / 1e9 / peak
         roof["note"] = ("achieved = algorithmic bytes the launch must fetch from DRAM (byte_model) / the scoring kernel's time from CUDA "
                         "events on the library's stream; traffic = dram bytes of the committed ncu capture of this kernel on this workload")
         line = {"metric": "reads/sec classified", "value": value, "unit": "reads/s", "n_gpus": world, "steps": steps,
